@@ -1,0 +1,145 @@
+"""ctypes binding of libesr_b200.so (declared in include/esr_b200.h).
+
+The product path has no fallback: if the library is missing or the device is not
+sm_100, importing callers get an exception, never a silent PyTorch path.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libesr_b200.so")
+
+MAX_KBLOCKS = 24
+KBLOCK_CH = 32
+CEM_MAX_TAPS = 64
+
+EPI_LRELU, EPI_RES1, EPI_RES2, EPI_ACCUM, EPI_MASK = 1, 2, 4, 8, 16
+
+
+class KBlock(C.Structure):
+    _fields_ = [("src", C.c_int32), ("chan", C.c_int32), ("w_off", C.c_uint32), ("dy_mask", C.c_uint8),
+                ("slice_mask", C.c_uint8), ("n_dy", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+class TensorNHWC(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("channels", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("src", TensorNHWC * 2),
+        ("cout_tile", C.c_int32), ("cout_tiles", C.c_int32), ("num_kblocks", C.c_int32),
+        ("kblocks", KBlock * MAX_KBLOCKS),
+        ("wpack", C.c_void_p), ("w_tile_bytes", C.c_uint32), ("bias", C.c_void_p),
+        ("flags", C.c_uint32), ("slope", C.c_float), ("alpha", C.c_float), ("beta", C.c_float),
+        ("res1", C.c_void_p), ("res1_stride", C.c_int32), ("res1_choff", C.c_int32),
+        ("res2", C.c_void_p), ("res2_stride", C.c_int32), ("res2_choff", C.c_int32),
+        ("out_bf16", C.c_void_p), ("out_bf16_stride", C.c_int32), ("out_bf16_choff", C.c_int32),
+        ("out_bf16_lo_choff", C.c_int32), ("up", C.c_int32), ("out_bf16_scale", C.c_float),
+        ("out_f32", C.c_void_p), ("out_f32_stride", C.c_int32), ("out_f32_choff", C.c_int32),
+        ("out_nchw", C.c_void_p), ("cout_real", C.c_int32),
+        ("mask", C.c_void_p), ("mask_stride", C.c_int32), ("mask_choff", C.c_int32),
+    ]
+
+
+class WRow(C.Structure):
+    _fields_ = [("idx", C.c_int16), ("ky", C.c_int8), ("reserved", C.c_int8)]
+
+
+class WSlot(C.Structure):
+    _fields_ = [("idx", C.c_int16), ("ky", C.c_int8), ("term", C.c_int8)]
+
+
+class XSlot(C.Structure):
+    _fields_ = [("c", C.c_int8), ("dy", C.c_int8), ("term", C.c_int8), ("reserved", C.c_int8)]
+
+
+class CemFilters(C.Structure):
+    _fields_ = [("sf", C.c_int32), ("pre", C.c_int32), ("n_ds", C.c_int32), ("n_inv", C.c_int32),
+                ("ds", C.c_float * CEM_MAX_TAPS), ("inv", C.c_float * CEM_MAX_TAPS)]
+
+
+# name -> (restype, argtypes); every symbol include/esr_b200.h declares
+_i32, _i64, _vp, _f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
+SIGNATURES = {
+    "esr_last_error": (C.c_char_p, []),
+    "esr_abi_version": (C.c_int, []),
+    "esr_device_check": (C.c_int, [C.c_int]),
+    "esr_conv3x3_tc": (C.c_int, [C.POINTER(ConvDesc), _vp]),
+    "esr_conv3x3_simt": (C.c_int, [C.POINTER(ConvDesc), _vp]),
+    "esr_pack_layout": (_i64, [_i32, _i32, _i32, C.POINTER(KBlock), C.POINTER(C.c_uint32)]),
+    "esr_pack_conv_weights": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i32, _i32, _i32, C.POINTER(KBlock),
+                                        C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "esr_expand_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32, _vp, _vp]),
+    "esr_expand_rows_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32, _vp, _vp]),
+    "esr_g_input_prep": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "esr_cem_pad_input": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_g_input_prep_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_cem_downscale": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_cem_inv_hth": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_cem_upscale": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_cem_project": (C.c_int, [C.POINTER(CemFilters), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "esr_cem_project_bwd": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "esr_seq_create": (_vp, []),
+    "esr_seq_destroy": (None, [_vp]),
+    "esr_seq_add_conv": (C.c_int, [_vp, C.POINTER(ConvDesc), _i32]),
+    "esr_seq_run": (C.c_int, [_vp, _vp]),
+    "esr_seq_num_launches": (_i32, [_vp]),
+}
+
+_lib = None
+
+
+class EsrError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EsrError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EsrError("libesr_b200: %s (status %d)" % (lib().esr_last_error().decode(), rc))
+
+
+_device_ok = {}
+
+
+def require_device(device_index):
+    if device_index not in _device_ok:
+        check(lib().esr_device_check(device_index))
+        _device_ok[device_index] = True
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def cem_filters_struct(sf, pre, ds_1d, inv_1d):
+    f = CemFilters()
+    f.sf, f.pre, f.n_ds, f.n_inv = int(sf), int(pre), len(ds_1d), len(inv_1d)
+    if len(ds_1d) > CEM_MAX_TAPS or len(inv_1d) > CEM_MAX_TAPS:
+        raise EsrError("CEM filter longer than %d taps" % CEM_MAX_TAPS)
+    for i, v in enumerate(ds_1d):
+        f.ds[i] = float(v)
+    for i, v in enumerate(inv_1d):
+        f.inv[i] = float(v)
+    return f

@@ -1,0 +1,73 @@
+// C-ABI glue: error reporting, device check and recorded launch sequences.
+#include <cuda.h>
+
+#include <cstring>
+#include <vector>
+
+#include "conv3x3.cuh"
+
+namespace esr {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int build_conv_launch(const esr_conv_desc& d, CUtensorMap* tm0, CUtensorMap* tm1, ConvLaunch* L);
+int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream);
+int launch_conv_simt(const ConvLaunch& L, cudaStream_t stream);
+
+struct SeqOp {
+    alignas(64) CUtensorMap tm0;
+    alignas(64) CUtensorMap tm1;
+    ConvLaunch L;
+    int use_simt;
+};
+
+}  // namespace esr
+
+struct esr_seq {
+    std::vector<esr::SeqOp> ops;
+};
+
+extern "C" const char* esr_last_error(void) { return esr::g_error; }
+extern "C" int esr_abi_version(void) { return 1; }
+
+extern "C" int esr_device_check(int device) {
+    cudaDeviceProp p;
+    ESR_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        esr::set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
+        return ESR_ERR_UNSUPPORTED;
+    }
+    return ESR_OK;
+}
+
+extern "C" esr_seq* esr_seq_create(void) { return new (std::nothrow) esr_seq(); }
+extern "C" void esr_seq_destroy(esr_seq* s) { delete s; }
+extern "C" int32_t esr_seq_num_launches(const esr_seq* s) { return s ? static_cast<int32_t>(s->ops.size()) : 0; }
+
+extern "C" int esr_seq_add_conv(esr_seq* s, const esr_conv_desc* d, int32_t use_simt) {
+    if (s == nullptr || d == nullptr) { esr::set_error("esr_seq_add_conv: null argument"); return ESR_ERR_INVALID; }
+    esr::SeqOp op;
+    std::memset(&op, 0, sizeof(op));
+    int rc = esr::build_conv_launch(*d, &op.tm0, &op.tm1, &op.L);
+    if (rc != ESR_OK) return rc;
+    op.use_simt = use_simt;
+    s->ops.push_back(op);
+    return ESR_OK;
+}
+
+extern "C" int esr_seq_run(const esr_seq* s, void* stream) {
+    if (s == nullptr) { esr::set_error("esr_seq_run: null sequence"); return ESR_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (const esr::SeqOp& op : s->ops) {
+        int rc = op.use_simt ? esr::launch_conv_simt(op.L, st) : esr::launch_conv_tc(op.tm0, op.tm1, op.L, st);
+        if (rc != ESR_OK) return rc;
+    }
+    return ESR_OK;
+}

@@ -1,0 +1,370 @@
+// CEM (Consistency Enforcing Module) fixed-filter operators, fp32, NCHW planes.
+//
+//   Down  (H)        : replicate-pad, correlate with the flipped ds kernel, keep phase `pre`
+//                      of every sf x sf block                      (CEMnet.py:157-162)
+//   InvHTH (K)       : replicate-pad, correlate with inv_hTh       (CEMnet.py:149-151)
+//   Up    (~H^T)     : zero-stuff x sf at phase `pre`, replicate-pad, correlate with
+//                      sf^2 * ds kernel (polyphase here)           (CEMnet.py:153-159)
+//   project          : out = crop(y + Up(K * (x - Down(y))))       (CEMnet.py:183-190)
+//
+// All three filters of the default (bicubic) configuration are rank-1, so every operator
+// runs as a horizontal pass into shared memory followed by a vertical pass.
+#include "esr_common.cuh"
+
+namespace esr {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------------------ Down
+// Block: DT_R x DT_C LR outputs of one (b,c) plane.
+constexpr int DT_R = 8, DT_C = 32;
+
+// out = (x ? x - Down(y) : Down(y)),  y: [P,H,W]  out/x: [P,H/sf,W/sf]   (P = B*C planes)
+__global__ void __launch_bounds__(256) cem_down_kernel(const __grid_constant__ esr_cem_filters f,
+                                                       const float* __restrict__ y, const float* __restrict__ x,
+                                                       float* __restrict__ out, int H, int W) {
+    extern __shared__ float sm[];
+    const int sf = f.sf, nt = f.n_ds, pad = f.n_ds / 2;
+    const int h = H / sf, w = W / sf;
+    const int plane = blockIdx.z;
+    const int i0 = blockIdx.y * DT_R, j0 = blockIdx.x * DT_C;
+    const int rows_in = (DT_R - 1) * sf + nt;          // HR rows feeding the tile
+    const int cols_in = (DT_C - 1) * sf + nt;
+    float* tile = sm;                                   // [rows_in][cols_in]
+    float* hbuf = sm + rows_in * cols_in;               // [rows_in][DT_C]
+    const float* yp = y + static_cast<size_t>(plane) * H * W;
+    const int r_base = i0 * sf + f.pre - pad, c_base = j0 * sf + f.pre - pad;
+    for (int idx = threadIdx.x; idx < rows_in * cols_in; idx += blockDim.x) {
+        const int r = idx / cols_in, c = idx - r * cols_in;
+        tile[idx] = __ldg(yp + static_cast<size_t>(clampi(r_base + r, 0, H - 1)) * W + clampi(c_base + c, 0, W - 1));
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows_in * DT_C; idx += blockDim.x) {
+        const int r = idx / DT_C, j = idx - r * DT_C;
+        const float* t = tile + r * cols_in + j * sf;
+        float acc = 0.f;
+        for (int k = 0; k < nt; ++k) acc = fmaf(f.ds[nt - 1 - k], t[k], acc);
+        hbuf[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < DT_R * DT_C; idx += blockDim.x) {
+        const int i = idx / DT_C, j = idx - i * DT_C;
+        if (i0 + i >= h || j0 + j >= w) continue;
+        float acc = 0.f;
+        for (int k = 0; k < nt; ++k) acc = fmaf(f.ds[nt - 1 - k], hbuf[(i * sf + k) * DT_C + j], acc);
+        const size_t o = (static_cast<size_t>(plane) * h + i0 + i) * w + j0 + j;
+        out[o] = x != nullptr ? x[o] - acc : acc;
+    }
+}
+
+// ---------------------------------------------------------------------- InvHTH
+constexpr int IT_R = 16, IT_C = 32;
+__global__ void __launch_bounds__(256) cem_inv_kernel(const __grid_constant__ esr_cem_filters f,
+                                                      const float* __restrict__ x, float* __restrict__ out, int h,
+                                                      int w) {
+    extern __shared__ float sm[];
+    const int nt = f.n_inv, pad = nt / 2;
+    const int plane = blockIdx.z;
+    const int i0 = blockIdx.y * IT_R, j0 = blockIdx.x * IT_C;
+    const int rows_in = IT_R + nt - 1, cols_in = IT_C + nt - 1;
+    float* tile = sm;
+    float* hbuf = sm + rows_in * cols_in;               // [rows_in][IT_C]
+    const float* xp = x + static_cast<size_t>(plane) * h * w;
+    for (int idx = threadIdx.x; idx < rows_in * cols_in; idx += blockDim.x) {
+        const int r = idx / cols_in, c = idx - r * cols_in;
+        tile[idx] = __ldg(xp + static_cast<size_t>(clampi(i0 + r - pad, 0, h - 1)) * w + clampi(j0 + c - pad, 0, w - 1));
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows_in * IT_C; idx += blockDim.x) {
+        const int r = idx / IT_C, j = idx - r * IT_C;
+        const float* t = tile + r * cols_in + j;
+        float acc = 0.f;
+        for (int k = 0; k < nt; ++k) acc = fmaf(f.inv[k], t[k], acc);
+        hbuf[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < IT_R * IT_C; idx += blockDim.x) {
+        const int i = idx / IT_C, j = idx - i * IT_C;
+        if (i0 + i >= h || j0 + j >= w) continue;
+        float acc = 0.f;
+        for (int k = 0; k < nt; ++k) acc = fmaf(f.inv[k], hbuf[(i + k) * IT_C + j], acc);
+        out[(static_cast<size_t>(plane) * h + i0 + i) * w + j0 + j] = acc;
+    }
+}
+
+// -------------------------------------------------------------------------- Up
+// out[Y-crop, X-crop] = (y ? y[Y,X] : 0) + sign * sum_{ty,tx} u[ty] u[tx] z[clamp(Y+ty-pad), clamp(X+tx-pad)],
+// z = x zero-stuffed at phase pre.  Block: UT_R x UT_C LR cells -> (UT_R*sf) x (UT_C*sf) HR pixels.
+constexpr int UT_R = 8, UT_C = 32;
+__global__ void __launch_bounds__(256) cem_up_kernel(const __grid_constant__ esr_cem_filters f,
+                                                     const float* __restrict__ x, const float* __restrict__ y,
+                                                     float* __restrict__ out, int h, int w, int crop, float sign) {
+    extern __shared__ float sm[];
+    const int sf = f.sf, nt = f.n_ds, pad = nt / 2, pre = f.pre;
+    const int H = h * sf, W = w * sf;
+    const int plane = blockIdx.z;
+    const int I0 = blockIdx.y * UT_R, J0 = blockIdx.x * UT_C;
+    const int ext = (nt - 1) / sf + 2;                  // LR halo cells needed on each side (conservative)
+    const int rows_in = UT_R + 2 * ext, cols_in = UT_C + 2 * ext;
+    float* tile = sm;                                   // x[I0-ext .., J0-ext ..] (zero outside)
+    float* hbuf = sm + rows_in * cols_in;               // [rows_in][UT_C*sf] horizontally upsampled
+    const float* xp = x + static_cast<size_t>(plane) * h * w;
+    for (int idx = threadIdx.x; idx < rows_in * cols_in; idx += blockDim.x) {
+        const int r = idx / cols_in, c = idx - r * cols_in;
+        const int rr = I0 - ext + r, cc = J0 - ext + c;
+        tile[idx] = (rr >= 0 && rr < h && cc >= 0 && cc < w) ? __ldg(xp + static_cast<size_t>(rr) * w + cc) : 0.f;
+    }
+    __syncthreads();
+    const int wc = UT_C * sf;
+    for (int idx = threadIdx.x; idx < rows_in * wc; idx += blockDim.x) {
+        const int r = idx / wc, cx = idx - r * wc;
+        const int X = J0 * sf + cx;
+        float acc = 0.f;
+        if (X < W) {
+            for (int t = 0; t < nt; ++t) {
+                const int m = clampi(X + t - pad, 0, W - 1);   // replicate pad of the stuffed image
+                const int q = m - pre;
+                if (q >= 0 && q % sf == 0) acc = fmaf(f.ds[t] * sf, tile[r * cols_in + (q / sf - (J0 - ext))], acc);
+            }
+        }
+        hbuf[idx] = acc;
+    }
+    __syncthreads();
+    const int Hout = H - 2 * crop, Wout = W - 2 * crop;
+    const int hr = UT_R * sf;
+    for (int idx = threadIdx.x; idx < hr * wc; idx += blockDim.x) {
+        const int ry = idx / wc, cx = idx - ry * wc;
+        const int Y = I0 * sf + ry, X = J0 * sf + cx;
+        if (Y < crop || Y >= H - crop || X < crop || X >= W - crop) continue;
+        float acc = 0.f;
+        for (int t = 0; t < nt; ++t) {
+            const int m = clampi(Y + t - pad, 0, H - 1);
+            const int q = m - pre;
+            if (q >= 0 && q % sf == 0) acc = fmaf(f.ds[t] * sf, hbuf[(q / sf - (I0 - ext)) * wc + cx], acc);
+        }
+        const size_t o = (static_cast<size_t>(plane) * Hout + (Y - crop)) * Wout + (X - crop);
+        const float base = y != nullptr ? __ldg(y + (static_cast<size_t>(plane) * H + Y) * W + X) : 0.f;
+        out[o] = base + sign * acc;
+    }
+}
+
+// ----------------------------------------------------------------- adjoint (backward)
+// Every CEM operator is, per axis, F: out[a] = sum_t taps[t] * src[clamp(sa*a + off + t - pad, 0, Ls-1)]
+// (src = the image for Down / K, the zero-stuffed image for Up).  The kernel below evaluates the
+// exact adjoint of F, including the fold of the replicate padding onto the border samples,
+//   gs[m] = sum_{a,t} [clamp(sa*a + off + t - pad) == m] taps[t] * g[a],
+// at the positions m = so*j + po, j in [0,nout), along one axis of a [planes,R,C] array.
+struct Adj1dArgs {
+    float taps[ESR_CEM_MAX_TAPS];
+    int nt, pad, sa, off, na, Ls, so, po, nout;
+    int axis;            // 0: along columns (contiguous), 1: along rows
+    int planes, other;   // `other` = extent of the untouched axis
+    float scale;         // multiplies the result
+    const float* g;      // [planes, (axis? na:other), (axis? other:na)]
+    float* out;          // [planes, (axis? nout:other), (axis? other:nout)]
+    const float* base;   // optional: out = base - result  (same shape as out)
+};
+
+__global__ void cem_adj1d_kernel(const __grid_constant__ Adj1dArgs a) {
+    const size_t total = static_cast<size_t>(a.planes) * a.other * a.nout;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        int j, o;
+        size_t p;
+        if (a.axis == 0) { j = static_cast<int>(idx % a.nout); o = static_cast<int>((idx / a.nout) % a.other); }
+        else { o = static_cast<int>(idx % a.other); j = static_cast<int>((idx / a.other) % a.nout); }
+        p = idx / (static_cast<size_t>(a.nout) * a.other);
+        const float* gl = a.axis == 0 ? a.g + (p * a.other + o) * a.na : a.g + p * a.na * a.other + o;
+        const size_t gstride = a.axis == 0 ? 1 : a.other;
+        const int m = a.so * j + a.po;
+        float acc = 0.f;
+        // t = m + pad - off - sa*i (interior); borders collect every (i,t) that clamps onto them
+        const int c0 = m + a.pad - a.off;
+        if (m > 0 && m < a.Ls - 1) {
+            int i_lo = (c0 - (a.nt - 1) + a.sa - 1);
+            i_lo = i_lo <= 0 ? 0 : i_lo / a.sa;
+            int i_hi = c0 < 0 ? -1 : c0 / a.sa;
+            if (i_hi > a.na - 1) i_hi = a.na - 1;
+            for (int i = i_lo; i <= i_hi; ++i) acc = fmaf(a.taps[c0 - a.sa * i], gl[i * gstride], acc);
+        } else {
+            for (int i = 0; i < a.na; ++i) {
+                const int base_pos = a.sa * i + a.off - a.pad;   // position of tap 0
+                float wsum = 0.f;
+                for (int t = 0; t < a.nt; ++t) {
+                    const int pos = base_pos + t;
+                    const int cl = pos < 0 ? 0 : (pos > a.Ls - 1 ? a.Ls - 1 : pos);
+                    if (cl == m) wsum += a.taps[t];
+                }
+                if (wsum != 0.f) acc = fmaf(wsum, gl[i * gstride], acc);
+            }
+        }
+        acc *= a.scale;
+        a.out[idx] = a.base != nullptr ? a.base[idx] - acc : acc;
+    }
+}
+
+// g_pad[Y,X] = (crop <= Y < H-crop && ...) ? g[Y-crop, X-crop] : 0   (adjoint of HR_unpadder)
+__global__ void cem_pad_zero_kernel(const float* __restrict__ g, float* __restrict__ out, int planes, int H, int W,
+                                    int crop) {
+    const size_t total = static_cast<size_t>(planes) * H * W;
+    const int Ho = H - 2 * crop, Wo = W - 2 * crop;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(idx % W);
+        const int Y = static_cast<int>((idx / W) % H);
+        const size_t p = idx / (static_cast<size_t>(W) * H);
+        const bool in = Y >= crop && Y < H - crop && X >= crop && X < W - crop;
+        out[idx] = in ? g[(p * Ho + (Y - crop)) * Wo + (X - crop)] : 0.f;
+    }
+}
+
+static int launch_adj1d(Adj1dArgs& a, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(a.planes) * a.other * a.nout;
+    const size_t want = (total + 255) / 256;
+    const int grid = static_cast<int>(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+    cem_adj1d_kernel<<<grid, 256, 0, s>>>(a);
+    return check_launch("cem_adj1d_kernel");
+}
+
+static size_t down_smem(const esr_cem_filters& f) {
+    const int rows_in = (DT_R - 1) * f.sf + f.n_ds, cols_in = (DT_C - 1) * f.sf + f.n_ds;
+    return sizeof(float) * (static_cast<size_t>(rows_in) * cols_in + static_cast<size_t>(rows_in) * DT_C);
+}
+static size_t inv_smem(const esr_cem_filters& f) {
+    const int rows_in = IT_R + f.n_inv - 1, cols_in = IT_C + f.n_inv - 1;
+    return sizeof(float) * (static_cast<size_t>(rows_in) * cols_in + static_cast<size_t>(rows_in) * IT_C);
+}
+static size_t up_smem(const esr_cem_filters& f) {
+    const int ext = (f.n_ds - 1) / f.sf + 2;
+    const int rows_in = UT_R + 2 * ext, cols_in = UT_C + 2 * ext;
+    return sizeof(float) * (static_cast<size_t>(rows_in) * cols_in + static_cast<size_t>(rows_in) * UT_C * f.sf);
+}
+
+static int check_filters(const esr_cem_filters* f) {
+    ESR_CHECK_ARG(f != nullptr, "null CEM filters");
+    ESR_CHECK_ARG(f->sf >= 2 && f->sf <= 4 && f->pre >= 0 && f->pre < f->sf, "unsupported CEM scale factor %d", f->sf);
+    ESR_CHECK_ARG(f->n_ds > 0 && f->n_ds <= ESR_CEM_MAX_TAPS && (f->n_ds & 1), "bad ds kernel length");
+    ESR_CHECK_ARG(f->n_inv > 0 && f->n_inv <= ESR_CEM_MAX_TAPS && (f->n_inv & 1), "bad inv_hTh length");
+    return ESR_OK;
+}
+
+static int set_smem(const void* fn, size_t bytes) {
+    if (bytes > 48 * 1024) ESR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    return ESR_OK;
+}
+
+int cem_down(const esr_cem_filters& f, const float* y, const float* x, int planes, int H, int W, float* out,
+             cudaStream_t s) {
+    ESR_CHECK_ARG(H % f.sf == 0 && W % f.sf == 0, "HR size %dx%d not divisible by %d", H, W, f.sf);
+    const size_t sm = down_smem(f);
+    int rc = set_smem(reinterpret_cast<const void*>(cem_down_kernel), sm);
+    if (rc) return rc;
+    dim3 grid(ceil_div(W / f.sf, DT_C), ceil_div(H / f.sf, DT_R), planes);
+    cem_down_kernel<<<grid, 256, sm, s>>>(f, y, x, out, H, W);
+    return check_launch("cem_down_kernel");
+}
+int cem_inv(const esr_cem_filters& f, const float* x, int planes, int h, int w, float* out, cudaStream_t s) {
+    const size_t sm = inv_smem(f);
+    int rc = set_smem(reinterpret_cast<const void*>(cem_inv_kernel), sm);
+    if (rc) return rc;
+    dim3 grid(ceil_div(w, IT_C), ceil_div(h, IT_R), planes);
+    cem_inv_kernel<<<grid, 256, sm, s>>>(f, x, out, h, w);
+    return check_launch("cem_inv_kernel");
+}
+int cem_up(const esr_cem_filters& f, const float* x, const float* y, int planes, int h, int w, int crop, float sign,
+           float* out, cudaStream_t s) {
+    const size_t sm = up_smem(f);
+    int rc = set_smem(reinterpret_cast<const void*>(cem_up_kernel), sm);
+    if (rc) return rc;
+    dim3 grid(ceil_div(w, UT_C), ceil_div(h, UT_R), planes);
+    cem_up_kernel<<<grid, 256, sm, s>>>(f, x, y, out, h, w, crop, sign);
+    return check_launch("cem_up_kernel");
+}
+
+}  // namespace esr
+
+using namespace esr;
+
+extern "C" int esr_cem_downscale(const esr_cem_filters* f, const float* y, int32_t B, int32_t C, int32_t H, int32_t W,
+                                 float* out, void* stream) {
+    int rc = check_filters(f);
+    if (rc) return rc;
+    ESR_CHECK_ARG(y && out && B > 0 && C > 0, "esr_cem_downscale: bad arguments");
+    return cem_down(*f, y, nullptr, B * C, H, W, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int esr_cem_inv_hth(const esr_cem_filters* f, const float* x, int32_t B, int32_t C, int32_t h, int32_t w,
+                               float* out, void* stream) {
+    int rc = check_filters(f);
+    if (rc) return rc;
+    ESR_CHECK_ARG(x && out && B > 0 && C > 0 && h > 0 && w > 0, "esr_cem_inv_hth: bad arguments");
+    return cem_inv(*f, x, B * C, h, w, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int esr_cem_upscale(const esr_cem_filters* f, const float* x, int32_t B, int32_t C, int32_t h, int32_t w,
+                               float* out, void* stream) {
+    int rc = check_filters(f);
+    if (rc) return rc;
+    ESR_CHECK_ARG(x && out && B > 0 && C > 0 && h > 0 && w > 0, "esr_cem_upscale: bad arguments");
+    return cem_up(*f, x, nullptr, B * C, h, w, 0, 1.f, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int esr_cem_project(const esr_cem_filters* f, const float* y, const float* x, int32_t B, int32_t C,
+                               int32_t H, int32_t W, int32_t crop, float* out, float* workspace, void* stream) {
+    int rc = check_filters(f);
+    if (rc) return rc;
+    ESR_CHECK_ARG(y && x && out && workspace && B > 0 && C > 0, "esr_cem_project: bad arguments");
+    ESR_CHECK_ARG(crop >= 0 && 2 * crop < H && 2 * crop < W, "esr_cem_project: crop %d too large", crop);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int h = H / f->sf, w = W / f->sf, planes = B * C;
+    float* d = workspace;
+    float* e = workspace + static_cast<size_t>(planes) * h * w;
+    if ((rc = cem_down(*f, y, x, planes, H, W, d, s))) return rc;
+    if ((rc = cem_inv(*f, d, planes, h, w, e, s))) return rc;
+    return cem_up(*f, e, y, planes, h, w, crop, 1.f, out, s);
+}
+
+extern "C" int esr_cem_project_bwd(const esr_cem_filters* f, const float* g_out, int32_t B, int32_t C, int32_t H,
+                                   int32_t W, int32_t crop, float* g_y, float* workspace, void* stream) {
+    int rc = check_filters(f);
+    if (rc) return rc;
+    ESR_CHECK_ARG(g_out && g_y && workspace && B > 0 && C > 0, "esr_cem_project_bwd: bad arguments");
+    ESR_CHECK_ARG(H % f->sf == 0 && W % f->sf == 0 && crop >= 0 && 2 * crop < H && 2 * crop < W,
+                  "esr_cem_project_bwd: bad geometry");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int sf = f->sf, h = H / sf, w = W / sf, planes = B * C;
+    const size_t nHR = static_cast<size_t>(planes) * H * W;
+    float* Gp = workspace;                                             // [planes,H,W]  zero-padded g_out
+    float* tA = Gp + nHR;                                              // [planes,H,w]
+    float* tB = tA + static_cast<size_t>(planes) * H * w;              // [planes,h,w]
+    float* tC = tB + static_cast<size_t>(planes) * h * w;              // [planes,h,w]
+    {
+        const size_t want = (nHR + 255) / 256;
+        const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+        cem_pad_zero_kernel<<<grid, 256, 0, s>>>(g_out, Gp, planes, H, W, crop);
+        if ((rc = check_launch("cem_pad_zero_kernel"))) return rc;
+    }
+    Adj1dArgs a;
+    // Up^T: Up = correlate(u = sf*ds) over the replicate-padded zero-stuffed image; sample at sf*i+pre.
+    for (int t = 0; t < f->n_ds; ++t) a.taps[t] = f->ds[t] * sf;
+    a.nt = f->n_ds; a.pad = f->n_ds / 2; a.sa = 1; a.off = 0; a.so = sf; a.po = f->pre; a.scale = 1.f; a.base = nullptr;
+    a.planes = planes;
+    a.axis = 0; a.other = H; a.na = W; a.Ls = W; a.nout = w; a.g = Gp; a.out = tA;
+    if ((rc = launch_adj1d(a, s))) return rc;
+    a.axis = 1; a.other = w; a.na = H; a.Ls = H; a.nout = h; a.g = tA; a.out = tB;
+    if ((rc = launch_adj1d(a, s))) return rc;
+    // K^T
+    for (int t = 0; t < f->n_inv; ++t) a.taps[t] = f->inv[t];
+    a.nt = f->n_inv; a.pad = f->n_inv / 2; a.sa = 1; a.off = 0; a.so = 1; a.po = 0;
+    a.axis = 0; a.other = h; a.na = w; a.Ls = w; a.nout = w; a.g = tB; a.out = tC;
+    if ((rc = launch_adj1d(a, s))) return rc;
+    a.axis = 1; a.other = w; a.na = h; a.Ls = h; a.nout = h; a.g = tC; a.out = tB;
+    if ((rc = launch_adj1d(a, s))) return rc;
+    // Down^T: Down = correlate(flipped ds) over the replicate-padded image, sampled at sf*i+pre.
+    for (int t = 0; t < f->n_ds; ++t) a.taps[t] = f->ds[f->n_ds - 1 - t];
+    a.nt = f->n_ds; a.pad = f->n_ds / 2; a.sa = sf; a.off = f->pre; a.so = 1; a.po = 0;
+    a.axis = 1; a.other = w; a.na = h; a.Ls = H; a.nout = H; a.g = tB; a.out = tA;
+    if ((rc = launch_adj1d(a, s))) return rc;
+    a.axis = 0; a.other = H; a.na = w; a.Ls = W; a.nout = W; a.g = tA; a.out = g_y; a.base = Gp;
+    return launch_adj1d(a, s);
+}

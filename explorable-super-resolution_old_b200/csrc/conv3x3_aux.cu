@@ -1,0 +1,224 @@
+// Auxiliary conv kernels: weight packing, the SIMT cross-check kernel that consumes the very
+// same descriptor / packed weights as the tcgen05 kernel, and the small-channel row expansion.
+#include <cuda_bf16.h>
+
+#include "conv3x3.cuh"
+
+namespace esr {
+
+// ------------------------------------------------------------------ SIMT check
+// One thread per (pixel, 16-channel chunk).  Walks the K-block list exactly like the MMA
+// issuer does, so any disagreement with the tcgen05 kernel is a TMA/UMMA problem and any
+// disagreement with the oracle is a packing/epilogue problem.
+__global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
+    const esr_conv_desc& d = L.d;
+    const int CT = d.cout_tile, N = 3 * CT;
+    const int chunks = d.cout_tiles * CT / 16;
+    const size_t total = static_cast<size_t>(d.B) * d.H * d.W * chunks;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int chunk = static_cast<int>(idx % chunks);
+        size_t pix = idx / chunks;
+        const int x = static_cast<int>(pix % d.W); pix /= d.W;
+        const int y = static_cast<int>(pix % d.H);
+        const int n = static_cast<int>(pix / d.H);
+        const int co0 = chunk * 16, ct = co0 / CT, col0 = co0 % CT;
+        const uint8_t* wt = reinterpret_cast<const uint8_t*>(d.wpack) + static_cast<size_t>(ct) * d.w_tile_bytes;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int kb = 0; kb < d.num_kblocks; ++kb) {
+            const esr_kblock& K = d.kblocks[kb];
+            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(d.src[K.src].ptr);
+            const int sc = d.src[K.src].channels;
+            int wi = 0;
+            for (int dy = 0; dy < 3; ++dy) {
+                if (!((K.dy_mask >> dy) & 1)) continue;
+                const uint8_t* wslab = wt + K.w_off + static_cast<size_t>(wi) * N * kRowBytes;
+                ++wi;
+                const int yy = y + dy - 1;
+                if (yy < 0 || yy >= d.H) continue;
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int xx = x + dx - 1;
+                    if (xx < 0 || xx >= d.W) continue;
+                    const __nv_bfloat16* a = src + ((static_cast<size_t>(n) * d.H + yy) * d.W + xx) * sc + K.chan;
+                    for (int k = 0; k < kKB; ++k) {
+                        if (!((K.slice_mask >> (k >> 4)) & 1)) continue;
+                        const float av = __bfloat162float(a[k]);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const __nv_bfloat16 w = *reinterpret_cast<const __nv_bfloat16*>(
+                                wslab + sw64_offset(dx * CT + col0 + i, k));
+                            v[i] = fmaf(av, __bfloat162float(w), v[i]);
+                        }
+                    }
+                }
+            }
+        }
+        conv_epilogue16(d, n, y, x, co0, v);
+    }
+}
+
+// --------------------------------------------------------------- weight packing
+struct PackArgs {
+    const float* wsrc;
+    long long off, s_row, s_slot, s_ky, s_kx;
+    const float* bias_src;
+    int cout_tile, cout_tiles, num_kblocks;
+    uint32_t w_tile_bytes;
+    esr_kblock kblocks[ESR_MAX_KBLOCKS];
+    const esr_wrow* rows;    // device [cout_tiles*cout_tile]
+    const esr_wslot* slots;  // device [num_kblocks*32]
+    uint8_t* out;
+    float* bias_out;
+};
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
+    const int CT = a.cout_tile, N = 3 * CT;
+    // element index space: [ct][kb][wi(3)][n][k]
+    const size_t per_kb = static_cast<size_t>(3) * N * kKB;
+    const size_t total = static_cast<size_t>(a.cout_tiles) * a.num_kblocks * per_kb;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        size_t r = idx;
+        const int k = static_cast<int>(r % kKB); r /= kKB;
+        const int n = static_cast<int>(r % N); r /= N;
+        const int wi = static_cast<int>(r % 3); r /= 3;
+        const int kb = static_cast<int>(r % a.num_kblocks);
+        const int ct = static_cast<int>(r / a.num_kblocks);
+        const esr_kblock& K = a.kblocks[kb];
+        if (wi >= K.n_dy) continue;
+        int dy = -1;  // filter row of the wi-th set bit
+        for (int b = 0, c = 0; b < 3; ++b)
+            if ((K.dy_mask >> b) & 1) { if (c == wi) dy = b; ++c; }
+        const int dx = n / CT, col = n % CT;
+        const esr_wrow row = a.rows[ct * CT + col];
+        const esr_wslot slot = a.slots[kb * kKB + k];
+        float w = 0.f;
+        if (row.idx >= 0 && slot.idx >= 0) {
+            int ky = dy;
+            bool live = true;
+            if (row.ky >= 0 || slot.ky >= 0) {      // pre-expanded over dy on one side: centre tap only
+                live = (dy == 1) && !(row.ky >= 0 && slot.ky >= 0);
+                ky = row.ky >= 0 ? row.ky : slot.ky;
+            }
+            if (live) w = a.wsrc[a.off + row.idx * a.s_row + slot.idx * a.s_slot + ky * a.s_ky + dx * a.s_kx];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 val = slot.term == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+        uint8_t* dst = a.out + static_cast<size_t>(ct) * a.w_tile_bytes + K.w_off +
+                       static_cast<size_t>(wi) * N * kRowBytes + sw64_offset(n, k);
+        *reinterpret_cast<__nv_bfloat16*>(dst) = val;
+    }
+    const int nb = a.cout_tiles * CT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
+        const esr_wrow row = a.rows[i];
+        a.bias_out[i] = (a.bias_src != nullptr && row.idx >= 0 && row.ky < 0) ? a.bias_src[row.idx] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------- small-channel expand
+struct ExpandArgs {
+    const float* src;
+    int B, C, H, W, nslots;
+    esr_xslot slots[64];
+    __nv_bfloat16* dst;
+};
+
+__global__ void expand_rows_kernel(const __grid_constant__ ExpandArgs a) {
+    const size_t total = static_cast<size_t>(a.B) * a.H * a.W * a.nslots;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int s = static_cast<int>(idx % a.nslots);
+        size_t pix = idx / a.nslots;
+        const int x = static_cast<int>(pix % a.W); pix /= a.W;
+        const int y = static_cast<int>(pix % a.H);
+        const int n = static_cast<int>(pix / a.H);
+        const esr_xslot sl = a.slots[s];
+        float v = 0.f;
+        const int yy = y + sl.dy;
+        if (sl.c >= 0 && yy >= 0 && yy < a.H)
+            v = __ldg(a.src + ((static_cast<size_t>(n) * a.C + sl.c) * a.H + yy) * a.W + x);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        a.dst[idx] = sl.term == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+int validate_conv_desc(const esr_conv_desc& d);
+void fill_launch(ConvLaunch* L, const esr_conv_desc& d);
+
+int launch_conv_simt(const ConvLaunch& L, cudaStream_t stream) {
+    const size_t total = static_cast<size_t>(L.d.B) * L.d.H * L.d.W * (L.d.cout_tiles * L.d.cout_tile / 16);
+    const int block = 128;
+    const int grid = static_cast<int>(total / block + 1 < 65535 * 16 ? total / block + 1 : 65535 * 16);
+    conv3x3_simt_kernel<<<grid, block, 0, stream>>>(L);
+    return check_launch("conv3x3_simt_kernel");
+}
+
+}  // namespace esr
+
+extern "C" int esr_conv3x3_simt(const esr_conv_desc* d, void* stream) {
+    if (d == nullptr) { esr::set_error("null conv desc"); return ESR_ERR_INVALID; }
+    int rc = esr::validate_conv_desc(*d);
+    if (rc != ESR_OK) return rc;
+    esr::ConvLaunch L;
+    esr::fill_launch(&L, *d);
+    return esr::launch_conv_simt(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_t num_kblocks, esr_kblock* kblocks,
+                                   uint32_t* w_tile_bytes) {
+    if ((cout_tile != 16 && cout_tile != 32) || cout_tiles <= 0 || num_kblocks <= 0 ||
+        num_kblocks > ESR_MAX_KBLOCKS || kblocks == nullptr) {
+        esr::set_error("esr_pack_layout: bad arguments");
+        return ESR_ERR_INVALID;
+    }
+    uint32_t off = 0;
+    for (int i = 0; i < num_kblocks; ++i) {
+        kblocks[i].n_dy = static_cast<uint8_t>(__builtin_popcount(kblocks[i].dy_mask & 7));
+        kblocks[i].w_off = off;
+        off += kblocks[i].n_dy * 3u * cout_tile * esr::kRowBytes;
+    }
+    if (w_tile_bytes) *w_tile_bytes = off;
+    return static_cast<int64_t>(off) * cout_tiles;
+}
+
+extern "C" int esr_pack_conv_weights(const float* wsrc, int64_t off, int64_t s_row, int64_t s_slot, int64_t s_ky,
+                                     int64_t s_kx, const float* bias_src, int32_t cout_tile, int32_t cout_tiles,
+                                     int32_t num_kblocks, const esr_kblock* kblocks, uint32_t w_tile_bytes,
+                                     const esr_wrow* rows_dev, const esr_wslot* slots_dev, void* wpack_out,
+                                     float* bias_out, void* stream) {
+    ESR_CHECK_ARG(wsrc && kblocks && rows_dev && slots_dev && wpack_out && bias_out, "esr_pack_conv_weights: null argument");
+    ESR_CHECK_ARG((cout_tile == 16 || cout_tile == 32) && cout_tiles > 0 && num_kblocks > 0 &&
+                  num_kblocks <= ESR_MAX_KBLOCKS, "esr_pack_conv_weights: bad sizes");
+    esr::PackArgs a;
+    a.wsrc = wsrc; a.off = off; a.s_row = s_row; a.s_slot = s_slot; a.s_ky = s_ky; a.s_kx = s_kx;
+    a.bias_src = bias_src; a.cout_tile = cout_tile; a.cout_tiles = cout_tiles; a.num_kblocks = num_kblocks;
+    a.w_tile_bytes = w_tile_bytes;
+    for (int i = 0; i < num_kblocks; ++i) a.kblocks[i] = kblocks[i];
+    a.rows = rows_dev; a.slots = slots_dev; a.out = static_cast<uint8_t*>(wpack_out); a.bias_out = bias_out;
+    const size_t total = static_cast<size_t>(cout_tiles) * num_kblocks * 3 * 3 * cout_tile * esr::kKB;
+    const int block = 256;
+    const int grid = static_cast<int>((total + block - 1) / block);
+    esr::pack_weights_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return esr::check_launch("pack_weights_kernel");
+}
+
+extern "C" int esr_expand_rows(const float* src_nchw, int32_t B, int32_t C, int32_t H, int32_t W,
+                               const esr_xslot* slots, int32_t nslots, void* dst_nhwc, void* stream) {
+    ESR_CHECK_ARG(src_nchw && slots && dst_nhwc, "esr_expand_rows: null argument");
+    ESR_CHECK_ARG(nslots > 0 && nslots <= 64 && nslots % 8 == 0, "esr_expand_rows: nslots must be a multiple of 8, <= 64");
+    esr::ExpandArgs a;
+    a.src = src_nchw; a.B = B; a.C = C; a.H = H; a.W = W; a.nslots = nslots;
+    for (int i = 0; i < nslots; ++i) {
+        ESR_CHECK_ARG(slots[i].c < C && slots[i].dy >= -1 && slots[i].dy <= 1, "esr_expand_rows: bad slot %d", i);
+        a.slots[i] = slots[i];
+    }
+    a.dst = static_cast<__nv_bfloat16*>(dst_nhwc);
+    const size_t total = static_cast<size_t>(B) * H * W * nslots;
+    const int block = 256;
+    const size_t want = (total + block - 1) / block;
+    const int grid = static_cast<int>(want < 148 * 32 ? want : 148 * 32);
+    esr::expand_rows_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return esr::check_launch("expand_rows_kernel");
+}

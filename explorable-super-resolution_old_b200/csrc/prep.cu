@@ -1,0 +1,227 @@
+// Input preparation for G: the eval-mode replication padding of CEM_PyTorch.forward
+// (CEM/CEMnet.py:170-181), the raw-view unpacking of Z and the bilinear 1/sf latent
+// downscale of RRDBNet.forward (models/modules/architecture.py:152-157), and their adjoints.
+#include "esr_common.cuh"
+
+namespace esr {
+
+__device__ __forceinline__ int clampi2(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+struct PrepArgs {
+    const float* in;   // [B, nz*sf*sf + 3, h, w]
+    int B, nz, h, w, m, sf;
+    float* lr_pad;     // [B,3,h+2m,w+2m], batch stride lr_bs floats
+    float* z_hr;       // [B,nz,sf(h+2m),sf(w+2m)], batch stride zhr_bs floats
+    float* z_lr;       // [B,nz,h+2m,w+2m], batch stride zlr_bs floats
+    long long lr_bs, zhr_bs, zlr_bs;
+};
+
+__global__ void prep_lr_kernel(const __grid_constant__ PrepArgs a) {
+    const int hp = a.h + 2 * a.m, wp = a.w + 2 * a.m, cin = a.nz * a.sf * a.sf + 3;
+    const size_t total = static_cast<size_t>(a.B) * 3 * hp * wp;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(idx % wp);
+        const int Y = static_cast<int>((idx / wp) % hp);
+        const int c = static_cast<int>((idx / (static_cast<size_t>(wp) * hp)) % 3);
+        const int b = static_cast<int>(idx / (static_cast<size_t>(wp) * hp * 3));
+        const int y = clampi2(Y - a.m, 0, a.h - 1), x = clampi2(X - a.m, 0, a.w - 1);
+        a.lr_pad[static_cast<size_t>(b) * a.lr_bs + (static_cast<size_t>(c) * hp + Y) * wp + X] =
+            __ldg(a.in + ((static_cast<size_t>(b) * cin + (cin - 3 + c)) * a.h + y) * a.w + x);
+    }
+}
+
+// Z lives in the first nz*sf*sf channels, reinterpreted (raw .view) as [nz, sf*h, sf*w].
+__device__ __forceinline__ float z_at(const PrepArgs& a, int b, int c, int Y, int X) {
+    const int cin = a.nz * a.sf * a.sf + 3;
+    const int Hh = a.sf * a.h, Wh = a.sf * a.w;
+    const int y = clampi2(Y - a.sf * a.m, 0, Hh - 1), x = clampi2(X - a.sf * a.m, 0, Wh - 1);
+    return __ldg(a.in + static_cast<size_t>(b) * cin * a.h * a.w + (static_cast<size_t>(c) * Hh + y) * Wh + x);
+}
+
+__global__ void prep_zhr_kernel(const __grid_constant__ PrepArgs a) {
+    const int Hp = a.sf * (a.h + 2 * a.m), Wp = a.sf * (a.w + 2 * a.m);
+    const size_t total = static_cast<size_t>(a.B) * a.nz * Hp * Wp;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(idx % Wp);
+        const int Y = static_cast<int>((idx / Wp) % Hp);
+        const int c = static_cast<int>((idx / (static_cast<size_t>(Wp) * Hp)) % a.nz);
+        const int b = static_cast<int>(idx / (static_cast<size_t>(Wp) * Hp * a.nz));
+        a.z_hr[static_cast<size_t>(b) * a.zhr_bs + (static_cast<size_t>(c) * Hp + Y) * Wp + X] = z_at(a, b, c, Y, X);
+    }
+}
+
+// bilinear, scale 1/sf, align_corners=False: source coordinate sf*x + (sf-1)/2.
+__global__ void prep_zlr_kernel(const __grid_constant__ PrepArgs a) {
+    const int hp = a.h + 2 * a.m, wp = a.w + 2 * a.m;
+    const size_t total = static_cast<size_t>(a.B) * a.nz * hp * wp;
+    const int lo = (a.sf - 1) / 2, hi = a.sf / 2;     // equal when sf is odd
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(idx % wp);
+        const int y = static_cast<int>((idx / wp) % hp);
+        const int c = static_cast<int>((idx / (static_cast<size_t>(wp) * hp)) % a.nz);
+        const int b = static_cast<int>(idx / (static_cast<size_t>(wp) * hp * a.nz));
+        const int Y0 = a.sf * y + lo, Y1 = a.sf * y + hi, X0 = a.sf * x + lo, X1 = a.sf * x + hi;
+        const float v = 0.25f * (z_at(a, b, c, Y0, X0) + z_at(a, b, c, Y0, X1) + z_at(a, b, c, Y1, X0) +
+                                 z_at(a, b, c, Y1, X1));
+        a.z_lr[static_cast<size_t>(b) * a.zlr_bs + (static_cast<size_t>(c) * hp + y) * wp + x] = v;
+    }
+}
+
+struct PrepBwdArgs {
+    const float* g_z_hr;  // [B,nz,sf*hp,sf*wp] or null
+    const float* g_z_lr;  // [B,nz,hp,wp] or null
+    int B, nz, h, w, m, sf;
+    float* g_in;          // [B, nz*sf*sf+3, h, w]
+};
+
+__device__ __forceinline__ float gz_total(const PrepBwdArgs& a, int b, int c, int Y, int X) {
+    const int hp = a.h + 2 * a.m, wp = a.w + 2 * a.m, Hp = a.sf * hp, Wp = a.sf * wp;
+    float v = 0.f;
+    if (a.g_z_hr) v = __ldg(a.g_z_hr + ((static_cast<size_t>(b) * a.nz + c) * Hp + Y) * Wp + X);
+    if (a.g_z_lr) {
+        const int lo = (a.sf - 1) / 2, hi = a.sf / 2;
+        const int ry = Y % a.sf, rx = X % a.sf;
+        const float wy = (ry == lo ? 0.5f : 0.f) + (ry == hi ? 0.5f : 0.f);
+        const float wx = (rx == lo ? 0.5f : 0.f) + (rx == hi ? 0.5f : 0.f);
+        if (wy != 0.f && wx != 0.f)
+            v += wy * wx * __ldg(a.g_z_lr + ((static_cast<size_t>(b) * a.nz + c) * hp + Y / a.sf) * wp + X / a.sf);
+    }
+    return v;
+}
+
+__global__ void prep_bwd_kernel(const __grid_constant__ PrepBwdArgs a) {
+    const int Hh = a.sf * a.h, Wh = a.sf * a.w, M = a.sf * a.m, cin = a.nz * a.sf * a.sf + 3;
+    const int Hp = Hh + 2 * M, Wp = Wh + 2 * M;
+    const size_t total = static_cast<size_t>(a.B) * a.nz * Hh * Wh;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(idx % Wh);
+        const int y = static_cast<int>((idx / Wh) % Hh);
+        const int c = static_cast<int>((idx / (static_cast<size_t>(Wh) * Hh)) % a.nz);
+        const int b = static_cast<int>(idx / (static_cast<size_t>(Wh) * Hh * a.nz));
+        // replicate-pad adjoint: border pixels collect the whole margin they were copied into
+        const int Y0 = y == 0 ? 0 : y + M, Y1 = y == Hh - 1 ? Hp - 1 : y + M;
+        const int X0 = x == 0 ? 0 : x + M, X1 = x == Wh - 1 ? Wp - 1 : x + M;
+        float acc = 0.f;
+        for (int Y = Y0; Y <= Y1; ++Y)
+            for (int X = X0; X <= X1; ++X) acc += gz_total(a, b, c, Y, X);
+        a.g_in[static_cast<size_t>(b) * cin * a.h * a.w + (static_cast<size_t>(c) * Hh + y) * Wh + x] = acc;
+    }
+}
+
+__global__ void zero_kernel(float* p, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        p[i] = 0.f;
+}
+
+// Adjoint of esr_expand_rows: g_src[b,c,y,x] = sum over slots s with c_s == c of g_e[b, y-dy_s, x, s].
+struct CollapseArgs {
+    const float* g_e;  // NHWC f32 [B,H,W,stride], slots start at choff
+    int B, C, H, W, nslots, stride, choff;
+    esr_xslot slots[64];
+    float* g_src;      // NCHW f32 [B,C,H,W]
+};
+
+__global__ void collapse_rows_kernel(const __grid_constant__ CollapseArgs a) {
+    const size_t total = static_cast<size_t>(a.B) * a.C * a.H * a.W;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(idx % a.W);
+        const int y = static_cast<int>((idx / a.W) % a.H);
+        const int c = static_cast<int>((idx / (static_cast<size_t>(a.W) * a.H)) % a.C);
+        const int b = static_cast<int>(idx / (static_cast<size_t>(a.W) * a.H * a.C));
+        float acc = 0.f;
+        for (int s = 0; s < a.nslots; ++s) {
+            if (a.slots[s].c != c) continue;
+            const int yy = y - a.slots[s].dy;
+            if (yy < 0 || yy >= a.H) continue;
+            acc += __ldg(a.g_e + ((static_cast<size_t>(b) * a.H + yy) * a.W + x) * a.stride + a.choff + s);
+        }
+        a.g_src[idx] = acc;
+    }
+}
+
+static int grid_for(size_t total) {
+    const size_t want = (total + 255) / 256;
+    return static_cast<int>(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+}
+
+}  // namespace esr
+
+using namespace esr;
+
+static int run_prep(PrepArgs a, cudaStream_t s) {
+    const int hp = a.h + 2 * a.m, wp = a.w + 2 * a.m;
+    if (a.lr_pad) {
+        prep_lr_kernel<<<grid_for(static_cast<size_t>(a.B) * 3 * hp * wp), 256, 0, s>>>(a);
+        if (int rc = check_launch("prep_lr_kernel")) return rc;
+    }
+    if (a.z_hr) {
+        prep_zhr_kernel<<<grid_for(static_cast<size_t>(a.B) * a.nz * hp * wp * a.sf * a.sf), 256, 0, s>>>(a);
+        if (int rc = check_launch("prep_zhr_kernel")) return rc;
+    }
+    if (a.z_lr) {
+        prep_zlr_kernel<<<grid_for(static_cast<size_t>(a.B) * a.nz * hp * wp), 256, 0, s>>>(a);
+        if (int rc = check_launch("prep_zlr_kernel")) return rc;
+    }
+    return ESR_OK;
+}
+
+extern "C" int esr_g_input_prep(const float* model_input, int32_t B, int32_t nz, int32_t h, int32_t w, int32_t m,
+                                int32_t sf, float* lr_pad, float* fea_in, float* z_hr, float* z_lr, void* stream) {
+    ESR_CHECK_ARG(model_input && B > 0 && nz >= 0 && h > 0 && w > 0 && m >= 0 && sf >= 1 && sf <= 4,
+                  "esr_g_input_prep: bad arguments");
+    ESR_CHECK_ARG(nz > 0 || (z_hr == nullptr && z_lr == nullptr), "esr_g_input_prep: latent outputs need nz > 0");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long hp = h + 2 * m, wp = w + 2 * m;
+    PrepArgs a{model_input, B, nz, h, w, m, sf, lr_pad, z_hr, z_lr, 3 * hp * wp, nz * hp * wp * sf * sf, nz * hp * wp};
+    if (int rc = run_prep(a, s)) return rc;
+    if (fea_in) {  // cat([z_lr, lr_pad], 1): the 3+nz channel input of the first conv (architecture.py:160)
+        PrepArgs c = a;
+        c.z_hr = nullptr;
+        c.lr_pad = fea_in + nz * hp * wp; c.lr_bs = (nz + 3) * hp * wp;
+        c.z_lr = nz > 0 ? fea_in : nullptr; c.zlr_bs = (nz + 3) * hp * wp;
+        if (int rc = run_prep(c, s)) return rc;
+    }
+    return ESR_OK;
+}
+
+// The padded input in the reference's own packed layout, for wrapped modules that are not ours.
+extern "C" int esr_cem_pad_input(const float* model_input, int32_t B, int32_t nz, int32_t h, int32_t w, int32_t m,
+                                 int32_t sf, float* packed_out, void* stream) {
+    ESR_CHECK_ARG(model_input && packed_out && B > 0 && nz >= 0 && h > 0 && w > 0 && m >= 0 && sf >= 1 && sf <= 4,
+                  "esr_cem_pad_input: bad arguments");
+    const long long hp = h + 2 * m, wp = w + 2 * m, cin = nz * sf * sf + 3;
+    PrepArgs a{model_input, B, nz, h, w, m, sf, packed_out + nz * sf * sf * hp * wp, nz > 0 ? packed_out : nullptr,
+               nullptr, cin * hp * wp, cin * hp * wp, 0};
+    return run_prep(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int esr_g_input_prep_bwd(const float* g_z_hr, const float* g_z_lr, int32_t B, int32_t nz, int32_t h,
+                                    int32_t w, int32_t m, int32_t sf, float* g_model_input, void* stream) {
+    ESR_CHECK_ARG(g_model_input && B > 0 && nz > 0 && h > 0 && w > 0 && m >= 0 && sf >= 1 && sf <= 4,
+                  "esr_g_input_prep_bwd: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n_in = static_cast<size_t>(B) * (nz * sf * sf + 3) * h * w;
+    zero_kernel<<<grid_for(n_in), 256, 0, s>>>(g_model_input, n_in);
+    if (int rc = check_launch("zero_kernel")) return rc;
+    PrepBwdArgs a{g_z_hr, g_z_lr, B, nz, h, w, m, sf, g_model_input};
+    prep_bwd_kernel<<<grid_for(static_cast<size_t>(B) * nz * h * w * sf * sf), 256, 0, s>>>(a);
+    return check_launch("prep_bwd_kernel");
+}
+
+extern "C" int esr_expand_rows_bwd(const float* g_e_nhwc, int32_t stride, int32_t choff, int32_t B, int32_t C,
+                                   int32_t H, int32_t W, const esr_xslot* slots, int32_t nslots, float* g_src_nchw,
+                                   void* stream) {
+    ESR_CHECK_ARG(g_e_nhwc && slots && g_src_nchw && nslots > 0 && nslots <= 64, "esr_expand_rows_bwd: bad arguments");
+    CollapseArgs a;
+    a.g_e = g_e_nhwc; a.B = B; a.C = C; a.H = H; a.W = W; a.nslots = nslots; a.stride = stride; a.choff = choff;
+    for (int i = 0; i < nslots; ++i) a.slots[i] = slots[i];
+    a.g_src = g_src_nchw;
+    collapse_rows_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("collapse_rows_kernel");
+}

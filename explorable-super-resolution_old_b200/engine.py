@@ -1,0 +1,345 @@
+"""Host-side engine: packs RRDBNet weights into the conv kernels' shared-memory image and lays
+out, per input geometry, the buffers and the recorded launch sequence of the G(+CEM) forward
+(and data-gradient backward).  PyTorch is used for device memory and streams only; every
+arithmetic step is a kernel of libesr_b200.so called through the C ABI.
+
+Layer graph = codes/models/modules/architecture.py:102-175 with block.py:196-270 unrolled.
+Data layout in HBM:
+  * one NHWC bf16 "dense block" buffer [B,H,W,192] per RDB: channels 0..63 = block input x0,
+    64+32i.. = growth x_{i+1}; conv i reads channels [0,64+32i) and writes its 32 outputs into
+    its own slice, so torch.cat never materialises;
+  * the residual trunk (RDB / RRDB / shortcut sums) stays fp32 NHWC [B,H,W,64];
+  * the 3-channel latent is expanded once per resolution over the filter rows into a 32-channel
+    bf16 tensor shared by all 346+2 convs that take it;
+  * the six convs outside the residual-scaled trunk (first, LR_conv, 2 upconvs, 2 HR convs) run
+    in split-bf16 (hi+lo operands, three MMA terms): they carry most of the bf16 rounding error
+    and only 7.8 % of the FLOPs.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from ._capi import KBlock, ConvDesc, WRow, WSlot, XSlot
+
+DY_ALL, DY_CENTRE = 0b111, 0b010
+NF, GC = 64, 32
+
+
+def _struct_array_to_device(arr, ctype, device):
+    """ctypes struct array -> uint8 CUDA tensor with the same bytes."""
+    raw = bytes(memoryview(arr))
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    return t
+
+
+class PackedConv:
+    """One logical 3x3 conv packed for the kernels: K-block list + swizzled bf16 weight image."""
+
+    def __init__(self, name, cout, kblocks, slots, rows, cout_tile):
+        self.name, self.cout, self.cout_tile = name, cout, cout_tile
+        self.cout_tiles = (cout + cout_tile - 1) // cout_tile
+        self.nkb = len(kblocks)
+        assert self.nkb <= capi.MAX_KBLOCKS, name
+        self.kblocks = (KBlock * capi.MAX_KBLOCKS)()
+        for i, (src, chan, dy_mask, slice_mask) in enumerate(kblocks):
+            self.kblocks[i].src, self.kblocks[i].chan = src, chan
+            self.kblocks[i].dy_mask, self.kblocks[i].slice_mask = dy_mask, slice_mask
+        wtb = C.c_uint32(0)
+        total = capi.lib().esr_pack_layout(cout_tile, self.cout_tiles, self.nkb, self.kblocks, C.byref(wtb))
+        if total < 0:
+            capi.check(int(total))
+        self.w_tile_bytes, self.total_bytes = wtb.value, int(total)
+        self.slots = (WSlot * (self.nkb * 32))()
+        for i, (idx, ky, term) in enumerate(slots):
+            self.slots[i].idx, self.slots[i].ky, self.slots[i].term = idx, ky, term
+        nrows = self.cout_tiles * cout_tile
+        self.rows = (WRow * nrows)()
+        for i in range(nrows):
+            idx, ky = rows[i] if i < len(rows) else (-1, -1)
+            self.rows[i].idx, self.rows[i].ky = idx, ky
+        self.wpack = self.bias = None
+
+    def pack(self, weight, bias, off, s_row, s_slot, s_ky, s_kx):
+        dev = weight.device
+        self.wpack = torch.empty(self.total_bytes, dtype=torch.uint8, device=dev)
+        self.bias = torch.empty(self.cout_tiles * self.cout_tile, dtype=torch.float32, device=dev)
+        rows_d = _struct_array_to_device(self.rows, WRow, dev)
+        slots_d = _struct_array_to_device(self.slots, WSlot, dev)
+        capi.check(capi.lib().esr_pack_conv_weights(
+            capi.ptr(weight), off, s_row, s_slot, s_ky, s_kx, capi.ptr(bias), self.cout_tile, self.cout_tiles,
+            self.nkb, self.kblocks, self.w_tile_bytes, capi.ptr(rows_d), capi.ptr(slots_d), capi.ptr(self.wpack),
+            capi.ptr(self.bias), capi.stream_ptr()))
+        self._keep = (rows_d, slots_d)  # until the stream has consumed them
+
+
+def expand_slots(nvals_channels, precise):
+    """Slot table of a row-expanded small-channel tensor.
+
+    values v = (dy, c) for dy in 0..2, c in range(nvals_channels).
+    precise: [hi(v)... | lo(v)... | hi(v)...] padded to a multiple of 32 (three split-bf16 terms)
+    else   : [hi(v)..., pad to 16 | lo(v)..., pad to 16]  (trunk uses slice 0 only)
+    Returns (xslots for esr_expand_rows, wslots template [(value index, dy, term)] per slot).
+    """
+    vals = [(dy, c) for dy in range(3) for c in range(nvals_channels)]
+    V = len(vals)
+    xs, ws = [], []
+    if precise:
+        n = ((3 * V + 31) // 32) * 32
+        for part, (xterm, wterm) in enumerate(((0, 0), (1, 0), (0, 1))):
+            for (dy, c) in vals:
+                xs.append((c, dy - 1, xterm))
+                ws.append((c, dy, wterm))
+        while len(xs) < n:
+            xs.append((-1, 0, 0))
+            ws.append((-1, -1, 0))
+    else:
+        assert V <= 16
+        for xterm in (0, 1):
+            for (dy, c) in vals:
+                xs.append((c, dy - 1, xterm))
+                ws.append((c, dy, 0))
+            while len(xs) % 16:
+                xs.append((-1, 0, 0))
+                ws.append((-1, -1, 0))
+    return xs, ws
+
+
+def _xslot_array(xs):
+    arr = (XSlot * len(xs))()
+    for i, (c, dy, term) in enumerate(xs):
+        arr[i].c, arr[i].dy, arr[i].term = c, dy, term
+    return arr
+
+
+class GEngine:
+    """Packed weights of one RRDBNet; geometry-independent."""
+
+    def __init__(self, nb, nz_in, all_layers, out_nc=3, in_nc=3, upscale=4, precise_outer=True):
+        if upscale not in (2, 4):
+            raise NotImplementedError("upscale %d: only x2 / x4 (nearest x2 upconv stages) are built" % upscale)
+        if in_nc != 3 or out_nc > 16:
+            raise NotImplementedError("in_nc must be 3 and out_nc <= 16")
+        self.nb, self.nz_in, self.all_layers = nb, nz_in, all_layers
+        self.nz = nz_in if all_layers else 0          # latent channels concatenated to every later conv
+        self.out_nc, self.upscale = out_nc, upscale
+        self.n_up = int(math.log2(upscale))
+        self.precise = precise_outer
+        self.convs = {}
+        self.version = None
+        self._build_specs()
+
+    # ------------------------------------------------------------------ specs
+    def _main_blocks(self, nch, precise, src=0):
+        """K blocks + weight slots for `nch` feature channels at buffer channels [0,nch) (hi) and,
+        in precise mode, their bf16 residues at [64,64+nch)."""
+        kb, sl = [], []
+        terms = ((0, 0), (64, 0), (0, 1)) if precise else ((0, 0),)
+        for base, wterm in terms:
+            for c0 in range(0, nch, 32):
+                kb.append((src, base + c0, DY_ALL, 0b11))
+                sl += [(self.nz + c0 + k, -1, wterm) for k in range(32)]
+        return kb, sl
+
+    def _latent_blocks(self, precise, src=1):
+        if self.nz == 0:
+            return [], []
+        _, ws = expand_slots(self.nz, precise=False)   # E_lat layout: [hi | lo], 16 + 16
+        kb, sl = [], []
+        if precise:
+            kb.append((src, 0, DY_CENTRE, 0b11))
+            sl += list(ws)                             # A_hi*W_hi and A_lo*W_hi
+            kb.append((src, 0, DY_CENTRE, 0b01))
+            sl += [(i, ky, 1) for (i, ky, _) in ws]    # A_hi*W_lo
+        else:
+            kb.append((src, 0, DY_CENTRE, 0b01))
+            sl += list(ws)
+        return kb, sl
+
+    def _build_specs(self):
+        p = self.precise
+        # first conv: every input is row-expanded (E_fea), centre tap only
+        self.fea_xslots, fea_ws = expand_slots(self.nz_in + 3, precise=True)
+        kb = [(0, c0, DY_CENTRE, 0b11) for c0 in range(0, len(fea_ws), 32)]
+        self._add("model.0", NF, kb, fea_ws, 32)
+        self.lat_xslots, _ = expand_slots(max(self.nz, 1), precise=False)
+        for r in range(self.nb):
+            for d in (1, 2, 3):
+                for i in range(5):
+                    kb, sl = self._main_blocks(NF + GC * i, False)
+                    kb2, sl2 = self._latent_blocks(False)
+                    self._add("model.1.sub.%d.RDB%d.convs.%d.0" % (r, d, i), GC if i < 4 else NF, kb + kb2, sl + sl2, 32)
+        outer = ["model.1.sub.%d" % self.nb] + ["model.%d.1" % (2 + u) for u in range(self.n_up)] + \
+                ["model.%d" % (2 + self.n_up), "model.%d" % (4 + self.n_up)]
+        self.outer_names = outer
+        for name in outer:
+            has_lat = not name.endswith(".1")          # upconvs take no latent (architecture.py:164-171)
+            kb, sl = self._main_blocks(NF, p)
+            if not has_lat:
+                sl = [(i - self.nz if i >= 0 else i, ky, t) for (i, ky, t) in sl]
+                kb2, sl2 = [], []
+            else:
+                kb2, sl2 = self._latent_blocks(p)
+            last = name == outer[-1]
+            self._add(name, self.out_nc if last else NF, kb + kb2, sl + sl2, 16 if last else 32)
+
+    def _add(self, name, cout, kblocks, slots, cout_tile):
+        rows = [(co, -1) for co in range(cout)]
+        self.convs[name] = PackedConv(name, cout, kblocks, slots, rows, cout_tile)
+
+    # ---------------------------------------------------------------- packing
+    def pack(self, params):
+        """params: dict name -> (weight OIHW f32 CUDA contiguous, bias f32 CUDA)."""
+        for name, pc in self.convs.items():
+            w, b = params[name]
+            cin = w.shape[1]
+            pc.pack(w, b, 0, cin * 9, 9, 3, 1)
+            pc.cin = cin
+
+    def flops_per_lr_pixel(self):
+        """Algorithmic MACs*2 of the reference network per (padded) LR pixel."""
+        total = 0
+        for name, pc in self.convs.items():
+            res = 1
+            if name in self.outer_names[1:]:
+                u = self.outer_names.index(name)
+                res = 4 ** min(u, self.n_up)
+            total += 2 * 9 * pc.cin * pc.cout * res
+        return total
+
+
+class GPlan:
+    """Buffers + recorded conv sequence for one geometry (B, h, w, margin)."""
+
+    def __init__(self, eng, B, h, w, m, device, with_cem_input=True, keep_activations=False, use_simt=False):
+        self.eng, self.B, self.h, self.w, self.m = eng, B, h, w, m
+        self.device = device
+        sf = eng.upscale
+        hp, wp = h + 2 * m, w + 2 * m
+        self.hp, self.wp, self.sf = hp, wp, sf
+        f32 = dict(dtype=torch.float32, device=device)
+        bf = dict(dtype=torch.bfloat16, device=device)
+        nzi, nz = eng.nz_in, eng.nz
+        self.lr_pad = torch.empty(B, 3, hp, wp, **f32)
+        self.fea_in = torch.empty(B, nzi + 3, hp, wp, **f32)
+        self.z_hr = torch.empty(B, nz, sf * hp, sf * wp, **f32) if nz else None
+        self.z_lr = torch.empty(B, nz, hp, wp, **f32) if nz else None
+        self.E_fea = torch.empty(B, hp, wp, len(eng.fea_xslots), **bf)
+        self.E_lat = torch.empty(B, hp, wp, 32, **bf) if nz else None
+        self.E_lath = torch.empty(B, sf * hp, sf * wp, 32, **bf) if nz else None
+        n_rdb = 3 * eng.nb
+        nbuf = n_rdb + 1 if keep_activations else 2
+        self.bufs = [torch.empty(B, hp, wp, 192, **bf) for _ in range(nbuf)]
+        self.T_fea = torch.empty(B, hp, wp, NF, **f32)
+        self.R = [torch.empty(B, hp, wp, NF, **f32) for _ in range(2)]
+        self.T = [torch.empty(B, hp, wp, NF, **f32) for _ in range(2)]
+        res = [(2 ** (u + 1)) for u in range(eng.n_up)]       # 2, 4
+        self.U = [torch.empty(B, r * hp, r * wp, 128, **bf) for r in res]   # nearest-upsampled inputs of the upconvs
+        H4, W4 = sf * hp, sf * wp
+        self.V1 = torch.empty(B, H4, W4, 128, **bf)
+        self.V2 = torch.empty(B, H4, W4, 128, **bf) if (keep_activations or eng.n_up < 2) else self.U[-1]
+        self.y = torch.empty(B, eng.out_nc, H4, W4, **f32)
+        self.seq = capi.lib().esr_seq_create()
+        self.descs = []
+        self._record_forward(use_simt)
+
+    def __del__(self):
+        try:
+            if getattr(self, "seq", None):
+                capi.lib().esr_seq_destroy(self.seq)
+        except Exception:
+            pass
+
+    def buf(self, g):
+        return self.bufs[g] if len(self.bufs) > 2 else self.bufs[g % 2]
+
+    def _desc(self, name, H, W, src0, src1=None, flags=0, alpha=1.0, beta=1.0, res1=None, res2=None,
+              out_bf16=None, out_choff=0, lo_choff=-1, up=1, out_f32=None, out_nchw=None):
+        pc = self.eng.convs[name]
+        d = ConvDesc()
+        d.B, d.H, d.W = self.B, H, W
+        d.src[0].ptr, d.src[0].channels = src0.data_ptr(), src0.shape[-1]
+        if src1 is not None:
+            d.src[1].ptr, d.src[1].channels = src1.data_ptr(), src1.shape[-1]
+        d.cout_tile, d.cout_tiles, d.num_kblocks = pc.cout_tile, pc.cout_tiles, pc.nkb
+        for i in range(pc.nkb):
+            d.kblocks[i] = pc.kblocks[i]
+        d.wpack, d.w_tile_bytes, d.bias = pc.wpack.data_ptr(), pc.w_tile_bytes, pc.bias.data_ptr()
+        d.flags, d.slope, d.alpha, d.beta = flags, 0.2, alpha, beta
+        if res1 is not None:
+            d.res1, d.res1_stride, d.res1_choff = res1.data_ptr(), res1.shape[-1], 0
+            d.flags |= capi.EPI_RES1
+        if res2 is not None:
+            d.res2, d.res2_stride, d.res2_choff = res2.data_ptr(), res2.shape[-1], 0
+            d.flags |= capi.EPI_RES2
+        d.up, d.out_bf16_scale, d.out_bf16_lo_choff = up, 1.0, lo_choff
+        if out_bf16 is not None:
+            d.out_bf16, d.out_bf16_stride, d.out_bf16_choff = out_bf16.data_ptr(), out_bf16.shape[-1], out_choff
+        if out_f32 is not None:
+            d.out_f32, d.out_f32_stride, d.out_f32_choff = out_f32.data_ptr(), out_f32.shape[-1], 0
+        if out_nchw is not None:
+            d.out_nchw, d.cout_real = out_nchw.data_ptr(), pc.cout
+        return d
+
+    def _record_forward(self, use_simt):
+        eng, hp, wp = self.eng, self.hp, self.wp
+        L = capi.EPI_LRELU
+        add = self.descs.append
+        lo = 64 if eng.precise else -1
+        add(self._desc("model.0", hp, wp, self.E_fea, out_f32=self.T_fea, out_bf16=self.buf(0)))
+        g = 0
+        for r in range(eng.nb):
+            rin = self.T_fea if r == 0 else self.R[r % 2]
+            rout = self.R[(r + 1) % 2]
+            for d in (1, 2, 3):
+                b = self.buf(g)
+                xin = rin if d == 1 else self.T[d % 2]
+                pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
+                for i in range(4):
+                    add(self._desc(pre + "%d.0" % i, hp, wp, b, self.E_lat, flags=L, out_bf16=b, out_choff=NF + GC * i))
+                last_rdb = (r == eng.nb - 1 and d == 3)
+                add(self._desc(pre + "4.0", hp, wp, b, self.E_lat, alpha=0.2, res1=xin,
+                               beta=0.2, res2=rin if d == 3 else None,
+                               out_f32=rout if d == 3 else self.T[(d + 1) % 2],
+                               out_bf16=self.buf(g + 1), out_choff=0, lo_choff=lo if last_rdb else -1))
+                g += 1
+        trunk_out = self.buf(g)
+        names = eng.outer_names
+        add(self._desc(names[0], hp, wp, trunk_out, self.E_lat, alpha=1.0, res1=self.T_fea,
+                       out_bf16=self.U[0], lo_choff=lo, up=2))
+        H, W = 2 * hp, 2 * wp
+        for u in range(eng.n_up):
+            last = u == eng.n_up - 1
+            dst = self.V1 if last else self.U[u + 1]
+            add(self._desc(names[1 + u], H, W, self.U[u], flags=L, out_bf16=dst, lo_choff=lo, up=1 if last else 2))
+            if not last:
+                H, W = 2 * H, 2 * W
+        add(self._desc(names[-2], H, W, self.V1, self.E_lath, flags=L, out_bf16=self.V2, lo_choff=lo))
+        add(self._desc(names[-1], H, W, self.V2, self.E_lath, out_nchw=self.y))
+        for d in self.descs:
+            capi.check(capi.lib().esr_seq_add_conv(self.seq, C.byref(d), 1 if use_simt else 0))
+        self.fea_x = _xslot_array(eng.fea_xslots)
+        self.lat_x = _xslot_array(eng.lat_xslots)
+
+    # ------------------------------------------------------------------ run
+    def run_g(self, model_input):
+        """model_input: contiguous f32 CUDA [B, 16*nz+3, h, w].  Fills self.y (raw generator output)."""
+        eng, l, st = self.eng, capi.lib(), capi.stream_ptr()
+        B, hp, wp, sf = self.B, self.hp, self.wp, self.sf
+        capi.check(l.esr_g_input_prep(capi.ptr(model_input), B, eng.nz_in, self.h, self.w, self.m, sf,
+                                      capi.ptr(self.lr_pad), capi.ptr(self.fea_in), capi.ptr(self.z_hr),
+                                      capi.ptr(self.z_lr), st))
+        capi.check(l.esr_expand_rows(capi.ptr(self.fea_in), B, eng.nz_in + 3, hp, wp, self.fea_x, len(self.fea_x),
+                                     capi.ptr(self.E_fea), st))
+        if eng.nz:
+            capi.check(l.esr_expand_rows(capi.ptr(self.z_lr), B, eng.nz, hp, wp, self.lat_x, 32, capi.ptr(self.E_lat), st))
+            capi.check(l.esr_expand_rows(capi.ptr(self.z_hr), B, eng.nz, sf * hp, sf * wp, self.lat_x, 32,
+                                         capi.ptr(self.E_lath), st))
+        capi.check(l.esr_seq_run(self.seq, st))
+        return self.y
+
+    def num_launches(self):
+        n = 3 + 1 + (2 if self.eng.nz else 0)  # prep (lr, fea_in x2 kernels..) counted loosely below
+        return capi.lib().esr_seq_num_launches(self.seq)

@@ -1,0 +1,150 @@
+"""RRDBNet generator, host side.  Drop-in for ``models.modules.architecture.RRDBNet``
+(codes/models/modules/architecture.py:102-175): same constructor, attributes and state_dict
+keys; ``forward`` runs the recorded sm_100a kernel sequence instead of 351 aten convs.
+
+The module tree below only holds parameters under the reference's names
+(``model.0``, ``model.1.sub.{r}.RDB{d}.convs.{i}.0``, ``model.1.sub.{nb}``, ``model.{2,3}.1``,
+``model.4``, ``model.6``; latent input channels first on dim 1) so that checkpoints and
+``process_loaded_state_dict`` (codes/models/base_model.py:113-144) keep working.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _capi as capi
+from .engine import GEngine, GPlan
+
+
+def _conv(cin, cout):
+    return nn.Conv2d(cin, cout, 3, 1, 1, bias=True)
+
+
+class _DenseBlock(nn.Module):            # parameter holder for ResidualDenseBlock_5C (block.py:196-242)
+    def __init__(self, nf, gc, nz):
+        super().__init__()
+        self.convs = nn.ModuleList(
+            [nn.Sequential(_conv(nf + i * gc + nz, gc), nn.LeakyReLU(0.2, True)) for i in range(4)] +
+            [nn.Sequential(_conv(nf + 4 * gc + nz, nf))])
+
+
+class _RRDB(nn.Module):                  # parameter holder for RRDB (block.py:245-270)
+    def __init__(self, nf, gc, nz):
+        super().__init__()
+        self.num_latent_channels = nz
+        self.RDB1, self.RDB2, self.RDB3 = _DenseBlock(nf, gc, nz), _DenseBlock(nf, gc, nz), _DenseBlock(nf, gc, nz)
+
+
+class _Trunk(nn.Module):                 # parameter holder for ShortcutBlock (block.py:76-97)
+    def __init__(self, nf, gc, nb, nz):
+        super().__init__()
+        self.num_latent_channels = nz
+        self.sub = nn.ModuleList([_RRDB(nf, gc, nz) for _ in range(nb)] + [_conv(nf + nz, nf)])
+
+
+class RRDBNet(nn.Module):
+    def __init__(self, in_nc, out_nc, nf, nb, gc=32, upscale=4, norm_type=None, act_type='leakyrelu', mode='CNA',
+                 upsample_mode='upconv', latent_input=None, num_latent_channels=None):
+        super().__init__()
+        if nf != 64:
+            raise NotImplementedError("nf=%d: the kernels are specialised for nf=64, gc=32" % nf)
+        if norm_type is not None or act_type != 'leakyrelu' or mode != 'CNA' or upsample_mode != 'upconv':
+            raise NotImplementedError("only norm_type=None, leakyrelu, mode='CNA', upconv are built (the production config)")
+        if latent_input is not None and 'HR_downscaled' not in latent_input:
+            raise NotImplementedError("latent_input_domain other than HR_downscaled is not built (SURVEY.md §8f rank 4)")
+        self.latent_input = latent_input
+        nz_in = num_latent_channels if (latent_input is not None and num_latent_channels) else 0
+        self.num_latent_channels = 1 * num_latent_channels if num_latent_channels is not None else None
+        self.upscale = upscale
+        all_layers = latent_input is not None and 'all_layers' in latent_input
+        nz = nz_in if all_layers else 0
+        gc = 32                                        # hard-coded in the reference (architecture.py:123)
+        n_up = 1 if upscale == 3 else int(math.log(upscale, 2))
+        mods = [_conv(in_nc + nz_in, nf), _Trunk(nf, gc, nb, nz)]
+        for _ in range(n_up):
+            mods.append(nn.Sequential(nn.Upsample(scale_factor=3 if upscale == 3 else 2, mode='nearest'),
+                                      _conv(nf, nf), nn.LeakyReLU(0.2, True)))
+        mods += [_conv(nf + nz, nf), nn.LeakyReLU(0.2, True), _conv(nf + nz, out_nc)]
+        self.model = nn.ModuleList(mods)
+        self._cfg = dict(nb=nb, nz_in=nz_in, all_layers=all_layers, out_nc=out_nc, in_nc=in_nc, upscale=upscale)
+        self._engine, self._engine_key, self._plans = None, None, {}
+        self.precise_outer = True
+        self.debug_simt = False
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _named_convs(self):
+        return {n[:-len(".weight")]: None for n, _ in self.named_parameters() if n.endswith(".weight")}
+
+    def engine(self):
+        params = dict(self.named_parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params.values()) + (self.precise_outer,)
+        if self._engine is None or key != self._engine_key:
+            eng = GEngine(precise_outer=self.precise_outer, **self._cfg)
+            packed = {}
+            for name in eng.convs:
+                w, b = params[name + ".weight"], params[name + ".bias"]
+                if not w.is_cuda:
+                    raise capi.EsrError("RRDBNet parameters live on %s; move the module to a B200 (no CPU path)" % w.device)
+                packed[name] = (w.detach().contiguous().float(), b.detach().contiguous().float())
+            eng.pack(packed)
+            self._engine, self._engine_key, self._plans = eng, key, {}
+        return self._engine
+
+    def plan(self, B, h, w, m, keep):
+        eng = self.engine()
+        key = (B, h, w, m, keep, self.debug_simt)
+        if key not in self._plans:
+            if len(self._plans) >= 4:
+                self._plans.pop(next(iter(self._plans)))
+            dev = next(self.parameters()).device
+            self._plans[key] = GPlan(eng, B, h, w, m, dev, keep_activations=keep, use_simt=self.debug_simt)
+        return self._plans[key]
+
+    def forward(self, x):
+        return run_generator(self, x, margin=0, cem_filters=None)
+
+
+class _GeneratorFn(torch.autograd.Function):
+    """G (+ optional CEM projection) as one autograd node: data gradient only."""
+
+    @staticmethod
+    def forward(ctx, x, net, margin, cem_filters, need_grad):
+        B, C, h, w = x.shape
+        plan = net.plan(B, h, w, margin, keep=need_grad)
+        sf = net.upscale
+        with torch.cuda.device(x.device):
+            y = plan.run_g(x)
+            if cem_filters is None:
+                out = y.clone()
+            else:
+                crop = sf * margin
+                out = torch.empty(B, y.size(1), y.size(2) - 2 * crop, y.size(3) - 2 * crop, device=x.device,
+                                  dtype=torch.float32)
+                ws = torch.empty(2 * B * y.size(1) * plan.hp * plan.wp, device=x.device, dtype=torch.float32)
+                capi.check(capi.lib().esr_cem_project(cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, y.size(1),
+                                                      y.size(2), y.size(3), crop, capi.ptr(out), capi.ptr(ws),
+                                                      capi.stream_ptr()))
+        ctx.plan, ctx.cem_filters, ctx.margin, ctx.net = plan, cem_filters, margin, net
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .backward import generator_backward
+        return generator_backward(ctx, g), None, None, None, None
+
+
+def run_generator(net, x, margin, cem_filters):
+    if not x.is_cuda:
+        raise capi.EsrError("RRDBNet.forward: expected a CUDA tensor; this package has no CPU or PyTorch fallback")
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    capi.require_device(dev)
+    nz_in = net._cfg["nz_in"]
+    sf = net.upscale
+    if x.size(1) != nz_in * sf * sf + 3:
+        raise ValueError("expected %d input channels (Z.view(B,%d,h,w) ++ LR), got %d" % (nz_in * sf * sf + 3, nz_in * sf * sf, x.size(1)))
+    need_grad = torch.is_grad_enabled() and x.requires_grad
+    if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+        raise NotImplementedError("weight gradients (GAN training step) are not built; freeze the generator "
+                                  "(Z_optimizer does, Z_optimization.py:545-553) or run under torch.no_grad()")
+    xc = x.contiguous().float()
+    return _GeneratorFn.apply(xc, net, margin, cem_filters, need_grad)

@@ -1,0 +1,224 @@
+/*
+ * esr_b200.h - C ABI of libesr_b200.so: hand-written sm_100a kernels for the
+ * Explorable-SR hot path (RRDBNet(+Z) -> CEM forward, and its data-gradient
+ * backward used by Z_optimization).
+ *
+ * The reference (YuvalBahat/Explorable-Super-Resolution_old) is pure Python and
+ * has no FFI; its boundary for this path is the nn.Module API, whose aten calls
+ * each entry point below replaces (file:line under /root/reference/codes):
+ *
+ *   esr_conv3x3_*         nn.Conv2d(k=3,p=1)(+LeakyReLU 0.2, *0.2 + residual, nearest x2)
+ *                         models/modules/block.py:129-155, :230-235, :262-270, :85-97, :294-301
+ *                         models/modules/architecture.py:151-175
+ *   esr_pack_conv_weights the OIHW fp32 state_dict tensors (models/base_model.py:100-144 contract)
+ *   esr_g_input_prep      CEM_PyTorch.forward pre-pad branch + RRDBNet.forward head
+ *                         CEM/CEMnet.py:170-181, models/modules/architecture.py:152-160
+ *   esr_cem_downscale     CEM_PyTorch.DownscaleOP       CEM/CEMnet.py:152,157-162
+ *   esr_cem_inv_hth       Conv_LR_with_Inv_hTh_OP       CEM/CEMnet.py:149-151
+ *   esr_cem_upscale       Upscale_OP                    CEM/CEMnet.py:153-159
+ *   esr_cem_project       CEM_PyTorch.forward :183-190  (out = y + Up(K*(x - Down y)), crop)
+ *   esr_cem_project_bwd   its adjoint w.r.t. y (autograd in the reference, Z_optimization.py:633)
+ *
+ * Conventions: every function returns 0 on success or a negative esr_status and
+ * records a message readable through esr_last_error() (thread-local).  No
+ * exceptions cross the boundary.  No device memory is allocated inside: callers
+ * pass device pointers, sizes and a cudaStream_t (as void*).  Kernels are
+ * enqueued on that stream and the call returns without synchronising.
+ * Layouts: "NCHW f32" = contiguous float [B,C,H,W]; "NHWC bf16" = contiguous
+ * __nv_bfloat16 [B,H,W,C].
+ */
+#ifndef ESR_B200_H
+#define ESR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum esr_status {
+    ESR_OK = 0,
+    ESR_ERR_INVALID = -1,   /* bad argument */
+    ESR_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+    ESR_ERR_UNSUPPORTED = -3 /* device is not sm_100 or feature not built */
+} esr_status;
+
+const char* esr_last_error(void);
+int esr_abi_version(void);
+/* 0 if `device` can run the kernels (compute capability 10.x). */
+int esr_device_check(int device);
+
+/* ------------------------------------------------------------------ conv3x3 */
+
+#define ESR_MAX_KBLOCKS 24
+#define ESR_KBLOCK_CH 32 /* channels per K block (64-byte rows, SWIZZLE_64B) */
+
+/* One K block = 32 consecutive channels of one NHWC bf16 source tensor. */
+typedef struct esr_kblock {
+    int32_t src;        /* index into esr_conv_desc.src[] */
+    int32_t chan;       /* first channel (multiple of 8) */
+    uint32_t w_off;     /* byte offset of the block's weights inside one cout tile image */
+    uint8_t dy_mask;    /* bit d: filter row d (0..2, i.e. dy=d-1) is applied; 0b010 for
+                           sources that were pre-expanded over dy */
+    uint8_t slice_mask; /* bit s: channels [16s,16s+16) of the block are used */
+    uint8_t n_dy;       /* popcount(dy_mask) */
+    uint8_t reserved;
+} esr_kblock;
+
+typedef struct esr_tensor_nhwc {
+    const void* ptr;  /* bf16 [B,H,W,channels] */
+    int32_t channels; /* multiple of 8 */
+} esr_tensor_nhwc;
+
+enum {
+    ESR_EPI_LRELU = 1u << 0,   /* v = v > 0 ? v : slope*v              (block.py:10-23) */
+    ESR_EPI_RES1 = 1u << 1,    /* v = alpha*v + res1                   (block.py:235)    */
+    ESR_EPI_RES2 = 1u << 2,    /* v = beta*v + res2                    (block.py:270)    */
+    ESR_EPI_ACCUM = 1u << 3,   /* v += out_f32 (read-modify-write; dgrad fan-in)         */
+    ESR_EPI_MASK = 1u << 4     /* bf16 output *= (mask > 0 ? 1 : slope) (LeakyReLU')     */
+};
+
+typedef struct esr_conv_desc {
+    int32_t B, H, W;          /* conv resolution (input == output, stride 1, zero pad 1) */
+    esr_tensor_nhwc src[2];
+    int32_t cout_tile;        /* 32 or 16 output channels per CTA tile */
+    int32_t cout_tiles;       /* ceil(Cout / cout_tile) */
+    int32_t num_kblocks;
+    esr_kblock kblocks[ESR_MAX_KBLOCKS];
+    const void* wpack;        /* esr_pack_conv_weights output */
+    uint32_t w_tile_bytes;    /* bytes per cout tile in wpack */
+    const float* bias;        /* [cout_tiles*cout_tile] f32 */
+    uint32_t flags;
+    float slope, alpha, beta;
+    const float* res1;        /* NHWC f32 [B,H,W,res1_stride], channel offset res1_choff */
+    int32_t res1_stride, res1_choff;
+    const float* res2;
+    int32_t res2_stride, res2_choff;
+    void* out_bf16;           /* NHWC bf16 [B,up*H,up*W,out_bf16_stride] or NULL */
+    int32_t out_bf16_stride, out_bf16_choff;
+    int32_t out_bf16_lo_choff; /* >=0: also store the bf16 residue v-bf16(v) there */
+    int32_t up;               /* 1, or 2 = write every output pixel as a 2x2 block (nn.Upsample nearest) */
+    float out_bf16_scale;     /* bf16 output = bf16(out_bf16_scale * v) */
+    float* out_f32;           /* NHWC f32 [B,H,W,out_f32_stride] or NULL */
+    int32_t out_f32_stride, out_f32_choff;
+    float* out_nchw;          /* NCHW f32 [B,cout_real,H,W] or NULL */
+    int32_t cout_real;
+    const void* mask;         /* NHWC bf16, same indexing as out_bf16 (ESR_EPI_MASK) */
+    int32_t mask_stride, mask_choff;
+} esr_conv_desc;
+
+/* tcgen05/TMEM/TMA implicit-GEMM kernel (the product path). */
+int esr_conv3x3_tc(const esr_conv_desc* d, void* stream);
+/* Same contract on CUDA cores, one thread per output; used by tests to isolate
+ * tensor-core/TMA faults from packing/epilogue faults.  Never used for timing. */
+int esr_conv3x3_simt(const esr_conv_desc* d, void* stream);
+
+/* Weight packing tables.  The kernels compute
+ *   out[row] = sum over taps (ky,kx) and channel slots of  A[slot] * Wl[row, slot, ky, kx]
+ * and the packer gathers the logical weights from an f32 device tensor:
+ *   Wl[row, slot, ky, kx] = wsrc[off + row.idx*s_row + slot.idx*s_slot + ky*s_ky + kx*s_kx]
+ * (element strides, possibly negative: dgrad is the transposed + flipped view of the
+ * same OIHW tensor).  A row or a slot with ky >= 0 belongs to a tensor that was
+ * pre-expanded over the filter rows: it contributes at the centre tap only, with
+ * filter row ky.  idx < 0 = zero row / slot. */
+typedef struct esr_wrow {
+    int16_t idx;
+    int8_t ky;   /* -1: follows the tap loop */
+    int8_t reserved;
+} esr_wrow;
+typedef struct esr_wslot {
+    int16_t idx;
+    int8_t ky;   /* -1: follows the tap loop */
+    int8_t term; /* 0: bf16(w)   1: bf16(w - bf16(w)) */
+} esr_wslot;
+
+/* Fills w_off / n_dy of every K block and returns the total packed size in bytes
+ * (cout_tiles * *w_tile_bytes), or a negative esr_status. */
+int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_t num_kblocks, esr_kblock* kblocks,
+                        uint32_t* w_tile_bytes);
+/* rows_dev: DEVICE array [cout_tiles*cout_tile]; slots_dev: DEVICE array [num_kblocks*32].
+ * bias_src (f32 device, indexed by row.idx) may be NULL.  bias_out: [cout_tiles*cout_tile]. */
+int esr_pack_conv_weights(const float* wsrc, int64_t off, int64_t s_row, int64_t s_slot, int64_t s_ky, int64_t s_kx,
+                          const float* bias_src, int32_t cout_tile, int32_t cout_tiles, int32_t num_kblocks,
+                          const esr_kblock* kblocks, uint32_t w_tile_bytes, const esr_wrow* rows_dev,
+                          const esr_wslot* slots_dev, void* wpack_out, float* bias_out, void* stream);
+
+/* ------------------------------------------------------- small-channel sources */
+
+typedef struct esr_xslot {
+    int8_t c;    /* source channel, -1 = zero */
+    int8_t dy;   /* row offset -1..1 */
+    int8_t term; /* 0: bf16(v)  1: bf16(v - bf16(v)) */
+    int8_t reserved;
+} esr_xslot;
+
+/* dst[b,y,x,s] (NHWC bf16, `nslots` channels) = term(src[b, c_s, y+dy_s, x]) with zeros
+ * outside the image.  `slots` is a HOST array [nslots], nslots <= 64. */
+int esr_expand_rows(const float* src_nchw, int32_t B, int32_t C, int32_t H, int32_t W, const esr_xslot* slots,
+                    int32_t nslots, void* dst_nhwc, void* stream);
+
+/* Adjoint of esr_expand_rows: g_src[b,c,y,x] = sum_{s: c_s == c} g_e[b, y-dy_s, x, choff+s]
+ * (g_e: NHWC f32 with `stride` channels).  hi and lo slots of the same value both contribute. */
+int esr_expand_rows_bwd(const float* g_e_nhwc, int32_t stride, int32_t choff, int32_t B, int32_t C, int32_t H,
+                        int32_t W, const esr_xslot* slots, int32_t nslots, float* g_src_nchw, void* stream);
+
+/* CEM_PyTorch pre-pad + RRDBNet head (CEMnet.py:170-181, architecture.py:152-160).
+ * model_input: NCHW f32 [B, sf*sf*nz+3, h, w] = cat(Z.view(B,sf*sf*nz,h,w), LR)  (raw .view packing,
+ * SRRaGAN_model.py:249-255).  Writes (any may be NULL), with hp=h+2m, wp=w+2m:
+ *   lr_pad [B,3,hp,wp]          replication-padded LR image (the CEM's x)
+ *   fea_in [B,nz+3,hp,wp]       cat(z_lr, lr_pad): input of the first conv
+ *   z_hr   [B,nz,sf*hp,sf*wp]   Z replication-padded by sf*m
+ *   z_lr   [B,nz,hp,wp]         bilinear(z_hr, 1/sf, align_corners=False) == mean of the centre
+ *                               2x2 (even sf) / the centre pixel (odd sf) of each sf x sf block */
+int esr_g_input_prep(const float* model_input, int32_t B, int32_t nz, int32_t h, int32_t w, int32_t m, int32_t sf,
+                     float* lr_pad, float* fea_in, float* z_hr, float* z_lr, void* stream);
+/* Same padding, emitted in the reference's packed layout [B, sf*sf*nz+3, hp, wp] (for wrapped
+ * generators that are not this library's RRDBNet). */
+int esr_cem_pad_input(const float* model_input, int32_t B, int32_t nz, int32_t h, int32_t w, int32_t m, int32_t sf,
+                      float* packed_out, void* stream);
+/* Adjoint of the above w.r.t. the Z channels: g_model_input[:, :16*nz] (+)= ... */
+int esr_g_input_prep_bwd(const float* g_z_hr, const float* g_z_lr, int32_t B, int32_t nz, int32_t h, int32_t w,
+                         int32_t m, int32_t sf, float* g_model_input, void* stream);
+
+/* ---------------------------------------------------------------------- CEM */
+
+#define ESR_CEM_MAX_TAPS 64
+typedef struct esr_cem_filters {
+    int32_t sf;       /* integer scale factor */
+    int32_t pre;      /* sampling phase (imresize_CEM.py:73-86) */
+    int32_t n_ds;     /* length of the 1-D factor of ds_kernel (17 for bicubic x4) */
+    int32_t n_inv;    /* length of the 1-D factor of inv_hTh (27) */
+    float ds[ESR_CEM_MAX_TAPS];  /* ds_kernel == outer(ds, ds) */
+    float inv[ESR_CEM_MAX_TAPS]; /* inv_hTh   == outer(inv, inv) */
+} esr_cem_filters;
+
+int esr_cem_downscale(const esr_cem_filters* f, const float* y, int32_t B, int32_t C, int32_t H, int32_t W,
+                      float* out, void* stream);
+int esr_cem_inv_hth(const esr_cem_filters* f, const float* x, int32_t B, int32_t C, int32_t h, int32_t w, float* out,
+                    void* stream);
+int esr_cem_upscale(const esr_cem_filters* f, const float* x, int32_t B, int32_t C, int32_t h, int32_t w, float* out,
+                    void* stream);
+/* out[B,C,H-2*crop,W-2*crop] = crop(y + Up(K * (x - Down(y)))).  y: [B,C,H,W], x: [B,C,H/sf,W/sf].
+ * workspace: 2*B*C*(H/sf)*(W/sf) floats. */
+int esr_cem_project(const esr_cem_filters* f, const float* y, const float* x, int32_t B, int32_t C, int32_t H,
+                    int32_t W, int32_t crop, float* out, float* workspace, void* stream);
+/* g_y[B,C,H,W] = pad(g_out) - Down^T(K^T(Up^T(pad(g_out)))), exact adjoint including the
+ * replicate-padding folds.  workspace: B*C*(H*W + H*(W/sf) + 2*(H/sf)*(W/sf)) floats. */
+int esr_cem_project_bwd(const esr_cem_filters* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
+                        int32_t crop, float* g_y, float* workspace, void* stream);
+
+/* --------------------------------------------------------- recorded sequences */
+/* A sequence is a host-side list of fully resolved kernel launches (tensor maps
+ * encoded once) that esr_seq_run replays on a stream without returning to the
+ * caller between layers: the 351-conv forward is one call. */
+typedef struct esr_seq esr_seq;
+esr_seq* esr_seq_create(void);
+void esr_seq_destroy(esr_seq* s);
+int esr_seq_add_conv(esr_seq* s, const esr_conv_desc* d, int32_t use_simt);
+int esr_seq_run(const esr_seq* s, void* stream);
+int32_t esr_seq_num_launches(const esr_seq* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESR_B200_H */

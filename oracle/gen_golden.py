@@ -1,0 +1,162 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/codes) on CPU.
+
+TEST INFRASTRUCTURE, build-container only (the reference tree does not exist on the GPU box).
+Run:  python -m oracle.gen_golden
+Every fixture stores the seeds / configuration needed to regenerate the weights and inputs with
+``esr_b200.synth`` plus the reference's outputs, so fixtures stay a few hundred KB in total.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims  # noqa: E402
+from esr_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def make_opt(nb, latent_input, is_train=False, patch=256):
+    return {"gpu_ids": None, "is_train": is_train, "datasets": {"train": {"patch_size": patch}},
+            "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input=latent_input,
+                              latent_input_domain="HR_downscaled", latent_channels=3, norm_type=None, mode="CNA",
+                              nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=4)}
+
+
+def build_ref_G(CEMnet, networks, nb, latent_input, kind, seed):
+    import CEM.imresize_CEM as im
+    im.imresize.kernels = {}
+    cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(4))
+    netG = networks.define_G(make_opt(nb, latent_input), CEM=cem, num_latent_channels=0 if latent_input == "None" else 3)
+    li = None if latent_input == "None" else latent_input + "_HR_downscaled"
+    w = synth.make_weights(kind, seed=seed, nb=nb, latent_input=li)
+    sd = netG.state_dict()
+    assert [k for k in sd if "Filter" not in k] == ["generated_image_model." + k for k in w]
+    sd.update({"generated_image_model." + k: v for k, v in w.items()})
+    netG.load_state_dict(sd)
+    return netG, cem
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    CEMnet, networks, arch, zopt = ref_shims.load_reference()
+    import CEM.imresize_CEM as im
+
+    # 1. filters --------------------------------------------------------------------------
+    filt = {}
+    for sf in (2, 3, 4):
+        im.imresize.kernels = {}
+        c = CEMnet.CEMnet(CEMnet.Get_CEM_Config(sf))
+        filt["ds_kernel_%d" % sf] = c.ds_kernel.astype(np.float32)
+        filt["inv_hTh_%d" % sf] = c.inv_hTh.astype(np.float64)
+        filt["margins_%d" % sf] = np.array([c.invalidity_margins_LR, c.invalidity_margins_HR,
+                                            c.ds_kernel_invalidity_half_size_LR, c.inv_hTh_invalidity_half_size])
+    np.savez_compressed(os.path.join(OUT, "cem_filters.npz"), **filt)
+
+    # 2. CEM operators and projection around a stub generator -----------------------------
+    class Stub(torch.nn.Module):
+        num_latent_channels, upscale = 3, 4
+
+        def forward(self, x):
+            return self.y
+
+    im.imresize.kernels = {}
+    cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(4))
+    stub = Stub()
+    wrapped = cem.WrapArchitecture_PyTorch(stub)
+    rng = np.random.default_rng(7)
+    y = torch.from_numpy(rng.random((2, 3, 48, 64), dtype=np.float32))
+    x = torch.from_numpy(rng.random((2, 3, 12, 16), dtype=np.float32))
+    stub.y = y
+    wrapped.train(True)
+    with torch.no_grad():
+        ops = dict(y=y.numpy(), x=x.numpy(), down=wrapped.DownscaleOP(y).numpy(), up=wrapped.Upscale_OP(x).numpy(),
+                   inv=wrapped.Conv_LR_with_Inv_hTh_OP(x).numpy(), project_train=wrapped(x).numpy())
+    # adjoint of the projection w.r.t. y through autograd
+    yg = y.clone().requires_grad_(True)
+    stub.y = yg
+    g = torch.from_numpy(rng.standard_normal((2, 3, 48, 64)).astype(np.float32))
+    (wrapped(x) * g).sum().backward()
+    ops["project_grad_g"], ops["project_grad_y"] = g.numpy(), yg.grad.numpy()
+    # eval mode: padded by 10/40, Z packed in front
+    lr, z = synth.make_inputs(1, 8, 12, seed=3)
+    mi = torch.cat([z.contiguous().view(1, 48, 8, 12), lr], 1)
+    stub.y = torch.from_numpy(rng.random((1, 3, 4 * 28, 4 * 32), dtype=np.float32))
+    wrapped.train(False)
+    with torch.no_grad():
+        ops["eval_model_input"], ops["eval_y"], ops["project_eval"] = mi.numpy(), stub.y.numpy(), wrapped(mi).numpy()
+    np.savez_compressed(os.path.join(OUT, "cem_ops.npz"), **ops)
+
+    # 3. G + CEM --------------------------------------------------------------------------
+    cases = [("prod_default", 23, "all_layers", "default", 0, 1, 12, 12, False),
+             ("prod_kaiming", 23, "all_layers", "kaiming", 1, 1, 10, 14, False),
+             ("nb2_train_mode", 2, "all_layers", "default", 2, 2, 16, 12, True),
+             ("nb2_first_layer", 2, "first_layer", "default", 3, 1, 12, 12, False),
+             ("nb1_no_latent", 1, "None", "default", 4, 1, 12, 16, False)]
+    out = {}
+    for name, nb, li, kind, seed, B, h, w, train in cases:
+        netG, _ = build_ref_G(CEMnet, networks, nb, li, kind, seed)
+        netG.train(train)
+        lr, z = synth.make_inputs(B, h, w, seed=seed)
+        mi = lr if li == "None" else torch.cat([z.contiguous().view(B, 48, h, w), lr], 1)
+        with torch.no_grad():
+            res = netG(mi)
+        out[name + "_out"] = res.numpy()
+        out[name + "_cfg"] = np.array([nb, seed, B, h, w, int(train)])
+        out[name + "_str"] = np.array([li, kind])
+        print(name, tuple(res.shape), float(res.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "g_cem.npz"), **out)
+
+    # 4. Z optimisation through the reference's Z_optimizer --------------------------------
+    class RefModel:
+        """Minimal stand-in for SRRaGANModel (codes/models/SRRaGAN_model.py:249-302 restated):
+        only what Z_optimizer touches."""
+
+        def __init__(self, netG):
+            self.netG, self.num_latent_channels, self.opt = netG, 3, {"scale": 4}
+
+        def ConcatLatent(self, LR_image, latent_input):
+            if LR_image.size()[2:] != latent_input.size()[2:]:
+                latent_input = latent_input.contiguous().view([latent_input.size(0), latent_input.size(1) * 16] + list(LR_image.size()[2:]))
+            self.model_input = torch.cat([latent_input, LR_image], dim=1)
+
+        def GetLatent(self):
+            latent = 1 * self.model_input[:, :-3, ...]
+            return latent.view([latent.size(0), 3] + [4 * v for v in latent.size()[2:]])
+
+        def feed_data(self, data, need_HR=True):
+            self.var_L = data["LR"]
+            self.ConcatLatent(self.var_L, data["Z"])
+
+    zres = {}
+    for name, objective, train_mode in (("tv_eval", "TV", False), ("l1_train", "l1", True)):
+        netG, cem = build_ref_G(CEMnet, networks, 2, "all_layers", "default", 5)
+        netG.train(train_mode)
+        lr, z0 = synth.make_inputs(1, 8, 8, seed=5)
+        model = RefModel(netG)
+        data = {"LR": lr, "Z": 0.5 * z0}
+        model.feed_data(data)
+        with torch.no_grad():
+            model.fake_H = netG(model.model_input)
+        if train_mode:
+            del model.__dict__["fake_H"]
+            tgt = torch.from_numpy(np.random.default_rng(11).random((1, 3, 32, 32), dtype=np.float32))
+            data["HR"] = tgt
+            zres[name + "_target"] = tgt.numpy()
+        opt = zopt.Z_optimizer(objective=objective, Z_size=[32, 32], model=model, Z_range=1.0, max_iters=4, data=data,
+                               initial_LR=0.1, batch_size=1, HR_unpadder=(lambda t: t) if train_mode else None)
+        if train_mode:
+            opt.feed_data(data)
+        Z = opt.optimize()
+        zres[name + "_loss"] = np.array(opt.loss_values, dtype=np.float64)
+        zres[name + "_Z"] = Z.numpy()
+        print(name, opt.loss_values)
+    np.savez_compressed(os.path.join(OUT, "zopt.npz"), **zres)
+
+
+if __name__ == "__main__":
+    main()
