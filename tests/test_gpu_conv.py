@@ -1,0 +1,94 @@
+"""conv3x3 kernels (tcgen05 and the SIMT cross-check) against the CPU oracle conv, through the C ABI."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from esr_b200 import _capi as capi
+from tests.helpers import plain_conv_case, conv_desc, run_conv, bf16_round
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3   # bf16 operands are exact in both paths; only fp32 accumulation order differs
+
+
+def _nchw(t_nhwc):
+    return t_nhwc.float().permute(0, 3, 1, 2).cpu()
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 8, 30, 32, 32), (2, 20, 20, 64, 32), (1, 13, 70, 96, 32),
+                                            (1, 9, 33, 192, 64), (1, 40, 61, 64, 3), (2, 17, 95, 160, 32)])
+def test_plain_conv_f32_out(cuda_device, impl, B, H, W, cin, cout):
+    c = plain_conv_case(cuda_device, B, H, W, cin, cout, seed=cin + cout + W)
+    pc = c["pc"]
+    out = torch.full((B, H, W, pc.cout_tiles * pc.cout_tile), 7.0, device=cuda_device)
+    d = conv_desc(pc, B, H, W, c["buf"])
+    d.out_f32, d.out_f32_stride = out.data_ptr(), out.shape[-1]
+    run_conv(d, impl)
+    got = _nchw(out)[:, :cout]
+    err = (got - c["ref"]).abs().max().item()
+    assert err < TOL, "max abs err %g" % err
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_dense_block_slice_write_and_lrelu(cuda_device, impl):
+    """conv reads channels [0,96) of a 192-channel buffer and writes LeakyReLU(out) as bf16 into [96,128)."""
+    B, H, W = 1, 21, 45
+    c = plain_conv_case(cuda_device, B, H, W, 96, 32, seed=5, buf_channels=192)
+    buf = c["buf"]
+    d = conv_desc(c["pc"], B, H, W, buf)
+    d.flags = capi.EPI_LRELU
+    d.out_bf16, d.out_bf16_stride, d.out_bf16_choff = buf.data_ptr(), 192, 96
+    run_conv(d, impl)
+    got = _nchw(buf)[:, 96:128]
+    ref = bf16_round(F.leaky_relu(c["ref"], 0.2))
+    assert (got - ref).abs().max().item() < 2e-2          # one bf16 ulp at |v|<=2
+    assert ((got - ref).abs() > 1e-6).float().mean().item() < 0.02
+    assert torch.equal(_nchw(buf)[:, :96], _nchw(c["buf"])[:, :96])
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_residual_epilogue_and_split_output(cuda_device, impl):
+    """v = 0.2*(0.2*conv + res1) + res2 -> fp32 trunk, bf16 hi/lo pair (RDB3 / last-RDB epilogue)."""
+    B, H, W = 2, 12, 37
+    c = plain_conv_case(cuda_device, B, H, W, 192, 64, seed=9)
+    g = torch.Generator().manual_seed(1)
+    r1, r2 = torch.rand(B, H, W, 64, generator=g), torch.rand(B, H, W, 64, generator=g)
+    r1d, r2d = r1.to(cuda_device), r2.to(cuda_device)
+    out32 = torch.zeros(B, H, W, 64, device=cuda_device)
+    outb = torch.zeros(B, H, W, 192, device=cuda_device, dtype=torch.bfloat16)
+    d = conv_desc(c["pc"], B, H, W, c["buf"])
+    d.flags = capi.EPI_RES1 | capi.EPI_RES2
+    d.alpha, d.beta = 0.2, 0.2
+    d.res1, d.res1_stride, d.res2, d.res2_stride = r1d.data_ptr(), 64, r2d.data_ptr(), 64
+    d.out_f32, d.out_f32_stride = out32.data_ptr(), 64
+    d.out_bf16, d.out_bf16_stride, d.out_bf16_choff, d.out_bf16_lo_choff = outb.data_ptr(), 192, 0, 64
+    run_conv(d, impl)
+    ref = 0.2 * (0.2 * c["ref"] + r1.permute(0, 3, 1, 2)) + r2.permute(0, 3, 1, 2)
+    assert (_nchw(out32) - ref).abs().max().item() < TOL
+    recon = _nchw(outb)[:, :64] + _nchw(outb)[:, 64:128]
+    assert (recon - ref).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_split_bf16_input_and_up2_output(cuda_device, impl):
+    """precise mode: hi/lo input pair, three MMA terms ~ fp32 conv; output replicated 2x2 (nearest)."""
+    B, H, W = 1, 11, 40
+    c = plain_conv_case(cuda_device, B, H, W, 64, 64, seed=3, precise=True)
+    outb = torch.zeros(B, 2 * H, 2 * W, 128, device=cuda_device, dtype=torch.bfloat16)
+    d = conv_desc(c["pc"], B, H, W, c["buf"])
+    d.up = 2
+    d.out_bf16, d.out_bf16_stride, d.out_bf16_choff, d.out_bf16_lo_choff = outb.data_ptr(), 128, 0, 64
+    run_conv(d, impl)
+    recon = _nchw(outb)[:, :64] + _nchw(outb)[:, 64:128]
+    ref = F.interpolate(c["ref"], scale_factor=2, mode="nearest")
+    assert (recon - ref).abs().max().item() < 2e-4
+
+
+def test_nchw_output_cout3(cuda_device):
+    B, H, W = 2, 19, 50
+    c = plain_conv_case(cuda_device, B, H, W, 64, 3, seed=4)
+    out = torch.zeros(B, 3, H, W, device=cuda_device)
+    d = conv_desc(c["pc"], B, H, W, c["buf"])
+    d.out_nchw, d.cout_real = out.data_ptr(), 3
+    run_conv(d, "tc")
+    assert (out.cpu() - c["ref"]).abs().max().item() < TOL

@@ -1,0 +1,104 @@
+"""Full RRDBNet(+Z) -> CEM forward on the GPU against (a) the reference's golden outputs, (b) the fp32
+CPU oracle and (c) the oracle emulating bf16 MMA operands (tight: separates indexing from rounding).
+
+Tolerances (BASELINE.json north_star): PSNR >= 50 dB and max|err| <= 1e-2 against the fp32 reference on
+[0,1]-scaled images; CEM consistency residual <= 1e-4 on the interior (>= 3 LR px from the border)."""
+import numpy as np
+import pytest
+import torch
+
+from esr_b200 import cem as pcem, networks, synth
+from oracle.cem_ops import concat_latent
+from oracle.rrdbnet import GCEMOracle
+from tests.helpers import psnr
+from tests.test_oracle_golden import CASES, oracle_for_case
+
+pytestmark = pytest.mark.gpu
+
+
+def build_product_G(dev, nb, latent, weights, train=False, sf=4):
+    opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 256}},
+           "network_G": dict(which_model_G="RRDB_net", CEM_arch=1,
+                             latent_input="None" if latent is None else latent.split("_HR_")[0],
+                             latent_input_domain="HR_downscaled", latent_channels=3, norm_type=None, mode="CNA",
+                             nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=sf)}
+    cemnet = pcem.CEMnet(pcem.Get_CEM_Config(sf))
+    netG = networks.define_G(opt, CEM=cemnet, num_latent_channels=3 if latent else 0)
+    sd = netG.state_dict()
+    keys = [k for k in sd if "Filter" not in k]
+    assert keys == ["generated_image_model." + k for k in weights], "state_dict key order differs from the reference"
+    sd.update({"generated_image_model." + k: v for k, v in weights.items()})
+    netG.load_state_dict(sd)
+    netG.to(dev)
+    netG.train(train)
+    for p in netG.parameters():
+        p.requires_grad_(False)
+    return netG
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_forward_matches_reference_golden(golden, cuda_device, name, impl):
+    g = golden("g_cem")
+    ora, mi, wts, cfg = oracle_for_case(g, name)
+    if impl == "simt" and cfg["nb"] > 2:
+        pytest.skip("SIMT cross-check only on the small nets")
+    netG = build_product_G(cuda_device, cfg["nb"], cfg["latent"], wts, train=cfg["train"])
+    netG.generated_image_model.debug_simt = impl == "simt"
+    with torch.no_grad():
+        out = netG(mi.to(cuda_device)).cpu()
+    ref = torch.from_numpy(g[name + "_out"])
+    err, p = (out - ref).abs().max().item(), psnr(out, ref)
+    assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB vs the reference" % (err, p)
+    # tight check against the oracle emulating the kernels' arithmetic (bf16 trunk operands; the six
+    # outer convs run split-bf16 ~ fp32)
+    ora_b, _, _, _ = oracle_for_case(g, name, operand_dtype=torch.bfloat16)
+    orig_conv = ora_b.net.conv
+    fp32_keys = {"model.0", "model.1.sub.%d" % cfg["nb"], "model.2.1", "model.3.1", "model.4", "model.6"}
+
+    def conv(x, key, act):
+        ora_b.net.od = None if key in fp32_keys else torch.bfloat16
+        return orig_conv(x, key, act)
+    ora_b.net.conv = conv
+    with torch.no_grad():
+        emu = ora_b.forward(mi)
+    err_e = (out - emu).abs().max().item()
+    assert err_e <= 2e-3, "max|err| %g vs bf16-emulating oracle" % err_e
+
+
+def test_consistency_and_fp32_oracle_larger_image(cuda_device):
+    """1x3x64x64 (BASELINE config 1): parity vs the fp32 oracle and the CEM consistency residual."""
+    wts = synth.make_weights("default", seed=0)
+    lr, z = synth.make_inputs(1, 64, 64, seed=0)
+    mi = concat_latent(lr, z)
+    netG = build_product_G(cuda_device, 23, "all_layers_HR_downscaled", wts)
+    with torch.no_grad():
+        out = netG(mi.to(cuda_device))
+        down = netG.DownscaleOP(out)
+    res = (down.cpu() - lr).abs()[:, :, 3:-3, 3:-3].max().item()
+    assert res <= 1e-4, "consistency residual %g" % res
+    with torch.no_grad():
+        ref = GCEMOracle(wts).forward(mi)
+    err, p = (out.cpu() - ref).abs().max().item(), psnr(out.cpu(), ref)
+    assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB" % (err, p)
+
+
+def test_batch_shards_are_bit_identical(cuda_device):
+    """batch sharding is exact - image i of a batch == the same image run alone."""
+    wts = synth.make_weights("kaiming", seed=2, nb=2)
+    lr, z = synth.make_inputs(3, 20, 24, seed=2)
+    mi = concat_latent(lr, z).to(cuda_device)
+    netG = build_product_G(cuda_device, 2, "all_layers_HR_downscaled", wts)
+    with torch.no_grad():
+        full = netG(mi).clone()
+        for i in range(3):
+            one = netG(mi[i:i + 1].contiguous())
+            assert torch.equal(one[0], full[i])
+
+
+def test_no_cpu_fallback():
+    wts = synth.make_weights("kaiming", seed=2, nb=1)
+    netG = build_product_G(torch.device("cpu"), 1, "all_layers_HR_downscaled", wts)
+    lr, z = synth.make_inputs(1, 8, 8)
+    with pytest.raises(Exception):
+        netG(concat_latent(lr, z))
