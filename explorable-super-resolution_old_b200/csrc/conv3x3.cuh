@@ -28,7 +28,11 @@ constexpr int kABytes = kHaloRows * kTileW * kRowBytes;  // 20480
 
 struct ConvLaunch {
     esr_conv_desc d;
-    int tiles_x, tiles_y, total_tiles;
+    int tiles_x, tiles_y, spatial_tiles, total_tiles;
+    uint32_t w_smem_bytes;   // resident weight region (w_tile_bytes rounded up to 1 KiB)
+    int nstages;             // depth of the A-tile ring that fits beside it
+    int debug;               // ESR_DEBUG_SKIP timing experiments (results invalid when non-zero)
+    unsigned long long* prof; // optional [gridDim][16] per-role cycle counters (esr_debug_set_profile_buffer)
 };
 
 // Byte offset of element (row n, channel k) inside a [rows x 32ch] SWIZZLE_64B K-major
@@ -37,50 +41,149 @@ __host__ __device__ inline uint32_t sw64_offset(uint32_t n, uint32_t k) {
     return n * 64u + ((((k >> 3) ^ (n >> 1)) & 3u) << 4) + (k & 7u) * 2u;
 }
 
-// Applies the fused epilogue to 16 consecutive output channels of one pixel.
-__device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, int n, int y, int x, int co0, float (&v)[16]) {
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf16_lo_part(float a) {     // a - bf16(a)
+    return a - __bfloat162float(__float2bfloat16_rn(a));
+}
+
+// 32-byte store: halves the number of store instructions (and L1 wavefronts) of the
+// pixel-strided NHWC writes.  Needs a 32-byte aligned address.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_global_v8f(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8f(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+// 16 consecutive floats, 32-byte vector accesses when `wide` (address 32-byte aligned)
+__device__ __forceinline__ void load16f(const float* p, float* r, bool wide) {
+    if (wide) { ld_global_v8f(p, r); ld_global_v8f(p + 8, r + 8); }
+    else {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(r + i) = *reinterpret_cast<const float4*>(p + i);
+    }
+}
+__device__ __forceinline__ void store16f(float* p, const float* r, bool wide) {
+    if (wide) { st_global_v8f(p, r); st_global_v8f(p + 8, r + 8); }
+    else {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(p + i) = *reinterpret_cast<const float4*>(r + i);
+    }
+}
+
+constexpr int kEpiGeneric = 0;   // every flag / output decided at run time
+constexpr int kEpiTrunk = 1;     // bias + LeakyReLU -> bf16 slice of the dense-block buffer (conv 0..3 of an RDB)
+
+// Address of 8 consecutive f32 channels [c, c+8) (c % 8 == 0) of pixel (n,y,x) in a trunk tensor with C = `stride`
+// channels: NHWC, or blocked [B, C/8, H, W, 8] where the 32 pixels of a warp form one contiguous 1 KiB run.
+__device__ __forceinline__ size_t f32_off(const esr_conv_desc& d, bool blocked, int stride, int n, int y, int x, int c) {
+    if (blocked)
+        return ((static_cast<size_t>(n) * (stride >> 3) + (c >> 3)) * d.H + y) * (static_cast<size_t>(d.W) * 8) +
+               static_cast<size_t>(x) * 8;
+    return ((static_cast<size_t>(n) * d.H + y) * d.W + x) * stride + c;
+}
+__device__ __forceinline__ void load16f_at(const esr_conv_desc& d, const float* base, int stride, int choff, int n,
+                                           int y, int x, int co0, float* r) {
+    const bool blocked = (d.flags & ESR_EPI_F32_BLOCKED) != 0;
+    if (blocked) {
+        ld_global_v8f(base + f32_off(d, true, stride, n, y, x, choff + co0), r);
+        ld_global_v8f(base + f32_off(d, true, stride, n, y, x, choff + co0 + 8), r + 8);
+    } else {
+        load16f(base + f32_off(d, false, stride, n, y, x, choff + co0), r, (d.flags & ESR_EPI_WIDE_OK) != 0);
+    }
+}
+__device__ __forceinline__ void store16f_at(const esr_conv_desc& d, float* base, int stride, int choff, int n, int y,
+                                            int x, int co0, const float* r) {
+    const bool blocked = (d.flags & ESR_EPI_F32_BLOCKED) != 0;
+    if (blocked) {
+        st_global_v8f(base + f32_off(d, true, stride, n, y, x, choff + co0), r);
+        st_global_v8f(base + f32_off(d, true, stride, n, y, x, choff + co0 + 8), r + 8);
+    } else {
+        store16f(base + f32_off(d, false, stride, n, y, x, choff + co0), r, (d.flags & ESR_EPI_WIDE_OK) != 0);
+    }
+}
+
+// Residual / accumulator / mask operands of one pixel's 16 channels.  They are fetched BEFORE the
+// epilogue warp waits for its accumulator, so their L2/HBM latency hides behind the tile's MMAs.
+struct EpiOperands {
+    float r1[16];   // out_f32 (ACCUM) or res1
+    float r2[16];   // res2
+    uint4 m[2];     // LeakyReLU mask source (bf16 x 16)
+};
+
+template <int MODE>
+__device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, int n, int y, int x, int co0,
+                                                       EpiOperands& P) {
+    if constexpr (MODE == kEpiTrunk) return;
+    const uint32_t flags = d.flags;
+    const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
+    if (flags & ESR_EPI_ACCUM) load16f_at(d, d.out_f32, d.out_f32_stride, d.out_f32_choff, n, y, x, co0, P.r1);
+    else if (flags & ESR_EPI_RES1) load16f_at(d, d.res1, d.res1_stride, d.res1_choff, n, y, x, co0, P.r1);
+    if (flags & ESR_EPI_RES2) load16f_at(d, d.res2, d.res2_stride, d.res2_choff, n, y, x, co0, P.r2);
+    if (flags & ESR_EPI_MASK) {
+        const uint4* m = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.mask) +
+                                                        pix * d.mask_stride + d.mask_choff + co0);
+        P.m[0] = __ldg(m);
+        P.m[1] = __ldg(m + 1);
+    }
+}
+
+// Applies the fused epilogue to 16 consecutive output channels of one pixel.  `bias` points at the
+// 16 biases of these channels (shared memory in the tcgen05 kernel, global in the SIMT check).
+template <int MODE>
+__device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const float* bias, int n, int y, int x,
+                                                int co0, float (&v)[16], const EpiOperands& P) {
     const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(d.bias + co0 + i));
+        const float4 b = *reinterpret_cast<const float4*>(bias + i);
         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
     }
-    if (d.flags & ESR_EPI_ACCUM) {
-        const float* o = d.out_f32 + pix * d.out_f32_stride + d.out_f32_choff + co0;
+    if constexpr (MODE == kEpiTrunk) {
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-            const float4 r = *reinterpret_cast<const float4*>(o + i);
-            v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+        for (int i = 0; i < 8; ++i)
+            pk[i] = pack_bf16x2(fmaxf(v[2 * i], d.slope * v[2 * i]), fmaxf(v[2 * i + 1], d.slope * v[2 * i + 1]));
+        st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
+        return;
+    }
+    const uint32_t flags = d.flags;
+    if (flags & ESR_EPI_ACCUM) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += P.r1[i];
+        if (flags & ESR_EPI_RES1) {
+            float r[16];
+            load16f_at(d, d.res1, d.res1_stride, d.res1_choff, n, y, x, co0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + r[i];
+        }
+    } else {
+        if (flags & ESR_EPI_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], d.slope * v[i]);
+        }
+        if (flags & ESR_EPI_RES1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + P.r1[i];
         }
     }
-    if (d.flags & ESR_EPI_LRELU) {
+    if (flags & ESR_EPI_RES2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : d.slope * v[i];
+        for (int i = 0; i < 16; ++i) v[i] = d.beta * v[i] + P.r2[i];
     }
-    if (d.flags & ESR_EPI_RES1) {
-        const float* r1 = d.res1 + pix * d.res1_stride + d.res1_choff + co0;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(r1 + i));
-            v[i] = d.alpha * v[i] + r.x; v[i + 1] = d.alpha * v[i + 1] + r.y;
-            v[i + 2] = d.alpha * v[i + 2] + r.z; v[i + 3] = d.alpha * v[i + 3] + r.w;
-        }
-    }
-    if (d.flags & ESR_EPI_RES2) {
-        const float* r2 = d.res2 + pix * d.res2_stride + d.res2_choff + co0;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(r2 + i));
-            v[i] = d.beta * v[i] + r.x; v[i + 1] = d.beta * v[i + 1] + r.y;
-            v[i + 2] = d.beta * v[i + 2] + r.z; v[i + 3] = d.beta * v[i + 3] + r.w;
-        }
-    }
-    if (d.out_f32 != nullptr) {
-        float* o = d.out_f32 + pix * d.out_f32_stride + d.out_f32_choff + co0;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
+    if (d.out_f32 != nullptr) store16f_at(d, d.out_f32, d.out_f32_stride, d.out_f32_choff, n, y, x, co0, v);
     if (d.out_nchw != nullptr) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -90,40 +193,39 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, int n, i
         }
     }
     if (d.out_bf16 != nullptr) {
-        float w[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = d.out_bf16_scale * v[i];
-        if (d.flags & ESR_EPI_MASK) {
-            const __nv_bfloat16* m = reinterpret_cast<const __nv_bfloat16*>(d.mask) + pix * d.mask_stride +
-                                     d.mask_choff + co0;
-            uint4 raw[2];
-            raw[0] = __ldg(reinterpret_cast<const uint4*>(m));
-            raw[1] = __ldg(reinterpret_cast<const uint4*>(m) + 1);
-            const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(raw);
+        for (int i = 0; i < 16; ++i) v[i] *= d.out_bf16_scale;
+        if (flags & ESR_EPI_MASK) {
+            const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(P.m);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] *= (__bfloat162float(mv[i]) > 0.f ? 1.f : d.slope);
+            for (int i = 0; i < 16; ++i) v[i] *= (__bfloat162float(mv[i]) > 0.f ? 1.f : d.slope);
         }
-        __align__(16) __nv_bfloat16 hi[16];
-        __align__(16) __nv_bfloat16 lo[16];
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            hi[i] = __float2bfloat16_rn(w[i]);
-            lo[i] = __float2bfloat16_rn(w[i] - __bfloat162float(hi[i]));
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        const uint4 h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        const bool want_lo = d.out_bf16_lo_choff >= 0;
+        uint4 l0 = h0, l1 = h1;
+        if (want_lo) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(bf16_lo_part(v[2 * i]), bf16_lo_part(v[2 * i + 1]));
+            l0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            l1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         const int up = d.up;
         const size_t ow = static_cast<size_t>(d.W) * up;
         __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
         for (int a = 0; a < up; ++a) {
-            for (int b = 0; b < up; ++b) {
+            for (int bb = 0; bb < up; ++bb) {
                 const size_t opix = (static_cast<size_t>(n) * d.H * up + static_cast<size_t>(y) * up + a) * ow +
-                                    static_cast<size_t>(x) * up + b;
+                                    static_cast<size_t>(x) * up + bb;
                 uint4* o = reinterpret_cast<uint4*>(ob + opix * d.out_bf16_stride + d.out_bf16_choff + co0);
-                o[0] = reinterpret_cast<const uint4*>(hi)[0];
-                o[1] = reinterpret_cast<const uint4*>(hi)[1];
-                if (d.out_bf16_lo_choff >= 0) {
+                o[0] = h0;
+                o[1] = h1;
+                if (want_lo) {
                     uint4* ol = reinterpret_cast<uint4*>(ob + opix * d.out_bf16_stride + d.out_bf16_lo_choff + co0);
-                    ol[0] = reinterpret_cast<const uint4*>(lo)[0];
-                    ol[1] = reinterpret_cast<const uint4*>(lo)[1];
+                    ol[0] = l0;
+                    ol[1] = l1;
                 }
             }
         }

@@ -55,7 +55,9 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
                 }
             }
         }
-        conv_epilogue16(d, n, y, x, co0, v);
+        EpiOperands ops;
+        conv_epilogue_prefetch<kEpiGeneric>(d, n, y, x, co0, ops);
+        conv_epilogue16<kEpiGeneric>(d, d.bias + co0, n, y, x, co0, v, ops);
     }
 }
 

@@ -1,57 +1,104 @@
 // conv3x3 as a tcgen05 / TMEM implicit GEMM fed by TMA (sm_100a only).
 //
-// One persistent CTA per SM, 6 warps:
+// One persistent CTA per SM, 10 warps:
 //   warp 0      TMA producer: per K block one 4-D tensor load of the 10 x 32 pixel halo
 //               tile (32 channels, SWIZZLE_64B, zero fill outside the image == the conv's
 //               zero padding) and one bulk copy of that block's pre-swizzled weights.
 //   warp 1      MMA issuer (one elected lane): tcgen05.mma M=128, N=3*cout_tile, K=16;
 //               filter rows are row-shifted views (start address + dy*2 KiB) of the halo tile.
 //               Also owns the TMEM allocation (512 columns = 2 accumulator stages x 2 bands x 128).
-//   warps 2..5  epilogue: tcgen05.ld the three dx slabs, combine them with warp shuffles,
-//               apply bias / LeakyReLU / residuals, store bf16 / fp32.
-// smem ring: kStages x (A 20 KiB + W up to 18 KiB); mbarriers full/empty per stage and
-// acc_full/acc_empty per accumulator stage, so TMA, MMA and epilogue of consecutive tiles overlap.
+//   warps 2..9  epilogue, one warp per (band, TMEM lane quadrant): tcgen05.ld the three dx slabs,
+//               combine them with warp shuffles, apply bias / LeakyReLU / residuals, store bf16 / fp32.
+// Every CTA owns one cout tile and keeps that tile's whole packed weight image (<= 124 KiB) resident
+// in shared memory; only the 20 KiB activation halo tiles stream through a 4-6 deep TMA ring.
+// mbarriers full/empty per ring stage and acc_full/acc_empty per accumulator stage let TMA, MMA and
+// the epilogue of consecutive tiles overlap.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "conv3x3.cuh"
 #include "ptx_sm100.cuh"
 
+// Per-role cycle counters (tools_prof.py); compiled in only with -DESR_PROFILE_ROLES.
+#ifdef ESR_PROFILE_ROLES
+#define ESR_PROF(...) __VA_ARGS__
+#else
+#define ESR_PROF(...)
+#endif
+
 namespace esr {
 
-constexpr int kStages = 5;
+constexpr int kMaxStages = 6;                      // A-tile ring depth (fewer when the weights are large)
 constexpr int kAccStages = 2;
 constexpr int kAccCols = 128;                      // TMEM columns reserved per band accumulator
 constexpr int kTmemCols = kAccStages * kBands * kAccCols;  // 512
-constexpr int kWBytesMax = 3 * 96 * kRowBytes;     // 18432
-constexpr int kStageBytes = kABytes + kWBytesMax;  // 38912 (multiple of 1024)
-constexpr int kNumThreads = 192;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kEpiWarps = 4 * kBands;              // one warp per (band, TMEM lane quadrant)
+constexpr int kNumThreads = 64 + 32 * kEpiWarps;   // 320: leaves ~200 registers per epilogue thread
+constexpr int kMaxBias = 256;                      // floats of bias staged in shared memory
+constexpr int kCtrlBytes = 256 + kMaxBias * 4;     // barriers + tmem slot, bias
+constexpr int kSmemMax = 227 * 1024;
+// High word of every shared-memory matrix descriptor used here: SBO = 512 B (8 rows x 64 B),
+// descriptor version 1, SWIZZLE_64B.  The low word is (smem address >> 4).
+constexpr uint32_t kDescHi = ((8u * kRowBytes) >> 4) | (1u << 14) | (4u << 29);
 
-template <int CT>
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Shared memory: [ weights of this CTA's cout tile (resident for the whole kernel) | A-tile ring |
+// barriers | bias ].  Every CTA owns one cout tile (blockIdx.x % cout_tiles) and walks spatial tiles.
+template <int CT, int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                   const __grid_constant__ ConvLaunch L) {
     constexpr int N = 3 * CT;
     constexpr uint32_t kIdesc = umma_idesc_bf16_m128(N);
+    constexpr uint32_t kARow16 = (kTileW * kRowBytes) >> 4;   // one halo-tile row, in 16-byte units
+    constexpr uint32_t kWSlab16 = (N * kRowBytes) >> 4;       // one [N x 32ch] weight slab
     const esr_conv_desc& d = L.d;
+    const int nstages = L.nstages;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint8_t* s_w = smem;
+    uint8_t* s_a = smem + L.w_smem_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + nstages * kABytes);
     uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + kStages;
-    uint64_t* acc_full = bars + 2 * kStages;
-    uint64_t* acc_empty = bars + 2 * kStages + kAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* acc_full = bars + 2 * kMaxStages;
+    uint64_t* acc_empty = acc_full + kAccStages;
+    uint64_t* w_full = acc_empty + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    ESR_PROF(if (L.prof && threadIdx.x == 0) L.prof[blockIdx.x * 16 + 12] = gtime_ns();)
+    const int ct = blockIdx.x % d.cout_tiles;
+    const int sp0 = blockIdx.x / d.cout_tiles, sp_step = gridDim.x / d.cout_tiles;
+    for (int i = threadIdx.x; i < CT; i += kNumThreads) s_bias[i] = d.bias[ct * CT + i];
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap0);
         tma_prefetch_desc(&tmap1);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+        mbar_init(w_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -62,6 +109,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ESR_PROF(if (L.prof && threadIdx.x == 0) L.prof[blockIdx.x * 16 + 13] = gtime_ns();)
+    pdl_launch_dependents();   // the next layer may start its prologue (weights, TMEM, barriers) on idle SMs
 
     const int nkb = d.num_kblocks;
     const int tiles_per_img = L.tiles_x * L.tiles_y;
@@ -69,109 +118,167 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (elect_one()) {
+            // weights first: they do not depend on the previous layer, so under programmatic dependent
+            // launch this copy overlaps the tail of the preceding kernel
+            const uint8_t* wt = reinterpret_cast<const uint8_t*>(d.wpack) + static_cast<size_t>(ct) * d.w_tile_bytes;
+            mbar_expect_tx(w_full, d.w_tile_bytes);
+            for (uint32_t off = 0; off < d.w_tile_bytes; off += 16384) {
+                const uint32_t n = d.w_tile_bytes - off < 16384 ? d.w_tile_bytes - off : 16384;
+                bulk_load_1d(s_w + off, wt + off, n, w_full);
+            }
             pdl_wait();
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < L.total_tiles; t += gridDim.x) {
-                const int ct = t % d.cout_tiles;
-                const int sp = t / d.cout_tiles;
+            ESR_PROF(long long p_wait = 0, p_t0 = clock64(), p_n = 0;)
+            for (int sp = sp0; sp < L.spatial_tiles; sp += sp_step) {
                 const int n = sp / tiles_per_img;
                 const int r = sp - n * tiles_per_img;
                 const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
                 const int x0 = tx * kTileWOut - 1, y0 = ty * kTileH - 1;
-                const uint8_t* wt = reinterpret_cast<const uint8_t*>(d.wpack) + static_cast<size_t>(ct) * d.w_tile_bytes;
                 for (int kb = 0; kb < nkb; ++kb) {
                     const esr_kblock& K = d.kblocks[kb];
+                    ESR_PROF(const long long w0c = clock64();)
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * kStageBytes;
-                    const uint32_t wbytes = static_cast<uint32_t>(K.n_dy) * N * kRowBytes;
-                    mbar_expect_tx(&full_bar[stage], kABytes + wbytes);
-                    tma_load_4d(sa, K.src == 0 ? &tmap0 : &tmap1, &full_bar[stage], K.chan, x0, y0, n);
-                    bulk_load_1d(sa + kABytes, wt + K.w_off, wbytes, &full_bar[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    ESR_PROF(p_wait += clock64() - w0c; ++p_n;)
+                    if ((L.debug & 1) && (kb & 1)) {
+                        mbar_arrive(&full_bar[stage]);            // timing experiment: no load
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], kABytes);
+                        tma_load_4d(s_a + stage * kABytes, K.src == 0 ? &tmap0 : &tmap1, &full_bar[stage], K.chan, x0, y0, n);
+                    }
+                    if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
             }
+            ESR_PROF(if (L.prof) {
+                unsigned long long* o = L.prof + blockIdx.x * 16;
+                o[0] = clock64() - p_t0; o[1] = p_wait; o[2] = p_n;
+            })
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
         if (elect_one()) {
+            const uint32_t w_lo = smem_u32(s_w) >> 4, a_lo = smem_u32(s_a) >> 4;
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-            for (int t = blockIdx.x; t < L.total_tiles; t += gridDim.x) {
+            ESR_PROF(long long m_t0 = clock64(), m_wacc = 0, m_wfull = 0;)
+            mbar_wait(w_full, 0);
+            ESR_PROF(const long long m_tw = clock64() - m_t0;)
+            for (int sp = sp0; sp < L.spatial_tiles; sp += sp_step) {
+                ESR_PROF(long long c0 = clock64();)
                 mbar_wait(&acc_empty[as], aphase ^ 1);
+                ESR_PROF(m_wacc += clock64() - c0;)
                 tc_fence_after();
-                uint32_t first[kBands];
-#pragma unroll
-                for (int b = 0; b < kBands; ++b) first[b] = 1;
+                const uint32_t acc0 = tmem_base + as * (kBands * kAccCols);
+                uint32_t nonfirst = 0;                 // 0 until the accumulators hold their first product
                 for (int kb = 0; kb < nkb; ++kb) {
-                    const esr_kblock& K = d.kblocks[kb];
+                    const uint32_t masks = *reinterpret_cast<const uint32_t*>(&d.kblocks[kb].dy_mask);
+                    const uint32_t dy_mask = masks & 0xff, slice_mask = (masks >> 8) & 0xff;
+                    const uint32_t w0 = w_lo + (d.kblocks[kb].w_off >> 4);
+                    ESR_PROF(c0 = clock64();)
                     mbar_wait(&full_bar[stage], phase);
+                    ESR_PROF(m_wfull += clock64() - c0;)
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                    const uint32_t sw = sa + kABytes;
-#pragma unroll
-                    for (int b = 0; b < kBands; ++b) {
-                        const uint32_t acc = tmem_base + (as * kBands + b) * kAccCols;
-                        int wi = 0;
+                    const uint32_t a0 = a_lo + stage * (kABytes >> 4);
+                    if ((L.debug & 2) && (kb & 1)) {
+                        // timing experiment: no MMAs for this block
+                    } else if (dy_mask == 7u && slice_mask == 3u) {
+                        // dense block: 2 bands x 3 filter rows x 2 K slices, all offsets immediate
+                        // consecutive MMAs alternate between the two band accumulators so that the
+                        // accumulate dependency of one never stalls the tensor pipe
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
-                            if (!((K.dy_mask >> dy) & 1)) continue;
-                            const uint32_t a_row = sa + (b * kBandRows + dy) * (kTileW * kRowBytes);
-                            const uint32_t w_row = sw + wi * (N * kRowBytes);
-                            ++wi;
 #pragma unroll
                             for (int s = 0; s < 2; ++s) {
-                                if (!((K.slice_mask >> s) & 1)) continue;
-                                umma_bf16(acc, umma_smem_desc(a_row + s * 32, kRowBytes),
-                                          umma_smem_desc(w_row + s * 32, kRowBytes), kIdesc, first[b] ? 0u : 1u);
-                                first[b] = 0;
+#pragma unroll
+                                for (int b = 0; b < kBands; ++b) {
+                                    umma_issue(acc0 + b * kAccCols, a0 + (b * kBandRows + dy) * kARow16 + s * 2,
+                                               w0 + dy * kWSlab16 + s * 2, kIdesc, (dy | s) ? 1u : nonfirst);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int b = 0; b < kBands; ++b) {
+                            uint32_t acc_flag = nonfirst, wi = 0;
+                            for (int dy = 0; dy < 3; ++dy) {
+                                if (!((dy_mask >> dy) & 1u)) continue;
+                                for (int s = 0; s < 2; ++s) {
+                                    if (!((slice_mask >> s) & 1u)) continue;
+                                    umma_issue(acc0 + b * kAccCols, a0 + (b * kBandRows + dy) * kARow16 + s * 2,
+                                               w0 + wi * kWSlab16 + s * 2, kIdesc, acc_flag);
+                                    acc_flag = 1;
+                                }
+                                ++wi;
                             }
                         }
                     }
-                    umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    nonfirst = 1;
+                    umma_commit(&empty_bar[stage]);   // frees the A stage when these MMAs retire
+                    if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&acc_full[as]);           // accumulators of this tile are complete
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
+            ESR_PROF(if (L.prof) {
+                unsigned long long* o = L.prof + blockIdx.x * 16;
+                o[3] = clock64() - m_t0; o[4] = m_wacc; o[5] = m_wfull; o[6] = m_tw; o[14] = gtime_ns();
+            })
         }
     } else {
         // ---------------------------------------------------------------- epilogue
         const int wq = warp & 3;                      // TMEM lane quadrant == row inside the band
+        const int b = (warp - 2) >> 2;                // band handled by this warp
+        constexpr int NH = CT / 16;                   // 16-channel halves of the cout tile
+        pdl_wait();                                   // residual / accumulate inputs come from earlier kernels
         uint32_t as = 0, aphase = 0;
-        for (int t = blockIdx.x; t < L.total_tiles; t += gridDim.x) {
-            const int ct = t % d.cout_tiles;
-            const int sp = t / d.cout_tiles;
+        ESR_PROF(long long e_t0 = clock64(), e_wait = 0, e_ld = 0, e_shfl = 0, e_n = 0;)
+        for (int sp = sp0; sp < L.spatial_tiles; sp += sp_step) {
             const int n = sp / tiles_per_img;
             const int r = sp - n * tiles_per_img;
             const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
             const int x = tx * kTileWOut - 1 + lane;
-            const bool col_ok = lane >= 1 && lane <= kTileWOut && x < d.W;
+            const int y = ty * kTileH + b * kBandRows + wq;
+            const bool ok = lane >= 1 && lane <= kTileWOut && x < d.W && y < d.H;
+            EpiOperands ops[NH];
+            if (ok) {                                 // issued before the wait: latency hides behind the MMAs
+#pragma unroll
+                for (int h = 0; h < NH; ++h) conv_epilogue_prefetch<MODE>(d, n, y, x, ct * CT + h * 16, ops[h]);
+            }
+            ESR_PROF(long long c0 = clock64();)
             mbar_wait(&acc_full[as], aphase);
+            ESR_PROF(long long c1 = clock64(); e_wait += c1 - c0; ++e_n;)
             tc_fence_after();
+            const uint32_t taddr = tmem_base + (as * kBands + b) * kAccCols + (static_cast<uint32_t>(wq * 32) << 16);
+            float vc[CT];
 #pragma unroll
-            for (int b = 0; b < kBands; ++b) {
-                const int y = ty * kTileH + b * kBandRows + wq;
-                const uint32_t taddr = tmem_base + (as * kBands + b) * kAccCols + (static_cast<uint32_t>(wq * 32) << 16);
+            for (int h = 0; h < NH; ++h) {            // 16 channels at a time keeps the register footprint bounded
+                float vl[16], vr[16];
+                tmem_ld_x16(taddr + 0 * CT + h * 16, vl);
+                tmem_ld_x16(taddr + 1 * CT + h * 16, *reinterpret_cast<float(*)[16]>(&vc[h * 16]));
+                tmem_ld_x16(taddr + 2 * CT + h * 16, vr);
+                tmem_ld_wait();
+                if (h == NH - 1) {                    // all TMEM reads of this warp are done: release early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[as]);
+                }
 #pragma unroll
-                for (int h = 0; h < CT / 16; ++h) {
-                    float vl[16], vc[16], vr[16];
-                    tmem_ld_x16(taddr + 0 * CT + h * 16, vl);
-                    tmem_ld_x16(taddr + 1 * CT + h * 16, vc);
-                    tmem_ld_x16(taddr + 2 * CT + h * 16, vr);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float fl = __shfl_up_sync(0xffffffffu, vl[i], 1);
-                        const float fr = __shfl_down_sync(0xffffffffu, vr[i], 1);
-                        vc[i] += fl + fr;
-                    }
-                    if (col_ok && y < d.H) conv_epilogue16(d, n, y, x, ct * CT + h * 16, vc);
+                for (int i = 0; i < 16; ++i) {
+                    const float fl = __shfl_up_sync(0xffffffffu, vl[i], 1);
+                    const float fr = __shfl_down_sync(0xffffffffu, vr[i], 1);
+                    vc[h * 16 + i] += fl + fr;
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            ESR_PROF(c0 = clock64(); e_ld += c0 - c1;)
+            if (ok) {
+#pragma unroll
+                for (int h = 0; h < NH; ++h)
+                    conv_epilogue16<MODE>(d, s_bias + h * 16, n, y, x, ct * CT + h * 16,
+                                          *reinterpret_cast<float(*)[16]>(&vc[h * 16]), ops[h]);
+            }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
+        ESR_PROF(if (L.prof && warp == 2 && lane == 1) {
+            unsigned long long* o = L.prof + blockIdx.x * 16;
+            o[7] = clock64() - e_t0; o[8] = e_wait; o[9] = e_ld; o[10] = e_shfl; o[11] = e_n; o[15] = gtime_ns();
+        })
     }
 
     tc_fence_before();
@@ -222,7 +329,7 @@ int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H,
 int validate_conv_desc(const esr_conv_desc& d) {
     ESR_CHECK_ARG(d.B > 0 && d.H > 0 && d.W > 0, "bad conv geometry %dx%dx%d", d.B, d.H, d.W);
     ESR_CHECK_ARG(d.cout_tile == 32 || d.cout_tile == 16, "cout_tile must be 16 or 32");
-    ESR_CHECK_ARG(d.cout_tiles > 0, "cout_tiles must be positive");
+    ESR_CHECK_ARG(d.cout_tiles > 0 && d.cout_tiles * d.cout_tile <= 256, "cout_tiles out of range");
     ESR_CHECK_ARG(d.num_kblocks > 0 && d.num_kblocks <= ESR_MAX_KBLOCKS, "num_kblocks out of range");
     ESR_CHECK_ARG(d.wpack != nullptr && d.bias != nullptr, "wpack/bias missing");
     ESR_CHECK_ARG((reinterpret_cast<uintptr_t>(d.wpack) & 15) == 0 && d.w_tile_bytes % 16 == 0, "wpack misaligned");
@@ -243,6 +350,12 @@ int validate_conv_desc(const esr_conv_desc& d) {
                                   (d.out_bf16_lo_choff < 0 || d.out_bf16_lo_choff % 8 == 0), "bf16 output misaligned");
     if (d.out_f32) ESR_CHECK_ARG(d.out_f32_stride % 4 == 0 && d.out_f32_choff % 4 == 0, "f32 output misaligned");
     if (d.flags & ESR_EPI_ACCUM) ESR_CHECK_ARG(d.out_f32 != nullptr, "ACCUM needs out_f32");
+    if (d.flags & ESR_EPI_F32_BLOCKED) {
+        ESR_CHECK_ARG((d.out_f32 == nullptr || (d.out_f32_stride % 8 == 0 && d.out_f32_choff % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out_f32) & 31) == 0)) &&
+                      (d.res1 == nullptr || (d.res1_stride % 8 == 0 && d.res1_choff % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res1) & 31) == 0)) &&
+                      (d.res2 == nullptr || (d.res2_stride % 8 == 0 && d.res2_choff % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res2) & 31) == 0)),
+                      "blocked f32 tensors need 8-channel multiples and 32-byte alignment");
+    }
     if (d.flags & ESR_EPI_RES1) ESR_CHECK_ARG(d.res1 && d.res1_stride % 4 == 0 && d.res1_choff % 4 == 0, "res1 misaligned");
     if (d.flags & ESR_EPI_RES2) ESR_CHECK_ARG(d.res2 && d.res2_stride % 4 == 0 && d.res2_choff % 4 == 0, "res2 misaligned");
     if (d.flags & ESR_EPI_MASK) ESR_CHECK_ARG(d.mask && d.out_bf16 && d.up == 1 && d.mask_stride % 8 == 0 && d.mask_choff % 8 == 0, "mask misaligned");
@@ -250,11 +363,30 @@ int validate_conv_desc(const esr_conv_desc& d) {
     return ESR_OK;
 }
 
+static unsigned long long* g_prof_buf = nullptr;
+static int g_use_pdl = []() { const char* v = getenv("ESR_NO_PDL"); return (v && atoi(v)) ? 0 : 1; }();
+
+static bool f32_wide_ok(const float* p, int stride, int choff) {
+    return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && stride % 8 == 0 && choff % 8 == 0);
+}
+
 void fill_launch(ConvLaunch* L, const esr_conv_desc& d) {
     L->d = d;
+    L->d.flags &= ~static_cast<uint32_t>(ESR_EPI_WIDE_OK);
+    if (f32_wide_ok(d.out_f32, d.out_f32_stride, d.out_f32_choff) && f32_wide_ok(d.res1, d.res1_stride, d.res1_choff) &&
+        f32_wide_ok(d.res2, d.res2_stride, d.res2_choff))
+        L->d.flags |= ESR_EPI_WIDE_OK;
     L->tiles_x = ceil_div(d.W, kTileWOut);
     L->tiles_y = ceil_div(d.H, kTileH);
-    L->total_tiles = d.B * L->tiles_x * L->tiles_y * d.cout_tiles;
+    L->spatial_tiles = d.B * L->tiles_x * L->tiles_y;
+    L->total_tiles = L->spatial_tiles * d.cout_tiles;
+    L->w_smem_bytes = (d.w_tile_bytes + 1023u) & ~1023u;
+    const int room = kSmemMax - 1024 - kCtrlBytes - static_cast<int>(L->w_smem_bytes);
+    int st = room / kABytes;
+    L->nstages = st > kMaxStages ? kMaxStages : st;
+    const char* dbg = getenv("ESR_DEBUG_SKIP");
+    L->debug = dbg ? atoi(dbg) : 0;
+    L->prof = g_prof_buf;
 }
 
 static int num_sms() {
@@ -268,18 +400,46 @@ static int num_sms() {
     return n;
 }
 
+static bool is_trunk_epilogue(const esr_conv_desc& d) {
+    return (d.flags & ~static_cast<uint32_t>(ESR_EPI_WIDE_OK | ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && d.out_bf16 != nullptr && d.out_f32 == nullptr && d.out_nchw == nullptr &&
+           d.out_bf16_lo_choff < 0 && d.up == 1 && d.out_bf16_scale == 1.0f && d.cout_tile == 32 &&
+           d.out_bf16_stride % 16 == 0 && d.out_bf16_choff % 16 == 0 &&
+           (reinterpret_cast<uintptr_t>(d.out_bf16) & 31) == 0;   // 32-byte stores
+}
+
 int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<32, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<32, kEpiTrunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<16, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_set = true;
     }
-    const int grid = L.total_tiles < num_sms() ? L.total_tiles : num_sms();
-    if (L.d.cout_tile == 32)
-        conv3x3_tc_kernel<32><<<grid, kNumThreads, kSmemBytes, stream>>>(tm0, tm1, L);
+    ESR_CHECK_ARG(L.nstages >= 2, "conv weights (%u B per cout tile) leave no room for the A-tile ring", L.d.w_tile_bytes);
+    // every CTA owns one cout tile: grid is a multiple of cout_tiles, at most one CTA per SM
+    int per_ct = num_sms() / L.d.cout_tiles;
+    if (per_ct > L.spatial_tiles) per_ct = L.spatial_tiles;
+    ESR_CHECK_ARG(per_ct >= 1, "too many cout tiles (%d) for %d SMs", L.d.cout_tiles, num_sms());
+    const int grid = per_ct * L.d.cout_tiles;
+    const int smem = 1024 + static_cast<int>(L.w_smem_bytes) + L.nstages * kABytes + kCtrlBytes;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaError_t e;
+    if (L.d.cout_tile == 16)
+        e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<16, kEpiGeneric>, tm0, tm1, L);
+    else if (is_trunk_epilogue(L.d))
+        e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<32, kEpiTrunk>, tm0, tm1, L);
     else
-        conv3x3_tc_kernel<16><<<grid, kNumThreads, kSmemBytes, stream>>>(tm0, tm1, L);
+        e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<32, kEpiGeneric>, tm0, tm1, L);
+    if (e != cudaSuccess) { set_error("conv3x3_tc_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
     return check_launch("conv3x3_tc_kernel");
 }
 
@@ -299,6 +459,10 @@ int build_conv_launch(const esr_conv_desc& d, CUtensorMap* tm0, CUtensorMap* tm1
 }
 
 }  // namespace esr
+
+// Debug aid: per-CTA, per-role cycle counters ([gridDim][16] uint64) written by subsequent tcgen05 conv
+// launches that are *built* after this call; pass NULL to switch off.
+extern "C" void esr_debug_set_profile_buffer(void* buf) { esr::g_prof_buf = static_cast<unsigned long long*>(buf); }
 
 extern "C" int esr_conv3x3_tc(const esr_conv_desc* d, void* stream) {
     if (d == nullptr) { esr::set_error("null conv desc"); return ESR_ERR_INVALID; }

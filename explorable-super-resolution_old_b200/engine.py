@@ -267,7 +267,7 @@ class GPlan:
         for i in range(pc.nkb):
             d.kblocks[i] = pc.kblocks[i]
         d.wpack, d.w_tile_bytes, d.bias = pc.wpack.data_ptr(), pc.w_tile_bytes, pc.bias.data_ptr()
-        d.flags, d.slope, d.alpha, d.beta = flags, 0.2, alpha, beta
+        d.flags, d.slope, d.alpha, d.beta = flags | capi.EPI_F32_BLOCKED, 0.2, alpha, beta   # trunk f32 = [B,8,H,W,8]
         if res1 is not None:
             d.res1, d.res1_stride, d.res1_choff = res1.data_ptr(), res1.shape[-1], 0
             d.flags |= capi.EPI_RES1
@@ -324,8 +324,8 @@ class GPlan:
         self.lat_x = _xslot_array(eng.lat_xslots)
 
     # ------------------------------------------------------------------ run
-    def run_g(self, model_input):
-        """model_input: contiguous f32 CUDA [B, 16*nz+3, h, w].  Fills self.y (raw generator output)."""
+    def run_prep(self, model_input):
+        """Padding / latent unpacking / row expansion of the packed [Z.view, LR] input."""
         eng, l, st = self.eng, capi.lib(), capi.stream_ptr()
         B, hp, wp, sf = self.B, self.hp, self.wp, self.sf
         capi.check(l.esr_g_input_prep(capi.ptr(model_input), B, eng.nz_in, self.h, self.w, self.m, sf,
@@ -337,9 +337,18 @@ class GPlan:
             capi.check(l.esr_expand_rows(capi.ptr(self.z_lr), B, eng.nz, hp, wp, self.lat_x, 32, capi.ptr(self.E_lat), st))
             capi.check(l.esr_expand_rows(capi.ptr(self.z_hr), B, eng.nz, sf * hp, sf * wp, self.lat_x, 32,
                                          capi.ptr(self.E_lath), st))
-        capi.check(l.esr_seq_run(self.seq, st))
+
+    def run_convs(self):
+        capi.check(capi.lib().esr_seq_run(self.seq, capi.stream_ptr()))
+
+    def run_g(self, model_input):
+        """model_input: contiguous f32 CUDA [B, 16*nz+3, h, w].  Fills self.y (raw generator output)."""
+        self.run_prep(model_input)
+        self.run_convs()
         return self.y
 
-    def num_launches(self):
-        n = 3 + 1 + (2 if self.eng.nz else 0)  # prep (lr, fea_in x2 kernels..) counted loosely below
-        return capi.lib().esr_seq_num_launches(self.seq)
+    def launches_per_forward(self, with_cem):
+        eng = self.eng
+        prep = 1 + 1 + (1 if eng.nz_in else 0) + (2 if eng.nz else 0)   # lr_pad, fea_in(lr [+z_lr]), z_hr, z_lr
+        expand = 1 + (2 if eng.nz else 0)
+        return prep + expand + capi.lib().esr_seq_num_launches(self.seq) + (3 if with_cem else 0)

@@ -75,7 +75,10 @@ enum {
     ESR_EPI_RES1 = 1u << 1,    /* v = alpha*v + res1                   (block.py:235)    */
     ESR_EPI_RES2 = 1u << 2,    /* v = beta*v + res2                    (block.py:270)    */
     ESR_EPI_ACCUM = 1u << 3,   /* v += out_f32 (read-modify-write; dgrad fan-in)         */
-    ESR_EPI_MASK = 1u << 4     /* bf16 output *= (mask > 0 ? 1 : slope) (LeakyReLU')     */
+    ESR_EPI_MASK = 1u << 4,    /* bf16 output *= (mask > 0 ? 1 : slope) (LeakyReLU')     */
+    ESR_EPI_F32_BLOCKED = 1u << 5, /* out_f32 / res1 / res2 use the blocked layout [B, C/8, H, W, 8] (coalesced
+                                      32-byte accesses across the pixels of a warp) instead of NHWC; *_stride is C */
+    ESR_EPI_WIDE_OK = 1u << 16 /* internal: set by the library when 32-byte accesses are legal */
 };
 
 typedef struct esr_conv_desc {
