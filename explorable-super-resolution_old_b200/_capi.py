@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libesr_b200.so")
 
 MAX_KBLOCKS = 24
+MAX_COUT_TILES = 8
 KBLOCK_CH = 32
 CEM_MAX_TAPS = 64
 
@@ -40,7 +41,17 @@ class ConvDesc(C.Structure):
         ("out_f32", C.c_void_p), ("out_f32_stride", C.c_int32), ("out_f32_choff", C.c_int32),
         ("out_nchw", C.c_void_p), ("cout_real", C.c_int32),
         ("mask", C.c_void_p), ("mask_stride", C.c_int32), ("mask_choff", C.c_int32),
+        ("tile_choff", C.c_int16 * MAX_COUT_TILES),
+        ("no_accum_tiles", C.c_uint16), ("no_bf16_tiles", C.c_uint16), ("no_res_tiles", C.c_uint16),
+        ("reserved16", C.c_uint16), ("gamma", C.c_float),
     ]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        for i in range(MAX_COUT_TILES):
+            self.tile_choff[i] = -1
+        self.gamma, self.alpha, self.beta, self.slope = 1.0, 1.0, 1.0, 0.2
+        self.up, self.out_bf16_scale, self.out_bf16_lo_choff = 1, 1.0, -1
 
 
 class WRow(C.Structure):
@@ -72,7 +83,11 @@ SIGNATURES = {
     "esr_pack_conv_weights": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i32, _i32, _i32, C.POINTER(KBlock),
                                         C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "esr_expand_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32, _vp, _vp]),
-    "esr_expand_rows_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32, _vp, _vp]),
+    "esr_expand_rows_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32,
+                                      _vp, _vp]),
+    "esr_debug_set_profile_buffer": (None, [_vp]),
+    "esr_grad_combine": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32,
+                                   _i32, _i32, _f, _f, _vp, _i32, _i32, _i32, _vp]),
     "esr_g_input_prep": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "esr_cem_pad_input": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "esr_g_input_prep_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -123,11 +123,23 @@ struct EpiOperands {
     uint4 m[2];     // LeakyReLU mask source (bf16 x 16)
 };
 
+// Output channel of column `col` of cout tile `ct` (dgrad launches re-route whole tiles).
+__device__ __forceinline__ int tile_channel(const esr_conv_desc& d, int ct, int col) {
+    const int base = d.tile_choff[ct];
+    return (base >= 0 ? base : ct * d.cout_tile) + col;
+}
+__device__ __forceinline__ uint32_t tile_flags(const esr_conv_desc& d, int ct) {
+    uint32_t f = d.flags;
+    if ((d.no_accum_tiles >> ct) & 1) f &= ~static_cast<uint32_t>(ESR_EPI_ACCUM);
+    if ((d.no_res_tiles >> ct) & 1) f &= ~static_cast<uint32_t>(ESR_EPI_RES1 | ESR_EPI_RES2);
+    return f;
+}
+
 template <int MODE>
-__device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, int n, int y, int x, int co0,
+__device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, int ct, int n, int y, int x, int co0,
                                                        EpiOperands& P) {
     if constexpr (MODE == kEpiTrunk) return;
-    const uint32_t flags = d.flags;
+    const uint32_t flags = tile_flags(d, ct);
     const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
     if (flags & ESR_EPI_ACCUM) load16f_at(d, d.out_f32, d.out_f32_stride, d.out_f32_choff, n, y, x, co0, P.r1);
     else if (flags & ESR_EPI_RES1) load16f_at(d, d.res1, d.res1_stride, d.res1_choff, n, y, x, co0, P.r1);
@@ -143,7 +155,7 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, i
 // Applies the fused epilogue to 16 consecutive output channels of one pixel.  `bias` points at the
 // 16 biases of these channels (shared memory in the tcgen05 kernel, global in the SIMT check).
 template <int MODE>
-__device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const float* bias, int n, int y, int x,
+__device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const float* bias, int ct, int n, int y, int x,
                                                 int co0, float (&v)[16], const EpiOperands& P) {
     const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
 #pragma unroll
@@ -159,7 +171,7 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
         st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
         return;
     }
-    const uint32_t flags = d.flags;
+    const uint32_t flags = tile_flags(d, ct);
     if (flags & ESR_EPI_ACCUM) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += P.r1[i];
@@ -167,7 +179,7 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
             float r[16];
             load16f_at(d, d.res1, d.res1_stride, d.res1_choff, n, y, x, co0, r);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + r[i];
+            for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + d.gamma * r[i];
         }
     } else {
         if (flags & ESR_EPI_LRELU) {
@@ -176,7 +188,7 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
         }
         if (flags & ESR_EPI_RES1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + P.r1[i];
+            for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + d.gamma * P.r1[i];
         }
     }
     if (flags & ESR_EPI_RES2) {
@@ -192,7 +204,7 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
                 d.out_nchw[((static_cast<size_t>(n) * d.cout_real + co) * d.H + y) * d.W + x] = v[i];
         }
     }
-    if (d.out_bf16 != nullptr) {
+    if (d.out_bf16 != nullptr && !((d.no_bf16_tiles >> ct) & 1)) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= d.out_bf16_scale;
         if (flags & ESR_EPI_MASK) {

@@ -56,8 +56,9 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
             }
         }
         EpiOperands ops;
-        conv_epilogue_prefetch<kEpiGeneric>(d, n, y, x, co0, ops);
-        conv_epilogue16<kEpiGeneric>(d, d.bias + co0, n, y, x, co0, v, ops);
+        const int cabs = tile_channel(d, ct, col0);
+        conv_epilogue_prefetch<kEpiGeneric>(d, ct, n, y, x, cabs, ops);
+        conv_epilogue16<kEpiGeneric>(d, d.bias + co0, ct, n, y, x, cabs, v, ops);
     }
 }
 

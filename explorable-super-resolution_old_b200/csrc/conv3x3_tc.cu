@@ -239,7 +239,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
             EpiOperands ops[NH];
             if (ok) {                                 // issued before the wait: latency hides behind the MMAs
 #pragma unroll
-                for (int h = 0; h < NH; ++h) conv_epilogue_prefetch<MODE>(d, n, y, x, ct * CT + h * 16, ops[h]);
+                for (int h = 0; h < NH; ++h) conv_epilogue_prefetch<MODE>(d, ct, n, y, x, tile_channel(d, ct, h * 16), ops[h]);
             }
             ESR_PROF(long long c0 = clock64();)
             mbar_wait(&acc_full[as], aphase);
@@ -270,7 +270,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
             if (ok) {
 #pragma unroll
                 for (int h = 0; h < NH; ++h)
-                    conv_epilogue16<MODE>(d, s_bias + h * 16, n, y, x, ct * CT + h * 16,
+                    conv_epilogue16<MODE>(d, s_bias + h * 16, ct, n, y, x, tile_channel(d, ct, h * 16),
                                           *reinterpret_cast<float(*)[16]>(&vc[h * 16]), ops[h]);
             }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
@@ -329,7 +329,9 @@ int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H,
 int validate_conv_desc(const esr_conv_desc& d) {
     ESR_CHECK_ARG(d.B > 0 && d.H > 0 && d.W > 0, "bad conv geometry %dx%dx%d", d.B, d.H, d.W);
     ESR_CHECK_ARG(d.cout_tile == 32 || d.cout_tile == 16, "cout_tile must be 16 or 32");
-    ESR_CHECK_ARG(d.cout_tiles > 0 && d.cout_tiles * d.cout_tile <= 256, "cout_tiles out of range");
+    ESR_CHECK_ARG(d.cout_tiles > 0 && d.cout_tiles <= ESR_MAX_COUT_TILES, "cout_tiles out of range");
+    for (int t = 0; t < d.cout_tiles; ++t)
+        ESR_CHECK_ARG(d.tile_choff[t] < 0 || d.tile_choff[t] % 16 == 0, "tile_choff[%d] must be a multiple of 16", t);
     ESR_CHECK_ARG(d.num_kblocks > 0 && d.num_kblocks <= ESR_MAX_KBLOCKS, "num_kblocks out of range");
     ESR_CHECK_ARG(d.wpack != nullptr && d.bias != nullptr, "wpack/bias missing");
     ESR_CHECK_ARG((reinterpret_cast<uintptr_t>(d.wpack) & 15) == 0 && d.w_tile_bytes % 16 == 0, "wpack misaligned");
@@ -401,6 +403,8 @@ static int num_sms() {
 }
 
 static bool is_trunk_epilogue(const esr_conv_desc& d) {
+    for (int t = 0; t < d.cout_tiles; ++t)
+        if (d.tile_choff[t] >= 0) return false;
     return (d.flags & ~static_cast<uint32_t>(ESR_EPI_WIDE_OK | ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && d.out_bf16 != nullptr && d.out_f32 == nullptr && d.out_nchw == nullptr &&
            d.out_bf16_lo_choff < 0 && d.up == 1 && d.out_bf16_scale == 1.0f && d.cout_tile == 32 &&
            d.out_bf16_stride % 16 == 0 && d.out_bf16_choff % 16 == 0 &&

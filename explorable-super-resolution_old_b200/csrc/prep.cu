@@ -1,6 +1,8 @@
 // Input preparation for G: the eval-mode replication padding of CEM_PyTorch.forward
 // (CEM/CEMnet.py:170-181), the raw-view unpacking of Z and the bilinear 1/sf latent
 // downscale of RRDBNet.forward (models/modules/architecture.py:152-157), and their adjoints.
+#include <cuda_bf16.h>
+
 #include "esr_common.cuh"
 
 namespace esr {
@@ -120,8 +122,8 @@ __global__ void zero_kernel(float* p, size_t n) {
 
 // Adjoint of esr_expand_rows: g_src[b,c,y,x] = sum over slots s with c_s == c of g_e[b, y-dy_s, x, s].
 struct CollapseArgs {
-    const float* g_e;  // NHWC f32 [B,H,W,stride], slots start at choff
-    int B, C, H, W, nslots, stride, choff;
+    const float* g_e;  // f32 [B,H,W,stride] (NHWC) or [B,stride/8,H,W,8] (blocked), slots start at choff
+    int B, C, H, W, nslots, stride, choff, blocked, n_acc, acc_stride;
     esr_xslot slots[64];
     float* g_src;      // NCHW f32 [B,C,H,W]
 };
@@ -139,7 +141,14 @@ __global__ void collapse_rows_kernel(const __grid_constant__ CollapseArgs a) {
             if (a.slots[s].c != c) continue;
             const int yy = y - a.slots[s].dy;
             if (yy < 0 || yy >= a.H) continue;
-            acc += __ldg(a.g_e + ((static_cast<size_t>(b) * a.H + yy) * a.W + x) * a.stride + a.choff + s);
+            for (int j = 0; j < a.n_acc; ++j) {
+            const int ch = a.choff + j * a.acc_stride + s;
+            const size_t off = a.blocked
+                ? ((static_cast<size_t>(b) * (a.stride >> 3) + (ch >> 3)) * a.H + yy) * (static_cast<size_t>(a.W) * 8) +
+                      static_cast<size_t>(x) * 8 + (ch & 7)
+                : ((static_cast<size_t>(b) * a.H + yy) * a.W + x) * a.stride + ch;
+            acc += __ldg(a.g_e + off);
+            }
         }
         a.g_src[idx] = acc;
     }
@@ -214,14 +223,105 @@ extern "C" int esr_g_input_prep_bwd(const float* g_z_hr, const float* g_z_lr, in
     return check_launch("prep_bwd_kernel");
 }
 
-extern "C" int esr_expand_rows_bwd(const float* g_e_nhwc, int32_t stride, int32_t choff, int32_t B, int32_t C,
-                                   int32_t H, int32_t W, const esr_xslot* slots, int32_t nslots, float* g_src_nchw,
-                                   void* stream) {
-    ESR_CHECK_ARG(g_e_nhwc && slots && g_src_nchw && nslots > 0 && nslots <= 64, "esr_expand_rows_bwd: bad arguments");
+extern "C" int esr_expand_rows_bwd(const float* g_e, int32_t stride, int32_t choff, int32_t blocked, int32_t n_acc,
+                                   int32_t acc_stride, int32_t B, int32_t C, int32_t H, int32_t W,
+                                   const esr_xslot* slots, int32_t nslots, float* g_src_nchw, void* stream) {
+    ESR_CHECK_ARG(g_e && slots && g_src_nchw && nslots > 0 && nslots <= 64, "esr_expand_rows_bwd: bad arguments");
+    ESR_CHECK_ARG(!blocked || stride % 8 == 0, "esr_expand_rows_bwd: blocked layout needs stride % 8 == 0");
     CollapseArgs a;
-    a.g_e = g_e_nhwc; a.B = B; a.C = C; a.H = H; a.W = W; a.nslots = nslots; a.stride = stride; a.choff = choff;
+    a.g_e = g_e; a.B = B; a.C = C; a.H = H; a.W = W; a.nslots = nslots; a.stride = stride; a.choff = choff;
+    a.blocked = blocked; a.n_acc = n_acc > 0 ? n_acc : 1; a.acc_stride = acc_stride;
     for (int i = 0; i < nslots; ++i) a.slots[i] = slots[i];
     a.g_src = g_src_nchw;
     collapse_rows_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("collapse_rows_kernel");
+}
+
+// ------------------------------------------------------------------ gradient plumbing
+namespace esr {
+
+struct CombineArgs {
+    const float* src; int src_stride, src_choff, pool;
+    const float* add; int add_stride, add_choff;
+    int B, H, W;
+    float* out_f32; int out_stride, out_choff;
+    const __nv_bfloat16* mask; int mask_stride, mask_choff, mask_sub;
+    float slope, scale;
+    __nv_bfloat16* out_bf16; int bf16_stride, hi_choff, lo_choff;
+};
+
+// one thread per (pixel, 8-channel block) of a 64-channel tensor
+__global__ void grad_combine_kernel(const __grid_constant__ CombineArgs a) {
+    const size_t total = static_cast<size_t>(a.B) * a.H * a.W * 8;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(idx % a.W);
+        const int y = static_cast<int>((idx / a.W) % a.H);
+        const int blk = static_cast<int>((idx / (static_cast<size_t>(a.W) * a.H)) % 8);
+        const int b = static_cast<int>(idx / (static_cast<size_t>(a.W) * a.H * 8));
+        const int c0 = blk * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        const int Hs = a.H * a.pool, Ws = a.W * a.pool;
+        for (int dy = 0; dy < a.pool; ++dy)
+            for (int dx = 0; dx < a.pool; ++dx) {
+                const int ch = a.src_choff + c0;
+                const float* p = a.src + ((static_cast<size_t>(b) * (a.src_stride >> 3) + (ch >> 3)) * Hs + (a.pool * y + dy)) *
+                                             (static_cast<size_t>(Ws) * 8) + static_cast<size_t>(a.pool * x + dx) * 8;
+                const float4 p0 = *reinterpret_cast<const float4*>(p), p1 = *reinterpret_cast<const float4*>(p + 4);
+                v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+                v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+            }
+        if (a.add != nullptr) {
+            const int ch = a.add_choff + c0;
+            const float* p = a.add + ((static_cast<size_t>(b) * (a.add_stride >> 3) + (ch >> 3)) * a.H + y) *
+                                         (static_cast<size_t>(a.W) * 8) + static_cast<size_t>(x) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += p[i];
+        }
+        if (a.out_f32 != nullptr) {
+            const int ch = a.out_choff + c0;
+            float* p = a.out_f32 + ((static_cast<size_t>(b) * (a.out_stride >> 3) + (ch >> 3)) * a.H + y) *
+                                       (static_cast<size_t>(a.W) * 8) + static_cast<size_t>(x) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p[i] = v[i];
+        }
+        if (a.out_bf16 != nullptr) {
+            float w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = a.scale * v[i];
+            if (a.mask != nullptr) {
+                const __nv_bfloat16* m = a.mask + ((static_cast<size_t>(b) * a.H * a.mask_sub + static_cast<size_t>(y) * a.mask_sub) *
+                                                       (static_cast<size_t>(a.W) * a.mask_sub) + static_cast<size_t>(x) * a.mask_sub) *
+                                                      a.mask_stride + a.mask_choff + c0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] *= (__bfloat162float(m[i]) > 0.f ? 1.f : a.slope);
+            }
+            __nv_bfloat16* o = a.out_bf16 + ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.bf16_stride;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(w[i]);
+                o[a.hi_choff + c0 + i] = h;
+                if (a.lo_choff >= 0) o[a.lo_choff + c0 + i] = __float2bfloat16_rn(w[i] - __bfloat162float(h));
+            }
+        }
+    }
+}
+
+}  // namespace esr
+
+extern "C" int esr_grad_combine(const float* src, int32_t src_stride, int32_t src_choff, int32_t pool, const float* add,
+                                int32_t add_stride, int32_t add_choff, int32_t B, int32_t H, int32_t W, float* out_f32,
+                                int32_t out_stride, int32_t out_choff, const void* mask, int32_t mask_stride,
+                                int32_t mask_choff, int32_t mask_sub, float slope, float scale, void* out_bf16,
+                                int32_t bf16_stride, int32_t hi_choff, int32_t lo_choff, void* stream) {
+    ESR_CHECK_ARG(src && B > 0 && H > 0 && W > 0 && (pool == 1 || pool == 2), "esr_grad_combine: bad arguments");
+    ESR_CHECK_ARG(src_stride % 8 == 0 && src_choff % 8 == 0 && (!add || (add_stride % 8 == 0 && add_choff % 8 == 0)) &&
+                  (!out_f32 || (out_stride % 8 == 0 && out_choff % 8 == 0)), "esr_grad_combine: f32 tensors are blocked by 8");
+    CombineArgs a{src, src_stride, src_choff, pool, add, add_stride, add_choff, B, H, W, out_f32, out_stride, out_choff,
+                  static_cast<const __nv_bfloat16*>(mask), mask_stride, mask_choff, mask_sub > 0 ? mask_sub : 1, slope, scale,
+                  static_cast<__nv_bfloat16*>(out_bf16), bf16_stride, hi_choff, lo_choff};
+    grad_combine_kernel<<<grid_for(static_cast<size_t>(B) * H * W * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("grad_combine_kernel");
 }

@@ -174,8 +174,9 @@ class GEngine:
         outer = ["model.1.sub.%d" % self.nb] + ["model.%d.1" % (2 + u) for u in range(self.n_up)] + \
                 ["model.%d" % (2 + self.n_up), "model.%d" % (4 + self.n_up)]
         self.outer_names = outer
+        self.upconv_names = set(outer[1:1 + self.n_up])
         for name in outer:
-            has_lat = not name.endswith(".1")          # upconvs take no latent (architecture.py:164-171)
+            has_lat = name not in self.upconv_names    # upconvs take no latent (architecture.py:164-171)
             kb, sl = self._main_blocks(NF, p)
             if not has_lat:
                 sl = [(i - self.nz if i >= 0 else i, ky, t) for (i, ky, t) in sl]

@@ -68,6 +68,7 @@ class RRDBNet(nn.Module):
         self.model = nn.ModuleList(mods)
         self._cfg = dict(nb=nb, nz_in=nz_in, all_layers=all_layers, out_nc=out_nc, in_nc=in_nc, upscale=upscale)
         self._engine, self._engine_key, self._plans = None, None, {}
+        self._packed_params, self._dgrad, self._bplans = None, None, {}
         self.precise_outer = True
         self.debug_simt = False
 
@@ -88,7 +89,20 @@ class RRDBNet(nn.Module):
                 packed[name] = (w.detach().contiguous().float(), b.detach().contiguous().float())
             eng.pack(packed)
             self._engine, self._engine_key, self._plans = eng, key, {}
+            self._packed_params, self._dgrad, self._bplans = packed, None, {}
         return self._engine
+
+    def backward_plan(self, plan):
+        from .backward import DgradSpecs, BackwardPlan
+        if self._dgrad is None:
+            self._dgrad = DgradSpecs(self._engine)
+            self._dgrad.pack(self._packed_params)
+        key = id(plan)
+        if key not in self._bplans:
+            if len(self._bplans) >= 2:
+                self._bplans.pop(next(iter(self._bplans)))
+            self._bplans[key] = (plan, BackwardPlan(plan, self._dgrad, use_simt=self.debug_simt))
+        return self._bplans[key][1]
 
     def plan(self, B, h, w, m, keep):
         eng = self.engine()

@@ -51,6 +51,7 @@ int esr_device_check(int device);
 /* ------------------------------------------------------------------ conv3x3 */
 
 #define ESR_MAX_KBLOCKS 24
+#define ESR_MAX_COUT_TILES 8
 #define ESR_KBLOCK_CH 32 /* channels per K block (64-byte rows, SWIZZLE_64B) */
 
 /* One K block = 32 consecutive channels of one NHWC bf16 source tensor. */
@@ -108,6 +109,13 @@ typedef struct esr_conv_desc {
     int32_t cout_real;
     const void* mask;         /* NHWC bf16, same indexing as out_bf16 (ESR_EPI_MASK) */
     int32_t mask_stride, mask_choff;
+    /* Per-cout-tile routing (used by the dgrad launches, where one launch produces the gradients of
+     * several channel groups plus the latent rows).  Output channel of (tile t, column j) is
+     * tile_choff[t] + j when tile_choff[t] >= 0, else t*cout_tile + j.  A set bit t in a no_* mask
+     * switches that feature off for tile t. */
+    int16_t tile_choff[ESR_MAX_COUT_TILES];
+    uint16_t no_accum_tiles, no_bf16_tiles, no_res_tiles, reserved16;
+    float gamma;              /* res1 multiplier: v = alpha*v + gamma*res1 */
 } esr_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM kernel (the product path). */
@@ -161,9 +169,24 @@ int esr_expand_rows(const float* src_nchw, int32_t B, int32_t C, int32_t H, int3
                     int32_t nslots, void* dst_nhwc, void* stream);
 
 /* Adjoint of esr_expand_rows: g_src[b,c,y,x] = sum_{s: c_s == c} g_e[b, y-dy_s, x, choff+s]
- * (g_e: NHWC f32 with `stride` channels).  hi and lo slots of the same value both contribute. */
-int esr_expand_rows_bwd(const float* g_e_nhwc, int32_t stride, int32_t choff, int32_t B, int32_t C, int32_t H,
-                        int32_t W, const esr_xslot* slots, int32_t nslots, float* g_src_nchw, void* stream);
+ * (g_e: f32 with `stride` channels, NHWC or, if blocked != 0, [B, stride/8, H, W, 8]).  hi and lo
+ * slots of the same value both contribute; n_acc accumulators at choff + j*acc_stride are summed. */
+int esr_expand_rows_bwd(const float* g_e, int32_t stride, int32_t choff, int32_t blocked, int32_t n_acc,
+                        int32_t acc_stride, int32_t B, int32_t C, int32_t H, int32_t W, const esr_xslot* slots,
+                        int32_t nslots, float* g_src_nchw, void* stream);
+
+/* Elementwise gradient plumbing between dgrad launches (nearest-upsample adjoint, residual sums,
+ * LeakyReLU', bf16 hi/lo emission), 64-channel tensors, f32 blocked [B,8,H,W,8]:
+ *   v[b,y,x,c] = sum_{a,b' < pool} src[b, pool*y+a, pool*x+b', c]  (+ add[b,y,x,c] if add != NULL)
+ *   out_f32 = v (optional);   w = scale * v * (mask ? (mask > 0 ? 1 : slope) : 1)
+ *   out_bf16[..., hi_choff + c] = bf16(w);  out_bf16[..., lo_choff + c] = bf16(w - bf16(w)) if lo_choff >= 0
+ * src is [B, src_stride/8, pool*H, pool*W, 8] at channel offset src_choff; mask is NHWC bf16
+ * [B, mask_sub*H, mask_sub*W, mask_stride] sampled at (mask_sub*y, mask_sub*x). */
+int esr_grad_combine(const float* src, int32_t src_stride, int32_t src_choff, int32_t pool, const float* add,
+                     int32_t add_stride, int32_t add_choff, int32_t B, int32_t H, int32_t W, float* out_f32,
+                     int32_t out_stride, int32_t out_choff, const void* mask, int32_t mask_stride, int32_t mask_choff,
+                     int32_t mask_sub, float slope, float scale, void* out_bf16, int32_t bf16_stride,
+                     int32_t hi_choff, int32_t lo_choff, void* stream);
 
 /* CEM_PyTorch pre-pad + RRDBNet head (CEMnet.py:170-181, architecture.py:152-160).
  * model_input: NCHW f32 [B, sf*sf*nz+3, h, w] = cat(Z.view(B,sf*sf*nz,h,w), LR)  (raw .view packing,
@@ -209,6 +232,10 @@ int esr_cem_project(const esr_cem_filters* f, const float* y, const float* x, in
  * replicate-padding folds.  workspace: B*C*(H*W + H*(W/sf) + 2*(H/sf)*(W/sf)) floats. */
 int esr_cem_project_bwd(const esr_cem_filters* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
                         int32_t crop, float* g_y, float* workspace, void* stream);
+
+/* Debug aid (tools_prof.py): per-CTA role cycle counters of later tcgen05 conv launches, when the
+ * library was built with -DESR_PROFILE_ROLES.  buf: [148][16] uint64 device memory or NULL. */
+void esr_debug_set_profile_buffer(void* buf);
 
 /* --------------------------------------------------------- recorded sequences */
 /* A sequence is a host-side list of fully resolved kernel launches (tensor maps

@@ -151,6 +151,11 @@ def main():
                                initial_LR=0.1, batch_size=1, HR_unpadder=(lambda t: t) if train_mode else None)
         if train_mode:
             opt.feed_data(data)
+            # training mode re-draws Z with torch's RNG (Z_optimization.py:559-560); pin it to a numpy draw
+            opt.random_Z_inits = False
+            z_init = torch.from_numpy(np.random.default_rng(13).standard_normal((1, 3, 32, 32)).astype(np.float32))
+            opt.Z_model.Z.data.copy_(z_init)
+            zres[name + "_Zinit"] = z_init.numpy()
         Z = opt.optimize()
         zres[name + "_loss"] = np.array(opt.loss_values, dtype=np.float64)
         zres[name + "_Z"] = Z.numpy()

