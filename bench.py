@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-zopt", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,6 +181,7 @@ def main():
             torch.distributed.barrier()
             torch.cuda.synchronize()
 
+    launches_per_fwd = plan.launches_per_forward(with_cem=True)
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -242,13 +244,47 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # BASELINE config 3: Z optimisation, 1x3x256x256 LR, objective 'TV', Adam lr 0.1 (rank 0 only, bounded)
+    zopt = None
+    if rank == 0 and not args.no_zopt:
+        from esr_b200.z_optimization import Z_optimizer, SRModelShim
+        del plan, out_dev, ws
+        G._plans.clear()
+        torch.cuda.empty_cache()
+        zh = 256
+        lr3, z3 = synth.make_inputs(1, zh, zh, seed=3)
+        model = SRModelShim(netG)
+        data = {"LR": lr3.to(dev), "Z": torch.zeros_like(z3).to(dev)}
+        model.feed_data(data)
+        with torch.no_grad():
+            model.fake_H = netG(model.model_input)
+        import io, contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            zo = Z_optimizer(objective="TV", Z_size=[SF * zh, SF * zh], model=model, Z_range=1.0, max_iters=2, data=data,
+                             initial_LR=0.1, batch_size=1)
+            zo.optimize()                                     # warm-up: builds plans, packs dgrad weights
+            torch.cuda.synchronize()
+            n_it = 10
+            zo.max_iters = n_it
+            z0e, z1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            z0e.record()
+            zo.optimize()
+            z1e.record()
+            torch.cuda.synchronize()
+        z_ms = z0e.elapsed_time(z1e) / n_it
+        hp3 = zh + 2 * MARGIN
+        zflops = 2 * G.engine().flops_per_lr_pixel() * hp3 * hp3
+        zopt = {"config": "1x3x256x256 LR, objective TV, Adam lr 0.1, eval/pre-pad (BASELINE config 3)",
+                "iters_per_s": 1e3 / z_ms, "ms_per_iter": z_ms, "iters_timed": n_it, "loss_first_last": [zo.loss_values[0], zo.loss_values[-1]],
+                "algorithmic_tflops": zflops / (z_ms * 1e-3) / 1e12}
+
     t = torch.tensor([ms, e2e_ms, conv_ms], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, e2e_ms, conv_ms = [float(v) for v in t.cpu()]
     out_mpix = BATCH * SF * SF * LR_H * LR_W / 1e6
     pk = peaks()
-    flops = plan.eng.flops_per_lr_pixel() * BATCH * plan.hp * plan.wp
+    flops = G.engine().flops_per_lr_pixel() * BATCH * (LR_H + 2 * MARGIN) * (LR_W + 2 * MARGIN)
     achieved = flops / (conv_ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": world * out_mpix / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -259,7 +295,7 @@ def main():
                    "cuda_graph": graph is not None, "images_per_pass": SUB},
         "e2e": {"value": world * out_mpix / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
-        "gpu_launches": args.steps * (BATCH // SUB) * plan.launches_per_forward(with_cem=True),
+        "gpu_launches": args.steps * (BATCH // SUB) * launches_per_fwd,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
                      "kernel": "conv3x3_tc_kernel (351 launches/step, %.3f ms/step; algorithmic %.1f GFLOP/step)"
@@ -268,6 +304,8 @@ def main():
         "phases_ms": {"prep": t_prep, "convs": t_conv, "cem": t_cem},
         "clocks": sampler.summary(),
     }
+    if zopt is not None:
+        line["zopt"] = zopt
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

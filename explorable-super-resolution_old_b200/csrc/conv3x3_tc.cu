@@ -20,7 +20,7 @@
 #include "conv3x3.cuh"
 #include "ptx_sm100.cuh"
 
-// Per-role cycle counters (tools_prof.py); compiled in only with -DESR_PROFILE_ROLES.
+// Per-role cycle counters (tools/prof.py); compiled in only with -DESR_PROFILE_ROLES.
 #ifdef ESR_PROFILE_ROLES
 #define ESR_PROF(...) __VA_ARGS__
 #else

@@ -233,7 +233,7 @@ int esr_cem_project(const esr_cem_filters* f, const float* y, const float* x, in
 int esr_cem_project_bwd(const esr_cem_filters* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
                         int32_t crop, float* g_y, float* workspace, void* stream);
 
-/* Debug aid (tools_prof.py): per-CTA role cycle counters of later tcgen05 conv launches, when the
+/* Debug aid (tools/prof.py): per-CTA role cycle counters of later tcgen05 conv launches, when the
  * library was built with -DESR_PROFILE_ROLES.  buf: [148][16] uint64 device memory or NULL. */
 void esr_debug_set_profile_buffer(void* buf);
 
