@@ -148,6 +148,172 @@ __global__ void __launch_bounds__(256) cem_up_kernel(const __grid_constant__ esr
     }
 }
 
+// --------------------------------------------------------------- x4 streaming fast paths
+// Register / warp-shuffle kernels for sf = 4 (the production scale).  A warp owns a strip of 28 LR
+// columns (lane l holds LR cell j0-2+l, i.e. one float4 of 4 HR pixels per HR row) and a segment of
+// kSegRows LR rows; the two halo cells on either side come from neighbouring lanes via shuffles, so
+// every HR float4 is loaded / stored exactly once per strip, fully coalesced (448 B per warp row).
+constexpr int kStripCells = 28;
+constexpr int kSegRows = 8;
+
+struct CemTab {            // polyphase tap tables, [phase][cell offset -2..2]
+    float down_h[4][5];    // down: weight of element e of cell j+c for output column j
+    float down_v[4][5];    // down: weight of HR row 4I+q for output row I-m, index [q][m+2]
+    float up[4][5];        // up: weight of cell j+c for HR phase phi (same table for rows)
+};
+
+__global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ y,
+                                                        const float* __restrict__ x, float* __restrict__ out, int H,
+                                                        int W) {
+    const int h = H >> 2, w = W >> 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int plane = blockIdx.z;
+    const int j = blockIdx.x * kStripCells - 2 + lane;             // LR cell of this lane
+    const int i0 = (blockIdx.y * 4 + warp) * kSegRows;
+    if (i0 >= h) return;
+    const int i1 = min(i0 + kSegRows, h);
+    const float* yp = y + static_cast<size_t>(plane) * H * W;
+    const bool inside = j >= 0 && j < w;
+    const int xcol = j < 0 ? 0 : W - 1;                            // replicate padding for cells outside the image
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;         // accumulators of LR rows I-2 .. I+2
+    auto load_group = [&](int I, float4 (&g)[4]) {                  // the 4 HR rows of LR row I (replicate padded)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int r = 4 * I + q;
+            r = r < 0 ? 0 : (r > H - 1 ? H - 1 : r);
+            const float* row = yp + static_cast<size_t>(r) * W;
+            if (inside) g[q] = __ldg(reinterpret_cast<const float4*>(row) + j);
+            else { const float e = __ldg(row + xcol); g[q] = make_float4(e, e, e, e); }
+        }
+    };
+    float4 cur[4], nx1[4], nx2[4];                                  // two groups (8 rows) of loads stay in flight
+    load_group(i0 - 2, cur);
+    load_group(i0 - 1, nx1);
+    for (int I = i0 - 2; I <= i1 + 1; ++I) {
+        if (I + 2 <= i1 + 1) load_group(I + 2, nx2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 c = cur[q];
+            float hsum = 0.f;
+#pragma unroll
+            for (int k = -2; k <= 2; ++k) {
+                float4 n;
+                if (k == 0) n = c;
+                else {
+                    n.x = __shfl_sync(0xffffffffu, c.x, lane + k);
+                    n.y = __shfl_sync(0xffffffffu, c.y, lane + k);
+                    n.z = __shfl_sync(0xffffffffu, c.z, lane + k);
+                    n.w = __shfl_sync(0xffffffffu, c.w, lane + k);
+                }
+                hsum = fmaf(T.down_h[0][k + 2], n.x, hsum);
+                hsum = fmaf(T.down_h[1][k + 2], n.y, hsum);
+                hsum = fmaf(T.down_h[2][k + 2], n.z, hsum);
+                hsum = fmaf(T.down_h[3][k + 2], n.w, hsum);
+            }
+            // row 4I+q feeds LR rows I-m, m = -2..2  (a0 <-> m=2 ... a4 <-> m=-2)
+            a0 = fmaf(T.down_v[q][4], hsum, a0);
+            a1 = fmaf(T.down_v[q][3], hsum, a1);
+            a2 = fmaf(T.down_v[q][2], hsum, a2);
+            a3 = fmaf(T.down_v[q][1], hsum, a3);
+            a4 = fmaf(T.down_v[q][0], hsum, a4);
+        }
+        const int i = I - 2;                                       // complete now
+        if (i >= i0 && i < i1 && lane >= 2 && lane < 2 + kStripCells && j < w) {
+            const size_t o = (static_cast<size_t>(plane) * h + i) * w + j;
+            out[o] = x != nullptr ? x[o] - a0 : a0;
+        }
+        a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { cur[q] = nx1[q]; nx1[q] = nx2[q]; }
+    }
+}
+
+// out[Y-crop, X-crop] = (y ? y : 0) + sign * Up(e)
+__global__ void __launch_bounds__(128) cem_up4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ e,
+                                                      const float* __restrict__ y, float* __restrict__ out, int h,
+                                                      int w, int crop, float sign) {
+    const int H = h << 2, W = w << 2;
+    const int Ho = H - 2 * crop, Wo = W - 2 * crop;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int plane = blockIdx.z;
+    const int j = blockIdx.x * kStripCells - 2 + lane;
+    const int i0 = (blockIdx.y * 4 + warp) * kSegRows;
+    if (i0 >= h) return;
+    const int i1 = min(i0 + kSegRows, h);
+    const float* ep = e + static_cast<size_t>(plane) * h * w;
+    const bool inside = j >= 0 && j < w;
+    const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w && 4 * j >= crop && 4 * j + 3 < W - crop;
+    auto load_y = [&](int i, float4 (&b)[4]) {                     // the 4 HR rows of LR row i (base image)
+#pragma unroll
+        for (int psi = 0; psi < 4; ++psi) {
+            const int Y = 4 * i + psi;
+            b[psi] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (writer && y != nullptr && Y >= crop && Y < H - crop)
+                b[psi] = __ldg(reinterpret_cast<const float4*>(y + (static_cast<size_t>(plane) * H + Y) * W) + j);
+        }
+    };
+    float4 yc[4], yn[4];
+    load_y(i0, yc);
+    for (int i = i0; i < i1; ++i) {
+        if (i + 1 < i1) load_y(i + 1, yn);                         // next row's HBM loads fly during this row's math
+        float hu[5][4];                                            // horizontally upsampled LR rows i-2..i+2, 4 HR phases
+#pragma unroll
+        for (int kv = 0; kv < 5; ++kv) {
+            const int ii = i + kv - 2;
+            const float v = (inside && ii >= 0 && ii < h) ? __ldg(ep + static_cast<size_t>(ii) * w + j) : 0.f;
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+            for (int k = -2; k <= 2; ++k) {
+                const float n = k == 0 ? v : __shfl_sync(0xffffffffu, v, lane + k);
+                p0 = fmaf(T.up[0][k + 2], n, p0);
+                p1 = fmaf(T.up[1][k + 2], n, p1);
+                p2 = fmaf(T.up[2][k + 2], n, p2);
+                p3 = fmaf(T.up[3][k + 2], n, p3);
+            }
+            hu[kv][0] = p0; hu[kv][1] = p1; hu[kv][2] = p2; hu[kv][3] = p3;
+        }
+        if (writer) {
+#pragma unroll
+            for (int psi = 0; psi < 4; ++psi) {
+                const int Y = 4 * i + psi;
+                if (Y < crop || Y >= H - crop) continue;
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int kv = 0; kv < 5; ++kv) {
+                    const float wv = T.up[psi][kv];
+                    r.x = fmaf(wv, hu[kv][0], r.x); r.y = fmaf(wv, hu[kv][1], r.y);
+                    r.z = fmaf(wv, hu[kv][2], r.z); r.w = fmaf(wv, hu[kv][3], r.w);
+                }
+                float4 b = yc[psi];
+                b.x = fmaf(sign, r.x, b.x); b.y = fmaf(sign, r.y, b.y); b.z = fmaf(sign, r.z, b.z); b.w = fmaf(sign, r.w, b.w);
+                *reinterpret_cast<float4*>(out + (static_cast<size_t>(plane) * Ho + (Y - crop)) * Wo + (4 * j - crop)) = b;
+            }
+        }
+#pragma unroll
+        for (int psi = 0; psi < 4; ++psi) yc[psi] = yn[psi];
+    }
+}
+
+static bool fast4_ok(const esr_cem_filters& f, int H, int W, int crop, const void* a, const void* b, const void* c) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return f.sf == 4 && f.n_ds == 17 && H % 4 == 0 && W % 4 == 0 && crop % 4 == 0 && al(a) && al(b) && al(c);
+}
+
+static CemTab make_tab(const esr_cem_filters& f) {
+    CemTab T;
+    const int nt = f.n_ds, pad = nt / 2, pre = f.pre;
+    for (int p = 0; p < 4; ++p)
+        for (int k = -2; k <= 2; ++k) {
+            const int td = 4 * k + p + pad - pre;        // down: HR sample 4(j+k)+p = 4j + pre + t - pad
+            const float wd = (td >= 0 && td < nt) ? f.ds[nt - 1 - td] : 0.f;
+            T.down_h[p][k + 2] = wd;
+            T.down_v[p][k + 2] = wd;                     // same relation with m = k (row 4I+q -> LR row I-m uses t = 4m+q+pad-pre)
+            const int tu = 4 * k + pad + pre - p;        // up: 4j+p + t - pad - pre = 4(j+k)
+            T.up[p][k + 2] = (tu >= 0 && tu < nt) ? f.ds[tu] * f.sf : 0.f;
+        }
+    return T;
+}
+
 // ----------------------------------------------------------------- adjoint (backward)
 // Every CEM operator is, per axis, F: out[a] = sum_t taps[t] * src[clamp(sa*a + off + t - pad, 0, Ls-1)]
 // (src = the image for Down / K, the zero-stuffed image for Up).  The kernel below evaluates the
@@ -256,6 +422,11 @@ static int set_smem(const void* fn, size_t bytes) {
 int cem_down(const esr_cem_filters& f, const float* y, const float* x, int planes, int H, int W, float* out,
              cudaStream_t s) {
     ESR_CHECK_ARG(H % f.sf == 0 && W % f.sf == 0, "HR size %dx%d not divisible by %d", H, W, f.sf);
+    if (fast4_ok(f, H, W, 0, y, nullptr, nullptr)) {
+        dim3 grid(ceil_div(W / 4, kStripCells), ceil_div(ceil_div(H / 4, kSegRows), 4), planes);
+        cem_down4_kernel<<<grid, 128, 0, s>>>(make_tab(f), y, x, out, H, W);
+        return check_launch("cem_down4_kernel");
+    }
     const size_t sm = down_smem(f);
     int rc = set_smem(reinterpret_cast<const void*>(cem_down_kernel), sm);
     if (rc) return rc;
@@ -273,6 +444,11 @@ int cem_inv(const esr_cem_filters& f, const float* x, int planes, int h, int w, 
 }
 int cem_up(const esr_cem_filters& f, const float* x, const float* y, int planes, int h, int w, int crop, float sign,
            float* out, cudaStream_t s) {
+    if (fast4_ok(f, h * 4, w * 4, crop, y, out, nullptr) && ((w * 4 - 2 * crop) % 4 == 0)) {
+        dim3 grid(ceil_div(w, kStripCells), ceil_div(ceil_div(h, kSegRows), 4), planes);
+        cem_up4_kernel<<<grid, 128, 0, s>>>(make_tab(f), x, y, out, h, w, crop, sign);
+        return check_launch("cem_up4_kernel");
+    }
     const size_t sm = up_smem(f);
     int rc = set_smem(reinterpret_cast<const void*>(cem_up_kernel), sm);
     if (rc) return rc;

@@ -128,22 +128,30 @@ struct ExpandArgs {
     __nv_bfloat16* dst;
 };
 
+// One thread per pixel: reads its <= 3 rows x C source values (coalesced along x in NCHW) and writes all
+// slots of the pixel as 16-byte vectors (consecutive pixels are contiguous in NHWC: fully coalesced).
 __global__ void expand_rows_kernel(const __grid_constant__ ExpandArgs a) {
-    const size_t total = static_cast<size_t>(a.B) * a.H * a.W * a.nslots;
-    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int s = static_cast<int>(idx % a.nslots);
-        size_t pix = idx / a.nslots;
-        const int x = static_cast<int>(pix % a.W); pix /= a.W;
-        const int y = static_cast<int>(pix % a.H);
-        const int n = static_cast<int>(pix / a.H);
-        const esr_xslot sl = a.slots[s];
-        float v = 0.f;
-        const int yy = y + sl.dy;
-        if (sl.c >= 0 && yy >= 0 && yy < a.H)
-            v = __ldg(a.src + ((static_cast<size_t>(n) * a.C + sl.c) * a.H + yy) * a.W + x);
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        a.dst[idx] = sl.term == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    const size_t total = static_cast<size_t>(a.B) * a.H * a.W;
+    for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+         pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(pix % a.W);
+        const int y = static_cast<int>((pix / a.W) % a.H);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(a.W) * a.H));
+        __nv_bfloat16* dst = a.dst + pix * a.nslots;
+        for (int s0 = 0; s0 < a.nslots; s0 += 8) {
+            __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const esr_xslot sl = a.slots[s0 + i];
+                float val = 0.f;
+                const int yy = y + sl.dy;
+                if (sl.c >= 0 && yy >= 0 && yy < a.H)    // <= 18 distinct addresses per pixel, coalesced along x, L1 hits
+                    val = __ldg(a.src + ((static_cast<size_t>(n) * a.C + sl.c) * a.H + yy) * a.W + x);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+                o[i] = sl.term == 0 ? hi : __float2bfloat16_rn(val - __bfloat162float(hi));
+            }
+            *reinterpret_cast<uint4*>(dst + s0) = *reinterpret_cast<const uint4*>(o);
+        }
     }
 }
 
@@ -218,10 +226,11 @@ extern "C" int esr_expand_rows(const float* src_nchw, int32_t B, int32_t C, int3
         a.slots[i] = slots[i];
     }
     a.dst = static_cast<__nv_bfloat16*>(dst_nhwc);
-    const size_t total = static_cast<size_t>(B) * H * W * nslots;
-    const int block = 256;
+    ESR_CHECK_ARG(C <= 8, "esr_expand_rows: at most 8 source channels");
+    const size_t total = static_cast<size_t>(B) * H * W;
+    const int block = 128;
     const size_t want = (total + block - 1) / block;
-    const int grid = static_cast<int>(want < 148 * 32 ? want : 148 * 32);
+    const int grid = static_cast<int>(want < 148 * 64 ? want : 148 * 64);
     esr::expand_rows_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return esr::check_launch("expand_rows_kernel");
 }
