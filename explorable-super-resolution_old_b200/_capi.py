@@ -43,7 +43,7 @@ class ConvDesc(C.Structure):
         ("mask", C.c_void_p), ("mask_stride", C.c_int32), ("mask_choff", C.c_int32),
         ("tile_choff", C.c_int16 * MAX_COUT_TILES),
         ("no_accum_tiles", C.c_uint16), ("no_bf16_tiles", C.c_uint16), ("no_res_tiles", C.c_uint16),
-        ("reserved16", C.c_uint16), ("gamma", C.c_float),
+        ("pair", C.c_uint16), ("gamma", C.c_float),
     ]
 
     def __init__(self, *a, **kw):
@@ -79,8 +79,8 @@ SIGNATURES = {
     "esr_device_check": (C.c_int, [C.c_int]),
     "esr_conv3x3_tc": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "esr_conv3x3_simt": (C.c_int, [C.POINTER(ConvDesc), _vp]),
-    "esr_pack_layout": (_i64, [_i32, _i32, _i32, C.POINTER(KBlock), C.POINTER(C.c_uint32)]),
-    "esr_pack_conv_weights": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i32, _i32, _i32, C.POINTER(KBlock),
+    "esr_pack_layout": (_i64, [_i32, _i32, _i32, _i32, C.POINTER(KBlock), C.POINTER(C.c_uint32)]),
+    "esr_pack_conv_weights": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, C.POINTER(KBlock),
                                         C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "esr_expand_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32, _vp, _vp]),
     "esr_expand_rows_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32,

@@ -24,6 +24,8 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
         const int n = static_cast<int>(pix / d.H);
         const int co0 = chunk * 16, ct = co0 / CT, col0 = co0 % CT;
         const uint8_t* wt = reinterpret_cast<const uint8_t*>(d.wpack) + static_cast<size_t>(ct) * d.w_tile_bytes;
+        const int slab_rows = d.pair ? N / 2 : N;            // pair layout: each CTA's half image holds N/2 rows per slab
+        const size_t half_bytes = d.w_tile_bytes / 2;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -34,7 +36,7 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
             int wi = 0;
             for (int dy = 0; dy < 3; ++dy) {
                 if (!((K.dy_mask >> dy) & 1)) continue;
-                const uint8_t* wslab = wt + K.w_off + static_cast<size_t>(wi) * N * kRowBytes;
+                const uint8_t* wslab = wt + K.w_off + static_cast<size_t>(wi) * slab_rows * kRowBytes;
                 ++wi;
                 const int yy = y + dy - 1;
                 if (yy < 0 || yy >= d.H) continue;
@@ -47,8 +49,9 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
                         const float av = __bfloat162float(a[k]);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
+                            const int nrow = dx * CT + col0 + i;
                             const __nv_bfloat16 w = *reinterpret_cast<const __nv_bfloat16*>(
-                                wslab + sw64_offset(dx * CT + col0 + i, k));
+                                wslab + (nrow / slab_rows) * half_bytes + sw64_offset(nrow % slab_rows, k));
                             v[i] = fmaf(av, __bfloat162float(w), v[i]);
                         }
                     }
@@ -67,7 +70,7 @@ struct PackArgs {
     const float* wsrc;
     long long off, s_row, s_slot, s_ky, s_kx;
     const float* bias_src;
-    int cout_tile, cout_tiles, num_kblocks;
+    int cout_tile, cout_tiles, pair, num_kblocks;
     uint32_t w_tile_bytes;
     esr_kblock kblocks[ESR_MAX_KBLOCKS];
     const esr_wrow* rows;    // device [cout_tiles*cout_tile]
@@ -109,8 +112,9 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
         }
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const __nv_bfloat16 val = slot.term == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
-        uint8_t* dst = a.out + static_cast<size_t>(ct) * a.w_tile_bytes + K.w_off +
-                       static_cast<size_t>(wi) * N * kRowBytes + sw64_offset(n, k);
+        const int slab_rows = a.pair ? N / 2 : N;            // pair layout: rows [r*N/2, (r+1)*N/2) live in CTA r's half image
+        uint8_t* dst = a.out + static_cast<size_t>(ct) * a.w_tile_bytes + (n / slab_rows) * (a.w_tile_bytes / 2) + K.w_off +
+                       static_cast<size_t>(wi) * slab_rows * kRowBytes + sw64_offset(n % slab_rows, k);
         *reinterpret_cast<__nv_bfloat16*>(dst) = val;
     }
     const int nb = a.cout_tiles * CT;
@@ -177,9 +181,13 @@ extern "C" int esr_conv3x3_simt(const esr_conv_desc* d, void* stream) {
     return esr::launch_conv_simt(L, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_t num_kblocks, esr_kblock* kblocks,
-                                   uint32_t* w_tile_bytes) {
-    if ((cout_tile != 16 && cout_tile != 32) || cout_tiles <= 0 || num_kblocks <= 0 ||
+static bool cout_tile_ok(int32_t cout_tile, int32_t pair) {
+    return pair ? (cout_tile == 32 || cout_tile == 64) : (cout_tile == 16 || cout_tile == 32);
+}
+
+extern "C" int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_t pair, int32_t num_kblocks,
+                                   esr_kblock* kblocks, uint32_t* w_tile_bytes) {
+    if (!cout_tile_ok(cout_tile, pair) || cout_tiles <= 0 || num_kblocks <= 0 ||
         num_kblocks > ESR_MAX_KBLOCKS || kblocks == nullptr) {
         esr::set_error("esr_pack_layout: bad arguments");
         return ESR_ERR_INVALID;
@@ -188,23 +196,24 @@ extern "C" int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_
     for (int i = 0; i < num_kblocks; ++i) {
         kblocks[i].n_dy = static_cast<uint8_t>(__builtin_popcount(kblocks[i].dy_mask & 7));
         kblocks[i].w_off = off;
-        off += kblocks[i].n_dy * 3u * cout_tile * esr::kRowBytes;
+        off += kblocks[i].n_dy * 3u * cout_tile * esr::kRowBytes / (pair ? 2u : 1u);
     }
+    if (pair) off *= 2;                                      // two half images per cout tile
     if (w_tile_bytes) *w_tile_bytes = off;
     return static_cast<int64_t>(off) * cout_tiles;
 }
 
 extern "C" int esr_pack_conv_weights(const float* wsrc, int64_t off, int64_t s_row, int64_t s_slot, int64_t s_ky,
                                      int64_t s_kx, const float* bias_src, int32_t cout_tile, int32_t cout_tiles,
-                                     int32_t num_kblocks, const esr_kblock* kblocks, uint32_t w_tile_bytes,
+                                     int32_t pair, int32_t num_kblocks, const esr_kblock* kblocks, uint32_t w_tile_bytes,
                                      const esr_wrow* rows_dev, const esr_wslot* slots_dev, void* wpack_out,
                                      float* bias_out, void* stream) {
     ESR_CHECK_ARG(wsrc && kblocks && rows_dev && slots_dev && wpack_out && bias_out, "esr_pack_conv_weights: null argument");
-    ESR_CHECK_ARG((cout_tile == 16 || cout_tile == 32) && cout_tiles > 0 && num_kblocks > 0 &&
+    ESR_CHECK_ARG(cout_tile_ok(cout_tile, pair) && cout_tiles > 0 && num_kblocks > 0 &&
                   num_kblocks <= ESR_MAX_KBLOCKS, "esr_pack_conv_weights: bad sizes");
     esr::PackArgs a;
     a.wsrc = wsrc; a.off = off; a.s_row = s_row; a.s_slot = s_slot; a.s_ky = s_ky; a.s_kx = s_kx;
-    a.bias_src = bias_src; a.cout_tile = cout_tile; a.cout_tiles = cout_tiles; a.num_kblocks = num_kblocks;
+    a.bias_src = bias_src; a.cout_tile = cout_tile; a.cout_tiles = cout_tiles; a.pair = pair ? 1 : 0; a.num_kblocks = num_kblocks;
     a.w_tile_bytes = w_tile_bytes;
     for (int i = 0; i < num_kblocks; ++i) a.kblocks[i] = kblocks[i];
     a.rows = rows_dev; a.slots = slots_dev; a.out = static_cast<uint8_t*>(wpack_out); a.bias_out = bias_out;

@@ -307,7 +307,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 [B,H,W,C] seen as a 4-D tensor (C, W, H, B); box = 32 ch x 32 px x 10 rows.
-int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W) {
+int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ESR_ERR_CUDA; }
     ESR_CHECK_ARG(t.ptr != nullptr && t.channels >= kKB && t.channels % 8 == 0,
@@ -317,7 +317,7 @@ int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H,
                                 static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(t.channels) * 2, static_cast<cuuint64_t>(W) * t.channels * 2,
                                    static_cast<cuuint64_t>(H) * W * t.channels * 2};
-    const cuuint32_t box[4] = {kKB, kTileW, kHaloRows, 1};
+    const cuuint32_t box[4] = {kKB, kTileW, static_cast<cuuint32_t>(box_rows), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(t.ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -328,7 +328,9 @@ int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H,
 
 int validate_conv_desc(const esr_conv_desc& d) {
     ESR_CHECK_ARG(d.B > 0 && d.H > 0 && d.W > 0, "bad conv geometry %dx%dx%d", d.B, d.H, d.W);
-    ESR_CHECK_ARG(d.cout_tile == 32 || d.cout_tile == 16, "cout_tile must be 16 or 32");
+    ESR_CHECK_ARG(d.pair ? (d.cout_tile == 32 || d.cout_tile == 64) : (d.cout_tile == 32 || d.cout_tile == 16),
+                  "cout_tile must be 16 or 32 (32 or 64 in pair mode)");
+    ESR_CHECK_ARG(!d.pair || d.w_tile_bytes % 32 == 0, "pair mode: w_tile_bytes must split into two 16-byte aligned halves");
     ESR_CHECK_ARG(d.cout_tiles > 0 && d.cout_tiles <= ESR_MAX_COUT_TILES, "cout_tiles out of range");
     for (int t = 0; t < d.cout_tiles; ++t)
         ESR_CHECK_ARG(d.tile_choff[t] < 0 || d.tile_choff[t] % 16 == 0, "tile_choff[%d] must be a multiple of 16", t);
@@ -344,7 +346,8 @@ int validate_conv_desc(const esr_conv_desc& d) {
                       d.src[k.src].channels);
         ESR_CHECK_ARG((k.dy_mask & 7) != 0 && (k.slice_mask & 3) != 0 && k.n_dy == __builtin_popcount(k.dy_mask & 7),
                       "kblock %d: bad masks", i);
-        ESR_CHECK_ARG(k.w_off % 512 == 0 && k.w_off + k.n_dy * 3u * d.cout_tile * kRowBytes <= d.w_tile_bytes,
+        ESR_CHECK_ARG(k.w_off % 512 == 0 &&
+                      k.w_off + k.n_dy * 3u * d.cout_tile * kRowBytes / (d.pair ? 2u : 1u) <= d.w_tile_bytes / (d.pair ? 2u : 1u),
                       "kblock %d: weight slab outside tile image", i);
     }
     ESR_CHECK_ARG(d.up == 1 || d.up == 2, "up must be 1 or 2");
@@ -389,9 +392,12 @@ void fill_launch(ConvLaunch* L, const esr_conv_desc& d) {
     const char* dbg = getenv("ESR_DEBUG_SKIP");
     L->debug = dbg ? atoi(dbg) : 0;
     L->prof = g_prof_buf;
+    L->pair_nb = 0;
 }
 
-static int num_sms() {
+int num_sms_cached();
+static int num_sms() { return num_sms_cached(); }
+int num_sms_cached() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
@@ -411,7 +417,10 @@ static bool is_trunk_epilogue(const esr_conv_desc& d) {
            (reinterpret_cast<uintptr_t>(d.out_bf16) & 31) == 0;   // 32-byte stores
 }
 
+int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream, int use_pdl);
+
 int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream) {
+    if (L.pair_nb) return launch_conv_tc2(tm0, tm1, L, stream, g_use_pdl);
     static bool attr_set = false;
     if (!attr_set) {
         ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<32, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
@@ -447,18 +456,25 @@ int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLau
     return check_launch("conv3x3_tc_kernel");
 }
 
+bool fill_launch_pair(ConvLaunch* L);
+
 int build_conv_launch(const esr_conv_desc& d, CUtensorMap* tm0, CUtensorMap* tm1, ConvLaunch* L) {
     int rc = validate_conv_desc(d);
     if (rc != ESR_OK) return rc;
-    rc = make_act_tensor_map(tm0, d.src[0], d.B, d.H, d.W);
+    fill_launch(L, d);
+    int box_rows = kHaloRows;
+    if (d.pair) {
+        ESR_CHECK_ARG(fill_launch_pair(L), "pair mode: weights (%u B per cout tile) leave no room for the A-tile ring", d.w_tile_bytes);
+        box_rows = L->pair_nb * kBandRows + 2;
+    }
+    rc = make_act_tensor_map(tm0, d.src[0], d.B, d.H, d.W, box_rows);
     if (rc != ESR_OK) return rc;
     if (d.src[1].ptr != nullptr) {
-        rc = make_act_tensor_map(tm1, d.src[1], d.B, d.H, d.W);
+        rc = make_act_tensor_map(tm1, d.src[1], d.B, d.H, d.W, box_rows);
         if (rc != ESR_OK) return rc;
     } else {
         *tm1 = *tm0;
     }
-    fill_launch(L, d);
     return ESR_OK;
 }
 

@@ -1,0 +1,395 @@
+// conv3x3 on CTA pairs: tcgen05.mma.cta_group::2 (M = 256 = two 4x32-pixel bands, one per CTA of a 2-CTA
+// cluster), same formulation as conv3x3_tc.cu (filter columns stacked along N, filter rows as row-shifted views
+// of one TMA halo tile, shuffle epilogue).
+//
+// Why pairs: a single-CTA M128 x N96 x K16 MMA reads 4 KiB of A and 3 KiB of B from shared memory and is bound
+// by that read (~96 B/clk -> 74 clk instead of 48, measured).  In a pair each CTA still reads its own 4 KiB of A
+// (its own spatial tile) but only HALF of B (the tensor cores exchange the halves), so
+//   N = 96  (cout tile 32, 2 bands/tile):  5.5 KiB per CTA per MMA  -> ~57 clk vs 48 ideal,
+//   N = 192 (cout tile 64, 1 band/tile):   7 KiB per CTA per 96-clk MMA -> tensor bound.
+// Each CTA keeps its half of the cout tile's packed weights resident (<= 124 KiB) and streams its own halo
+// tiles through a TMA ring; the leader CTA's elected thread issues every MMA; full / accumulator-empty barriers
+// live in the leader and collect remote arrivals, empty / accumulator-full barriers are multicast commits.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "conv3x3.cuh"
+#include "ptx_sm100.cuh"
+
+namespace esr {
+
+namespace pair {
+
+constexpr int kMaxStages = 6;
+constexpr int kAccStages = 2;
+constexpr int kEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kEpiWarps;   // 320
+constexpr int kTmemCols = 512;
+constexpr int kCtrlBytes = 256 + 256;              // barriers + tmem slot, 64 floats of bias
+constexpr int kSmemMax = 227 * 1024;
+constexpr uint32_t kDescHi = ((8u * kRowBytes) >> 4) | (1u << 14) | (4u << 29);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_local(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_try_wait_cluster(bar, parity); ++it) {
+        if (it > (1u << 26)) { __trap(); }
+    }
+}
+// TMA tile load whose completion bytes are credited to the barrier at `leader_bar_addr` (CTA 0 of the pair)
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const void* tmap, uint32_t leader_bar_addr, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar_addr), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_issue2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once all prior MMAs of the pair have completed
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_bf16_m256(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+// CT = output channels per pair tile (32 -> N = 96, two bands per CTA; 64 -> N = 192, one band per CTA).
+template <int CT, int MODE>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                   const __grid_constant__ ConvLaunch L) {
+    constexpr int N = 3 * CT;                      // MMA N of the pair
+    constexpr int NB = CT == 32 ? 2 : 1;           // bands per CTA tile
+    constexpr int kRows = NB * kBandRows + 2;      // halo rows per A tile
+    constexpr int kATile = kRows * kTileW * kRowBytes;
+    constexpr int kAccSlot = CT == 32 ? 128 : 256; // TMEM columns per band accumulator
+    constexpr uint32_t kIdesc = idesc_bf16_m256(N);
+    constexpr uint32_t kARow16 = (kTileW * kRowBytes) >> 4;
+    constexpr uint32_t kWSlab16 = ((N / 2) * kRowBytes) >> 4;     // this CTA's half of one [N x 32ch] slab
+    const esr_conv_desc& d = L.d;
+    const int nstages = L.nstages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_w = smem;
+    uint8_t* s_a = smem + L.w_smem_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + nstages * kATile);
+    uint64_t* full_bar = bars;                      // waited in the leader only
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* acc_full = bars + 2 * kMaxStages;
+    uint64_t* acc_empty = acc_full + kAccStages;    // waited in the leader only
+    uint64_t* w_full = acc_empty + kAccStages;      // local weight copy
+    uint64_t* w_ready = w_full + 1;                 // leader: both halves resident
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_ready + 1);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int ct = cluster_id % d.cout_tiles;
+    const int pair0 = cluster_id / d.cout_tiles, pair_step = num_clusters / d.cout_tiles;
+    const int num_pairs = (L.spatial_tiles + 1) >> 1;
+    for (int i = threadIdx.x; i < CT; i += kNumThreads) s_bias[i] = d.bias[ct * CT + i];
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap0);
+        tma_prefetch_desc(&tmap1);
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
+        mbar_init(w_full, 1);
+        mbar_init(w_ready, 2);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc2(tmem_slot, kTmemCols);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    cluster_sync_all();                             // both CTAs' barriers and TMEM are ready
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+
+    const int nkb = d.num_kblocks;
+    const int tiles_per_img = L.tiles_x * L.tiles_y;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one per CTA)
+        if (elect_one()) {
+            const uint32_t half_bytes = d.w_tile_bytes >> 1;                         // this CTA's half image
+            const uint8_t* wt = reinterpret_cast<const uint8_t*>(d.wpack) + static_cast<size_t>(ct) * d.w_tile_bytes +
+                                static_cast<size_t>(rank) * half_bytes;
+            mbar_expect_tx_local(w_full, half_bytes);
+            for (uint32_t off = 0; off < half_bytes; off += 16384) {
+                const uint32_t n = half_bytes - off < 16384 ? half_bytes - off : 16384;
+                bulk_load_1d(s_w + off, wt + off, n, w_full);
+            }
+            pdl_wait();
+            uint32_t stage = 0, phase = 0;
+            bool w_signalled = false;
+            for (int p = pair0; p < num_pairs; p += pair_step) {
+                int sp = 2 * p + static_cast<int>(rank);
+                if (sp >= L.spatial_tiles) sp = L.spatial_tiles - 1;       // odd tail: duplicate tile, stores masked
+                const int n = sp / tiles_per_img;
+                const int r = sp - n * tiles_per_img;
+                const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
+                const int x0 = tx * kTileWOut - 1, y0 = ty * (NB * kBandRows) - 1;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const esr_kblock& K = d.kblocks[kb];
+                    mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+                    const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);   // both CTAs' tiles
+                    else mbar_arrive_cluster(lead_full);
+                    tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
+                    if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
+                }
+                if (!w_signalled) {                                        // after the ring is primed: report the weights
+                    mbar_wait(w_full, 0);
+                    mbar_arrive_cluster(mapa_u32(smem_u32(w_ready), 0));
+                    w_signalled = true;
+                }
+            }
+            if (!w_signalled) { mbar_wait(w_full, 0); mbar_arrive_cluster(mapa_u32(smem_u32(w_ready), 0)); }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer (leader CTA only)
+        if (rank == 0 && elect_one()) {
+            const uint32_t w_lo = smem_u32(s_w) >> 4, a_lo = smem_u32(s_a) >> 4;
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            mbar_wait_cluster(w_ready, 0);
+            for (int p = pair0; p < num_pairs; p += pair_step) {
+                mbar_wait_cluster(&acc_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + as * (NB * kAccSlot);
+                uint32_t nonfirst = 0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t masks = *reinterpret_cast<const uint32_t*>(&d.kblocks[kb].dy_mask);
+                    const uint32_t dy_mask = masks & 0xff, slice_mask = (masks >> 8) & 0xff;
+                    const uint32_t w0 = w_lo + (d.kblocks[kb].w_off >> 4);
+                    mbar_wait_cluster(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = a_lo + stage * (kATile >> 4);
+                    if (dy_mask == 7u && slice_mask == 3u) {
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                                for (int b = 0; b < NB; ++b) {
+                                    umma_issue2(acc0 + b * kAccSlot, a0 + (b * kBandRows + dy) * kARow16 + s * 2,
+                                                w0 + dy * kWSlab16 + s * 2, kIdesc, (dy | s) ? 1u : nonfirst);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int b = 0; b < NB; ++b) {
+                            uint32_t acc_flag = nonfirst, wi = 0;
+                            for (int dy = 0; dy < 3; ++dy) {
+                                if (!((dy_mask >> dy) & 1u)) continue;
+                                for (int s = 0; s < 2; ++s) {
+                                    if (!((slice_mask >> s) & 1u)) continue;
+                                    umma_issue2(acc0 + b * kAccSlot, a0 + (b * kBandRows + dy) * kARow16 + s * 2,
+                                                w0 + wi * kWSlab16 + s * 2, kIdesc, acc_flag);
+                                    acc_flag = 1;
+                                }
+                                ++wi;
+                            }
+                        }
+                    }
+                    nonfirst = 1;
+                    umma_commit2(&empty_bar[stage]);
+                    if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
+                }
+                umma_commit2(&acc_full[as]);
+                if (++as == kAccStages) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (each CTA: its own tile)
+        const int wq = warp & 3;
+        const int e = (warp - 2) >> 2;                 // 0/1
+        const int b = NB == 2 ? e : 0;                 // band (N = 96) ...
+        const int cbase = NB == 2 ? 0 : e * 32;        // ... or 32-channel half of the 64 (N = 192)
+        const uint32_t lead_acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
+        pdl_wait();
+        uint32_t as = 0, aphase = 0;
+        for (int p = pair0; p < num_pairs; p += pair_step) {
+            const int sp_raw = 2 * p + static_cast<int>(rank);
+            const bool tile_ok = sp_raw < L.spatial_tiles;
+            const int sp = tile_ok ? sp_raw : L.spatial_tiles - 1;
+            const int n = sp / tiles_per_img;
+            const int r = sp - n * tiles_per_img;
+            const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
+            const int x = tx * kTileWOut - 1 + lane;
+            const int y = ty * (NB * kBandRows) + b * kBandRows + wq;
+            const bool ok = tile_ok && lane >= 1 && lane <= kTileWOut && x < d.W && y < d.H;
+            EpiOperands ops[2];
+            if (ok) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    conv_epilogue_prefetch<MODE>(d, ct, n, y, x, tile_channel(d, ct, cbase + h * 16), ops[h]);
+            }
+            mbar_wait_cluster(&acc_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * (NB * kAccSlot) + b * kAccSlot + cbase + (static_cast<uint32_t>(wq * 32) << 16);
+            float vc[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float vl[16], vr[16];
+                tmem_ld_x16(taddr + 0 * CT + h * 16, vl);
+                tmem_ld_x16(taddr + 1 * CT + h * 16, *reinterpret_cast<float(*)[16]>(&vc[h * 16]));
+                tmem_ld_x16(taddr + 2 * CT + h * 16, vr);
+                tmem_ld_wait();
+                if (h == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(lead_acc_empty0 + as * 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float fl = __shfl_up_sync(0xffffffffu, vl[i], 1);
+                    const float fr = __shfl_down_sync(0xffffffffu, vr[i], 1);
+                    vc[h * 16 + i] += fl + fr;
+                }
+            }
+            if (ok) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    conv_epilogue16<MODE>(d, s_bias + cbase + h * 16, ct, n, y, x, tile_channel(d, ct, cbase + h * 16),
+                                          *reinterpret_cast<float(*)[16]>(&vc[h * 16]), ops[h]);
+            }
+            if (++as == kAccStages) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                             // nobody frees TMEM / exits while the pair's MMAs may still read it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace pair
+
+int num_sms_cached();
+
+static bool is_trunk_epilogue2(const esr_conv_desc& d) {
+    for (int t = 0; t < d.cout_tiles; ++t)
+        if (d.tile_choff[t] >= 0) return false;
+    return (d.flags & ~static_cast<uint32_t>(ESR_EPI_WIDE_OK | ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && d.out_bf16 != nullptr &&
+           d.out_f32 == nullptr && d.out_nchw == nullptr && d.out_bf16_lo_choff < 0 && d.up == 1 && d.out_bf16_scale == 1.0f &&
+           d.out_bf16_stride % 16 == 0 && d.out_bf16_choff % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out_bf16) & 31) == 0;
+}
+
+// Fills the pair-mode launch geometry; returns false if the weights leave no room for the A ring.
+bool fill_launch_pair(ConvLaunch* L) {
+    const esr_conv_desc& d = L->d;
+    const int nb = d.cout_tile == 32 ? 2 : 1;
+    const int a_tile = (nb * kBandRows + 2) * kTileW * kRowBytes;
+    L->pair_nb = nb;
+    L->tiles_y = ceil_div(d.H, nb * kBandRows);
+    L->spatial_tiles = d.B * L->tiles_x * L->tiles_y;
+    L->total_tiles = L->spatial_tiles * d.cout_tiles;
+    L->w_smem_bytes = (d.w_tile_bytes / 2 + 1023u) & ~1023u;
+    const int room = pair::kSmemMax - 1024 - pair::kCtrlBytes - static_cast<int>(L->w_smem_bytes);
+    int st = room / a_tile;
+    L->nstages = st > pair::kMaxStages ? pair::kMaxStages : st;
+    return L->nstages >= 2;
+}
+
+int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream, int use_pdl) {
+    using namespace pair;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<32, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<32, kEpiTrunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr_set = true;
+    }
+    const int nb = L.d.cout_tile == 32 ? 2 : 1;
+    const int a_tile = (nb * kBandRows + 2) * kTileW * kRowBytes;
+    const int num_pairs = (L.spatial_tiles + 1) / 2;
+    int per_ct = (num_sms_cached() / 2) / L.d.cout_tiles;       // clusters per cout tile
+    if (per_ct > num_pairs) per_ct = num_pairs;
+    ESR_CHECK_ARG(per_ct >= 1, "too many cout tiles (%d) for pair mode", L.d.cout_tiles);
+    const int grid = 2 * per_ct * L.d.cout_tiles;
+    const int smem = 1024 + static_cast<int>(L.w_smem_bytes) + L.nstages * a_tile + kCtrlBytes;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 2 : 1;
+    cudaError_t e;
+    if (L.d.cout_tile == 64)
+        e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<64, kEpiGeneric>, tm0, tm1, L);
+    else if (is_trunk_epilogue2(L.d))
+        e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<32, kEpiTrunk>, tm0, tm1, L);
+    else
+        e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<32, kEpiGeneric>, tm0, tm1, L);
+    if (e != cudaSuccess) { set_error("conv3x3_tc2_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
+    return check_launch("conv3x3_tc2_kernel");
+}
+
+}  // namespace esr

@@ -38,8 +38,8 @@ def _struct_array_to_device(arr, ctype, device):
 class PackedConv:
     """One logical 3x3 conv packed for the kernels: K-block list + swizzled bf16 weight image."""
 
-    def __init__(self, name, cout, kblocks, slots, rows, cout_tile):
-        self.name, self.cout, self.cout_tile = name, cout, cout_tile
+    def __init__(self, name, cout, kblocks, slots, rows, cout_tile, pair=False):
+        self.name, self.cout, self.cout_tile, self.pair = name, cout, cout_tile, int(bool(pair))
         self.cout_tiles = (cout + cout_tile - 1) // cout_tile
         self.nkb = len(kblocks)
         assert self.nkb <= capi.MAX_KBLOCKS, name
@@ -48,7 +48,7 @@ class PackedConv:
             self.kblocks[i].src, self.kblocks[i].chan = src, chan
             self.kblocks[i].dy_mask, self.kblocks[i].slice_mask = dy_mask, slice_mask
         wtb = C.c_uint32(0)
-        total = capi.lib().esr_pack_layout(cout_tile, self.cout_tiles, self.nkb, self.kblocks, C.byref(wtb))
+        total = capi.lib().esr_pack_layout(cout_tile, self.cout_tiles, self.pair, self.nkb, self.kblocks, C.byref(wtb))
         if total < 0:
             capi.check(int(total))
         self.w_tile_bytes, self.total_bytes = wtb.value, int(total)
@@ -70,7 +70,7 @@ class PackedConv:
         slots_d = _struct_array_to_device(self.slots, WSlot, dev)
         capi.check(capi.lib().esr_pack_conv_weights(
             capi.ptr(weight), off, s_row, s_slot, s_ky, s_kx, capi.ptr(bias), self.cout_tile, self.cout_tiles,
-            self.nkb, self.kblocks, self.w_tile_bytes, capi.ptr(rows_d), capi.ptr(slots_d), capi.ptr(self.wpack),
+            self.pair, self.nkb, self.kblocks, self.w_tile_bytes, capi.ptr(rows_d), capi.ptr(slots_d), capi.ptr(self.wpack),
             capi.ptr(self.bias), capi.stream_ptr()))
         self._keep = (rows_d, slots_d)  # until the stream has consumed them
 
@@ -264,7 +264,7 @@ class GPlan:
         d.src[0].ptr, d.src[0].channels = src0.data_ptr(), src0.shape[-1]
         if src1 is not None:
             d.src[1].ptr, d.src[1].channels = src1.data_ptr(), src1.shape[-1]
-        d.cout_tile, d.cout_tiles, d.num_kblocks = pc.cout_tile, pc.cout_tiles, pc.nkb
+        d.cout_tile, d.cout_tiles, d.num_kblocks, d.pair = pc.cout_tile, pc.cout_tiles, pc.nkb, pc.pair
         for i in range(pc.nkb):
             d.kblocks[i] = pc.kblocks[i]
         d.wpack, d.w_tile_bytes, d.bias = pc.wpack.data_ptr(), pc.w_tile_bytes, pc.bias.data_ptr()

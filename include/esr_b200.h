@@ -85,7 +85,7 @@ enum {
 typedef struct esr_conv_desc {
     int32_t B, H, W;          /* conv resolution (input == output, stride 1, zero pad 1) */
     esr_tensor_nhwc src[2];
-    int32_t cout_tile;        /* 32 or 16 output channels per CTA tile */
+    int32_t cout_tile;        /* output channels per tile: 16 or 32; 64 only with pair != 0 */
     int32_t cout_tiles;       /* ceil(Cout / cout_tile) */
     int32_t num_kblocks;
     esr_kblock kblocks[ESR_MAX_KBLOCKS];
@@ -114,7 +114,9 @@ typedef struct esr_conv_desc {
      * tile_choff[t] + j when tile_choff[t] >= 0, else t*cout_tile + j.  A set bit t in a no_* mask
      * switches that feature off for tile t. */
     int16_t tile_choff[ESR_MAX_COUT_TILES];
-    uint16_t no_accum_tiles, no_bf16_tiles, no_res_tiles, reserved16;
+    uint16_t no_accum_tiles, no_bf16_tiles, no_res_tiles;
+    uint16_t pair;            /* != 0: wpack is in the pair layout (esr_pack_layout pair=1) and the launch runs on
+                                 2-CTA clusters with tcgen05.mma.cta_group::2 (M = 256: one 4x32-pixel band per CTA) */
     float gamma;              /* res1 multiplier: v = alpha*v + gamma*res1 */
 } esr_conv_desc;
 
@@ -144,13 +146,17 @@ typedef struct esr_wslot {
 } esr_wslot;
 
 /* Fills w_off / n_dy of every K block and returns the total packed size in bytes
- * (cout_tiles * *w_tile_bytes), or a negative esr_status. */
-int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_t num_kblocks, esr_kblock* kblocks,
+ * (cout_tiles * *w_tile_bytes), or a negative esr_status.
+ * pair = 0: one image per cout tile, slabs of N = 3*cout_tile rows (dx-major) x 32 channels.
+ * pair = 1: the image of a cout tile is two half images (w_tile_bytes/2 each), one per CTA of a pair: CTA r holds
+ *           rows [r*N/2, (r+1)*N/2) of every slab (the B operand split of cta_group::2); w_off is the offset
+ *           inside a half image.  cout_tile may then also be 64. */
+int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_t pair, int32_t num_kblocks, esr_kblock* kblocks,
                         uint32_t* w_tile_bytes);
 /* rows_dev: DEVICE array [cout_tiles*cout_tile]; slots_dev: DEVICE array [num_kblocks*32].
  * bias_src (f32 device, indexed by row.idx) may be NULL.  bias_out: [cout_tiles*cout_tile]. */
 int esr_pack_conv_weights(const float* wsrc, int64_t off, int64_t s_row, int64_t s_slot, int64_t s_ky, int64_t s_kx,
-                          const float* bias_src, int32_t cout_tile, int32_t cout_tiles, int32_t num_kblocks,
+                          const float* bias_src, int32_t cout_tile, int32_t cout_tiles, int32_t pair, int32_t num_kblocks,
                           const esr_kblock* kblocks, uint32_t w_tile_bytes, const esr_wrow* rows_dev,
                           const esr_wslot* slots_dev, void* wpack_out, float* bias_out, void* stream);
 

@@ -18,7 +18,7 @@ def psnr(a, b):
     return float(10 * torch.log10(1.0 / ((a.double() - b.double()) ** 2).mean()))
 
 
-def plain_conv_case(dev, B, H, W, cin, cout, seed=0, buf_channels=None, chan0=0, precise=False):
+def plain_conv_case(dev, B, H, W, cin, cout, seed=0, buf_channels=None, chan0=0, precise=False, pair=False, cout_tile=None):
     """Random conv with `cin` (multiple of 32) NHWC bf16 input channels living at [chan0, chan0+cin) of
     a buffer with `buf_channels` channels.  precise: input given as hi/lo pair (lo at +64, cin must be 64)."""
     g = torch.Generator().manual_seed(seed)
@@ -38,8 +38,8 @@ def plain_conv_case(dev, B, H, W, cin, cout, seed=0, buf_channels=None, chan0=0,
         for c0 in range(0, cin, 32):
             kb.append((0, base + c0, DY_ALL, 0b11))
             slots += [(c0 + k, -1, wterm) for k in range(32)]
-    ct = 16 if cout <= 16 else 32
-    pc = PackedConv("test", cout, kb, slots, [(co, -1) for co in range(cout)], ct)
+    ct = cout_tile or (16 if cout <= 16 else 32)
+    pc = PackedConv("test", cout, kb, slots, [(co, -1) for co in range(cout)], ct, pair=pair)
     wd, bd = w.to(dev).contiguous(), b.to(dev).contiguous()
     pc.pack(wd, bd, 0, cin * 9, 9, 3, 1)
     torch.cuda.synchronize()
@@ -55,7 +55,7 @@ def conv_desc(pc, B, H, W, src0, src1=None):
     d.src[0].ptr, d.src[0].channels = src0.data_ptr(), src0.shape[-1]
     if src1 is not None:
         d.src[1].ptr, d.src[1].channels = src1.data_ptr(), src1.shape[-1]
-    d.cout_tile, d.cout_tiles, d.num_kblocks = pc.cout_tile, pc.cout_tiles, pc.nkb
+    d.cout_tile, d.cout_tiles, d.num_kblocks, d.pair = pc.cout_tile, pc.cout_tiles, pc.nkb, pc.pair
     for i in range(pc.nkb):
         d.kblocks[i] = pc.kblocks[i]
     d.wpack, d.w_tile_bytes, d.bias = pc.wpack.data_ptr(), pc.w_tile_bytes, pc.bias.data_ptr()

@@ -30,6 +30,48 @@ def test_plain_conv_f32_out(cuda_device, impl, B, H, W, cin, cout):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,W,cin,cout,ct", [(1, 8, 30, 32, 32, 32), (2, 20, 20, 64, 32, 32), (1, 13, 70, 96, 64, 32),
+                                               (1, 9, 33, 192, 64, 64), (3, 21, 95, 160, 32, 32), (2, 23, 61, 64, 64, 64),
+                                               (1, 4, 30, 32, 64, 64), (1, 37, 151, 64, 128, 64)])
+def test_pair_conv_f32_out(cuda_device, impl, B, H, W, cin, cout, ct):
+    """cta_group::2 kernel (CTA pairs, M = 256) and the pair weight layout: odd tile counts, one or two cout
+    tiles, N = 96 (two bands per CTA) and N = 192 (one band per CTA)."""
+    c = plain_conv_case(cuda_device, B, H, W, cin, cout, seed=cin + cout + W, pair=True, cout_tile=ct)
+    pc = c["pc"]
+    out = torch.full((B, H, W, pc.cout_tiles * pc.cout_tile), 7.0, device=cuda_device)
+    d = conv_desc(pc, B, H, W, c["buf"])
+    d.out_f32, d.out_f32_stride = out.data_ptr(), out.shape[-1]
+    run_conv(d, impl)
+    got = _nchw(out)[:, :cout]
+    err = (got - c["ref"]).abs().max().item()
+    assert err < TOL, "max abs err %g" % err
+
+
+@pytest.mark.parametrize("ct", [32, 64])
+def test_pair_residual_epilogue(cuda_device, ct):
+    """conv5-like launch in pair mode: v = 0.2*(0.2*conv + res1) + res2 -> blocked fp32 trunk + bf16 slice."""
+    B, H, W = 2, 12, 37
+    c = plain_conv_case(cuda_device, B, H, W, 192, 64, seed=9, pair=True, cout_tile=ct)
+    g = torch.Generator().manual_seed(1)
+    r1, r2 = torch.rand(B, H, W, 64, generator=g), torch.rand(B, H, W, 64, generator=g)
+    blk = lambda t: t.view(B, H, W, 8, 8).permute(0, 3, 1, 2, 4).contiguous()       # [B, C/8, H, W, 8]
+    r1d, r2d = blk(r1).to(cuda_device), blk(r2).to(cuda_device)
+    out32 = torch.zeros(B, 8, H, W, 8, device=cuda_device)
+    outb = torch.zeros(B, H, W, 192, device=cuda_device, dtype=torch.bfloat16)
+    d = conv_desc(c["pc"], B, H, W, c["buf"])
+    d.flags = capi.EPI_RES1 | capi.EPI_RES2 | capi.EPI_F32_BLOCKED
+    d.alpha, d.beta = 0.2, 0.2
+    d.res1, d.res1_stride, d.res2, d.res2_stride = r1d.data_ptr(), 64, r2d.data_ptr(), 64
+    d.out_f32, d.out_f32_stride = out32.data_ptr(), 64
+    d.out_bf16, d.out_bf16_stride, d.out_bf16_choff = outb.data_ptr(), 192, 0
+    run_conv(d, "tc")
+    ref = 0.2 * (0.2 * c["ref"] + r1.permute(0, 3, 1, 2)) + r2.permute(0, 3, 1, 2)
+    got = out32.cpu().permute(0, 1, 4, 2, 3).reshape(B, 64, H, W)
+    assert (got - ref).abs().max().item() < TOL
+    assert (_nchw(outb)[:, :64] - bf16_round(ref)).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_dense_block_slice_write_and_lrelu(cuda_device, impl):
     """conv reads channels [0,96) of a 192-channel buffer and writes LeakyReLU(out) as bf16 into [96,128)."""
     B, H, W = 1, 21, 45

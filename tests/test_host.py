@@ -120,6 +120,12 @@ def test_library_exports_every_declared_symbol():
     kb[0].dy_mask, kb[0].slice_mask = 0b111, 0b11
     kb[1].dy_mask, kb[1].slice_mask = 0b010, 0b01
     wtb = ctypes.c_uint32(0)
-    total = lib.esr_pack_layout(32, 2, 2, kb, ctypes.byref(wtb))
+    total = lib.esr_pack_layout(32, 2, 0, 2, kb, ctypes.byref(wtb))
     assert (wtb.value, total, kb[1].w_off, kb[0].n_dy, kb[1].n_dy) == (18432 + 6144, 2 * 24576, 18432, 3, 1)
-    assert lib.esr_pack_layout(7, 1, 1, kb, ctypes.byref(wtb)) < 0 and b"esr_pack_layout" in lib.esr_last_error()
+    # pair layout: same bytes per cout tile, split into two half images; w_off is relative to a half
+    total = lib.esr_pack_layout(32, 2, 1, 2, kb, ctypes.byref(wtb))
+    assert (wtb.value, total, kb[1].w_off) == (18432 + 6144, 2 * 24576, 9216)
+    total = lib.esr_pack_layout(64, 1, 1, 2, kb, ctypes.byref(wtb))
+    assert (wtb.value, total, kb[1].w_off) == (2 * 24576, 2 * 24576, 18432)
+    assert lib.esr_pack_layout(64, 1, 0, 2, kb, ctypes.byref(wtb)) < 0          # 64-channel tiles need pair mode
+    assert lib.esr_pack_layout(7, 1, 0, 1, kb, ctypes.byref(wtb)) < 0 and b"esr_pack_layout" in lib.esr_last_error()
