@@ -1,6 +1,7 @@
 // C-ABI glue: error reporting, device check and recorded launch sequences.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -65,9 +66,20 @@ extern "C" int esr_seq_add_conv(esr_seq* s, const esr_conv_desc* d, int32_t use_
 extern "C" int esr_seq_run(const esr_seq* s, void* stream) {
     if (s == nullptr) { esr::set_error("esr_seq_run: null sequence"); return ESR_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool sync_each = []() { const char* v = getenv("ESR_SEQ_SYNC"); return v && atoi(v); }();   // debug aid
+    int idx = 0;
     for (const esr::SeqOp& op : s->ops) {
         int rc = op.use_simt ? esr::launch_conv_simt(op.L, st) : esr::launch_conv_tc(op.tm0, op.tm1, op.L, st);
         if (rc != ESR_OK) return rc;
+        if (sync_each) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                esr::set_error("sequence op %d (cout_tile %d x %d, pair %d, %d k-blocks, %dx%dx%d) failed: %s", idx, op.L.d.cout_tile,
+                               op.L.d.cout_tiles, op.L.d.pair, op.L.d.num_kblocks, op.L.d.B, op.L.d.H, op.L.d.W, cudaGetErrorString(e));
+                return ESR_ERR_CUDA;
+            }
+        }
+        ++idx;
     }
     return ESR_OK;
 }

@@ -132,7 +132,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     uint64_t* acc_full = bars + 2 * kMaxStages;
     uint64_t* acc_empty = acc_full + kAccStages;    // waited in the leader only
     uint64_t* w_full = acc_empty + kAccStages;      // local weight copy
-    uint64_t* w_ready = w_full + 1;                 // leader: both halves resident
+    uint64_t* w_ready = w_full + 1;                 // leader: the peer's half is resident too
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_ready + 1);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
@@ -151,7 +151,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
         mbar_init(w_full, 1);
-        mbar_init(w_ready, 2);
+        mbar_init(w_ready, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -180,7 +180,6 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             }
             pdl_wait();
             uint32_t stage = 0, phase = 0;
-            bool w_signalled = false;
             for (int p = pair0; p < num_pairs; p += pair_step) {
                 int sp = 2 * p + static_cast<int>(rank);
                 if (sp >= L.spatial_tiles) sp = L.spatial_tiles - 1;       // odd tail: duplicate tile, stores masked
@@ -197,19 +196,21 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                     tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
                     if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
-                if (!w_signalled) {                                        // after the ring is primed: report the weights
-                    mbar_wait(w_full, 0);
-                    mbar_arrive_cluster(mapa_u32(smem_u32(w_ready), 0));
-                    w_signalled = true;
-                }
             }
-            if (!w_signalled) { mbar_wait(w_full, 0); mbar_arrive_cluster(mapa_u32(smem_u32(w_ready), 0)); }
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer (leader CTA only)
-        if (rank == 0 && elect_one()) {
+        if (rank != 0) {
+            // the peer's weight half has landed: tell the leader (the producer thread must not wait for it, it
+            // would stall the A ring; a tile may have more K blocks than the ring has stages)
+            if (elect_one()) {
+                mbar_wait(w_full, 0);
+                mbar_arrive_cluster(mapa_u32(smem_u32(w_ready), 0));
+            }
+        } else if (elect_one()) {
             const uint32_t w_lo = smem_u32(s_w) >> 4, a_lo = smem_u32(s_a) >> 4;
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            mbar_wait(w_full, 0);
             mbar_wait_cluster(w_ready, 0);
             for (int p = pair0; p < num_pairs; p += pair_step) {
                 mbar_wait_cluster(&acc_empty[as], aphase ^ 1);

@@ -17,6 +17,7 @@ Data layout in HBM:
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -117,7 +118,7 @@ def _xslot_array(xs):
 class GEngine:
     """Packed weights of one RRDBNet; geometry-independent."""
 
-    def __init__(self, nb, nz_in, all_layers, out_nc=3, in_nc=3, upscale=4, precise_outer=True):
+    def __init__(self, nb, nz_in, all_layers, out_nc=3, in_nc=3, upscale=4, precise_outer=True, pair=True):
         if upscale not in (2, 4):
             raise NotImplementedError("upscale %d: only x2 / x4 (nearest x2 upconv stages) are built" % upscale)
         if in_nc != 3 or out_nc > 16:
@@ -127,6 +128,8 @@ class GEngine:
         self.out_nc, self.upscale = out_nc, upscale
         self.n_up = int(math.log2(upscale))
         self.precise = precise_outer
+        # CTA-pair (cta_group::2) kernels wherever cout >= 32; ESR_PAIR=0 keeps the single-CTA kernel (A/B timing)
+        self.pair = pair and os.environ.get("ESR_PAIR", "1") != "0"
         self.convs = {}
         self.version = None
         self._build_specs()
@@ -188,7 +191,10 @@ class GEngine:
 
     def _add(self, name, cout, kblocks, slots, cout_tile):
         rows = [(co, -1) for co in range(cout)]
-        self.convs[name] = PackedConv(name, cout, kblocks, slots, rows, cout_tile)
+        pair = self.pair and cout_tile == 32
+        if pair and cout % 64 == 0:
+            cout_tile = 64                             # N = 192: the activation tile is read once for all 64 channels
+        self.convs[name] = PackedConv(name, cout, kblocks, slots, rows, cout_tile, pair=pair)
 
     # ---------------------------------------------------------------- packing
     def pack(self, params):

@@ -32,7 +32,10 @@ def test_plain_conv_f32_out(cuda_device, impl, B, H, W, cin, cout):
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("B,H,W,cin,cout,ct", [(1, 8, 30, 32, 32, 32), (2, 20, 20, 64, 32, 32), (1, 13, 70, 96, 64, 32),
                                                (1, 9, 33, 192, 64, 64), (3, 21, 95, 160, 32, 32), (2, 23, 61, 64, 64, 64),
-                                               (1, 4, 30, 32, 64, 64), (1, 37, 151, 64, 128, 64)])
+                                               (1, 4, 30, 32, 64, 64), (1, 37, 151, 64, 128, 64),
+                                               # several tiles per cluster (ring / accumulator-stage reuse) and
+                                               # more K blocks per tile than ring stages
+                                               (8, 70, 95, 224, 64, 64), (8, 70, 95, 256, 32, 32), (9, 41, 61, 64, 64, 32)])
 def test_pair_conv_f32_out(cuda_device, impl, B, H, W, cin, cout, ct):
     """cta_group::2 kernel (CTA pairs, M = 256) and the pair weight layout: odd tile counts, one or two cout
     tiles, N = 96 (two bands per CTA) and N = 192 (one band per CTA)."""

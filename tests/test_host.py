@@ -95,7 +95,7 @@ def test_engine_layout_arithmetic():
     c0 = e.convs["model.1.sub.0.RDB1.convs.0.0"]
     assert (c0.nkb, c0.cout_tiles, c0.w_tile_bytes) == (3, 1, 2 * 18432 + 6144)
     c4 = e.convs["model.1.sub.0.RDB1.convs.4.0"]
-    assert (c4.nkb, c4.cout_tiles) == (7, 2) and c4.w_tile_bytes <= 124 * 1024
+    assert (c4.nkb, c4.cout_tile, c4.cout_tiles, c4.pair) == (7, 64, 1, 1) and c4.w_tile_bytes // 2 <= 124 * 1024
     lr_conv = e.convs["model.1.sub.23"]
     assert lr_conv.nkb == 8 and [k.chan for k in list(lr_conv.kblocks)[:6]] == [0, 32, 64, 96, 0, 32]
     xs, ws = expand_slots(6, precise=True)
