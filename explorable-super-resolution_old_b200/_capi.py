@@ -15,6 +15,7 @@ KBLOCK_CH = 32
 CEM_MAX_TAPS = 64
 
 EPI_LRELU, EPI_RES1, EPI_RES2, EPI_ACCUM, EPI_MASK, EPI_F32_BLOCKED = 1, 2, 4, 8, 16, 32
+CONV_F16, EPI_OUT_F16 = 64, 128
 
 
 class KBlock(C.Structure):

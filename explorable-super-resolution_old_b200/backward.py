@@ -198,16 +198,16 @@ class BackwardPlan:
         # ---- HR convs
         pc = self.specs.convs[names[-1]]
         self._conv(names[-1], H4, W4, self.E6, self.GH, 96, out_bf16=self.GV, bf16_stride=128, lo_choff=lo,
-                   only_bf16_tiles=(0, 1), mask=plan.V2, mask_stride=128)
+                   only_bf16_tiles=(0, 1), mask=plan.V2, mask_stride=plan.V2.shape[-1])
         self._conv(names[-2], H4, W4, self.GV, self.GH, 96, accum=nz > 0, no_accum=0b011, out_bf16=self.GV1,
-                   bf16_stride=128, lo_choff=lo, only_bf16_tiles=(0, 1), mask=plan.V1, mask_stride=128)
+                   bf16_stride=128, lo_choff=lo, only_bf16_tiles=(0, 1), mask=plan.V1, mask_stride=plan.V1.shape[-1])
         # ---- upconvs, top down; each followed by the 2x2 sum-pool adjoint of the nearest upsample
         for u in reversed(range(eng.n_up)):
             res = 2 ** (u + 1)
             self._conv(names[1 + u], res * hp, res * wp, self.GVu[u], self.GU[u], 64)
             lowH, lowW = res // 2 * hp, res // 2 * wp
             if u > 0:      # below sits upconv u-1, whose LeakyReLU output was stored 2x2-replicated in plan.U[u]
-                self._combine(self.GU[u], 64, 0, 2, None, lowH, lowW, None, plan.U[u], 128, 2, 1.0, self.GVu[u - 1], eng.precise)
+                self._combine(self.GU[u], 64, 0, 2, None, lowH, lowW, None, plan.U[u], plan.U[u].shape[-1], 2, 1.0, self.GVu[u - 1], eng.precise)
             else:          # below sits the trunk shortcut sum (no activation)
                 self._combine(self.GU[0], 64, 0, 2, None, lowH, lowW, self.Gsc, None, 0, 1, 1.0, self.GS, eng.precise)
         # ---- LR_conv: H = d(last RRDB output) -> frame (3nb)%4, emits 0.04*H for RDB3.conv5 of the last RRDB

@@ -11,6 +11,7 @@
 // which is why each 32-column tile produces 30 output columns.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "esr_common.cuh"
 
@@ -45,6 +46,22 @@ __host__ __device__ inline uint32_t sw64_offset(uint32_t n, uint32_t k) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&p);
+}
+// two floats -> packed fp16 pair (a in the low half), round to nearest, overflow saturates to +-65504
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// 16-bit operand storage: term 0 = bf16(v), 1 = bf16(v - bf16(v)), 2 = fp16(v)
+__device__ __forceinline__ uint16_t operand_bits(float v, int term) {
+    if (term == 2) return static_cast<uint16_t>(pack_f16x2_sat(v, 0.f) & 0xffffu);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 r = term == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    return *reinterpret_cast<const uint16_t*>(&r);
+}
+__device__ __forceinline__ float operand_value(uint16_t bits, bool f16) {
+    return f16 ? __half2float(*reinterpret_cast<const __half*>(&bits)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&bits));
 }
 __device__ __forceinline__ float bf16_lo_part(float a) {     // a - bf16(a)
     return a - __bfloat162float(__float2bfloat16_rn(a));
@@ -86,6 +103,12 @@ __device__ __forceinline__ void store16f(float* p, const float* r, bool wide) {
 
 constexpr int kEpiGeneric = 0;   // every flag / output decided at run time
 constexpr int kEpiTrunk = 1;     // bias + LeakyReLU -> bf16 slice of the dense-block buffer (conv 0..3 of an RDB)
+constexpr int kEpiRes = 2;       // conv 4 of an RDB: alpha*(acc+bias) + gamma*res1 [, beta*. + res2] -> blocked f32 trunk
+                                 // + 16-bit slice (block.py:235, :270)
+constexpr int kEpiAct = 3;       // bias [+ LeakyReLU] -> 16-bit NHWC (bf16 or fp16), optionally replicated 2x2 (upconv / HR conv)
+constexpr int kEpiNchw = 4;      // bias -> f32 NCHW, first cout_real channels (last conv of the generator)
+// The generic epilogue costs ~5000 clk per 128-pixel x 64-channel tile (issue bound: two epilogue warps per
+// scheduler walking run-time flags); the specialised ones are bound by the TMEM read of the three dx slabs (~1600).
 
 // Address of 8 consecutive f32 channels [c, c+8) (c % 8 == 0) of pixel (n,y,x) in a trunk tensor with C = `stride`
 // channels: NHWC, or blocked [B, C/8, H, W, 8] where the 32 pixels of a warp form one contiguous 1 KiB run.
@@ -139,7 +162,16 @@ __device__ __forceinline__ uint32_t tile_flags(const esr_conv_desc& d, int ct) {
 template <int MODE>
 __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, int ct, int n, int y, int x, int co0,
                                                        EpiOperands& P) {
-    if constexpr (MODE == kEpiTrunk) return;
+    if constexpr (MODE == kEpiTrunk || MODE == kEpiAct || MODE == kEpiNchw) return;
+    if constexpr (MODE == kEpiRes) {
+        ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
+        ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
+        if (d.flags & ESR_EPI_RES2) {
+            ld_global_v8f(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0), P.r2);
+            ld_global_v8f(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0 + 8), P.r2 + 8);
+        }
+        return;
+    }
     const uint32_t flags = tile_flags(d, ct);
     const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
     if (flags & ESR_EPI_ACCUM) load16f_at(d, d.out_f32, d.out_f32_stride, d.out_f32_choff, n, y, x, co0, P.r1);
@@ -170,6 +202,60 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
         for (int i = 0; i < 8; ++i)
             pk[i] = pack_bf16x2(fmaxf(v[2 * i], d.slope * v[2 * i]), fmaxf(v[2 * i + 1], d.slope * v[2 * i + 1]));
         st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
+        return;
+    }
+    if constexpr (MODE == kEpiRes) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + d.gamma * P.r1[i];
+        if (d.flags & ESR_EPI_RES2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = d.beta * v[i] + P.r2[i];
+        }
+        st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), v);
+        st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
+        uint32_t pk[8];
+        if (d.flags & ESR_EPI_OUT_F16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        }
+        st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
+        return;
+    }
+    if constexpr (MODE == kEpiAct) {
+        if (d.flags & ESR_EPI_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], d.slope * v[i]);
+        }
+        uint32_t pk[8];
+        if (d.flags & ESR_EPI_OUT_F16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        }
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + d.out_bf16_choff + co0;
+        if (d.up == 1) {
+            st_global_v8(ob + pix * d.out_bf16_stride, pk);
+        } else {                                     // nearest x2: the next conv reads the upsampled tensor
+            const size_t ow = static_cast<size_t>(d.W) * 2;
+            const size_t o00 = (static_cast<size_t>(n) * d.H * 2 + static_cast<size_t>(y) * 2) * ow + static_cast<size_t>(x) * 2;
+            st_global_v8(ob + o00 * d.out_bf16_stride, pk);
+            st_global_v8(ob + (o00 + 1) * d.out_bf16_stride, pk);
+            st_global_v8(ob + (o00 + ow) * d.out_bf16_stride, pk);
+            st_global_v8(ob + (o00 + ow + 1) * d.out_bf16_stride, pk);
+        }
+        return;
+    }
+    if constexpr (MODE == kEpiNchw) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int co = co0 + i;
+            if (co < d.cout_real) d.out_nchw[((static_cast<size_t>(n) * d.cout_real + co) * d.H + y) * d.W + x] = v[i];
+        }
         return;
     }
     const uint32_t flags = tile_flags(d, ct);
@@ -209,13 +295,18 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= d.out_bf16_scale;
         if (flags & ESR_EPI_MASK) {
-            const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(P.m);
+            const uint16_t* mv = reinterpret_cast<const uint16_t*>(P.m);   // raw bits: bf16 or fp16 activations
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= (__bfloat162float(mv[i]) > 0.f ? 1.f : d.slope);
+            for (int i = 0; i < 16; ++i) v[i] *= ((mv[i] & 0x8000u) == 0 && (mv[i] & 0x7fffu) != 0) ? 1.f : d.slope;
         }
         uint32_t pk[8];
+        if (flags & ESR_EPI_OUT_F16) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) pk[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        }
         const uint4 h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         const bool want_lo = d.out_bf16_lo_choff >= 0;
         uint4 l0 = h0, l1 = h1;
@@ -243,6 +334,29 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
             }
         }
     }
+}
+
+// Picks the cheapest epilogue specialisation that implements the descriptor exactly.
+inline int classify_epilogue(const esr_conv_desc& d) {
+    for (int t = 0; t < d.cout_tiles; ++t)
+        if (d.tile_choff[t] >= 0) return kEpiGeneric;
+    if (d.no_accum_tiles || d.no_bf16_tiles || d.no_res_tiles) return kEpiGeneric;
+    const uint32_t f = d.flags & ~static_cast<uint32_t>(ESR_EPI_WIDE_OK | ESR_CONV_F16);
+    const auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    const bool bf_ok = d.out_bf16 != nullptr && d.out_bf16_lo_choff < 0 && d.out_bf16_scale == 1.0f && d.out_bf16_stride % 16 == 0 &&
+                       d.out_bf16_choff % 16 == 0 && al32(d.out_bf16);
+    if ((f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && bf_ok && d.out_f32 == nullptr && d.out_nchw == nullptr &&
+        d.up == 1 && d.cout_tile == 32)
+        return kEpiTrunk;
+    if ((f & ~static_cast<uint32_t>(ESR_EPI_RES2 | ESR_EPI_OUT_F16)) == (ESR_EPI_RES1 | ESR_EPI_F32_BLOCKED) && bf_ok && d.up == 1 &&
+        d.out_f32 != nullptr && d.out_nchw == nullptr && d.res1 != nullptr && (!(f & ESR_EPI_RES2) || d.res2 != nullptr))
+        return kEpiRes;      // blocked-layout alignment was validated (validate_conv_desc)
+    if ((f & ~static_cast<uint32_t>(ESR_EPI_LRELU | ESR_EPI_OUT_F16 | ESR_EPI_F32_BLOCKED)) == 0 && bf_ok && d.out_f32 == nullptr &&
+        d.out_nchw == nullptr)
+        return kEpiAct;
+    if ((f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == 0 && d.out_nchw != nullptr && d.out_bf16 == nullptr && d.out_f32 == nullptr)
+        return kEpiNchw;
+    return kEpiGeneric;
 }
 
 }  // namespace esr

@@ -26,12 +26,13 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
         const uint8_t* wt = reinterpret_cast<const uint8_t*>(d.wpack) + static_cast<size_t>(ct) * d.w_tile_bytes;
         const int slab_rows = d.pair ? N / 2 : N;            // pair layout: each CTA's half image holds N/2 rows per slab
         const size_t half_bytes = d.w_tile_bytes / 2;
+        const bool f16 = (d.flags & ESR_CONV_F16) != 0;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
         for (int kb = 0; kb < d.num_kblocks; ++kb) {
             const esr_kblock& K = d.kblocks[kb];
-            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(d.src[K.src].ptr);
+            const uint16_t* src = reinterpret_cast<const uint16_t*>(d.src[K.src].ptr);
             const int sc = d.src[K.src].channels;
             int wi = 0;
             for (int dy = 0; dy < 3; ++dy) {
@@ -43,16 +44,16 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
                 for (int dx = 0; dx < 3; ++dx) {
                     const int xx = x + dx - 1;
                     if (xx < 0 || xx >= d.W) continue;
-                    const __nv_bfloat16* a = src + ((static_cast<size_t>(n) * d.H + yy) * d.W + xx) * sc + K.chan;
+                    const uint16_t* a = src + ((static_cast<size_t>(n) * d.H + yy) * d.W + xx) * sc + K.chan;
                     for (int k = 0; k < kKB; ++k) {
                         if (!((K.slice_mask >> (k >> 4)) & 1)) continue;
-                        const float av = __bfloat162float(a[k]);
+                        const float av = operand_value(a[k], f16);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int nrow = dx * CT + col0 + i;
-                            const __nv_bfloat16 w = *reinterpret_cast<const __nv_bfloat16*>(
+                            const uint16_t w = *reinterpret_cast<const uint16_t*>(
                                 wslab + (nrow / slab_rows) * half_bytes + sw64_offset(nrow % slab_rows, k));
-                            v[i] = fmaf(av, __bfloat162float(w), v[i]);
+                            v[i] = fmaf(av, operand_value(w, f16), v[i]);
                         }
                     }
                 }
@@ -110,12 +111,11 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
             }
             if (live) w = a.wsrc[a.off + row.idx * a.s_row + slot.idx * a.s_slot + ky * a.s_ky + dx * a.s_kx];
         }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        const __nv_bfloat16 val = slot.term == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+        const uint16_t val = operand_bits(w, slot.term);
         const int slab_rows = a.pair ? N / 2 : N;            // pair layout: rows [r*N/2, (r+1)*N/2) live in CTA r's half image
         uint8_t* dst = a.out + static_cast<size_t>(ct) * a.w_tile_bytes + (n / slab_rows) * (a.w_tile_bytes / 2) + K.w_off +
                        static_cast<size_t>(wi) * slab_rows * kRowBytes + sw64_offset(n % slab_rows, k);
-        *reinterpret_cast<__nv_bfloat16*>(dst) = val;
+        *reinterpret_cast<uint16_t*>(dst) = val;
     }
     const int nb = a.cout_tiles * CT;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
@@ -143,7 +143,7 @@ __global__ void expand_rows_kernel(const __grid_constant__ ExpandArgs a) {
         const int n = static_cast<int>(pix / (static_cast<size_t>(a.W) * a.H));
         __nv_bfloat16* dst = a.dst + pix * a.nslots;
         for (int s0 = 0; s0 < a.nslots; s0 += 8) {
-            __align__(16) __nv_bfloat16 o[8];
+            __align__(16) uint16_t o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const esr_xslot sl = a.slots[s0 + i];
@@ -151,8 +151,7 @@ __global__ void expand_rows_kernel(const __grid_constant__ ExpandArgs a) {
                 const int yy = y + sl.dy;
                 if (sl.c >= 0 && yy >= 0 && yy < a.H)    // <= 18 distinct addresses per pixel, coalesced along x, L1 hits
                     val = __ldg(a.src + ((static_cast<size_t>(n) * a.C + sl.c) * a.H + yy) * a.W + x);
-                const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-                o[i] = sl.term == 0 ? hi : __float2bfloat16_rn(val - __bfloat162float(hi));
+                o[i] = operand_bits(val, sl.term);
             }
             *reinterpret_cast<uint4*>(dst + s0) = *reinterpret_cast<const uint4*>(o);
         }

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                   const __grid_constant__ ConvLaunch L) {
     constexpr int N = 3 * CT;
-    constexpr uint32_t kIdesc = umma_idesc_bf16_m128(N);
+    // operand format bits: a_format [7,10) and b_format [10,13) are 1 for bf16, 0 for fp16
+    const uint32_t kIdesc = umma_idesc_bf16_m128(N) & ((L.d.flags & ESR_CONV_F16) ? ~((1u << 7) | (1u << 10)) : ~0u);
     constexpr uint32_t kARow16 = (kTileW * kRowBytes) >> 4;   // one halo-tile row, in 16-byte units
     constexpr uint32_t kWSlab16 = (N * kRowBytes) >> 4;       // one [N x 32ch] weight slab
     const esr_conv_desc& d = L.d;
@@ -408,24 +409,21 @@ int num_sms_cached() {
     return n;
 }
 
-static bool is_trunk_epilogue(const esr_conv_desc& d) {
-    for (int t = 0; t < d.cout_tiles; ++t)
-        if (d.tile_choff[t] >= 0) return false;
-    return (d.flags & ~static_cast<uint32_t>(ESR_EPI_WIDE_OK | ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && d.out_bf16 != nullptr && d.out_f32 == nullptr && d.out_nchw == nullptr &&
-           d.out_bf16_lo_choff < 0 && d.up == 1 && d.out_bf16_scale == 1.0f && d.cout_tile == 32 &&
-           d.out_bf16_stride % 16 == 0 && d.out_bf16_choff % 16 == 0 &&
-           (reinterpret_cast<uintptr_t>(d.out_bf16) & 31) == 0;   // 32-byte stores
-}
-
 int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream, int use_pdl);
 
 int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream) {
     if (L.pair_nb) return launch_conv_tc2(tm0, tm1, L, stream, g_use_pdl);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ConvLaunch);
+    static const KernelFn kernels[2][5] = {
+        {conv3x3_tc_kernel<16, kEpiGeneric>, conv3x3_tc_kernel<16, kEpiGeneric>, conv3x3_tc_kernel<16, kEpiGeneric>,
+         conv3x3_tc_kernel<16, kEpiGeneric>, conv3x3_tc_kernel<16, kEpiNchw>},
+        {conv3x3_tc_kernel<32, kEpiGeneric>, conv3x3_tc_kernel<32, kEpiTrunk>, conv3x3_tc_kernel<32, kEpiRes>,
+         conv3x3_tc_kernel<32, kEpiAct>, conv3x3_tc_kernel<32, kEpiGeneric>}};
     static bool attr_set = false;
     if (!attr_set) {
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<32, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<32, kEpiTrunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<16, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 5; ++b)
+                ESR_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_set = true;
     }
     ESR_CHECK_ARG(L.nstages >= 2, "conv weights (%u B per cout tile) leave no room for the A-tile ring", L.d.w_tile_bytes);
@@ -445,13 +443,7 @@ int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLau
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    cudaError_t e;
-    if (L.d.cout_tile == 16)
-        e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<16, kEpiGeneric>, tm0, tm1, L);
-    else if (is_trunk_epilogue(L.d))
-        e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<32, kEpiTrunk>, tm0, tm1, L);
-    else
-        e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<32, kEpiGeneric>, tm0, tm1, L);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[L.d.cout_tile == 16 ? 0 : 1][classify_epilogue(L.d)], tm0, tm1, L);
     if (e != cudaSuccess) { set_error("conv3x3_tc_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
     return check_launch("conv3x3_tc_kernel");
 }

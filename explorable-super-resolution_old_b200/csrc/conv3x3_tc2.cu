@@ -17,11 +17,24 @@
 #include "conv3x3.cuh"
 #include "ptx_sm100.cuh"
 
+// Per-role cycle counters (tools/prof.py); compiled in only with -DESR_PROFILE_ROLES.
+#ifdef ESR_PROFILE_ROLES
+#define ESR_PROF(...) __VA_ARGS__
+#else
+#define ESR_PROF(...)
+#endif
+
 namespace esr {
 
 namespace pair {
 
-constexpr int kMaxStages = 6;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+constexpr int kMaxStages = 10;
 constexpr int kAccStages = 2;
 constexpr int kEpiWarps = 8;
 constexpr int kNumThreads = 64 + 32 * kEpiWarps;   // 320
@@ -44,27 +57,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
+// Remote arrive WITHOUT cluster-scope release: that form compiles to MEMBAR.ALL.GPU (it would drain the epilogue's
+// global stores on every tile).  Nothing written by the generic proxy is handed over through these barriers: the
+// accumulator hand-back is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_local(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    for (uint32_t it = 0; !mbar_try_wait_cluster(bar, parity); ++it) {
-        if (it > (1u << 26)) { __trap(); }
-    }
 }
 // TMA tile load whose completion bytes are credited to the barrier at `leader_bar_addr` (CTA 0 of the pair)
 __device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const void* tmap, uint32_t leader_bar_addr, int c0, int c1,
@@ -116,7 +116,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     constexpr int kRows = NB * kBandRows + 2;      // halo rows per A tile
     constexpr int kATile = kRows * kTileW * kRowBytes;
     constexpr int kAccSlot = CT == 32 ? 128 : 256; // TMEM columns per band accumulator
-    constexpr uint32_t kIdesc = idesc_bf16_m256(N);
+    // operand format bits: a_format [7,10) and b_format [10,13) are 1 for bf16, 0 for fp16
+    const uint32_t kIdesc = idesc_bf16_m256(N) & ((L.d.flags & ESR_CONV_F16) ? ~((1u << 7) | (1u << 10)) : ~0u);
     constexpr uint32_t kARow16 = (kTileW * kRowBytes) >> 4;
     constexpr uint32_t kWSlab16 = ((N / 2) * kRowBytes) >> 4;     // this CTA's half of one [N x 32ch] slab
     const esr_conv_desc& d = L.d;
@@ -139,6 +140,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
+    ESR_PROF(if (L.prof && threadIdx.x == 0) L.prof[blockIdx.x * 16 + 12] = gtime_ns();)
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int ct = cluster_id % d.cout_tiles;
     const int pair0 = cluster_id / d.cout_tiles, pair_step = num_clusters / d.cout_tiles;
@@ -148,7 +150,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap0);
         tma_prefetch_desc(&tmap1);
-        for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
         mbar_init(w_full, 1);
         mbar_init(w_ready, 1);
@@ -162,6 +164,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     cluster_sync_all();                             // both CTAs' barriers and TMEM are ready
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ESR_PROF(if (L.prof && threadIdx.x == 0) L.prof[blockIdx.x * 16 + 13] = gtime_ns();)
     pdl_launch_dependents();
 
     const int nkb = d.num_kblocks;
@@ -180,6 +183,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             }
             pdl_wait();
             uint32_t stage = 0, phase = 0;
+            ESR_PROF(long long p_wait = 0, p_t0 = clock64(), p_n = 0; if (L.prof) L.prof[blockIdx.x * 16 + 6] = gtime_ns();)
             for (int p = pair0; p < num_pairs; p += pair_step) {
                 int sp = 2 * p + static_cast<int>(rank);
                 if (sp >= L.spatial_tiles) sp = L.spatial_tiles - 1;       // odd tail: duplicate tile, stores masked
@@ -189,14 +193,22 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                 const int x0 = tx * kTileWOut - 1, y0 = ty * (NB * kBandRows) - 1;
                 for (int kb = 0; kb < nkb; ++kb) {
                     const esr_kblock& K = d.kblocks[kb];
-                    mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+                    ESR_PROF(const long long w0c = clock64();)
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ESR_PROF(p_wait += clock64() - w0c; ++p_n;)
                     const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                    if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);   // both CTAs' tiles
-                    else mbar_arrive_cluster(lead_full);
+                    // only the leader arrives, expecting both CTAs' tiles; the peer's bytes may be credited before
+                    // that (a transiently negative tx-count is legal), never to an older phase: the peer issues
+                    // only after its copy of the multicast "stage free" commit
+                    if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
                     tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
                     if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
             }
+            ESR_PROF(if (L.prof) {
+                unsigned long long* o = L.prof + blockIdx.x * 16;
+                o[0] = clock64() - p_t0; o[1] = p_wait; o[2] = p_n;
+            })
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer (leader CTA only)
@@ -210,10 +222,14 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         } else if (elect_one()) {
             const uint32_t w_lo = smem_u32(s_w) >> 4, a_lo = smem_u32(s_a) >> 4;
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            ESR_PROF(long long m_t0 = clock64(), m_wacc = 0, m_wfull = 0; bool first_full = true;)
             mbar_wait(w_full, 0);
-            mbar_wait_cluster(w_ready, 0);
+            mbar_wait(w_ready, 0);
+            ESR_PROF(const long long m_tw = clock64() - m_t0;)
             for (int p = pair0; p < num_pairs; p += pair_step) {
-                mbar_wait_cluster(&acc_empty[as], aphase ^ 1);
+                ESR_PROF(long long c0 = clock64();)
+                mbar_wait(&acc_empty[as], aphase ^ 1);
+                ESR_PROF(m_wacc += clock64() - c0;)
                 tc_fence_after();
                 const uint32_t acc0 = tmem_base + as * (NB * kAccSlot);
                 uint32_t nonfirst = 0;
@@ -221,7 +237,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                     const uint32_t masks = *reinterpret_cast<const uint32_t*>(&d.kblocks[kb].dy_mask);
                     const uint32_t dy_mask = masks & 0xff, slice_mask = (masks >> 8) & 0xff;
                     const uint32_t w0 = w_lo + (d.kblocks[kb].w_off >> 4);
-                    mbar_wait_cluster(&full_bar[stage], phase);
+                    ESR_PROF(c0 = clock64();)
+                    mbar_wait(&full_bar[stage], phase);
+                    ESR_PROF(m_wfull += clock64() - c0; if (first_full && L.prof) { L.prof[blockIdx.x * 16 + 10] = gtime_ns(); first_full = false; })
                     tc_fence_after();
                     const uint32_t a0 = a_lo + stage * (kATile >> 4);
                     if (dy_mask == 7u && slice_mask == 3u) {
@@ -258,6 +276,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                 umma_commit2(&acc_full[as]);
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
+            ESR_PROF(if (L.prof) {
+                unsigned long long* o = L.prof + blockIdx.x * 16;
+                o[3] = clock64() - m_t0; o[4] = m_wacc; o[5] = m_wfull; o[9] = m_tw; o[14] = gtime_ns();
+            })
         }
     } else {
         // ---------------------------------------------------------------- epilogue (each CTA: its own tile)
@@ -268,6 +290,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         const uint32_t lead_acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
         pdl_wait();
         uint32_t as = 0, aphase = 0;
+        ESR_PROF(long long e_t0 = clock64(), e_wait = 0, e_n = 0;)
         for (int p = pair0; p < num_pairs; p += pair_step) {
             const int sp_raw = 2 * p + static_cast<int>(rank);
             const bool tile_ok = sp_raw < L.spatial_tiles;
@@ -284,7 +307,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                 for (int h = 0; h < 2; ++h)
                     conv_epilogue_prefetch<MODE>(d, ct, n, y, x, tile_channel(d, ct, cbase + h * 16), ops[h]);
             }
-            mbar_wait_cluster(&acc_full[as], aphase);
+            ESR_PROF(long long c0 = clock64();)
+            mbar_wait(&acc_full[as], aphase);
+            ESR_PROF(e_wait += clock64() - c0; ++e_n;)
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * (NB * kAccSlot) + b * kAccSlot + cbase + (static_cast<uint32_t>(wq * 32) << 16);
             float vc[32];
@@ -315,6 +340,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
+        ESR_PROF(if (L.prof && warp == 2 && lane == 1) {
+            unsigned long long* o = L.prof + blockIdx.x * 16;
+            o[7] = clock64() - e_t0; o[8] = e_wait; o[11] = e_n; o[15] = gtime_ns();
+        })
     }
 
     tc_fence_before();
@@ -328,14 +357,6 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
 }  // namespace pair
 
 int num_sms_cached();
-
-static bool is_trunk_epilogue2(const esr_conv_desc& d) {
-    for (int t = 0; t < d.cout_tiles; ++t)
-        if (d.tile_choff[t] >= 0) return false;
-    return (d.flags & ~static_cast<uint32_t>(ESR_EPI_WIDE_OK | ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && d.out_bf16 != nullptr &&
-           d.out_f32 == nullptr && d.out_nchw == nullptr && d.out_bf16_lo_choff < 0 && d.up == 1 && d.out_bf16_scale == 1.0f &&
-           d.out_bf16_stride % 16 == 0 && d.out_bf16_choff % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out_bf16) & 31) == 0;
-}
 
 // Fills the pair-mode launch geometry; returns false if the weights leave no room for the A ring.
 bool fill_launch_pair(ConvLaunch* L) {
@@ -355,11 +376,17 @@ bool fill_launch_pair(ConvLaunch* L) {
 
 int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream, int use_pdl) {
     using namespace pair;
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ConvLaunch);
+    static const KernelFn kernels[2][4] = {
+        {conv3x3_tc2_kernel<32, kEpiGeneric>, conv3x3_tc2_kernel<32, kEpiTrunk>, conv3x3_tc2_kernel<32, kEpiRes>,
+         conv3x3_tc2_kernel<32, kEpiAct>},
+        {conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiRes>,
+         conv3x3_tc2_kernel<64, kEpiAct>}};
     static bool attr_set = false;
     if (!attr_set) {
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<32, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<32, kEpiTrunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        ESR_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, kEpiGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 4; ++b)
+                ESR_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_set = true;
     }
     const int nb = L.d.cout_tile == 32 ? 2 : 1;
@@ -382,13 +409,9 @@ int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLa
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 2 : 1;
-    cudaError_t e;
-    if (L.d.cout_tile == 64)
-        e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<64, kEpiGeneric>, tm0, tm1, L);
-    else if (is_trunk_epilogue2(L.d))
-        e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<32, kEpiTrunk>, tm0, tm1, L);
-    else
-        e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<32, kEpiGeneric>, tm0, tm1, L);
+    int mode = classify_epilogue(L.d);
+    if (mode > kEpiAct) mode = kEpiGeneric;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[L.d.cout_tile == 64 ? 1 : 0][mode], tm0, tm1, L);
     if (e != cudaSuccess) { set_error("conv3x3_tc2_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
     return check_launch("conv3x3_tc2_kernel");
 }

@@ -296,7 +296,10 @@ __global__ void grad_combine_kernel(const __grid_constant__ CombineArgs a) {
                                                        (static_cast<size_t>(a.W) * a.mask_sub) + static_cast<size_t>(x) * a.mask_sub) *
                                                       a.mask_stride + a.mask_choff + c0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] *= (__bfloat162float(m[i]) > 0.f ? 1.f : a.slope);
+                for (int i = 0; i < 8; ++i) {   // sign test on the raw bits: the stored activation may be bf16 or fp16
+                    const uint16_t bits = reinterpret_cast<const uint16_t*>(m)[i];
+                    w[i] *= ((bits & 0x8000u) == 0 && (bits & 0x7fffu) != 0) ? 1.f : a.slope;
+                }
             }
             __nv_bfloat16* o = a.out_bf16 + ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.bf16_stride;
 #pragma unroll

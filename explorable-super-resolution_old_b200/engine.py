@@ -11,9 +11,11 @@ Data layout in HBM:
   * the residual trunk (RDB / RRDB / shortcut sums) stays fp32 NHWC [B,H,W,64];
   * the 3-channel latent is expanded once per resolution over the filter rows into a 32-channel
     bf16 tensor shared by all 346+2 convs that take it;
-  * the six convs outside the residual-scaled trunk (first, LR_conv, 2 upconvs, 2 HR convs) run
-    in split-bf16 (hi+lo operands, three MMA terms): they carry most of the bf16 rounding error
-    and only 7.8 % of the FLOPs.
+  * the six convs outside the residual-scaled trunk (first, LR_conv, 2 upconvs, 2 HR convs) carry
+    most of the operand-rounding error (oracle experiment in DESIGN.md: all-bf16 55 dB / 8e-3 max,
+    bf16 trunk + fp16 outer 72 dB / 1e-3) and 7.8 % of the FLOPs.  outer_mode "f16" (default) runs them
+    with fp16 operands (one MMA term, fp32 accumulate); "split" keeps bf16 hi+lo pairs (three terms,
+    ~2^-16 relative); "bf16" is the plain single-term bf16 form.
 """
 import ctypes as C
 import math
@@ -76,18 +78,27 @@ class PackedConv:
         self._keep = (rows_d, slots_d)  # until the stream has consumed them
 
 
-def expand_slots(nvals_channels, precise):
+def expand_slots(nvals_channels, precise, second="lo"):
     """Slot table of a row-expanded small-channel tensor.
 
     values v = (dy, c) for dy in 0..2, c in range(nvals_channels).
-    precise: [hi(v)... | lo(v)... | hi(v)...] padded to a multiple of 32 (three split-bf16 terms)
-    else   : [hi(v)..., pad to 16 | lo(v)..., pad to 16]  (trunk uses slice 0 only)
+    precise == "f16": [fp16(v)...] padded to a multiple of 32 (one term)
+    precise is True : [hi(v)... | lo(v)... | hi(v)...] padded to a multiple of 32 (three split-bf16 terms)
+    else            : [hi(v)..., pad to 16 | second(v)..., pad to 16] where second is the bf16 residue ("lo") or
+                      fp16(v) ("f16"); the trunk convs read slice 0 only, the outer convs slice 1 (f16) or both
     Returns (xslots for esr_expand_rows, wslots template [(value index, dy, term)] per slot).
     """
     vals = [(dy, c) for dy in range(3) for c in range(nvals_channels)]
     V = len(vals)
     xs, ws = [], []
-    if precise:
+    if precise == "f16":
+        for (dy, c) in vals:
+            xs.append((c, dy - 1, 2))
+            ws.append((c, dy, 2))
+        while len(xs) % 32:
+            xs.append((-1, 0, 0))
+            ws.append((-1, -1, 0))
+    elif precise:
         n = ((3 * V + 31) // 32) * 32
         for part, (xterm, wterm) in enumerate(((0, 0), (1, 0), (0, 1))):
             for (dy, c) in vals:
@@ -98,10 +109,10 @@ def expand_slots(nvals_channels, precise):
             ws.append((-1, -1, 0))
     else:
         assert V <= 16
-        for xterm in (0, 1):
+        for xterm in (0, 2 if second == "f16" else 1):
             for (dy, c) in vals:
                 xs.append((c, dy - 1, xterm))
-                ws.append((c, dy, 0))
+                ws.append((c, dy, 2 if xterm == 2 else 0))
             while len(xs) % 16:
                 xs.append((-1, 0, 0))
                 ws.append((-1, -1, 0))
@@ -118,7 +129,8 @@ def _xslot_array(xs):
 class GEngine:
     """Packed weights of one RRDBNet; geometry-independent."""
 
-    def __init__(self, nb, nz_in, all_layers, out_nc=3, in_nc=3, upscale=4, precise_outer=True, pair=True):
+    def __init__(self, nb, nz_in, all_layers, out_nc=3, in_nc=3, upscale=4, precise_outer=True, pair=True,
+                 outer_mode=None):
         if upscale not in (2, 4):
             raise NotImplementedError("upscale %d: only x2 / x4 (nearest x2 upconv stages) are built" % upscale)
         if in_nc != 3 or out_nc > 16:
@@ -127,7 +139,9 @@ class GEngine:
         self.nz = nz_in if all_layers else 0          # latent channels concatenated to every later conv
         self.out_nc, self.upscale = out_nc, upscale
         self.n_up = int(math.log2(upscale))
-        self.precise = precise_outer
+        self.precise = precise_outer                   # backward: split-bf16 gradient operands for the outer convs
+        self.outer_mode = outer_mode or os.environ.get("ESR_OUTER_MODE") or ("f16" if precise_outer else "bf16")
+        assert self.outer_mode in ("f16", "split", "bf16")
         # CTA-pair (cta_group::2) kernels wherever cout >= 32; ESR_PAIR=0 keeps the single-CTA kernel (A/B timing)
         self.pair = pair and os.environ.get("ESR_PAIR", "1") != "0"
         self.convs = {}
@@ -135,23 +149,26 @@ class GEngine:
         self._build_specs()
 
     # ------------------------------------------------------------------ specs
-    def _main_blocks(self, nch, precise, src=0):
-        """K blocks + weight slots for `nch` feature channels at buffer channels [0,nch) (hi) and,
-        in precise mode, their bf16 residues at [64,64+nch)."""
+    def _main_blocks(self, nch, mode, src=0):
+        """K blocks + weight slots for `nch` feature channels at buffer channels [0,nch) (bf16 hi, or fp16 in mode
+        "f16") and, in mode "split", their bf16 residues at [64,64+nch)."""
         kb, sl = [], []
-        terms = ((0, 0), (64, 0), (0, 1)) if precise else ((0, 0),)
+        terms = {"split": ((0, 0), (64, 0), (0, 1)), "f16": ((0, 2),)}.get(mode, ((0, 0),))
         for base, wterm in terms:
             for c0 in range(0, nch, 32):
                 kb.append((src, base + c0, DY_ALL, 0b11))
                 sl += [(self.nz + c0 + k, -1, wterm) for k in range(32)]
         return kb, sl
 
-    def _latent_blocks(self, precise, src=1):
+    def _latent_blocks(self, mode, src=1):
         if self.nz == 0:
             return [], []
-        _, ws = expand_slots(self.nz, precise=False)   # E_lat layout: [hi | lo], 16 + 16
+        _, ws = expand_slots(self.nz, precise=False, second=self.lat_second)   # E_lat layout: [hi | lo or f16], 16 + 16
         kb, sl = [], []
-        if precise:
+        if mode == "f16":
+            kb.append((src, 0, DY_CENTRE, 0b10))       # the fp16 copy of the latent rows lives in slice 1
+            sl += list(ws)
+        elif mode == "split":
             kb.append((src, 0, DY_CENTRE, 0b11))
             sl += list(ws)                             # A_hi*W_hi and A_lo*W_hi
             kb.append((src, 0, DY_CENTRE, 0b01))
@@ -162,17 +179,18 @@ class GEngine:
         return kb, sl
 
     def _build_specs(self):
-        p = self.precise
+        p = self.outer_mode
+        self.lat_second = "f16" if p == "f16" else "lo"
         # first conv: every input is row-expanded (E_fea), centre tap only
-        self.fea_xslots, fea_ws = expand_slots(self.nz_in + 3, precise=True)
+        self.fea_xslots, fea_ws = expand_slots(self.nz_in + 3, precise="f16" if p == "f16" else True)
         kb = [(0, c0, DY_CENTRE, 0b11) for c0 in range(0, len(fea_ws), 32)]
         self._add("model.0", NF, kb, fea_ws, 32)
-        self.lat_xslots, _ = expand_slots(max(self.nz, 1), precise=False)
+        self.lat_xslots, _ = expand_slots(max(self.nz, 1), precise=False, second=self.lat_second)
         for r in range(self.nb):
             for d in (1, 2, 3):
                 for i in range(5):
-                    kb, sl = self._main_blocks(NF + GC * i, False)
-                    kb2, sl2 = self._latent_blocks(False)
+                    kb, sl = self._main_blocks(NF + GC * i, "bf16")
+                    kb2, sl2 = self._latent_blocks("bf16")
                     self._add("model.1.sub.%d.RDB%d.convs.%d.0" % (r, d, i), GC if i < 4 else NF, kb + kb2, sl + sl2, 32)
         outer = ["model.1.sub.%d" % self.nb] + ["model.%d.1" % (2 + u) for u in range(self.n_up)] + \
                 ["model.%d" % (2 + self.n_up), "model.%d" % (4 + self.n_up)]
@@ -188,6 +206,7 @@ class GEngine:
                 kb2, sl2 = self._latent_blocks(p)
             last = name == outer[-1]
             self._add(name, self.out_nc if last else NF, kb + kb2, sl + sl2, 16 if last else 32)
+        self.f16_convs = set(["model.0"] + outer) if p == "f16" else set()
 
     def _add(self, name, cout, kblocks, slots, cout_tile):
         rows = [(co, -1) for co in range(cout)]
@@ -243,10 +262,11 @@ class GPlan:
         self.R = [torch.empty(B, hp, wp, NF, **f32) for _ in range(2)]
         self.T = [torch.empty(B, hp, wp, NF, **f32) for _ in range(2)]
         res = [(2 ** (u + 1)) for u in range(eng.n_up)]       # 2, 4
-        self.U = [torch.empty(B, r * hp, r * wp, 128, **bf) for r in res]   # nearest-upsampled inputs of the upconvs
+        oc = 128 if eng.outer_mode == "split" else 64        # split mode stores bf16 hi | lo pairs
+        self.U = [torch.empty(B, r * hp, r * wp, oc, **bf) for r in res]   # nearest-upsampled inputs of the upconvs
         H4, W4 = sf * hp, sf * wp
-        self.V1 = torch.empty(B, H4, W4, 128, **bf)
-        self.V2 = torch.empty(B, H4, W4, 128, **bf) if (keep_activations or eng.n_up < 2) else self.U[-1]
+        self.V1 = torch.empty(B, H4, W4, oc, **bf)
+        self.V2 = torch.empty(B, H4, W4, oc, **bf) if (keep_activations or eng.n_up < 2) else self.U[-1]
         self.y = torch.empty(B, eng.out_nc, H4, W4, **f32)
         self.seq = capi.lib().esr_seq_create()
         self.descs = []
@@ -275,6 +295,8 @@ class GPlan:
             d.kblocks[i] = pc.kblocks[i]
         d.wpack, d.w_tile_bytes, d.bias = pc.wpack.data_ptr(), pc.w_tile_bytes, pc.bias.data_ptr()
         d.flags, d.slope, d.alpha, d.beta = flags | capi.EPI_F32_BLOCKED, 0.2, alpha, beta   # trunk f32 = [B,8,H,W,8]
+        if name in self.eng.f16_convs:
+            d.flags |= capi.CONV_F16
         if res1 is not None:
             d.res1, d.res1_stride, d.res1_choff = res1.data_ptr(), res1.shape[-1], 0
             d.flags |= capi.EPI_RES1
@@ -294,7 +316,8 @@ class GPlan:
         eng, hp, wp = self.eng, self.hp, self.wp
         L = capi.EPI_LRELU
         add = self.descs.append
-        lo = 64 if eng.precise else -1
+        lo = 64 if eng.outer_mode == "split" else -1
+        F16 = capi.EPI_OUT_F16 if eng.outer_mode == "f16" else 0      # outputs consumed by an fp16 conv
         add(self._desc("model.0", hp, wp, self.E_fea, out_f32=self.T_fea, out_bf16=self.buf(0)))
         g = 0
         for r in range(eng.nb):
@@ -307,23 +330,23 @@ class GPlan:
                 for i in range(4):
                     add(self._desc(pre + "%d.0" % i, hp, wp, b, self.E_lat, flags=L, out_bf16=b, out_choff=NF + GC * i))
                 last_rdb = (r == eng.nb - 1 and d == 3)
-                add(self._desc(pre + "4.0", hp, wp, b, self.E_lat, alpha=0.2, res1=xin,
+                add(self._desc(pre + "4.0", hp, wp, b, self.E_lat, flags=F16 if last_rdb else 0, alpha=0.2, res1=xin,
                                beta=0.2, res2=rin if d == 3 else None,
                                out_f32=rout if d == 3 else self.T[(d + 1) % 2],
                                out_bf16=self.buf(g + 1), out_choff=0, lo_choff=lo if last_rdb else -1))
                 g += 1
         trunk_out = self.buf(g)
         names = eng.outer_names
-        add(self._desc(names[0], hp, wp, trunk_out, self.E_lat, alpha=1.0, res1=self.T_fea,
+        add(self._desc(names[0], hp, wp, trunk_out, self.E_lat, flags=F16, alpha=1.0, res1=self.T_fea,
                        out_bf16=self.U[0], lo_choff=lo, up=2))
         H, W = 2 * hp, 2 * wp
         for u in range(eng.n_up):
             last = u == eng.n_up - 1
             dst = self.V1 if last else self.U[u + 1]
-            add(self._desc(names[1 + u], H, W, self.U[u], flags=L, out_bf16=dst, lo_choff=lo, up=1 if last else 2))
+            add(self._desc(names[1 + u], H, W, self.U[u], flags=L | F16, out_bf16=dst, lo_choff=lo, up=1 if last else 2))
             if not last:
                 H, W = 2 * H, 2 * W
-        add(self._desc(names[-2], H, W, self.V1, self.E_lath, flags=L, out_bf16=self.V2, lo_choff=lo))
+        add(self._desc(names[-2], H, W, self.V1, self.E_lath, flags=L | F16, out_bf16=self.V2, lo_choff=lo))
         add(self._desc(names[-1], H, W, self.V2, self.E_lath, out_nchw=self.y))
         for d in self.descs:
             capi.check(capi.lib().esr_seq_add_conv(self.seq, C.byref(d), 1 if use_simt else 0))

@@ -70,6 +70,7 @@ class RRDBNet(nn.Module):
         self._engine, self._engine_key, self._plans = None, None, {}
         self._packed_params, self._dgrad, self._bplans = None, None, {}
         self.precise_outer = True
+        self.outer_mode = None                         # None: engine default ("f16"); "split" | "bf16" for experiments
         self.debug_simt = False
 
     # ------------------------------------------------------------------ engine plumbing
@@ -78,9 +79,9 @@ class RRDBNet(nn.Module):
 
     def engine(self):
         params = dict(self.named_parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params.values()) + (self.precise_outer,)
+        key = tuple((p.data_ptr(), p._version) for p in params.values()) + (self.precise_outer, self.outer_mode)
         if self._engine is None or key != self._engine_key:
-            eng = GEngine(precise_outer=self.precise_outer, **self._cfg)
+            eng = GEngine(precise_outer=self.precise_outer, outer_mode=self.outer_mode, **self._cfg)
             packed = {}
             for name in eng.convs:
                 w, b = params[name + ".weight"], params[name + ".bias"]

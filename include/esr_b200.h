@@ -79,6 +79,10 @@ enum {
     ESR_EPI_MASK = 1u << 4,    /* bf16 output *= (mask > 0 ? 1 : slope) (LeakyReLU')     */
     ESR_EPI_F32_BLOCKED = 1u << 5, /* out_f32 / res1 / res2 use the blocked layout [B, C/8, H, W, 8] (coalesced
                                       32-byte accesses across the pixels of a warp) instead of NHWC; *_stride is C */
+    ESR_CONV_F16 = 1u << 6,    /* MMA operands of this launch (every K block and the packed weights, term 2) are IEEE
+                                  fp16 instead of bf16: the convs outside the residual-scaled trunk, whose operand
+                                  rounding dominates the output error, 11 significant bits instead of 8 */
+    ESR_EPI_OUT_F16 = 1u << 7, /* out_bf16 receives fp16 (round to nearest, saturating) instead of bf16 */
     ESR_EPI_WIDE_OK = 1u << 16 /* internal: set by the library when 32-byte accesses are legal */
 };
 
@@ -142,7 +146,7 @@ typedef struct esr_wrow {
 typedef struct esr_wslot {
     int16_t idx;
     int8_t ky;   /* -1: follows the tap loop */
-    int8_t term; /* 0: bf16(w)   1: bf16(w - bf16(w)) */
+    int8_t term; /* 0: bf16(w)   1: bf16(w - bf16(w))   2: fp16(w) */
 } esr_wslot;
 
 /* Fills w_off / n_dy of every K block and returns the total packed size in bytes
@@ -165,7 +169,7 @@ int esr_pack_conv_weights(const float* wsrc, int64_t off, int64_t s_row, int64_t
 typedef struct esr_xslot {
     int8_t c;    /* source channel, -1 = zero */
     int8_t dy;   /* row offset -1..1 */
-    int8_t term; /* 0: bf16(v)  1: bf16(v - bf16(v)) */
+    int8_t term; /* 0: bf16(v)  1: bf16(v - bf16(v))  2: fp16(v) */
     int8_t reserved;
 } esr_xslot;
 

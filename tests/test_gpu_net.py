@@ -51,19 +51,36 @@ def test_forward_matches_reference_golden(golden, cuda_device, name, impl):
     err, p = (out - ref).abs().max().item(), psnr(out, ref)
     assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB vs the reference" % (err, p)
     # tight check against the oracle emulating the kernels' arithmetic (bf16 trunk operands; the six
-    # outer convs run split-bf16 ~ fp32)
+    # outer convs run with fp16 operands)
     ora_b, _, _, _ = oracle_for_case(g, name, operand_dtype=torch.bfloat16)
     orig_conv = ora_b.net.conv
-    fp32_keys = {"model.0", "model.1.sub.%d" % cfg["nb"], "model.2.1", "model.3.1", "model.4", "model.6"}
+    outer_keys = {"model.0", "model.1.sub.%d" % cfg["nb"], "model.2.1", "model.3.1", "model.4", "model.6"}
 
     def conv(x, key, act):
-        ora_b.net.od = None if key in fp32_keys else torch.bfloat16
+        ora_b.net.od = torch.float16 if key in outer_keys else torch.bfloat16
         return orig_conv(x, key, act)
     ora_b.net.conv = conv
     with torch.no_grad():
         emu = ora_b.forward(mi)
     err_e = (out - emu).abs().max().item()
     assert err_e <= 2e-3, "max|err| %g vs bf16-emulating oracle" % err_e
+
+
+@pytest.mark.parametrize("mode,tol", [("f16", 2e-3), ("split", 1e-3), ("bf16", 1e-2)])
+def test_outer_conv_operand_modes(cuda_device, mode, tol):
+    """The three operand formats of the six outer convs against the fp32 oracle (default-init weights: the
+    hard case): fp16 single term (default), split-bf16 hi/lo (three terms), plain bf16."""
+    wts = synth.make_weights("default", seed=3, nb=2)
+    lr, z = synth.make_inputs(2, 24, 20, seed=3)
+    mi = concat_latent(lr, z)
+    netG = build_product_G(cuda_device, 2, "all_layers_HR_downscaled", wts)
+    netG.generated_image_model.outer_mode = mode
+    with torch.no_grad():
+        out = netG(mi.to(cuda_device)).cpu()
+        ref = GCEMOracle(wts, nb=2).forward(mi)
+    assert netG.generated_image_model.engine().outer_mode == mode
+    err = (out - ref).abs().max().item()
+    assert err <= tol, "mode %s: max|err| %g" % (mode, err)
 
 
 def test_consistency_and_fp32_oracle_larger_image(cuda_device):

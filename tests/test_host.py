@@ -96,13 +96,24 @@ def test_engine_layout_arithmetic():
     assert (c0.nkb, c0.cout_tiles, c0.w_tile_bytes) == (3, 1, 2 * 18432 + 6144)
     c4 = e.convs["model.1.sub.0.RDB1.convs.4.0"]
     assert (c4.nkb, c4.cout_tile, c4.cout_tiles, c4.pair) == (7, 64, 1, 1) and c4.w_tile_bytes // 2 <= 124 * 1024
+    # outer convs, default mode: fp16 operands, one term (2 main K blocks + the fp16 latent slice)
     lr_conv = e.convs["model.1.sub.23"]
+    assert e.outer_mode == "f16" and "model.1.sub.23" in e.f16_convs and "model.1.sub.0.RDB1.convs.0.0" not in e.f16_convs
+    assert lr_conv.nkb == 3 and [(k.chan, k.slice_mask) for k in list(lr_conv.kblocks)[:3]] == [(0, 3), (32, 3), (0, 2)]
+    assert all(sl.term == 2 for sl in list(lr_conv.slots)[:64])
+    # split-bf16 mode: hi/lo pairs, three MMA terms
+    es = GEngine(nb=23, nz_in=3, all_layers=True, outer_mode="split")
+    lr_conv = es.convs["model.1.sub.23"]
     assert lr_conv.nkb == 8 and [k.chan for k in list(lr_conv.kblocks)[:6]] == [0, 32, 64, 96, 0, 32]
     xs, ws = expand_slots(6, precise=True)
     assert len(xs) == 64 and xs[0] == (0, -1, 0) and xs[18] == (0, -1, 1) and ws[36] == (0, 0, 1)
+    xs, ws = expand_slots(6, precise="f16")
+    assert len(xs) == 32 and xs[0] == (0, -1, 2) and ws[17] == (5, 2, 2) and xs[18] == (-1, 0, 0)
+    xs, ws = expand_slots(3, precise=False, second="f16")
+    assert len(xs) == 32 and xs[8] == (2, 1, 0) and xs[16] == (0, -1, 2) and ws[16] == (0, 0, 2) and ws[9] == (-1, -1, 0)
     # LR_conv must not be mistaken for an upconv when nb == 1 ("model.1.sub.1")
     e1 = GEngine(nb=1, nz_in=3, all_layers=True)
-    assert e1.convs["model.1.sub.1"].nkb == 8 and "model.1.sub.1" not in e1.upconv_names
+    assert e1.convs["model.1.sub.1"].nkb == 3 and "model.1.sub.1" not in e1.upconv_names
 
 
 def test_library_exports_every_declared_symbol():

@@ -1,17 +1,20 @@
+"""Summarises an ncu --csv launch list (gpu__time_duration [+ tensor pipe %]) per kernel and per layer position."""
 import csv, collections, sys
-path = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/launches.csv'
-lines=[l for l in open(path) if not l.startswith('==')]
-r=list(csv.DictReader(lines))
-seq=collections.OrderedDict()
-for row in r:
-    seq.setdefault(row['ID'], {'name':row['Kernel Name'][:40]})[row['Metric Name']]=float(row['Metric Value'].replace(',',''))
-L=list(seq.values())
-convs=[x for x in L if 'conv3x3_tc' in x['name']]
-T='gpu__time_duration.sum'; P='sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'
-print(len(convs))
-for x in convs[3:9]: print(x['name'][:28], round(x[T]/1e3,1), round(x.get(P,0),1))
-print('tail')
-for x in convs[-7:]: print(x['name'][:28], round(x[T]/1e3,1), round(x.get(P,0),1))
-agg=collections.defaultdict(float)
-for x in L: agg[x['name']]+=x[T]
-for k,v in sorted(agg.items(), key=lambda kv:-kv[1]): print(k, round(v/1e6,3),'ms')
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, data = None, []
+for r in rows:
+    if 'Kernel Name' in r: hdr = r; continue
+    if hdr and len(r) == len(hdr): data.append(dict(zip(hdr, r)))
+t, p, names = {}, {}, {}
+for d in data:
+    i = int(d['ID']); names[i] = d['Kernel Name'].split('(')[0][-40:]
+    v = float(d['Metric Value'].replace(',', ''))
+    if d['Metric Name'].startswith('gpu__time'): t[i] = v / 1000
+    else: p[i] = v
+ids = sorted(t)
+tot = collections.Counter(); cnt = collections.Counter()
+for i in ids: tot[names[i]] += t[i]; cnt[names[i]] += 1
+for k, v in tot.most_common(): print('%-42s n=%3d total %9.1f us' % (k, cnt[k], v))
+print('total', sum(t.values()))
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 14
+for i in ids[:n] + ids[-n:]: print(i, names[i], round(t[i], 1), p.get(i))
