@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) cem_up_kernel(const __grid_constant__ esr
 // kSegRows LR rows; the two halo cells on either side come from neighbouring lanes via shuffles, so
 // every HR float4 is loaded / stored exactly once per strip, fully coalesced (448 B per warp row).
 constexpr int kStripCells = 28;
-constexpr int kSegRows = 8;
+constexpr int kSegRows = 8;          // LR rows per warp (host-chosen launch parameter of the kernels below)
 
 struct CemTab {            // polyphase tap tables, [phase][cell offset -2..2]
     float down_h[4][5];    // down: weight of element e of cell j+c for output column j
@@ -164,14 +164,14 @@ struct CemTab {            // polyphase tap tables, [phase][cell offset -2..2]
 
 __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ y,
                                                         const float* __restrict__ x, float* __restrict__ out, int H,
-                                                        int W) {
+                                                        int W, int seg) {
     const int h = H >> 2, w = W >> 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int plane = blockIdx.z;
     const int j = blockIdx.x * kStripCells - 2 + lane;             // LR cell of this lane
-    const int i0 = (blockIdx.y * 4 + warp) * kSegRows;
+    const int i0 = (blockIdx.y * 4 + warp) * seg;
     if (i0 >= h) return;
-    const int i1 = min(i0 + kSegRows, h);
+    const int i1 = min(i0 + seg, h);
     const float* yp = y + static_cast<size_t>(plane) * H * W;
     const bool inside = j >= 0 && j < w;
     const int xcol = j < 0 ? 0 : W - 1;                            // replicate padding for cells outside the image
@@ -186,29 +186,25 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
             else { const float e = __ldg(row + xcol); g[q] = make_float4(e, e, e, e); }
         }
     };
-    float4 cur[4], nx1[4], nx2[4];                                  // two groups (8 rows) of loads stay in flight
-    load_group(i0 - 2, cur);
-    load_group(i0 - 1, nx1);
+    float4 g0[4], g1[4], g2[4], g3[4];                              // three groups (12 HR rows) of loads stay in flight
+    load_group(i0 - 2, g0);
+    load_group(i0 - 1, g1);
+    load_group(i0, g2);
     for (int I = i0 - 2; I <= i1 + 1; ++I) {
-        if (I + 2 <= i1 + 1) load_group(I + 2, nx2);
+        if (I + 3 <= i1 + 1) load_group(I + 3, g3);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 c = cur[q];
+            const float4 c = g0[q];
+            // this cell's contribution to the output columns (own cell) - k, k = -2..2; the neighbours' partial sums
+            // arrive by one shuffle each (4 per HR row instead of 16 raw-pixel shuffles)
             float hsum = 0.f;
 #pragma unroll
             for (int k = -2; k <= 2; ++k) {
-                float4 n;
-                if (k == 0) n = c;
-                else {
-                    n.x = __shfl_sync(0xffffffffu, c.x, lane + k);
-                    n.y = __shfl_sync(0xffffffffu, c.y, lane + k);
-                    n.z = __shfl_sync(0xffffffffu, c.z, lane + k);
-                    n.w = __shfl_sync(0xffffffffu, c.w, lane + k);
-                }
-                hsum = fmaf(T.down_h[0][k + 2], n.x, hsum);
-                hsum = fmaf(T.down_h[1][k + 2], n.y, hsum);
-                hsum = fmaf(T.down_h[2][k + 2], n.z, hsum);
-                hsum = fmaf(T.down_h[3][k + 2], n.w, hsum);
+                float p = T.down_h[0][k + 2] * c.x;
+                p = fmaf(T.down_h[1][k + 2], c.y, p);
+                p = fmaf(T.down_h[2][k + 2], c.z, p);
+                p = fmaf(T.down_h[3][k + 2], c.w, p);
+                hsum += k == 0 ? p : __shfl_sync(0xffffffffu, p, lane + k);
             }
             // row 4I+q feeds LR rows I-m, m = -2..2  (a0 <-> m=2 ... a4 <-> m=-2)
             a0 = fmaf(T.down_v[q][4], hsum, a0);
@@ -224,11 +220,122 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
         }
         a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { cur[q] = nx1[q]; nx1[q] = nx2[q]; }
+        for (int q = 0; q < 4; ++q) { g0[q] = g1[q]; g1[q] = g2[q]; g2[q] = g3[q]; }
     }
 }
 
-// out[Y-crop, X-crop] = (y ? y : 0) + sign * Up(e)
+// out = crop(y + Up(K * d)) with the 27x27 (HH^T)^-1 correlation fused in: the block builds the tile of
+// e = K * d it needs (its LR rows +-2, 32 cells) in shared memory with two separable passes over a replicate-
+// clamped tile of d, then every warp streams its LR rows: horizontal polyphase taps straight from the shared
+// e tile (no shuffles), a rolling 5-row window for the vertical taps, y and out as coalesced float4 rows.
+struct InvTaps {
+    float t[ESR_CEM_MAX_TAPS];
+    int n;
+};
+
+__global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__ CemTab T, const __grid_constant__ InvTaps K,
+                                                         const float* __restrict__ d, const float* __restrict__ y,
+                                                         float* __restrict__ out, int h, int w, int crop, int seg) {
+    extern __shared__ float sm[];
+    const int H = h << 2, W = w << 2;
+    const int Ho = H - 2 * crop, Wo = W - 2 * crop;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int plane = blockIdx.z;
+    const int jb = blockIdx.x * kStripCells - 2;                   // LR cell of lane 0
+    const int j = jb + lane;
+    const int ib = blockIdx.y * 4 * seg;                           // first LR row of the block
+    const int RB = 4 * seg, pad = K.n >> 1;
+    const int Re = RB + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad;
+    float* dt = sm;                                                // [Rd][Cd]  d, replicate clamped
+    float* hb = dt + Rd * Cd;                                      // [Rd][32]  horizontal pass
+    float* et = hb + Rd * 32;                                      // [Re][32]  e (zero outside the image)
+    const int i0 = ib + warp * seg, i1 = min(i0 + seg, h);
+    const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w && 4 * j >= crop && 4 * j + 3 < W - crop;
+    auto load_y = [&](int i, float4 (&b)[4]) {                     // the 4 HR rows of LR row i (base image)
+#pragma unroll
+        for (int psi = 0; psi < 4; ++psi) {
+            const int Y = 4 * i + psi;
+            b[psi] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (writer && i < i1 && Y >= crop && Y < H - crop)
+                b[psi] = __ldg(reinterpret_cast<const float4*>(y + (static_cast<size_t>(plane) * H + Y) * W) + j);
+        }
+    };
+    float4 yc[4], yn[4];
+    load_y(i0, yc);                                                // HBM loads fly while the e tile is built
+    load_y(i0 + 1, yn);
+    const float* dp = d + static_cast<size_t>(plane) * h * w;
+    for (int idx = threadIdx.x; idx < Rd * Cd; idx += 128) {
+        const int r = idx / Cd, c = idx - r * Cd;
+        dt[idx] = __ldg(dp + static_cast<size_t>(clampi(ib - 2 - pad + r, 0, h - 1)) * w + clampi(jb - pad + c, 0, w - 1));
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < Rd * 32; idx += 128) {
+        const int r = idx >> 5, c = idx & 31;
+        const float* t = dt + r * Cd + c;
+        float acc = 0.f;
+        for (int k = 0; k < K.n; ++k) acc = fmaf(K.t[k], t[k], acc);
+        hb[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < Re * 32; idx += 128) {
+        const int r = idx >> 5, c = idx & 31;
+        const int ii = ib - 2 + r, jj = jb + c;
+        float acc = 0.f;
+        if (ii >= 0 && ii < h && jj >= 0 && jj < w) {
+            const float* t = hb + r * 32 + c;
+            for (int k = 0; k < K.n; ++k) acc = fmaf(K.t[k], t[k * 32], acc);
+        }
+        et[idx] = acc;
+    }
+    __syncthreads();
+    if (i0 >= h) return;
+    // horizontally upsampled e rows i-2 .. i+2 (4 HR phases each); et row index of LR row ii is ii - ib + 2
+    float hu[5][4];
+    auto hrow = [&](int ii, float (&o)[4]) {
+        const float* e = et + (ii - ib + 2) * 32;
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+        for (int k = -2; k <= 2; ++k) {
+            const float n = e[min(max(lane + k, 0), 31)];
+            p0 = fmaf(T.up[0][k + 2], n, p0);
+            p1 = fmaf(T.up[1][k + 2], n, p1);
+            p2 = fmaf(T.up[2][k + 2], n, p2);
+            p3 = fmaf(T.up[3][k + 2], n, p3);
+        }
+        o[0] = p0; o[1] = p1; o[2] = p2; o[3] = p3;
+    };
+#pragma unroll
+    for (int kv = 0; kv < 4; ++kv) hrow(i0 - 2 + kv, hu[kv]);
+    for (int i = i0; i < i1; ++i) {
+        hrow(i + 2, hu[4]);
+        float4 yn2[4];
+        load_y(i + 2, yn2);
+        if (writer) {
+#pragma unroll
+            for (int psi = 0; psi < 4; ++psi) {
+                const int Y = 4 * i + psi;
+                if (Y < crop || Y >= H - crop) continue;
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int kv = 0; kv < 5; ++kv) {
+                    const float wv = T.up[psi][kv];
+                    r.x = fmaf(wv, hu[kv][0], r.x); r.y = fmaf(wv, hu[kv][1], r.y);
+                    r.z = fmaf(wv, hu[kv][2], r.z); r.w = fmaf(wv, hu[kv][3], r.w);
+                }
+                const float4 b = yc[psi];
+                r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+                *reinterpret_cast<float4*>(out + (static_cast<size_t>(plane) * Ho + (Y - crop)) * Wo + (4 * j - crop)) = r;
+            }
+        }
+#pragma unroll
+        for (int kv = 0; kv < 4; ++kv)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hu[kv][q] = hu[kv + 1][q];
+#pragma unroll
+        for (int psi = 0; psi < 4; ++psi) { yc[psi] = yn[psi]; yn[psi] = yn2[psi]; }
+    }
+}
+
 __global__ void __launch_bounds__(128) cem_up4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ e,
                                                       const float* __restrict__ y, float* __restrict__ out, int h,
                                                       int w, int crop, float sign) {
@@ -292,6 +399,15 @@ __global__ void __launch_bounds__(128) cem_up4_kernel(const __grid_constant__ Ce
 #pragma unroll
         for (int psi = 0; psi < 4; ++psi) yc[psi] = yn[psi];
     }
+}
+
+// LR rows per warp of the streaming kernels: long segments amortise the 4-row (down) / 30-row (d tile) halos,
+// short ones keep >= 16 warps per SM in flight on small problems (config 4: 3 planes of 512 x 512 cells).
+static int pick_seg(int planes, int h, int w) {
+    const long strips = ceil_div(w, kStripCells);
+    for (int seg = 32; seg > 8; seg >>= 1)
+        if (strips * ceil_div(h, seg) * planes >= 148L * 16) return seg;
+    return 8;
 }
 
 static bool fast4_ok(const esr_cem_filters& f, int H, int W, int crop, const void* a, const void* b, const void* c) {
@@ -423,8 +539,9 @@ int cem_down(const esr_cem_filters& f, const float* y, const float* x, int plane
              cudaStream_t s) {
     ESR_CHECK_ARG(H % f.sf == 0 && W % f.sf == 0, "HR size %dx%d not divisible by %d", H, W, f.sf);
     if (fast4_ok(f, H, W, 0, y, nullptr, nullptr)) {
-        dim3 grid(ceil_div(W / 4, kStripCells), ceil_div(ceil_div(H / 4, kSegRows), 4), planes);
-        cem_down4_kernel<<<grid, 128, 0, s>>>(make_tab(f), y, x, out, H, W);
+        const int seg = pick_seg(planes, H / 4, W / 4);
+        dim3 grid(ceil_div(W / 4, kStripCells), ceil_div(ceil_div(H / 4, seg), 4), planes);
+        cem_down4_kernel<<<grid, 128, 0, s>>>(make_tab(f), y, x, out, H, W, seg);
         return check_launch("cem_down4_kernel");
     }
     const size_t sm = down_smem(f);
@@ -455,6 +572,22 @@ int cem_up(const esr_cem_filters& f, const float* x, const float* y, int planes,
     dim3 grid(ceil_div(w, UT_C), ceil_div(h, UT_R), planes);
     cem_up_kernel<<<grid, 256, sm, s>>>(f, x, y, out, h, w, crop, sign);
     return check_launch("cem_up_kernel");
+}
+
+// Fused (HH^T)^-1 + Up + residual add, x4 only; d = x - Down(y).
+int cem_invup4(const esr_cem_filters& f, const float* d, const float* y, int planes, int h, int w, int crop, float* out,
+               cudaStream_t s) {
+    InvTaps K;
+    K.n = f.n_inv;
+    for (int i = 0; i < f.n_inv; ++i) K.t[i] = f.inv[i];
+    const int seg = pick_seg(planes, h, w) > 16 ? 16 : pick_seg(planes, h, w), pad = f.n_inv / 2;   // <= 16: smem tile
+    const int Re = 4 * seg + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad;
+    const size_t sm = sizeof(float) * (static_cast<size_t>(Rd) * Cd + static_cast<size_t>(Rd) * 32 + static_cast<size_t>(Re) * 32);
+    int rc = set_smem(reinterpret_cast<const void*>(cem_invup4_kernel), sm);
+    if (rc) return rc;
+    dim3 grid(ceil_div(w, kStripCells), ceil_div(h, 4 * seg), planes);
+    cem_invup4_kernel<<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
+    return check_launch("cem_invup4_kernel");
 }
 
 }  // namespace esr
@@ -496,6 +629,8 @@ extern "C" int esr_cem_project(const esr_cem_filters* f, const float* y, const f
     float* d = workspace;
     float* e = workspace + static_cast<size_t>(planes) * h * w;
     if ((rc = cem_down(*f, y, x, planes, H, W, d, s))) return rc;
+    if (fast4_ok(*f, H, W, crop, y, out, d) && ((W - 2 * crop) % 4 == 0))
+        return cem_invup4(*f, d, y, planes, h, w, crop, out, s);          // two launches: Down, then K + Up + add
     if ((rc = cem_inv(*f, d, planes, h, w, e, s))) return rc;
     return cem_up(*f, e, y, planes, h, w, crop, 1.f, out, s);
 }
