@@ -46,18 +46,29 @@ class DgradSpecs:
                     sl += [(c0 + k, -1, term) for k in range(32)]
             return kb, sl
 
+        # Trunk: the backward of an RDB is itself a dense block on the gradients.  With g_m = d(pre-activation of
+        # conv m) (m = 1..4) and g_5 = d(conv5 output) stored in one bf16 buffer GB = [g5 | g1 | g2 | g3 | g4],
+        #   d(x_j) = sum_{m > j} W_m[:, x_j]^T (*) g_m          (conv m reads x_0 .. x_{m-1}: block.py:230-235)
+        # is ONE conv launch per j whose K runs over the g_m it needs (accumulated in TMEM, no fp32 read-modify-write
+        # fan-in) and whose N is the slice x_j.  Launch "k" (k = 5..1) produces d(x_{k-1}); k = 1 also emits the 9
+        # row-expanded latent rows of the whole block.  Weights: U[co_slot, ci] = W_m[co, ci] gathered per RDB.
+        self.trunk = {}
         for r in range(eng.nb):
             for d in (1, 2, 3):
-                for i in range(5):
-                    name = "model.1.sub.%d.RDB%d.convs.%d.0" % (r, d, i)
-                    cout = GC if i < 4 else NF
-                    if i < 4:
-                        kb = [(0, NF + GC * i, DY_ALL, 0b11)]
+                pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
+                for k in (5, 4, 3, 2, 1):
+                    ms = [5] + [m for m in (4, 3, 2, 1) if m >= k]          # convs that read x_{k-1}
+                    kb, sl = [], []
+                    for m in ms:
+                        base = 0 if m == 5 else NF + GC * (m - 1)           # channels of g_m inside GB
+                        for c0 in range(0, NF if m == 5 else GC, 32):
+                            kb.append((0, base + c0, DY_ALL, 0b11))
+                            sl += [(base + c0 + c, -1, 0) for c in range(32)]
+                    if k >= 2:
+                        rows = [(nz + NF + GC * (k - 2) + c, -1) for c in range(GC)]
                     else:
-                        kb = [(0, 0, DY_ALL, 0b11), (0, 32, DY_ALL, 0b11)]
-                    sl = [(k, -1, 0) for k in range(cout)]
-                    rows = [(nz + c, -1) for c in range(NF + GC * i)] + (_lat_rows(nz) if nz else [])
-                    self.convs[name] = PackedConv(name + ".dgrad", len(rows), kb, sl, rows, 32)
+                        rows = [(nz + c, -1) for c in range(NF)] + (_lat_rows(nz) if nz else [])
+                    self.trunk[pre + "%d" % k] = PackedConv(pre + "dgrad%d" % k, len(rows), kb, sl, rows, 32, pair=eng.pair)
         names = eng.outer_names
         for name in names[:-1]:
             is_up = name in eng.upconv_names
@@ -86,6 +97,19 @@ class DgradSpecs:
             cin = w.shape[1]
             # logical dgrad weight [row = ci, slot = co, ky, kx] = W[co, ci, 2-ky, 2-kx]
             pc.pack(w, None, 8, 9, cin * 9, -3, -1)
+        eng = self.eng
+        for r in range(eng.nb):
+            for d in (1, 2, 3):
+                pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
+                ws = [params[pre + "%d.0" % i][0] for i in range(5)]
+                ci = ws[4].shape[1]
+                U = torch.zeros(NF + 4 * GC, ci, 3, 3, dtype=torch.float32, device=ws[0].device)   # [co_slot, ci, ky, kx]
+                U[:NF] = ws[4]
+                for m in range(1, 5):
+                    U[NF + GC * (m - 1):NF + GC * m, :ws[m - 1].shape[1]] = ws[m - 1]
+                for k in (5, 4, 3, 2, 1):
+                    self.trunk[pre + "%d" % k].pack(U, None, 8, 9, ci * 9, -3, -1)
+                torch.cuda.current_stream().synchronize()      # U is reused RDB by RDB
 
 
 class BackwardPlan:
@@ -98,7 +122,8 @@ class BackwardPlan:
         f32 = dict(dtype=torch.float32, device=dev)
         bf = dict(dtype=torch.bfloat16, device=dev)
         self.GF32 = torch.zeros(B * 4 * FRAME * hp * wp, **f32)
-        self.GB = torch.zeros(B, hp, wp, 192, **bf)
+        self.GBs = [torch.zeros(B, hp, wp, 192, **bf) for _ in range(2)]   # RDB g works in GBs[g % 2]; its d(x_0) launch reads
+                                                                         # all of it and writes the next g_5 into the other one
         self.GS = torch.zeros(B, hp, wp, 128, **bf)
         self.Gsc = torch.zeros(B * 64 * hp * wp, **f32)
         self.GFea = torch.zeros(B, hp, wp, 128, **bf)
@@ -134,31 +159,33 @@ class BackwardPlan:
     # ------------------------------------------------------------------ recording helpers
     def _conv(self, name, H, W, src, out_f32, out_stride, out_choff=0, accum=False, no_accum=0, lat_tile_to=None,
               out_bf16=None, bf16_stride=0, lo_choff=-1, scale=1.0, only_bf16_tiles=None, mask=None, mask_stride=0,
-              res1=None, res1_choff=0, gamma=1.0, res2=None, res2_choff=0, no_res=0):
-        pc = self.specs.convs[name]
+              res1=None, res1_choff=0, gamma=1.0, res2=None, res2_choff=0, no_res=0, pc=None, bf16_choff=0, mask_choff=0):
+        pc = pc if pc is not None else self.specs.convs[name]
         d = ConvDesc()
         d.B, d.H, d.W = self.plan.B, H, W
         d.src[0].ptr, d.src[0].channels = src.data_ptr(), src.shape[-1]
-        d.cout_tile, d.cout_tiles, d.num_kblocks = pc.cout_tile, pc.cout_tiles, pc.nkb
+        d.cout_tile, d.cout_tiles, d.num_kblocks, d.pair = pc.cout_tile, pc.cout_tiles, pc.nkb, pc.pair
         for i in range(pc.nkb):
             d.kblocks[i] = pc.kblocks[i]
         d.wpack, d.w_tile_bytes, d.bias = pc.wpack.data_ptr(), pc.w_tile_bytes, pc.bias.data_ptr()
         d.flags = capi.EPI_F32_BLOCKED | (capi.EPI_ACCUM if accum else 0)
         d.no_accum_tiles = no_accum
-        d.out_f32, d.out_f32_stride, d.out_f32_choff = out_f32.data_ptr(), out_stride, out_choff
+        if out_f32 is not None:
+            d.out_f32, d.out_f32_stride, d.out_f32_choff = out_f32.data_ptr(), out_stride, out_choff
         if lat_tile_to is not None:
             d.tile_choff[pc.cout_tiles - 1] = lat_tile_to
         if out_bf16 is not None:
-            d.out_bf16, d.out_bf16_stride, d.out_bf16_choff = out_bf16.data_ptr(), bf16_stride, 0
+            d.out_bf16, d.out_bf16_stride, d.out_bf16_choff = out_bf16.data_ptr(), bf16_stride, bf16_choff
             d.out_bf16_lo_choff, d.out_bf16_scale = lo_choff, scale
-            allt = (1 << pc.cout_tiles) - 1
-            keep = 0
-            for t in only_bf16_tiles:
-                keep |= 1 << t
-            d.no_bf16_tiles = allt & ~keep
+            if only_bf16_tiles is not None:
+                allt = (1 << pc.cout_tiles) - 1
+                keep = 0
+                for t in only_bf16_tiles:
+                    keep |= 1 << t
+                d.no_bf16_tiles = allt & ~keep
         if mask is not None:
             d.flags |= capi.EPI_MASK
-            d.mask, d.mask_stride, d.mask_choff = mask.data_ptr(), mask_stride, 0
+            d.mask, d.mask_stride, d.mask_choff = mask.data_ptr(), mask_stride, mask_choff
         if res1 is not None:
             d.flags |= capi.EPI_RES1
             d.res1, d.res1_stride, d.res1_choff, d.gamma = res1.data_ptr(), out_stride, res1_choff, gamma
@@ -216,7 +243,7 @@ class BackwardPlan:
         q0 = n_rdb % 4
         touched.add(q0)
         self._conv(names[0], hp, wp, self.GS, self.GF32, 4 * FRAME, out_choff=FRAME * q0, lat_tile_to=LAT_OFF if nz else None,
-                   out_bf16=self.GB, bf16_stride=192, scale=0.04, only_bf16_tiles=(0, 1))
+                   out_bf16=self.GBs[(n_rdb - 1) % 2], bf16_stride=192, scale=0.04, only_bf16_tiles=(0, 1))
         # ---- the trunk, last RDB first
         for g in reversed(range(n_rdb)):
             r, dd = divmod(g, 3)            # dd = 0,1,2 -> RDB1,2,3
@@ -224,23 +251,26 @@ class BackwardPlan:
             first_touch = q not in touched
             touched.add(q)
             buf = plan.bufs[g]
+            GB = self.GBs[g % 2]
             pre = "model.1.sub.%d.RDB%d.convs." % (r, dd + 1)
-            for k in (5, 4, 3, 2, 1):
-                pc = self.specs.convs[pre + "%d.0" % (k - 1)]
-                lat = lat_bit(pc) if nz else 0
-                main_bits = ((1 << pc.cout_tiles) - 1) & ~lat
-                kw = dict(out_choff=FRAME * q, lat_tile_to=LAT_OFF if nz else None, accum=True)
-                if k == 5:
-                    kw["no_accum"] = main_bits | (lat if first_touch else 0)
-                if k >= 2:        # d(x_{k-1}) is final after this launch: emit LeakyReLU'(x_{k-1}) * d(x_{k-1})
-                    kw.update(out_bf16=self.GB, bf16_stride=192, only_bf16_tiles=(k,), mask=buf, mask_stride=192)
-                else:             # d(x_0) final: add the residual paths, emit 0.2x (0.04x across an RRDB boundary)
-                    kw.update(res1=self.GF32, res1_choff=FRAME * ((g + 1) % 4), gamma=0.2 if dd == 2 else 1.0, no_res=lat)
-                    if dd == 0:
-                        kw.update(res2=self.GF32, res2_choff=FRAME * ((3 * r + 3) % 4))
-                    if g > 0:
-                        kw.update(out_bf16=self.GB, bf16_stride=192, only_bf16_tiles=(0, 1), scale=0.04 if dd == 0 else 0.2)
-                self._conv(pre + "%d.0" % (k - 1), hp, wp, self.GB, self.GF32, 4 * FRAME, **kw)
+            for k in (5, 4, 3, 2):
+                # d(x_{k-1}) complete in one launch (K over g_5, g_4 .. g_k); emit g_{k-1} = LeakyReLU'(x_{k-1}) * d(x_{k-1})
+                ch = NF + GC * (k - 2)
+                self._conv(None, hp, wp, GB, None, 0, pc=self.specs.trunk[pre + "%d" % k], out_bf16=GB, bf16_stride=192,
+                           bf16_choff=ch, mask=buf, mask_stride=192, mask_choff=ch)
+            # d(x_0): all five convs read it; add the residual paths, emit 0.2x (0.04x across an RRDB boundary) as the
+            # g_5 of the RDB below; the last cout tile holds the block's 9 latent rows (accumulated per frame)
+            pc = self.specs.trunk[pre + "1"]
+            lat = lat_bit(pc) if nz else 0
+            main_bits = ((1 << pc.cout_tiles) - 1) & ~lat
+            kw = dict(out_choff=FRAME * q, lat_tile_to=LAT_OFF if nz else None, accum=nz > 0,
+                      no_accum=main_bits | (lat if first_touch else 0),
+                      res1=self.GF32, res1_choff=FRAME * ((g + 1) % 4), gamma=0.2 if dd == 2 else 1.0, no_res=lat)
+            if dd == 0:
+                kw.update(res2=self.GF32, res2_choff=FRAME * ((3 * r + 3) % 4))
+            if g > 0:
+                kw.update(out_bf16=self.GBs[(g - 1) % 2], bf16_stride=192, only_bf16_tiles=(0, 1), scale=0.04 if dd == 0 else 0.2)
+            self._conv(None, hp, wp, GB, self.GF32, 4 * FRAME, pc=pc, **kw)
         # ---- d(fea) = d(RRDB0 input) + shortcut gradient -> first conv's latent rows
         if eng.nz_in:
             self._combine(self.GF32, 4 * FRAME, 0, 1, self.Gsc, hp, wp, None, None, 0, 1, 1.0, self.GFea, eng.precise)

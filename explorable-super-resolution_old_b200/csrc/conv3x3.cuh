@@ -107,6 +107,7 @@ constexpr int kEpiRes = 2;       // conv 4 of an RDB: alpha*(acc+bias) + gamma*r
                                  // + 16-bit slice (block.py:235, :270)
 constexpr int kEpiAct = 3;       // bias [+ LeakyReLU] -> 16-bit NHWC (bf16 or fp16), optionally replicated 2x2 (upconv / HR conv)
 constexpr int kEpiNchw = 4;      // bias -> f32 NCHW, first cout_real channels (last conv of the generator)
+constexpr int kEpiMask = 5;      // dgrad of a trunk conv: (acc + bias) * LeakyReLU'(stored activation) -> bf16 slice
 // The generic epilogue costs ~5000 clk per 128-pixel x 64-channel tile (issue bound: two epilogue warps per
 // scheduler walking run-time flags); the specialised ones are bound by the TMEM read of the three dx slabs (~1600).
 
@@ -163,6 +164,14 @@ template <int MODE>
 __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, int ct, int n, int y, int x, int co0,
                                                        EpiOperands& P) {
     if constexpr (MODE == kEpiTrunk || MODE == kEpiAct || MODE == kEpiNchw) return;
+    if constexpr (MODE == kEpiMask) {
+        const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
+        const uint4* m = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.mask) +
+                                                        pix * d.mask_stride + d.mask_choff + co0);
+        P.m[0] = __ldg(m);
+        P.m[1] = __ldg(m + 1);
+        return;
+    }
     if constexpr (MODE == kEpiRes) {
         ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
         ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
@@ -248,6 +257,18 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
             st_global_v8(ob + (o00 + ow) * d.out_bf16_stride, pk);
             st_global_v8(ob + (o00 + ow + 1) * d.out_bf16_stride, pk);
         }
+        return;
+    }
+    if constexpr (MODE == kEpiMask) {
+        const uint16_t* mv = reinterpret_cast<const uint16_t*>(P.m);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float s0 = ((mv[2 * i] & 0x8000u) == 0 && (mv[2 * i] & 0x7fffu) != 0) ? 1.f : d.slope;
+            const float s1 = ((mv[2 * i + 1] & 0x8000u) == 0 && (mv[2 * i + 1] & 0x7fffu) != 0) ? 1.f : d.slope;
+            pk[i] = pack_bf16x2(v[2 * i] * s0, v[2 * i + 1] * s1);
+        }
+        st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
         return;
     }
     if constexpr (MODE == kEpiNchw) {
@@ -356,6 +377,9 @@ inline int classify_epilogue(const esr_conv_desc& d) {
         return kEpiAct;
     if ((f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == 0 && d.out_nchw != nullptr && d.out_bf16 == nullptr && d.out_f32 == nullptr)
         return kEpiNchw;
+    if ((f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == ESR_EPI_MASK && bf_ok && d.out_f32 == nullptr && d.out_nchw == nullptr &&
+        d.up == 1 && d.cout_tile == 32 && d.mask != nullptr && d.mask_stride % 8 == 0 && d.mask_choff % 8 == 0)
+        return kEpiMask;
     return kEpiGeneric;
 }
 

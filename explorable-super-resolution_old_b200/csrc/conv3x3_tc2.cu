@@ -377,15 +377,16 @@ bool fill_launch_pair(ConvLaunch* L) {
 int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream, int use_pdl) {
     using namespace pair;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ConvLaunch);
-    static const KernelFn kernels[2][4] = {
+    // indexed by classify_epilogue(): Generic, Trunk, Res, Act, (Nchw -> Generic), Mask
+    static const KernelFn kernels[2][6] = {
         {conv3x3_tc2_kernel<32, kEpiGeneric>, conv3x3_tc2_kernel<32, kEpiTrunk>, conv3x3_tc2_kernel<32, kEpiRes>,
-         conv3x3_tc2_kernel<32, kEpiAct>},
+         conv3x3_tc2_kernel<32, kEpiAct>, conv3x3_tc2_kernel<32, kEpiGeneric>, conv3x3_tc2_kernel<32, kEpiMask>},
         {conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiRes>,
-         conv3x3_tc2_kernel<64, kEpiAct>}};
+         conv3x3_tc2_kernel<64, kEpiAct>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>}};
     static bool attr_set = false;
     if (!attr_set) {
         for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < 6; ++b)
                 ESR_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_set = true;
     }
@@ -409,8 +410,7 @@ int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLa
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 2 : 1;
-    int mode = classify_epilogue(L.d);
-    if (mode > kEpiAct) mode = kEpiGeneric;
+    const int mode = classify_epilogue(L.d);
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[L.d.cout_tile == 64 ? 1 : 0][mode], tm0, tm1, L);
     if (e != cudaSuccess) { set_error("conv3x3_tc2_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
     return check_launch("conv3x3_tc2_kernel");
