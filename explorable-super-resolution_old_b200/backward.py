@@ -75,7 +75,7 @@ class DgradSpecs:
             has_lat = nz > 0 and not is_up
             kb, sl = outer_blocks()
             rows = [((0 if is_up else nz) + c, -1) for c in range(NF)] + (_lat_rows(nz) if has_lat else [])
-            self.convs[name] = PackedConv(name + ".dgrad", len(rows), kb, sl, rows, 32)
+            self.convs[name] = PackedConv(name + ".dgrad", len(rows), kb, sl, rows, 32, pair=eng.pair)
         # last conv (out_nc -> 64 [+latent]): its input gradient arrives as NCHW f32 and is row-"expanded"
         # (dy = 0 only) into [hi | lo | hi] slots
         onc = eng.out_nc
@@ -84,10 +84,10 @@ class DgradSpecs:
         sl = [(c, -1, t) for t in (0, 0, 1) for c in range(onc)] + [(-1, -1, 0)] * (32 - 3 * onc)
         rows = [(nz + c, -1) for c in range(NF)] + (_lat_rows(nz) if nz else [])
         self.convs[names[-1]] = PackedConv(names[-1] + ".dgrad", len(rows), [(0, 0, DY_ALL, 0b01 if 3 * onc <= 16 else 0b11)],
-                                           sl, rows, 32)
+                                           sl, rows, 32, pair=eng.pair)
         # first conv: only the latent rows are needed (the LR image takes no gradient)
         kb, sl = outer_blocks()
-        self.convs["model.0"] = PackedConv("model.0.dgrad", 32, kb, sl, _lat_rows(eng.nz_in), 32) if eng.nz_in else None
+        self.convs["model.0"] = PackedConv("model.0.dgrad", 32, kb, sl, _lat_rows(eng.nz_in), 32, pair=eng.pair) if eng.nz_in else None
 
     def pack(self, params):
         for name, pc in self.convs.items():

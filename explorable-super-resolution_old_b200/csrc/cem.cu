@@ -469,7 +469,14 @@ __global__ void cem_adj1d_kernel(const __grid_constant__ Adj1dArgs a) {
             if (i_hi > a.na - 1) i_hi = a.na - 1;
             for (int i = i_lo; i <= i_hi; ++i) acc = fmaf(a.taps[c0 - a.sa * i], gl[i * gstride], acc);
         } else {
-            for (int i = 0; i < a.na; ++i) {
+            // only the samples whose window reaches past the border can clamp onto it (conservative bounds; the
+            // exact test is inside): pos <= 0 needs sa*i <= pad - off, pos >= Ls-1 needs sa*i >= Ls-1-off+pad-(nt-1)
+            int i_lo = 0, i_hi = a.na - 1;
+            if (a.Ls > 1) {
+                if (m == 0) { i_hi = (a.pad - a.off) / a.sa + 1; if (i_hi > a.na - 1) i_hi = a.na - 1; }
+                else { i_lo = (a.Ls - 1 - a.off + a.pad - (a.nt - 1)) / a.sa - 1; if (i_lo < 0) i_lo = 0; }
+            }
+            for (int i = i_lo; i <= i_hi; ++i) {
                 const int base_pos = a.sa * i + a.off - a.pad;   // position of tap 0
                 float wsum = 0.f;
                 for (int t = 0; t < a.nt; ++t) {

@@ -108,6 +108,8 @@ constexpr int kEpiRes = 2;       // conv 4 of an RDB: alpha*(acc+bias) + gamma*r
 constexpr int kEpiAct = 3;       // bias [+ LeakyReLU] -> 16-bit NHWC (bf16 or fp16), optionally replicated 2x2 (upconv / HR conv)
 constexpr int kEpiNchw = 4;      // bias -> f32 NCHW, first cout_real channels (last conv of the generator)
 constexpr int kEpiMask = 5;      // dgrad of a trunk conv: (acc + bias) * LeakyReLU'(stored activation) -> bf16 slice
+constexpr int kEpiDx0 = 6;       // dgrad of a block input: per cout tile either v + out_f32 (accumulate, routed latent rows) or
+                                 // alpha*v + gamma*res1 [, beta*. + res2] -> blocked f32 [+ scale*v as bf16]
 // The generic epilogue costs ~5000 clk per 128-pixel x 64-channel tile (issue bound: two epilogue warps per
 // scheduler walking run-time flags); the specialised ones are bound by the TMEM read of the three dx slabs (~1600).
 
@@ -164,6 +166,21 @@ template <int MODE>
 __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, int ct, int n, int y, int x, int co0,
                                                        EpiOperands& P) {
     if constexpr (MODE == kEpiTrunk || MODE == kEpiAct || MODE == kEpiNchw) return;
+    if constexpr (MODE == kEpiDx0) {
+        const uint32_t flags = tile_flags(d, ct);
+        if (flags & ESR_EPI_ACCUM) {
+            ld_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), P.r1);
+            ld_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), P.r1 + 8);
+        } else if (flags & ESR_EPI_RES1) {
+            ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
+            ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
+        }
+        if (flags & ESR_EPI_RES2) {
+            ld_global_v8f(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0), P.r2);
+            ld_global_v8f(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0 + 8), P.r2 + 8);
+        }
+        return;
+    }
     if constexpr (MODE == kEpiMask) {
         const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
         const uint4* m = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.mask) +
@@ -256,6 +273,29 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
             st_global_v8(ob + (o00 + 1) * d.out_bf16_stride, pk);
             st_global_v8(ob + (o00 + ow) * d.out_bf16_stride, pk);
             st_global_v8(ob + (o00 + ow + 1) * d.out_bf16_stride, pk);
+        }
+        return;
+    }
+    if constexpr (MODE == kEpiDx0) {
+        const uint32_t flags = tile_flags(d, ct);
+        if (flags & ESR_EPI_ACCUM) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += P.r1[i];
+        } else if (flags & ESR_EPI_RES1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + d.gamma * P.r1[i];
+        }
+        if (flags & ESR_EPI_RES2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = d.beta * v[i] + P.r2[i];
+        }
+        st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), v);
+        st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
+        if (d.out_bf16 != nullptr && !((d.no_bf16_tiles >> ct) & 1)) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(d.out_bf16_scale * v[2 * i], d.out_bf16_scale * v[2 * i + 1]);
+            st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
         }
         return;
     }
@@ -359,11 +399,23 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
 
 // Picks the cheapest epilogue specialisation that implements the descriptor exactly.
 inline int classify_epilogue(const esr_conv_desc& d) {
-    for (int t = 0; t < d.cout_tiles; ++t)
-        if (d.tile_choff[t] >= 0) return kEpiGeneric;
-    if (d.no_accum_tiles || d.no_bf16_tiles || d.no_res_tiles) return kEpiGeneric;
     const uint32_t f = d.flags & ~static_cast<uint32_t>(ESR_EPI_WIDE_OK | ESR_CONV_F16);
     const auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    bool routed = d.no_accum_tiles || d.no_bf16_tiles || d.no_res_tiles;
+    for (int t = 0; t < d.cout_tiles; ++t) routed = routed || d.tile_choff[t] >= 0;
+    if ((f & ESR_EPI_F32_BLOCKED) && (f & ~static_cast<uint32_t>(ESR_EPI_RES1 | ESR_EPI_RES2 | ESR_EPI_ACCUM | ESR_EPI_F32_BLOCKED)) == 0 &&
+        (routed || (f & ESR_EPI_ACCUM)) && d.out_f32 != nullptr && d.out_nchw == nullptr && d.up == 1 && d.cout_tile == 32 &&
+        (d.out_bf16 == nullptr || (d.out_bf16_lo_choff < 0 && d.out_bf16_stride % 16 == 0 && d.out_bf16_choff % 16 == 0 &&
+                                   al32(d.out_bf16)))) {
+        bool ok = true;                    // a tile either accumulates or takes residuals, and routed tiles stay 16-aligned
+        for (int t = 0; t < d.cout_tiles; ++t) {
+            const bool acc = (f & ESR_EPI_ACCUM) && !((d.no_accum_tiles >> t) & 1);
+            const bool res = (f & (ESR_EPI_RES1 | ESR_EPI_RES2)) && !((d.no_res_tiles >> t) & 1);
+            ok = ok && !(acc && res) && (d.tile_choff[t] < 0 || d.tile_choff[t] % 8 == 0);
+        }
+        if (ok) return kEpiDx0;
+    }
+    if (routed) return kEpiGeneric;
     const bool bf_ok = d.out_bf16 != nullptr && d.out_bf16_lo_choff < 0 && d.out_bf16_scale == 1.0f && d.out_bf16_stride % 16 == 0 &&
                        d.out_bf16_choff % 16 == 0 && al32(d.out_bf16);
     if ((f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && bf_ok && d.out_f32 == nullptr && d.out_nchw == nullptr &&

@@ -381,4 +381,4 @@ class GPlan:
         eng = self.eng
         prep = 1 + 1 + (1 if eng.nz_in else 0) + (2 if eng.nz else 0)   # lr_pad, fea_in(lr [+z_lr]), z_hr, z_lr
         expand = 1 + (2 if eng.nz else 0)
-        return prep + expand + capi.lib().esr_seq_num_launches(self.seq) + (3 if with_cem else 0)
+        return prep + expand + capi.lib().esr_seq_num_launches(self.seq) + (2 if with_cem else 0)   # CEM x4: Down, K+Up

@@ -34,3 +34,55 @@ def run_sharded(fn, batch, gather=True):
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine)
     return torch.cat([p[:h - l] for p, (l, h) in zip(parts, sizes)], 0)
+
+
+class HostPipeline:
+    """Host-buffer entry point for inference: ``netG`` over a pinned host batch, in chunks, with the host->device
+    copy of chunk i+1 and the device->host copy of chunk i-1 running on their own streams while chunk i computes.
+    The chunks go through ``netG`` one after the other on the caller's stream (so they share one set of plan
+    buffers, and a chunk's dense-block working set is the L2-friendly size), only the PCIe copies overlap.
+    Calls return once everything is enqueued, so consecutive calls pipeline too (the next batch's upload runs under
+    this batch's compute).  ``join()`` makes the caller's stream wait for the last download, ``wait()`` blocks the
+    host until it is complete; read ``host_out`` only after one of them."""
+
+    def __init__(self, netG, chunk=8):
+        self.netG, self.chunk = netG, chunk
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self._done = None
+
+    def __call__(self, host_in, host_out):
+        assert host_in.is_pinned() and host_out.is_pinned(), "HostPipeline needs pinned host buffers (asynchronous copies)"
+        dev = next(self.netG.parameters()).device
+        cur = torch.cuda.current_stream()
+        n = host_in.size(0)
+        ranges = [(lo, min(lo + self.chunk, n)) for lo in range(0, n, self.chunk)]
+        xs, evs = [], []
+        with torch.cuda.stream(self.s_in):
+            for lo, hi in ranges:
+                x = host_in[lo:hi].to(dev, non_blocking=True)
+                x.record_stream(cur)
+                ev = torch.cuda.Event()
+                ev.record(self.s_in)
+                xs.append(x)
+                evs.append(ev)
+        for (lo, hi), x, ev in zip(ranges, xs, evs):
+            cur.wait_event(ev)
+            with torch.no_grad():
+                out = self.netG(x)
+            done = torch.cuda.Event()
+            done.record(cur)
+            out.record_stream(self.s_out)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                host_out[lo:hi].copy_(out, non_blocking=True)
+        self._done = torch.cuda.Event()
+        self._done.record(self.s_out)
+        return host_out
+
+    def join(self):
+        if self._done is not None:
+            torch.cuda.current_stream().wait_event(self._done)
+
+    def wait(self):
+        if self._done is not None:
+            self._done.synchronize()

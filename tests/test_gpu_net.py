@@ -113,6 +113,23 @@ def test_batch_shards_are_bit_identical(cuda_device):
             assert torch.equal(one[0], full[i])
 
 
+def test_host_pipeline_matches_direct_call(cuda_device):
+    """parallel.HostPipeline (chunked, copies overlapped with compute) returns what netG(x) returns."""
+    from esr_b200.parallel import HostPipeline
+    wts = synth.make_weights("kaiming", seed=4, nb=1)
+    lr, z = synth.make_inputs(5, 16, 20, seed=4)
+    mi = concat_latent(lr, z).contiguous()
+    netG = build_product_G(cuda_device, 1, "all_layers_HR_downscaled", wts)
+    with torch.no_grad():
+        ref = netG(mi.to(cuda_device)).cpu()
+    host_in, host_out = mi.pin_memory(), torch.empty(5, 3, 64, 80).pin_memory()
+    pipe = HostPipeline(netG, chunk=2)
+    for _ in range(2):                                      # back-to-back calls pipeline as well
+        pipe(host_in, host_out)
+    pipe.wait()
+    assert torch.equal(host_out, ref)
+
+
 def test_no_cpu_fallback():
     wts = synth.make_weights("kaiming", seed=2, nb=1)
     netG = build_product_G(torch.device("cpu"), 1, "all_layers_HR_downscaled", wts)
