@@ -9,6 +9,7 @@ One "step" = one G+CEM forward over a batch of 16 synthetic 3x128x128 LR images 
 batch of 16 (batch sharding, no data-path collective: images are independent), scaling = weak.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -191,30 +192,41 @@ def main():
     host_out = torch.empty(BATCH, 3, SF * LR_H, SF * LR_W).pin_memory()
 
     SUB = int(os.environ.get("ESR_SUBBATCH", BATCH))       # images per pass through the layer sequence
-    assert BATCH % SUB == 0
-    plan = G.plan(SUB, LR_H, LR_W, MARGIN, keep=False)
+    NSTREAMS = int(os.environ.get("ESR_STREAMS", 1))        # sub-batches in flight (each on its own stream / buffers)
+    assert BATCH % SUB == 0 and (BATCH // SUB) % NSTREAMS == 0
+    plans = [G.plan(SUB, LR_H, LR_W, MARGIN, keep=False, slot=i) for i in range(NSTREAMS)]
+    plan = plans[0]
     filters = netG._filters
     out_dev = torch.empty(BATCH, 3, SF * LR_H, SF * LR_W, device=dev)
-    ws = torch.empty(2 * SUB * 3 * plan.hp * plan.wp, device=dev)
+    wss = [torch.empty(2 * SUB * 3 * plan.hp * plan.wp, device=dev) for _ in range(NSTREAMS)]
+    ws = wss[0]
+    side = [torch.cuda.Stream() for _ in range(NSTREAMS)] if NSTREAMS > 1 else []
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     H4, W4 = SF * plan.hp, SF * plan.wp
 
     def step(record=False):
-        l, st = capi.lib(), capi.stream_ptr()
-        for i0 in range(0, BATCH, SUB):
-            first, last = i0 == 0, i0 + SUB == BATCH
-            if record and first:
-                ev[0].record()
-            plan.run_prep(x_dev[i0:i0 + SUB])
-            if record and first:
-                ev[1].record()
-            plan.run_convs()
-            if record and first:
-                ev[2].record()
-            capi.check(l.esr_cem_project(filters, capi.ptr(plan.y), capi.ptr(plan.lr_pad), SUB, 3, H4, W4, SF * MARGIN,
-                                         capi.ptr(out_dev[i0:i0 + SUB]), capi.ptr(ws), st))
-            if record and first:
-                ev[3].record()
+        l = capi.lib()
+        main = torch.cuda.current_stream()
+        for s_ in side:
+            s_.wait_stream(main)
+        for k, i0 in enumerate(range(0, BATCH, SUB)):
+            first = i0 == 0
+            pl, w_ = plans[k % NSTREAMS], wss[k % NSTREAMS]
+            with torch.cuda.stream(side[k % NSTREAMS]) if side else contextlib.nullcontext():
+                if record and first:
+                    ev[0].record()
+                pl.run_prep(x_dev[i0:i0 + SUB])
+                if record and first:
+                    ev[1].record()
+                pl.run_convs()
+                if record and first:
+                    ev[2].record()
+                capi.check(l.esr_cem_project(filters, capi.ptr(pl.y), capi.ptr(pl.lr_pad), SUB, 3, H4, W4, SF * MARGIN,
+                                             capi.ptr(out_dev[i0:i0 + SUB]), capi.ptr(w_), capi.stream_ptr()))
+                if record and first:
+                    ev[3].record()
+        for s_ in side:
+            main.wait_stream(s_)
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,7 +272,7 @@ def main():
     c0.record()
     for _ in range(args.steps):
         for _i in range(BATCH // SUB):
-            plan.run_convs()
+            plans[_i % NSTREAMS].run_convs()
     c1.record()
     torch.cuda.synchronize()
     conv_ms = c0.elapsed_time(c1) / args.steps
@@ -269,7 +281,7 @@ def main():
     # back to pinned host memory; parallel.HostPipeline overlaps the PCIe copies of one half batch with the
     # other half's compute (both copies of every step are inside the timed region)
     from esr_b200.parallel import HostPipeline
-    pipe = HostPipeline(netG, chunk=BATCH // 2)
+    pipe = HostPipeline(netG, chunk=int(os.environ.get("ESR_E2E_CHUNK", BATCH)))
 
     def e2e_step():
         pipe(host_in, host_out)
@@ -293,7 +305,7 @@ def main():
     zopt = None
     if rank == 0 and not args.no_zopt:
         from esr_b200.z_optimization import Z_optimizer, SRModelShim
-        del plan, out_dev, ws
+        del plan, plans, out_dev, ws, wss
         G._plans.clear()
         torch.cuda.empty_cache()
         zh = 256
@@ -303,7 +315,7 @@ def main():
         model.feed_data(data)
         with torch.no_grad():
             model.fake_H = netG(model.model_input)
-        import io, contextlib
+        import io
         with contextlib.redirect_stdout(io.StringIO()):
             zo = Z_optimizer(objective="TV", Z_size=[SF * zh, SF * zh], model=model, Z_range=1.0, max_iters=2, data=data,
                              initial_LR=0.1, batch_size=1)
@@ -337,7 +349,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16 MMA operands, fp32 accumulate/trunk/CEM", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "batch shard x%d" % world,
                    "l2": "per-step working set (~4.5 GB of activations) >> 126 MB L2, no flush needed",
-                   "cuda_graph": graph is not None, "images_per_pass": SUB},
+                   "cuda_graph": graph is not None, "images_per_pass": SUB, "passes_in_flight": NSTREAMS},
         "e2e": {"value": world * out_mpix / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
         "gpu_launches": args.steps * (BATCH // SUB) * launches_per_fwd,

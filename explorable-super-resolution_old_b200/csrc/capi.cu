@@ -59,6 +59,8 @@ extern "C" int esr_seq_add_conv(esr_seq* s, const esr_conv_desc* d, int32_t use_
     int rc = esr::build_conv_launch(*d, &op.tm0, &op.tm1, &op.L);
     if (rc != ESR_OK) return rc;
     op.use_simt = use_simt;
+    static const bool snake = []() { const char* v = getenv("ESR_NO_SNAKE"); return !(v && atoi(v)); }();
+    op.L.reverse = snake ? static_cast<int>(s->ops.size() & 1) : 0;     // alternate the tile walk layer by layer
     s->ops.push_back(op);
     return ESR_OK;
 }

@@ -33,6 +33,8 @@ struct ConvLaunch {
     uint32_t w_smem_bytes;   // resident weight region (w_tile_bytes rounded up to 1 KiB)
     int nstages;             // depth of the A-tile ring that fits beside it
     int pair_nb;             // 0: single-CTA kernel; else bands per CTA tile of the cta_group::2 kernel
+    int reverse;             // walk the spatial tiles last-to-first: consecutive layers of a recorded sequence alternate
+                             // direction, so a layer starts on the data the previous one touched last (still in L2)
     int debug;               // ESR_DEBUG_SKIP timing experiments (results invalid when non-zero)
     unsigned long long* prof; // optional [gridDim][16] per-role cycle counters (esr_debug_set_profile_buffer)
 };

@@ -130,7 +130,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
             pdl_wait();
             uint32_t stage = 0, phase = 0;
             ESR_PROF(long long p_wait = 0, p_t0 = clock64(), p_n = 0;)
-            for (int sp = sp0; sp < L.spatial_tiles; sp += sp_step) {
+            for (int spi = sp0; spi < L.spatial_tiles; spi += sp_step) {
+                const int sp = L.reverse ? L.spatial_tiles - 1 - spi : spi;
                 const int n = sp / tiles_per_img;
                 const int r = sp - n * tiles_per_img;
                 const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
@@ -230,7 +231,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_consta
         pdl_wait();                                   // residual / accumulate inputs come from earlier kernels
         uint32_t as = 0, aphase = 0;
         ESR_PROF(long long e_t0 = clock64(), e_wait = 0, e_ld = 0, e_shfl = 0, e_n = 0;)
-        for (int sp = sp0; sp < L.spatial_tiles; sp += sp_step) {
+        for (int spi = sp0; spi < L.spatial_tiles; spi += sp_step) {
+            const int sp = L.reverse ? L.spatial_tiles - 1 - spi : spi;
             const int n = sp / tiles_per_img;
             const int r = sp - n * tiles_per_img;
             const int ty = r / L.tiles_x, tx = r - ty * L.tiles_x;
@@ -394,6 +396,7 @@ void fill_launch(ConvLaunch* L, const esr_conv_desc& d) {
     L->debug = dbg ? atoi(dbg) : 0;
     L->prof = g_prof_buf;
     L->pair_nb = 0;
+    L->reverse = 0;
 }
 
 int num_sms_cached();

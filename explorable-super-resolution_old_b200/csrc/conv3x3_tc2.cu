@@ -185,7 +185,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             uint32_t stage = 0, phase = 0;
             ESR_PROF(long long p_wait = 0, p_t0 = clock64(), p_n = 0; if (L.prof) L.prof[blockIdx.x * 16 + 6] = gtime_ns();)
             for (int p = pair0; p < num_pairs; p += pair_step) {
-                int sp = 2 * p + static_cast<int>(rank);
+                int sp = 2 * (L.reverse ? num_pairs - 1 - p : p) + static_cast<int>(rank);
                 if (sp >= L.spatial_tiles) sp = L.spatial_tiles - 1;       // odd tail: duplicate tile, stores masked
                 const int n = sp / tiles_per_img;
                 const int r = sp - n * tiles_per_img;
@@ -292,7 +292,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         uint32_t as = 0, aphase = 0;
         ESR_PROF(long long e_t0 = clock64(), e_wait = 0, e_n = 0;)
         for (int p = pair0; p < num_pairs; p += pair_step) {
-            const int sp_raw = 2 * p + static_cast<int>(rank);
+            const int sp_raw = 2 * (L.reverse ? num_pairs - 1 - p : p) + static_cast<int>(rank);
             const bool tile_ok = sp_raw < L.spatial_tiles;
             const int sp = tile_ok ? sp_raw : L.spatial_tiles - 1;
             const int n = sp / tiles_per_img;

@@ -105,9 +105,11 @@ class RRDBNet(nn.Module):
             self._bplans[key] = (plan, BackwardPlan(plan, self._dgrad, use_simt=self.debug_simt))
         return self._bplans[key][1]
 
-    def plan(self, B, h, w, m, keep):
+    def plan(self, B, h, w, m, keep, slot=0):
+        """Buffers + recorded launches for one geometry.  `slot` selects an independent buffer set, for callers
+        that keep several sub-batches in flight on different streams."""
         eng = self.engine()
-        key = (B, h, w, m, keep, self.debug_simt)
+        key = (B, h, w, m, keep, self.debug_simt, slot)
         if key not in self._plans:
             if len(self._plans) >= 4:
                 self._plans.pop(next(iter(self._plans)))
