@@ -285,12 +285,12 @@ def main():
 
     def e2e_step():
         pipe(host_in, host_out)
-    for _ in range(2):
+    for _ in range(max(args.warmup, 4)):                      # the caching allocator settles after a few calls
         e2e_step()
     pipe.wait()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(3, args.steps // 2)
+    n_e2e = max(5, args.steps)
     f0.record()
     for _ in range(n_e2e):
         e2e_step()

@@ -45,9 +45,11 @@ class HostPipeline:
     this batch's compute).  ``join()`` makes the caller's stream wait for the last download, ``wait()`` blocks the
     host until it is complete; read ``host_out`` only after one of them."""
 
-    def __init__(self, netG, chunk=8):
+    def __init__(self, netG, chunk=16):
         self.netG, self.chunk = netG, chunk
         self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self._x, self._free, self._k = [None, None], [None, None], 0     # two device staging slots for the inputs
+        self._live = []                                                    # outputs whose download is still in flight
         self._done = None
 
     def __call__(self, host_in, host_out):
@@ -55,28 +57,33 @@ class HostPipeline:
         dev = next(self.netG.parameters()).device
         cur = torch.cuda.current_stream()
         n = host_in.size(0)
-        ranges = [(lo, min(lo + self.chunk, n)) for lo in range(0, n, self.chunk)]
-        xs, evs = [], []
-        with torch.cuda.stream(self.s_in):
-            for lo, hi in ranges:
-                x = host_in[lo:hi].to(dev, non_blocking=True)
-                x.record_stream(cur)
-                ev = torch.cuda.Event()
-                ev.record(self.s_in)
-                xs.append(x)
-                evs.append(ev)
-        for (lo, hi), x, ev in zip(ranges, xs, evs):
-            cur.wait_event(ev)
+        for lo in range(0, n, self.chunk):
+            hi = min(lo + self.chunk, n)
+            slot = self._k & 1
+            self._k += 1
+            if self._x[slot] is None or self._x[slot].shape[1:] != host_in.shape[1:] or self._x[slot].size(0) < hi - lo:
+                self._x[slot] = torch.empty((self.chunk,) + tuple(host_in.shape[1:]), dtype=host_in.dtype, device=dev)
+                self._free[slot] = None
+            x = self._x[slot][:hi - lo]
+            up = torch.cuda.Event()
+            with torch.cuda.stream(self.s_in):
+                if self._free[slot] is not None:
+                    self.s_in.wait_event(self._free[slot])     # the chunk that last used this slot has been consumed
+                x.copy_(host_in[lo:hi], non_blocking=True)
+                up.record(self.s_in)
+            cur.wait_event(up)
             with torch.no_grad():
                 out = self.netG(x)
             done = torch.cuda.Event()
             done.record(cur)
-            out.record_stream(self.s_out)
+            self._free[slot] = done
+            down = torch.cuda.Event()
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(done)
                 host_out[lo:hi].copy_(out, non_blocking=True)
-        self._done = torch.cuda.Event()
-        self._done.record(self.s_out)
+                down.record(self.s_out)
+            self._live = [(o, e) for (o, e) in self._live if not e.query()] + [(out, down)]
+            self._done = down
         return host_out
 
     def join(self):
