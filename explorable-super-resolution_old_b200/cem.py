@@ -274,6 +274,15 @@ class CEM_PyTorch(nn.Module):
         self._margin_LR = int(CEMnet.invalidity_margins_LR)
         self.pre_pad = False
 
+    def capture(self, x_static, slot=0):
+        """(graph, out) replaying forward(x_static) without autograd (inference serving, parallel.HostPipeline), or
+        None when the wrapped generator is not this package's RRDBNet."""
+        from .rrdbnet import RRDBNet, capture_inference
+        G = self.generated_image_model
+        if not isinstance(G, RRDBNet):
+            return None
+        return capture_inference(G, x_static, self._margin_LR if self.pre_pad else 0, self._filters, slot=slot)
+
     def forward(self, x):
         from .rrdbnet import RRDBNet, run_generator
         G = self.generated_image_model

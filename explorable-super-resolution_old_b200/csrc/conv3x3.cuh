@@ -33,6 +33,8 @@ struct ConvLaunch {
     uint32_t w_smem_bytes;   // resident weight region (w_tile_bytes rounded up to 1 KiB)
     int nstages;             // depth of the A-tile ring that fits beside it
     int pair_nb;             // 0: single-CTA kernel; else bands per CTA tile of the cta_group::2 kernel
+    int a_stream;            // activation tiles of source 0 are dead after this launch (conv 4 of an RDB reads the whole
+                             // dense block for the last time): TMA loads them with an L2 evict_first policy
     int reverse;             // walk the spatial tiles last-to-first: consecutive layers of a recorded sequence alternate
                              // direction, so a layer starts on the data the previous one touched last (still in L2)
     int debug;               // ESR_DEBUG_SKIP timing experiments (results invalid when non-zero)
@@ -84,6 +86,19 @@ __device__ __forceinline__ void st_global_v8f(float* p, const float* v) {
 }
 __device__ __forceinline__ void ld_global_v8f(const float* p, float* v) {
     asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+// Streaming variants for the fp32 trunk: each value is written once and read once, five launches (~0.6 GB of other
+// traffic) later, so it can never be an L2 hit; evict_first keeps it from displacing the bf16 dense-block lines
+// that the next layer re-reads.
+__device__ __forceinline__ void st_global_v8f_stream(float* p, const float* v) {
+    asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8f_stream(const float* p, float* v) {
+    asm volatile("ld.global.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }
@@ -192,11 +207,11 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, i
         return;
     }
     if constexpr (MODE == kEpiRes) {
-        ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
-        ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
+        ld_global_v8f_stream(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
+        ld_global_v8f_stream(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
         if (d.flags & ESR_EPI_RES2) {
-            ld_global_v8f(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0), P.r2);
-            ld_global_v8f(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0 + 8), P.r2 + 8);
+            ld_global_v8f_stream(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0), P.r2);
+            ld_global_v8f_stream(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0 + 8), P.r2 + 8);
         }
         return;
     }
@@ -239,8 +254,8 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = d.beta * v[i] + P.r2[i];
         }
-        st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), v);
-        st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
+        st_global_v8f_stream(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), v);
+        st_global_v8f_stream(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
         uint32_t pk[8];
         if (d.flags & ESR_EPI_OUT_F16) {
 #pragma unroll

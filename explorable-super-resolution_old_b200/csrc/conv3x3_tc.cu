@@ -397,6 +397,8 @@ void fill_launch(ConvLaunch* L, const esr_conv_desc& d) {
     L->prof = g_prof_buf;
     L->pair_nb = 0;
     L->reverse = 0;
+    static const bool hints = []() { const char* v = getenv("ESR_NO_L2_HINTS"); return !(v && atoi(v)); }();
+    L->a_stream = hints && classify_epilogue(L->d) == kEpiRes;
 }
 
 int num_sms_cached();

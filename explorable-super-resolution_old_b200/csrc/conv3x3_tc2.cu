@@ -76,6 +76,20 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const void* tma
         "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair_hint(void* smem_dst, const void* tmap, uint32_t leader_bar_addr, int c0,
+                                                      int c1, int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar_addr), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
                  : "memory");
@@ -183,6 +197,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             }
             pdl_wait();
             uint32_t stage = 0, phase = 0;
+            const uint64_t stream_policy = l2_policy_evict_first();
             ESR_PROF(long long p_wait = 0, p_t0 = clock64(), p_n = 0; if (L.prof) L.prof[blockIdx.x * 16 + 6] = gtime_ns();)
             for (int p = pair0; p < num_pairs; p += pair_step) {
                 int sp = 2 * (L.reverse ? num_pairs - 1 - p : p) + static_cast<int>(rank);
@@ -201,7 +216,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                     // that (a transiently negative tx-count is legal), never to an older phase: the peer issues
                     // only after its copy of the multicast "stage free" commit
                     if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
-                    tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
+                    if (L.a_stream && K.src == 0)
+                        tma_load_4d_pair_hint(s_a + stage * kATile, &tmap0, lead_full, K.chan, x0, y0, n, stream_policy);
+                    else
+                        tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
                     if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
             }

@@ -45,8 +45,10 @@ class HostPipeline:
     this batch's compute).  ``join()`` makes the caller's stream wait for the last download, ``wait()`` blocks the
     host until it is complete; read ``host_out`` only after one of them."""
 
-    def __init__(self, netG, chunk=16):
+    def __init__(self, netG, chunk=16, use_graph=True):
         self.netG, self.chunk = netG, chunk
+        self.use_graph = use_graph                                         # replay the chunk's forward as a CUDA graph
+        self._graphs = {}                                                  # (slot, rows) -> (graph, static output)
         self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
         self._x, self._free, self._k = [None, None], [None, None], 0     # two device staging slots for the inputs
         self._live = []                                                    # outputs whose download is still in flight
@@ -72,8 +74,7 @@ class HostPipeline:
                 x.copy_(host_in[lo:hi], non_blocking=True)
                 up.record(self.s_in)
             cur.wait_event(up)
-            with torch.no_grad():
-                out = self.netG(x)
+            out = self._forward(slot, x)
             done = torch.cuda.Event()
             done.record(cur)
             self._free[slot] = done
@@ -85,6 +86,20 @@ class HostPipeline:
             self._live = [(o, e) for (o, e) in self._live if not e.query()] + [(out, down)]
             self._done = down
         return host_out
+
+    def _forward(self, slot, x):
+        """netG(x) for the staging slot: through the module's captured inference graph when it offers one
+        (CEM_PyTorch.capture: fixed input slot, fixed output buffer), else the eager module call."""
+        if self.use_graph and hasattr(self.netG, "capture"):
+            key = (slot, x.size(0))
+            if key not in self._graphs:
+                self._graphs[key] = self.netG.capture(x, slot=slot) or False
+            ent = self._graphs[key]
+            if ent:
+                ent[0].replay()
+                return ent[1]
+        with torch.no_grad():
+            return self.netG(x)
 
     def join(self):
         if self._done is not None:

@@ -150,6 +150,45 @@ class _GeneratorFn(torch.autograd.Function):
         return generator_backward(ctx, g), None, None, None, None
 
 
+def capture_inference(net, x_static, margin, cem_filters, slot=0):
+    """CUDA graph of the whole inference forward (input plumbing, the 351 convs, CEM projection) reading the fixed
+    device buffer `x_static` and writing a fixed output buffer.  Returns (graph, out).  Replaying it costs one launch
+    on the host; `slot` selects a private set of plan buffers so that several graphs can be in flight."""
+    if not x_static.is_cuda or x_static.dtype != torch.float32 or not x_static.is_contiguous():
+        raise capi.EsrError("capture_inference: expected a contiguous float32 CUDA tensor")
+    capi.require_device(x_static.device.index if x_static.device.index is not None else torch.cuda.current_device())
+    B, C, h, w = x_static.shape
+    sf = net.upscale
+    if C != net._cfg["nz_in"] * sf * sf + 3:
+        raise ValueError("expected %d input channels, got %d" % (net._cfg["nz_in"] * sf * sf + 3, C))
+    plan = net.plan(B, h, w, margin, keep=False, slot=slot)
+    crop = sf * margin
+    H4, W4 = sf * plan.hp, sf * plan.wp
+    onc = plan.y.size(1)
+    out = torch.empty(B, onc, H4 - 2 * crop, W4 - 2 * crop, device=x_static.device, dtype=torch.float32)
+    ws = torch.empty(2 * B * onc * plan.hp * plan.wp, device=x_static.device, dtype=torch.float32) if cem_filters is not None else None
+
+    def run():
+        y = plan.run_g(x_static)
+        if cem_filters is None:
+            out.copy_(y)
+        else:
+            capi.check(capi.lib().esr_cem_project(cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, onc, H4, W4, crop,
+                                                  capi.ptr(out), capi.ptr(ws), capi.stream_ptr()))
+    with torch.cuda.device(x_static.device):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()                                      # warm-up outside the capture (lazy initialisation in the library)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run()
+    graph._esr_keep = (plan, ws, x_static)
+    return graph, out
+
+
 def run_generator(net, x, margin, cem_filters):
     if not x.is_cuda:
         raise capi.EsrError("RRDBNet.forward: expected a CUDA tensor; this package has no CPU or PyTorch fallback")
