@@ -55,6 +55,22 @@ class ConvDesc(C.Structure):
         self.up, self.out_bf16_scale, self.out_bf16_lo_choff = 1, 1.0, -1
 
 
+RDB_MAX_LAYERS, RDB_MAX_KBLOCKS = 4, 8
+
+
+class RdbLayer(C.Structure):
+    _fields_ = [("num_kblocks", C.c_int32), ("kblocks", KBlock * RDB_MAX_KBLOCKS), ("wpack", C.c_void_p),
+                ("w_tile_bytes", C.c_uint32), ("bias", C.c_void_p), ("out_choff", C.c_int32)]
+
+
+class RdbGrowthDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("src", TensorNHWC * 2),
+                ("num_layers", C.c_int32), ("layers", RdbLayer * RDB_MAX_LAYERS),
+                ("out", C.c_void_p), ("out_stride", C.c_int32), ("mode", C.c_int32), ("slope", C.c_float),
+                ("mask", C.c_void_p), ("mask_stride", C.c_int32), ("imgs_per_chunk", C.c_int32),
+                ("flags", C.c_void_p), ("flags_use", C.c_int32), ("flags_zero", C.c_int32)]
+
+
 class WRow(C.Structure):
     _fields_ = [("idx", C.c_int16), ("ky", C.c_int8), ("reserved", C.c_int8)]
 
@@ -100,6 +116,9 @@ SIGNATURES = {
     "esr_seq_create": (_vp, []),
     "esr_seq_destroy": (None, [_vp]),
     "esr_seq_add_conv": (C.c_int, [_vp, C.POINTER(ConvDesc), _i32]),
+    "esr_seq_add_rdb_growth": (C.c_int, [_vp, C.POINTER(RdbGrowthDesc)]),
+    "esr_rdb_growth_flag_words": (_i64, [_i32, _i32, _i32]),
+    "esr_rdb_growth_tc": (C.c_int, [C.POINTER(RdbGrowthDesc), _vp]),
     "esr_seq_run": (C.c_int, [_vp, _vp]),
     "esr_seq_num_launches": (_i32, [_vp]),
 }

@@ -29,10 +29,17 @@ struct SeqOp {
     int use_simt;
 };
 
+struct RdbOp;                                   // conv3x3_tc2.cu
+RdbOp* new_rdb_op(const esr_rdb_growth_desc& d, int* rc);
+void delete_rdb_op(RdbOp* op);
+int launch_rdb_growth(const RdbOp& op, cudaStream_t stream, int use_pdl);
+
 }  // namespace esr
 
 struct esr_seq {
     std::vector<esr::SeqOp> ops;
+    std::vector<esr::RdbOp*> rdb;               // ops[i].use_simt == -1 - k  <=>  fused growth launch rdb[k]
+    ~esr_seq() { for (esr::RdbOp* r : rdb) esr::delete_rdb_op(r); }
 };
 
 extern "C" const char* esr_last_error(void) { return esr::g_error; }
@@ -65,18 +72,51 @@ extern "C" int esr_seq_add_conv(esr_seq* s, const esr_conv_desc* d, int32_t use_
     return ESR_OK;
 }
 
+extern "C" int esr_seq_add_rdb_growth(esr_seq* s, const esr_rdb_growth_desc* d) {
+    if (s == nullptr || d == nullptr) { esr::set_error("esr_seq_add_rdb_growth: null argument"); return ESR_ERR_INVALID; }
+    int rc = ESR_OK;
+    esr::RdbOp* r = esr::new_rdb_op(*d, &rc);
+    if (r == nullptr) return rc;
+    esr::SeqOp op;
+    std::memset(&op, 0, sizeof(op));
+    op.use_simt = -1 - static_cast<int>(s->rdb.size());
+    s->rdb.push_back(r);
+    s->ops.push_back(op);
+    return ESR_OK;
+}
+
+extern "C" int64_t esr_rdb_growth_flag_words(int32_t B, int32_t H, int32_t W) {
+    if (B <= 0 || H <= 0 || W <= 0) return ESR_ERR_INVALID;
+    const int64_t tiles = static_cast<int64_t>(B) * esr::ceil_div(W, esr::kTileWOut) * esr::ceil_div(H, 2 * esr::kBandRows);
+    return 3 * ESR_RDB_MAX_LAYERS * tiles;
+}
+
+extern "C" int esr_rdb_growth_tc(const esr_rdb_growth_desc* d, void* stream) {
+    if (d == nullptr) { esr::set_error("null rdb_growth desc"); return ESR_ERR_INVALID; }
+    int rc = ESR_OK;
+    esr::RdbOp* r = esr::new_rdb_op(*d, &rc);
+    if (r == nullptr) return rc;
+    rc = esr::launch_rdb_growth(*r, static_cast<cudaStream_t>(stream), 0);
+    esr::delete_rdb_op(r);
+    return rc;
+}
+
 extern "C" int esr_seq_run(const esr_seq* s, void* stream) {
     if (s == nullptr) { esr::set_error("esr_seq_run: null sequence"); return ESR_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool sync_each = []() { const char* v = getenv("ESR_SEQ_SYNC"); return v && atoi(v); }();   // debug aid
     int idx = 0;
+    static const int use_pdl = []() { const char* v = getenv("ESR_NO_PDL"); return (v && atoi(v)) ? 0 : 1; }();
     for (const esr::SeqOp& op : s->ops) {
-        int rc = op.use_simt ? esr::launch_conv_simt(op.L, st) : esr::launch_conv_tc(op.tm0, op.tm1, op.L, st);
+        int rc;
+        if (op.use_simt < 0) rc = esr::launch_rdb_growth(*s->rdb[-1 - op.use_simt], st, use_pdl);
+        else rc = op.use_simt ? esr::launch_conv_simt(op.L, st) : esr::launch_conv_tc(op.tm0, op.tm1, op.L, st);
         if (rc != ESR_OK) return rc;
         if (sync_each) {
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) {
-                esr::set_error("sequence op %d (cout_tile %d x %d, pair %d, %d k-blocks, %dx%dx%d) failed: %s", idx, op.L.d.cout_tile,
+                esr::set_error("sequence op %d (%s cout_tile %d x %d, pair %d, %d k-blocks, %dx%dx%d) failed: %s", idx,
+                               op.use_simt < 0 ? "fused growth convs," : "conv,", op.L.d.cout_tile,
                                op.L.d.cout_tiles, op.L.d.pair, op.L.d.num_kblocks, op.L.d.B, op.L.d.H, op.L.d.W, cudaGetErrorString(e));
                 return ESR_ERR_CUDA;
             }

@@ -9,6 +9,8 @@
 //
 // All three filters of the default (bicubic) configuration are rank-1, so every operator
 // runs as a horizontal pass into shared memory followed by a vertical pass.
+#include <cstdlib>
+
 #include "esr_common.cuh"
 
 namespace esr {
@@ -162,65 +164,76 @@ struct CemTab {            // polyphase tap tables, [phase][cell offset -2..2]
     float up[4][5];        // up: weight of cell j+c for HR phase phi (same table for rows)
 };
 
-__global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ y,
+// Vertical taps first: every HR row costs 20 FMAs into five float4 accumulators (LR rows I-2..I+2) and no
+// shuffles; the horizontal taps run once per LR row on the finished accumulator (20 FMAs for the cell's five
+// partial sums, which neighbours exchange with 4 shuffles).  Loads: a ring of three 4-row groups addressed
+// statically (the row loop is unrolled by 3), two groups (8 HR rows, 4 KiB per warp) in flight.
+__global__ void __launch_bounds__(128, 4) cem_down4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ y,
                                                         const float* __restrict__ x, float* __restrict__ out, int H,
                                                         int W, int seg) {
     const int h = H >> 2, w = W >> 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int plane = blockIdx.z;
     const int j = blockIdx.x * kStripCells - 2 + lane;             // LR cell of this lane
-    const int i0 = (blockIdx.y * 4 + warp) * seg;
+    const int i0 = (blockIdx.y * 4 + warp) * seg;                   // seg is a multiple of 4
     if (i0 >= h) return;
     const int i1 = min(i0 + seg, h);
     const float* yp = y + static_cast<size_t>(plane) * H * W;
     const bool inside = j >= 0 && j < w;
-    const int xcol = j < 0 ? 0 : W - 1;                            // replicate padding for cells outside the image
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;         // accumulators of LR rows I-2 .. I+2
+    const float* col = yp + (inside ? 4 * j : (j < 0 ? 0 : W - 1));   // replicate padding for cells outside the image
+    const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w;
     auto load_group = [&](int I, float4 (&g)[4]) {                  // the 4 HR rows of LR row I (replicate padded)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            int r = 4 * I + q;
-            r = r < 0 ? 0 : (r > H - 1 ? H - 1 : r);
-            const float* row = yp + static_cast<size_t>(r) * W;
-            if (inside) g[q] = __ldg(reinterpret_cast<const float4*>(row) + j);
-            else { const float e = __ldg(row + xcol); g[q] = make_float4(e, e, e, e); }
+            const int r = min(max(4 * I + q, 0), H - 1);
+            const float* p = col + static_cast<size_t>(r) * W;
+            if (inside) g[q] = __ldg(reinterpret_cast<const float4*>(p));
+            else { const float e = __ldg(p); g[q] = make_float4(e, e, e, e); }
         }
     };
-    float4 g0[4], g1[4], g2[4], g3[4];                              // three groups (12 HR rows) of loads stay in flight
-    load_group(i0 - 2, g0);
-    load_group(i0 - 1, g1);
-    load_group(i0, g2);
-    for (int I = i0 - 2; I <= i1 + 1; ++I) {
-        if (I + 3 <= i1 + 1) load_group(I + 3, g3);
+    float4 acc[5];                                                  // LR rows I-2 .. I+2 (4 HR columns of the cell each)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 c = g0[q];
-            // this cell's contribution to the output columns (own cell) - k, k = -2..2; the neighbours' partial sums
-            // arrive by one shuffle each (4 per HR row instead of 16 raw-pixel shuffles)
+    for (int m = 0; m < 5; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g[3][4];
+    load_group(i0 - 2, g[0]);
+    load_group(i0 - 1, g[1]);
+    const int last = i1 + 1;
+    for (int Ib = i0 - 2; Ib <= last; Ib += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int I = Ib + u;
+            if (I > last) break;                                    // warp-uniform
+            if (I + 2 <= last) load_group(I + 2, g[(u + 2) % 3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 c = g[u][q];
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {                       // row 4I+q feeds LR row I-2+m with tap index 4-m
+                    const float wv = T.down_v[q][4 - m];
+                    acc[m].x = fmaf(wv, c.x, acc[m].x); acc[m].y = fmaf(wv, c.y, acc[m].y);
+                    acc[m].z = fmaf(wv, c.z, acc[m].z); acc[m].w = fmaf(wv, c.w, acc[m].w);
+                }
+            }
+            // LR row I-2 is complete: this cell's contribution to the output columns (own cell) - k, k = -2..2
+            const float4 a = acc[0];
             float hsum = 0.f;
 #pragma unroll
             for (int k = -2; k <= 2; ++k) {
-                float p = T.down_h[0][k + 2] * c.x;
-                p = fmaf(T.down_h[1][k + 2], c.y, p);
-                p = fmaf(T.down_h[2][k + 2], c.z, p);
-                p = fmaf(T.down_h[3][k + 2], c.w, p);
+                float p = T.down_h[0][k + 2] * a.x;
+                p = fmaf(T.down_h[1][k + 2], a.y, p);
+                p = fmaf(T.down_h[2][k + 2], a.z, p);
+                p = fmaf(T.down_h[3][k + 2], a.w, p);
                 hsum += k == 0 ? p : __shfl_sync(0xffffffffu, p, lane + k);
             }
-            // row 4I+q feeds LR rows I-m, m = -2..2  (a0 <-> m=2 ... a4 <-> m=-2)
-            a0 = fmaf(T.down_v[q][4], hsum, a0);
-            a1 = fmaf(T.down_v[q][3], hsum, a1);
-            a2 = fmaf(T.down_v[q][2], hsum, a2);
-            a3 = fmaf(T.down_v[q][1], hsum, a3);
-            a4 = fmaf(T.down_v[q][0], hsum, a4);
-        }
-        const int i = I - 2;                                       // complete now
-        if (i >= i0 && i < i1 && lane >= 2 && lane < 2 + kStripCells && j < w) {
-            const size_t o = (static_cast<size_t>(plane) * h + i) * w + j;
-            out[o] = x != nullptr ? x[o] - a0 : a0;
-        }
-        a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = 0.f;
+            const int i = I - 2;
+            if (i >= i0 && i < i1 && writer) {
+                const size_t o = (static_cast<size_t>(plane) * h + i) * w + j;
+                out[o] = x != nullptr ? x[o] - hsum : hsum;
+            }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { g0[q] = g1[q]; g1[q] = g2[q]; g2[q] = g3[q]; }
+            for (int m = 0; m < 4; ++m) acc[m] = acc[m + 1];
+            acc[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -404,6 +417,8 @@ __global__ void __launch_bounds__(128) cem_up4_kernel(const __grid_constant__ Ce
 // LR rows per warp of the streaming kernels: long segments amortise the 4-row (down) / 30-row (d tile) halos,
 // short ones keep >= 16 warps per SM in flight on small problems (config 4: 3 planes of 512 x 512 cells).
 static int pick_seg(int planes, int h, int w) {
+    static const int forced = []() { const char* v = getenv("ESR_CEM_SEG"); return v ? atoi(v) : 0; }();   // tuning aid
+    if (forced == 8 || forced == 16 || forced == 32) return forced;
     const long strips = ceil_div(w, kStripCells);
     for (int seg = 32; seg > 8; seg >>= 1)
         if (strips * ceil_div(h, seg) * planes >= 148L * 16) return seg;

@@ -13,6 +13,8 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
+#include <new>
 
 #include "conv3x3.cuh"
 #include "ptx_sm100.cuh"
@@ -372,9 +374,420 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     }
 }
 
+
+// ============================================================ fused growth convs of a dense block
+// One persistent launch = up to four convs (cout 32 each) over the same NHWC buffer; see esr_rdb_growth_desc.
+// Work items are (chunk, layer, tile pair) in that order; cluster k takes items k, k+74, ...  An item of layer
+// l > 0 may be loaded once layer l-1 of its tile's 3x3 neighbourhood has been stored: every epilogue warp bumps
+// a per-(layer, tile) counter after its stores (generic->async proxy fence + __threadfence + atomicAdd), the TMA
+// producer polls the up-to-nine counters (acquire) before its first load of the item.  Every dependency points to
+// an item with a smaller index, all clusters are resident and walk their items in increasing order, and an item's
+// MMAs / epilogue never wait on a flag, so the launch cannot deadlock.
+struct RdbLayerDev {
+    int nkb, out_choff;
+    uint32_t w_smem_off, w_half_bytes;      // this CTA's half image: offset in the resident weight region, size
+    const uint8_t* wpack;                   // cout tile image in global memory (two halves)
+    const float* bias;
+    esr_kblock kb[ESR_RDB_MAX_KBLOCKS];
+};
+struct RdbLaunch {
+    int B, H, W, nlayers;
+    RdbLayerDev layer[ESR_RDB_MAX_LAYERS];
+    __nv_bfloat16* out;
+    int out_stride, mode;
+    float slope;
+    const uint16_t* mask;
+    int mask_stride;
+    int tiles_x, tiles_y, tiles_per_img, tiles_c, ppc, chunks, total_items, spatial_tiles;
+    uint32_t* flags;                        // [nlayers][spatial_tiles] counters of this launch
+    uint32_t* flags_zero;                   // same size, cleared for a later launch
+    int nstages;
+    uint32_t w_smem_bytes;
+};
+
+constexpr int kRdbStages = 6;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct RdbItem { int layer, n, ty, tx, gt; bool ok; };
+__device__ __forceinline__ RdbItem rdb_decode(const RdbLaunch& R, int item, uint32_t rank) {
+    const int per_chunk = R.nlayers * R.ppc;
+    const int c = item / per_chunk, rem = item - c * per_chunk;
+    RdbItem it;
+    it.layer = rem / R.ppc;
+    int tl = 2 * (rem - it.layer * R.ppc) + static_cast<int>(rank);
+    it.ok = tl < R.tiles_c;
+    if (!it.ok) tl = R.tiles_c - 1;                                 // odd tail: duplicate tile, nothing stored
+    it.gt = c * R.tiles_c + tl;
+    it.n = it.gt / R.tiles_per_img;
+    const int r = it.gt - it.n * R.tiles_per_img;
+    it.ty = r / R.tiles_x;
+    it.tx = r - it.ty * R.tiles_x;
+    return it;
+}
+
+template <int MODE>   // kEpiTrunk: bias + LeakyReLU;  kEpiMask: (acc + bias) * LeakyReLU'(mask)
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                          const __grid_constant__ RdbLaunch R) {
+    constexpr int CT = 32, N = 96, NB = 2;
+    constexpr int kATile = (NB * kBandRows + 2) * kTileW * kRowBytes;   // 20 KiB
+    constexpr int kAccSlot = 128;
+    constexpr uint32_t kIdesc = idesc_bf16_m256(N);
+    constexpr uint32_t kARow16 = (kTileW * kRowBytes) >> 4;
+    constexpr uint32_t kWSlab16 = ((N / 2) * kRowBytes) >> 4;
+    const int nstages = R.nstages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_w = smem;
+    uint8_t* s_a = smem + R.w_smem_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + nstages * kATile);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kRdbStages;
+    uint64_t* acc_full = bars + 2 * kRdbStages;
+    uint64_t* acc_empty = acc_full + kAccStages;
+    uint64_t* w_full = acc_empty + kAccStages;
+    uint64_t* w_ready = w_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_ready + 1);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [nlayers][32]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    for (int i = threadIdx.x; i < R.nlayers * CT; i += kNumThreads) s_bias[i] = R.layer[i / CT].bias[i % CT];
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap0);
+        tma_prefetch_desc(&tmap1);
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
+        mbar_init(w_full, 1);
+        mbar_init(w_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc2(tmem_slot, kTmemCols);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one per CTA)
+        if (elect_one()) {
+            uint32_t wbytes = 0;
+            for (int l = 0; l < R.nlayers; ++l) wbytes += R.layer[l].w_half_bytes;
+            mbar_expect_tx_local(w_full, wbytes);
+            for (int l = 0; l < R.nlayers; ++l) {
+                const RdbLayerDev& Ly = R.layer[l];
+                const uint8_t* wt = Ly.wpack + static_cast<size_t>(rank) * Ly.w_half_bytes;
+                for (uint32_t off = 0; off < Ly.w_half_bytes; off += 16384) {
+                    const uint32_t n = Ly.w_half_bytes - off < 16384 ? Ly.w_half_bytes - off : 16384;
+                    bulk_load_1d(s_w + Ly.w_smem_off + off, wt + off, n, w_full);
+                }
+            }
+            pdl_wait();
+            uint32_t stage = 0, phase = 0;
+            for (int item = cluster_id; item < R.total_items; item += num_clusters) {
+                const RdbItem it = rdb_decode(R, item, rank);
+                if (it.layer > 0) {
+                    // layer-1 of the 3x3 tile neighbourhood must be in memory before this item's first load
+                    const uint32_t* f = R.flags + static_cast<size_t>(it.layer - 1) * R.spatial_tiles +
+                                        static_cast<size_t>(it.n) * R.tiles_per_img;
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int yy = it.ty + dy;
+                        if (yy < 0 || yy >= R.tiles_y) continue;
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int xx = it.tx + dx;
+                            if (xx < 0 || xx >= R.tiles_x) continue;
+                            const uint32_t* fp = f + yy * R.tiles_x + xx;
+                            for (uint32_t spin = 0; ld_acquire_u32(fp) < static_cast<uint32_t>(kEpiWarps); ++spin) {
+                                if (spin > (1u << 24)) { __trap(); }
+                            }
+                        }
+                    }
+                    fence_proxy_async_all();
+                }
+                const RdbLayerDev& Ly = R.layer[it.layer];
+                const int x0 = it.tx * kTileWOut - 1, y0 = it.ty * (NB * kBandRows) - 1;
+                for (int kb = 0; kb < Ly.nkb; ++kb) {
+                    const esr_kblock& K = Ly.kb[kb];
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
+                    tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, it.n);
+                    if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer (leader CTA only)
+        if (rank != 0) {
+            if (elect_one()) {
+                mbar_wait(w_full, 0);
+                mbar_arrive_cluster(mapa_u32(smem_u32(w_ready), 0));
+            }
+        } else if (elect_one()) {
+            const uint32_t w_lo = smem_u32(s_w) >> 4, a_lo = smem_u32(s_a) >> 4;
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            mbar_wait(w_full, 0);
+            mbar_wait(w_ready, 0);
+            const int per_chunk = R.nlayers * R.ppc;
+            for (int item = cluster_id; item < R.total_items; item += num_clusters) {
+                const RdbLayerDev& Ly = R.layer[(item % per_chunk) / R.ppc];
+                mbar_wait(&acc_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + as * (NB * kAccSlot);
+                uint32_t nonfirst = 0;
+                for (int kb = 0; kb < Ly.nkb; ++kb) {
+                    const uint32_t masks = *reinterpret_cast<const uint32_t*>(&Ly.kb[kb].dy_mask);
+                    const uint32_t dy_mask = masks & 0xff, slice_mask = (masks >> 8) & 0xff;
+                    const uint32_t w0 = w_lo + ((Ly.w_smem_off + Ly.kb[kb].w_off) >> 4);
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = a_lo + stage * (kATile >> 4);
+                    if (dy_mask == 7u && slice_mask == 3u) {
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                                for (int b = 0; b < NB; ++b) {
+                                    umma_issue2(acc0 + b * kAccSlot, a0 + (b * kBandRows + dy) * kARow16 + s * 2,
+                                                w0 + dy * kWSlab16 + s * 2, kIdesc, (dy | s) ? 1u : nonfirst);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int b = 0; b < NB; ++b) {
+                            uint32_t acc_flag = nonfirst, wi = 0;
+                            for (int dy = 0; dy < 3; ++dy) {
+                                if (!((dy_mask >> dy) & 1u)) continue;
+                                for (int s = 0; s < 2; ++s) {
+                                    if (!((slice_mask >> s) & 1u)) continue;
+                                    umma_issue2(acc0 + b * kAccSlot, a0 + (b * kBandRows + dy) * kARow16 + s * 2,
+                                                w0 + wi * kWSlab16 + s * 2, kIdesc, acc_flag);
+                                    acc_flag = 1;
+                                }
+                                ++wi;
+                            }
+                        }
+                    }
+                    nonfirst = 1;
+                    umma_commit2(&empty_bar[stage]);
+                    if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
+                }
+                umma_commit2(&acc_full[as]);
+                if (++as == kAccStages) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (each CTA: its own tile)
+        const int wq = warp & 3;
+        const int b = (warp - 2) >> 2;
+        const uint32_t lead_acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
+        pdl_wait();
+        {   // clear the counter third a later launch will use (nobody reads it during this launch)
+            const int nwords = R.nlayers * R.spatial_tiles;
+            const int t = blockIdx.x * (kEpiWarps * 32) + (threadIdx.x - 64);
+            for (int i = t; i < nwords; i += gridDim.x * kEpiWarps * 32) R.flags_zero[i] = 0u;
+        }
+        uint32_t as = 0, aphase = 0;
+        for (int item = cluster_id; item < R.total_items; item += num_clusters) {
+            const RdbItem it = rdb_decode(R, item, rank);
+            const RdbLayerDev& Ly = R.layer[it.layer];
+            const int x = it.tx * kTileWOut - 1 + lane;
+            const int y = it.ty * (NB * kBandRows) + b * kBandRows + wq;
+            const bool ok = it.ok && lane >= 1 && lane <= kTileWOut && x < R.W && y < R.H;
+            const size_t pix = (static_cast<size_t>(it.n) * R.H + y) * R.W + x;
+            uint4 mk[4];
+            if (MODE == kEpiMask && ok) {
+                const uint4* m = reinterpret_cast<const uint4*>(R.mask + pix * R.mask_stride + Ly.out_choff);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mk[i] = __ldg(m + i);
+            }
+            mbar_wait(&acc_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * (NB * kAccSlot) + b * kAccSlot + (static_cast<uint32_t>(wq * 32) << 16);
+            float vc[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float vl[16], vr[16];
+                tmem_ld_x16(taddr + 0 * CT + h * 16, vl);
+                tmem_ld_x16(taddr + 1 * CT + h * 16, *reinterpret_cast<float(*)[16]>(&vc[h * 16]));
+                tmem_ld_x16(taddr + 2 * CT + h * 16, vr);
+                tmem_ld_wait();
+                if (h == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(lead_acc_empty0 + as * 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float fl = __shfl_up_sync(0xffffffffu, vl[i], 1);
+                    const float fr = __shfl_down_sync(0xffffffffu, vr[i], 1);
+                    vc[h * 16 + i] += fl + fr;
+                }
+            }
+            if (ok) {
+                const float* bias = s_bias + it.layer * CT;
+                uint32_t pk[16];
+                const uint16_t* mv = reinterpret_cast<const uint16_t*>(mk);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v0 = vc[2 * i] + bias[2 * i], v1 = vc[2 * i + 1] + bias[2 * i + 1];
+                    if (MODE == kEpiMask) {
+                        v0 *= ((mv[2 * i] & 0x8000u) == 0 && (mv[2 * i] & 0x7fffu) != 0) ? 1.f : R.slope;
+                        v1 *= ((mv[2 * i + 1] & 0x8000u) == 0 && (mv[2 * i + 1] & 0x7fffu) != 0) ? 1.f : R.slope;
+                    } else {
+                        v0 = fmaxf(v0, R.slope * v0);
+                        v1 = fmaxf(v1, R.slope * v1);
+                    }
+                    pk[i] = pack_bf16x2(v0, v1);
+                }
+                __nv_bfloat16* o = R.out + pix * R.out_stride + Ly.out_choff;
+                st_global_v8(o, *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]));
+                st_global_v8(o + 16, *reinterpret_cast<const uint32_t(*)[8]>(&pk[8]));
+            }
+            if (it.ok && it.layer + 1 < R.nlayers) {
+                // publish: this warp's part of (layer, tile) is stored
+                fence_proxy_async_all();
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(R.flags + static_cast<size_t>(it.layer) * R.spatial_tiles + it.gt, 1u);
+            }
+            if (++as == kAccStages) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, kTmemCols);
+    }
+}
+
 }  // namespace pair
 
 int num_sms_cached();
+
+int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W, int box_rows);
+
+struct RdbOp {
+    alignas(64) CUtensorMap tm0;
+    alignas(64) CUtensorMap tm1;
+    pair::RdbLaunch R;
+};
+
+int build_rdb_growth(const esr_rdb_growth_desc& d, RdbOp* op) {
+    using namespace pair;
+    ESR_CHECK_ARG(d.B > 0 && d.H > 0 && d.W > 0, "rdb_growth: bad geometry");
+    ESR_CHECK_ARG(d.num_layers >= 1 && d.num_layers <= ESR_RDB_MAX_LAYERS, "rdb_growth: 1..4 layers");
+    ESR_CHECK_ARG(d.src[0].ptr && d.out && d.flags, "rdb_growth: null buffer");
+    ESR_CHECK_ARG(d.out_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 31) == 0, "rdb_growth: output misaligned");
+    ESR_CHECK_ARG(d.mode == 0 || (d.mode == 1 && d.mask && d.mask_stride % 8 == 0), "rdb_growth: bad mode / mask");
+    ESR_CHECK_ARG(d.flags_use >= 0 && d.flags_use < 3 && d.flags_zero >= 0 && d.flags_zero < 3 && d.flags_use != d.flags_zero,
+                  "rdb_growth: flags_use / flags_zero must be different thirds");
+    RdbLaunch& R = op->R;
+    memset(&R, 0, sizeof(R));
+    R.B = d.B; R.H = d.H; R.W = d.W; R.nlayers = d.num_layers;
+    uint32_t woff = 0;
+    for (int l = 0; l < d.num_layers; ++l) {
+        const esr_rdb_layer& s = d.layers[l];
+        ESR_CHECK_ARG(s.num_kblocks > 0 && s.num_kblocks <= ESR_RDB_MAX_KBLOCKS && s.wpack && s.bias, "rdb_growth: bad layer %d", l);
+        ESR_CHECK_ARG(s.w_tile_bytes % 32 == 0 && (reinterpret_cast<uintptr_t>(s.wpack) & 15) == 0, "rdb_growth: wpack misaligned");
+        ESR_CHECK_ARG(s.out_choff % 16 == 0 && s.out_choff + 32 <= d.out_stride, "rdb_growth: bad out_choff");
+        RdbLayerDev& D = R.layer[l];
+        D.nkb = s.num_kblocks; D.out_choff = s.out_choff; D.w_smem_off = woff; D.w_half_bytes = s.w_tile_bytes / 2;
+        D.wpack = static_cast<const uint8_t*>(s.wpack); D.bias = s.bias;
+        for (int k = 0; k < s.num_kblocks; ++k) {
+            const esr_kblock& kb = s.kblocks[k];
+            ESR_CHECK_ARG((kb.src == 0 || (kb.src == 1 && d.src[1].ptr)) && kb.chan >= 0 && kb.chan % 8 == 0 &&
+                          kb.chan + kKB <= d.src[kb.src].channels && (kb.dy_mask & 7) && (kb.slice_mask & 3) && kb.w_off % 512 == 0 &&
+                          kb.w_off + kb.n_dy * 48u * kRowBytes <= D.w_half_bytes, "rdb_growth: bad K block %d of layer %d", k, l);
+            D.kb[k] = kb;
+        }
+        woff += (D.w_half_bytes + 1023u) & ~1023u;
+    }
+    R.w_smem_bytes = woff;
+    R.out = static_cast<__nv_bfloat16*>(d.out); R.out_stride = d.out_stride; R.mode = d.mode; R.slope = d.slope;
+    R.mask = static_cast<const uint16_t*>(d.mask); R.mask_stride = d.mask_stride;
+    R.tiles_x = ceil_div(d.W, kTileWOut);
+    R.tiles_y = ceil_div(d.H, 2 * kBandRows);
+    R.tiles_per_img = R.tiles_x * R.tiles_y;
+    R.spatial_tiles = d.B * R.tiles_per_img;
+    int ic = d.imgs_per_chunk > 0 ? d.imgs_per_chunk : 4;
+    if (ic > d.B || d.B % ic != 0) ic = d.B;
+    R.tiles_c = ic * R.tiles_per_img;
+    R.ppc = (R.tiles_c + 1) / 2;
+    R.chunks = d.B / ic;
+    R.total_items = R.chunks * R.nlayers * R.ppc;
+    const size_t third = static_cast<size_t>(ESR_RDB_MAX_LAYERS) * R.spatial_tiles;
+    R.flags = d.flags + third * d.flags_use;
+    R.flags_zero = d.flags + third * d.flags_zero;
+    constexpr int a_tile = (2 * kBandRows + 2) * kTileW * kRowBytes;
+    const int ctrl = 256 + ESR_RDB_MAX_LAYERS * 32 * 4;
+    const int room = kSmemMax - 1024 - ctrl - static_cast<int>(R.w_smem_bytes);
+    int st = room / a_tile;
+    R.nstages = st > kRdbStages ? kRdbStages : st;
+    ESR_CHECK_ARG(R.nstages >= 2, "rdb_growth: weights (%u B per CTA) leave no room for the A-tile ring", R.w_smem_bytes);
+    int rc = make_act_tensor_map(&op->tm0, d.src[0], d.B, d.H, d.W, 2 * kBandRows + 2);
+    if (rc != ESR_OK) return rc;
+    if (d.src[1].ptr != nullptr) return make_act_tensor_map(&op->tm1, d.src[1], d.B, d.H, d.W, 2 * kBandRows + 2);
+    op->tm1 = op->tm0;
+    return ESR_OK;
+}
+
+RdbOp* new_rdb_op(const esr_rdb_growth_desc& d, int* rc) {
+    RdbOp* op = new (std::nothrow) RdbOp();
+    if (op == nullptr) { set_error("out of host memory"); *rc = ESR_ERR_INVALID; return nullptr; }
+    *rc = build_rdb_growth(d, op);
+    if (*rc != ESR_OK) { delete op; return nullptr; }
+    return op;
+}
+void delete_rdb_op(RdbOp* op) { delete op; }
+
+int launch_rdb_growth(const RdbOp& op, cudaStream_t stream, int use_pdl) {
+    using namespace pair;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_rdb_growth_kernel<kEpiTrunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        ESR_CUDA(cudaFuncSetAttribute(conv3x3_rdb_growth_kernel<kEpiMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr_set = true;
+    }
+    const pair::RdbLaunch& R = op.R;
+    constexpr int a_tile = (2 * kBandRows + 2) * kTileW * kRowBytes;
+    int clusters = num_sms_cached() / 2;
+    if (clusters > R.ppc) clusters = R.ppc;               // never more clusters than items of one (chunk, layer)
+    const int smem = 1024 + static_cast<int>(R.w_smem_bytes) + R.nstages * a_tile + 256 + ESR_RDB_MAX_LAYERS * 32 * 4;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 2 : 1;
+    const cudaError_t e = R.mode == 0 ? cudaLaunchKernelEx(&cfg, conv3x3_rdb_growth_kernel<kEpiTrunk>, op.tm0, op.tm1, R)
+                                      : cudaLaunchKernelEx(&cfg, conv3x3_rdb_growth_kernel<kEpiMask>, op.tm0, op.tm1, R);
+    if (e != cudaSuccess) { set_error("conv3x3_rdb_growth_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
+    return check_launch("conv3x3_rdb_growth_kernel");
+}
 
 // Fills the pair-mode launch geometry; returns false if the weights leave no room for the A ring.
 bool fill_launch_pair(ConvLaunch* L) {

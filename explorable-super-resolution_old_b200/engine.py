@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _capi as capi
-from ._capi import KBlock, ConvDesc, WRow, WSlot, XSlot
+from ._capi import KBlock, ConvDesc, WRow, WSlot, XSlot, RdbGrowthDesc
 
 DY_ALL, DY_CENTRE = 0b111, 0b010
 NF, GC = 64, 32
@@ -270,6 +270,10 @@ class GPlan:
         self.y = torch.empty(B, eng.out_nc, H4, W4, **f32)
         self.seq = capi.lib().esr_seq_create()
         self.descs = []
+        # fused growth convs (conv 0..3 of every RDB in one persistent launch with tile-level dependencies)
+        self.fuse_rdb = eng.pair and not use_simt and os.environ.get("ESR_FUSE_RDB", "1") != "0"
+        self.rdb_flags = torch.zeros(int(capi.lib().esr_rdb_growth_flag_words(B, hp, wp)), dtype=torch.int32, device=device) \
+            if self.fuse_rdb else None
         self._record_forward(use_simt)
 
     def __del__(self):
@@ -312,10 +316,37 @@ class GPlan:
             d.out_nchw, d.cout_real = out_nchw.data_ptr(), pc.cout
         return d
 
+    def _growth_desc(self, names, buf, lat, k, n, mode=0, mask=None):
+        """esr_rdb_growth_desc of launch k of n: the convs `names` read / write the dense-block buffer `buf`."""
+        d = RdbGrowthDesc()
+        d.B, d.H, d.W = self.B, self.hp, self.wp
+        d.src[0].ptr, d.src[0].channels = buf.data_ptr(), buf.shape[-1]
+        if lat is not None:
+            d.src[1].ptr, d.src[1].channels = lat.data_ptr(), lat.shape[-1]
+        d.num_layers = len(names)
+        for l, (pc, choff) in enumerate(names):
+            assert pc.pair and pc.cout_tile == 32 and pc.cout_tiles == 1 and pc.nkb <= capi.RDB_MAX_KBLOCKS
+            ly = d.layers[l]
+            ly.num_kblocks = pc.nkb
+            for i in range(pc.nkb):
+                ly.kblocks[i] = pc.kblocks[i]
+            ly.wpack, ly.w_tile_bytes, ly.bias, ly.out_choff = pc.wpack.data_ptr(), pc.w_tile_bytes, pc.bias.data_ptr(), choff
+        d.out, d.out_stride, d.mode, d.slope = buf.data_ptr(), buf.shape[-1], mode, 0.2
+        if mask is not None:
+            d.mask, d.mask_stride = mask.data_ptr(), mask.shape[-1]
+        d.imgs_per_chunk = int(os.environ.get("ESR_RDB_CHUNK", 0))
+        d.flags = self.rdb_flags.data_ptr()
+        assert n >= 2
+        use = lambda i: 2 if (i == n - 1 and n % 2 == 1) else i % 2       # consecutive launches never share a third,
+        d.flags_use, d.flags_zero = use(k), use((k + 1) % n)               # including last -> first of the next replay
+        return d
+
     def _record_forward(self, use_simt):
         eng, hp, wp = self.eng, self.hp, self.wp
         L = capi.EPI_LRELU
-        add = self.descs.append
+        self.ops = []                                      # ConvDesc | RdbGrowthDesc, in launch order
+        add = lambda d: (self.descs.append(d), self.ops.append(d))
+        n_rdb = 3 * eng.nb
         lo = 64 if eng.outer_mode == "split" else -1
         F16 = capi.EPI_OUT_F16 if eng.outer_mode == "f16" else 0      # outputs consumed by an fp16 conv
         add(self._desc("model.0", hp, wp, self.E_fea, out_f32=self.T_fea, out_bf16=self.buf(0)))
@@ -327,8 +358,12 @@ class GPlan:
                 b = self.buf(g)
                 xin = rin if d == 1 else self.T[d % 2]
                 pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
-                for i in range(4):
-                    add(self._desc(pre + "%d.0" % i, hp, wp, b, self.E_lat, flags=L, out_bf16=b, out_choff=NF + GC * i))
+                if self.fuse_rdb:
+                    self.ops.append(self._growth_desc([(eng.convs[pre + "%d.0" % i], NF + GC * i) for i in range(4)], b,
+                                                      self.E_lat, g, n_rdb))
+                else:
+                    for i in range(4):
+                        add(self._desc(pre + "%d.0" % i, hp, wp, b, self.E_lat, flags=L, out_bf16=b, out_choff=NF + GC * i))
                 last_rdb = (r == eng.nb - 1 and d == 3)
                 add(self._desc(pre + "4.0", hp, wp, b, self.E_lat, flags=F16 if last_rdb else 0, alpha=0.2, res1=xin,
                                beta=0.2, res2=rin if d == 3 else None,
@@ -348,8 +383,11 @@ class GPlan:
                 H, W = 2 * H, 2 * W
         add(self._desc(names[-2], H, W, self.V1, self.E_lath, flags=L | F16, out_bf16=self.V2, lo_choff=lo))
         add(self._desc(names[-1], H, W, self.V2, self.E_lath, out_nchw=self.y))
-        for d in self.descs:
-            capi.check(capi.lib().esr_seq_add_conv(self.seq, C.byref(d), 1 if use_simt else 0))
+        for d in self.ops:
+            if isinstance(d, RdbGrowthDesc):
+                capi.check(capi.lib().esr_seq_add_rdb_growth(self.seq, C.byref(d)))
+            else:
+                capi.check(capi.lib().esr_seq_add_conv(self.seq, C.byref(d), 1 if use_simt else 0))
         self.fea_x = _xslot_array(eng.fea_xslots)
         self.lat_x = _xslot_array(eng.lat_xslots)
 

@@ -130,6 +130,42 @@ int esr_conv3x3_tc(const esr_conv_desc* d, void* stream);
  * tensor-core/TMA faults from packing/epilogue faults.  Never used for timing. */
 int esr_conv3x3_simt(const esr_conv_desc* d, void* stream);
 
+/* Fused growth convs of a dense block (block.py:230-235: conv 0..3 of ResidualDenseBlock_5C; also the mirrored dgrad
+ * launches 5..2 of the backward): ONE persistent launch runs up to four 3x3 convs that each read channel windows of
+ * the same NHWC bf16 buffer (+ the latent rows) and write 32 new channels into it.  Layer l+1 of a tile starts as
+ * soon as layer l of its 3x3 tile neighbourhood is stored (per-tile counters in `flags`), so there is no launch
+ * boundary, pipeline drain or grid barrier between the layers; the batch is walked in chunks of `imgs_per_chunk`
+ * images so that a chunk's dense block is still in L2 when the next layer reads it.  CTA pairs (cta_group::2),
+ * cout tile 32, weights of all layers resident in shared memory. */
+#define ESR_RDB_MAX_LAYERS 4
+#define ESR_RDB_MAX_KBLOCKS 8
+typedef struct esr_rdb_layer {
+    int32_t num_kblocks;
+    esr_kblock kblocks[ESR_RDB_MAX_KBLOCKS]; /* pair layout (esr_pack_layout pair=1), cout_tile 32, one cout tile */
+    const void* wpack;
+    uint32_t w_tile_bytes;
+    const float* bias;                       /* 32 floats */
+    int32_t out_choff;                       /* channel slice [out_choff, out_choff+32) of `out` written by this layer */
+} esr_rdb_layer;
+typedef struct esr_rdb_growth_desc {
+    int32_t B, H, W;
+    esr_tensor_nhwc src[2];  /* src[0]: the dense-block buffer the K blocks read; src[1]: latent rows or NULL */
+    int32_t num_layers;      /* 1..4; layer l may read what layers < l wrote */
+    esr_rdb_layer layers[ESR_RDB_MAX_LAYERS];
+    void* out;               /* NHWC bf16 [B,H,W,out_stride]; normally == src[0].ptr */
+    int32_t out_stride;
+    int32_t mode;            /* 0: out = bf16(LeakyReLU(acc + bias))   1: out = bf16((acc + bias) * LeakyReLU'(mask)) */
+    float slope;
+    const void* mask;        /* mode 1: NHWC bf16/fp16 activations, sign read at the output's own channel offset */
+    int32_t mask_stride;
+    int32_t imgs_per_chunk;  /* <= 0: library default (4, or B if it does not divide B) */
+    uint32_t* flags;         /* device scratch of esr_rdb_growth_flag_words() uint32, zero-filled ONCE by the caller */
+    int32_t flags_use;       /* 0..2: third of `flags` this launch counts in (must be all zero when it starts) */
+    int32_t flags_zero;      /* 0..2, != flags_use: third this launch clears for a later launch */
+} esr_rdb_growth_desc;
+int64_t esr_rdb_growth_flag_words(int32_t B, int32_t H, int32_t W);
+int esr_rdb_growth_tc(const esr_rdb_growth_desc* d, void* stream);
+
 /* Weight packing tables.  The kernels compute
  *   out[row] = sum over taps (ky,kx) and channel slots of  A[slot] * Wl[row, slot, ky, kx]
  * and the packer gathers the logical weights from an f32 device tensor:
@@ -255,6 +291,7 @@ typedef struct esr_seq esr_seq;
 esr_seq* esr_seq_create(void);
 void esr_seq_destroy(esr_seq* s);
 int esr_seq_add_conv(esr_seq* s, const esr_conv_desc* d, int32_t use_simt);
+int esr_seq_add_rdb_growth(esr_seq* s, const esr_rdb_growth_desc* d);
 int esr_seq_run(const esr_seq* s, void* stream);
 int32_t esr_seq_num_launches(const esr_seq* s);
 

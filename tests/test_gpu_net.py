@@ -113,6 +113,28 @@ def test_batch_shards_are_bit_identical(cuda_device):
             assert torch.equal(one[0], full[i])
 
 
+@pytest.mark.parametrize("B,h,w,chunk", [(1, 16, 20, 0), (8, 30, 41, 4), (6, 24, 70, 2), (3, 52, 33, 1)])
+def test_fused_growth_convs_bit_identical_to_separate_launches(cuda_device, monkeypatch, B, h, w, chunk):
+    """conv 0..3 of every RDB as ONE persistent launch with tile-level dependencies (esr_rdb_growth_tc) against the
+    same convs as four launches: several chunks, several tiles per cluster, odd tile counts; run twice (the flag
+    thirds rotate and are cleared by the launches themselves)."""
+    wts = synth.make_weights("default", seed=5, nb=2)
+    lr, z = synth.make_inputs(B, h, w, seed=5)
+    mi = concat_latent(lr, z).to(cuda_device)
+    netG = build_product_G(cuda_device, 2, "all_layers_HR_downscaled", wts)
+    G = netG.generated_image_model
+    monkeypatch.setenv("ESR_RDB_CHUNK", str(chunk))
+    with torch.no_grad():
+        fused = [netG(mi).clone() for _ in range(3)]
+        assert list(G._plans.values())[-1].fuse_rdb
+        monkeypatch.setenv("ESR_FUSE_RDB", "0")
+        G._plans.clear()
+        ref = netG(mi).clone()
+        assert not list(G._plans.values())[-1].fuse_rdb
+    for f in fused:
+        assert torch.equal(f, ref)
+
+
 def test_host_pipeline_matches_direct_call(cuda_device):
     """parallel.HostPipeline (chunked, copies overlapped with compute) returns what netG(x) returns."""
     from esr_b200.parallel import HostPipeline
