@@ -31,6 +31,7 @@ struct SeqOp {
 
 struct RdbOp;                                   // conv3x3_tc2.cu
 RdbOp* new_rdb_op(const esr_rdb_growth_desc& d, int* rc);
+void rdb_op_set_reverse(RdbOp* op, int reverse);
 void delete_rdb_op(RdbOp* op);
 int launch_rdb_growth(const RdbOp& op, cudaStream_t stream, int use_pdl);
 
@@ -80,6 +81,8 @@ extern "C" int esr_seq_add_rdb_growth(esr_seq* s, const esr_rdb_growth_desc* d) 
     esr::SeqOp op;
     std::memset(&op, 0, sizeof(op));
     op.use_simt = -1 - static_cast<int>(s->rdb.size());
+    static const bool snake = []() { const char* v = getenv("ESR_NO_SNAKE"); return !(v && atoi(v)); }();
+    esr::rdb_op_set_reverse(r, snake ? static_cast<int>(s->ops.size() & 1) : 0);   // alternate with the neighbouring launches
     s->rdb.push_back(r);
     s->ops.push_back(op);
     return ESR_OK;

@@ -401,11 +401,14 @@ struct RdbLaunch {
     int tiles_x, tiles_y, tiles_per_img, tiles_c, ppc, chunks, total_items, spatial_tiles;
     uint32_t* flags;                        // [nlayers][spatial_tiles] counters of this launch
     uint32_t* flags_zero;                   // same size, cleared for a later launch
+    int reverse;                            // walk chunks and tiles last-to-first (alternates launch by launch: L2 reuse)
+    uint32_t m_per_chunk, m_ppc, m_tpi, m_tx;   // ceil(2^32 / d): n / d == __umulhi(n, m) for n * d < 2^32 (no XU divisions)
     int nstages;
     uint32_t w_smem_bytes;
 };
 
-constexpr int kRdbStages = 6;
+constexpr int kRdbStages = 10;
+constexpr int kRdbThreads = kNumThreads + 32;   // + one publisher warp (GPU-scope fence + counter bump, off the epilogue's path)
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
@@ -417,22 +420,25 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 struct RdbItem { int layer, n, ty, tx, gt; bool ok; };
 __device__ __forceinline__ RdbItem rdb_decode(const RdbLaunch& R, int item, uint32_t rank) {
     const int per_chunk = R.nlayers * R.ppc;
-    const int c = item / per_chunk, rem = item - c * per_chunk;
+    int c = static_cast<int>(__umulhi(static_cast<uint32_t>(item), R.m_per_chunk));
+    const int rem = item - c * per_chunk;
     RdbItem it;
-    it.layer = rem / R.ppc;
-    int tl = 2 * (rem - it.layer * R.ppc) + static_cast<int>(rank);
+    it.layer = static_cast<int>(__umulhi(static_cast<uint32_t>(rem), R.m_ppc));
+    int p = rem - it.layer * R.ppc;
+    if (R.reverse) { c = R.chunks - 1 - c; p = R.ppc - 1 - p; }
+    int tl = 2 * p + static_cast<int>(rank);
     it.ok = tl < R.tiles_c;
     if (!it.ok) tl = R.tiles_c - 1;                                 // odd tail: duplicate tile, nothing stored
     it.gt = c * R.tiles_c + tl;
-    it.n = it.gt / R.tiles_per_img;
+    it.n = static_cast<int>(__umulhi(static_cast<uint32_t>(it.gt), R.m_tpi));
     const int r = it.gt - it.n * R.tiles_per_img;
-    it.ty = r / R.tiles_x;
+    it.ty = static_cast<int>(__umulhi(static_cast<uint32_t>(r), R.m_tx));
     it.tx = r - it.ty * R.tiles_x;
     return it;
 }
 
 template <int MODE>   // kEpiTrunk: bias + LeakyReLU;  kEpiMask: (acc + bias) * LeakyReLU'(mask)
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kRdbThreads, 1)
 conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                           const __grid_constant__ RdbLaunch R) {
     constexpr int CT = 32, N = 96, NB = 2;
@@ -455,19 +461,21 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
     uint64_t* w_full = acc_empty + kAccStages;
     uint64_t* w_ready = w_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_ready + 1);
+    uint32_t* stored_cnt = tmem_slot + 1;           // monotonic: +1 per epilogue warp per item whose stores are issued
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [nlayers][32]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    for (int i = threadIdx.x; i < R.nlayers * CT; i += kNumThreads) s_bias[i] = R.layer[i / CT].bias[i % CT];
+    for (int i = threadIdx.x; i < R.nlayers * CT; i += kRdbThreads) s_bias[i] = R.layer[i / CT].bias[i % CT];
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap0);
         tma_prefetch_desc(&tmap1);
         for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
+        *stored_cnt = 0u;
         mbar_init(w_full, 1);
         mbar_init(w_ready, 1);
         fence_mbar_init();
@@ -483,7 +491,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
     pdl_launch_dependents();
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (one per CTA)
+        // ------------------------------------------------------------ TMA producer (one per CTA; whole warp polls)
         if (elect_one()) {
             uint32_t wbytes = 0;
             for (int l = 0; l < R.nlayers; ++l) wbytes += R.layer[l].w_half_bytes;
@@ -496,28 +504,40 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                     bulk_load_1d(s_w + Ly.w_smem_off + off, wt + off, n, w_full);
                 }
             }
-            pdl_wait();
-            uint32_t stage = 0, phase = 0;
-            for (int item = cluster_id; item < R.total_items; item += num_clusters) {
+        }
+        __syncwarp();
+        pdl_wait();
+        // Lane l < 9 watches neighbour (l/3-1, l%3-1) of the item's tile: one L2 round trip per item for all nine
+        // counters, and the counters of the NEXT item are requested before this item's loads are issued, so the
+        // answer is normally back (and positive: the neighbours ran ~2 rounds earlier) when it is needed.
+        const int ndy = lane / 3 - 1, ndx = lane % 3 - 1;
+        auto poll = [&](int item) -> uint32_t {
+            if (lane >= 9 || item >= R.total_items) return kEpiWarps;
+            const RdbItem it = rdb_decode(R, item, rank);
+            const int yy = it.ty + ndy, xx = it.tx + ndx;
+            if (it.layer == 0 || yy < 0 || yy >= R.tiles_y || xx < 0 || xx >= R.tiles_x) return kEpiWarps;
+#ifdef ESR_RDB_NO_DEPS
+            return kEpiWarps;      // timing experiment only (results invalid)
+#endif
+            return ld_acquire_u32(R.flags + static_cast<size_t>(it.layer - 1) * R.spatial_tiles +
+                                  static_cast<size_t>(it.n) * R.tiles_per_img + yy * R.tiles_x + xx);
+        };
+        uint32_t stage = 0, phase = 0;
+        uint32_t seen = poll(cluster_id);
+        for (int item = cluster_id; item < R.total_items; item += num_clusters) {
+#ifndef ESR_RDB_NO_POLL
+            for (uint32_t spin = 0; !__all_sync(0xffffffffu, seen >= static_cast<uint32_t>(kEpiWarps)); ++spin) {
+                if (spin > (1u << 24)) { __trap(); }
+                seen = poll(item);
+            }
+#endif
+            // (the generic->async proxy fence of this hand-over sits on the writer side, in publish(): a full proxy
+            // fence here would also wait for this thread's TMA loads in flight and serialise the items)
+#ifndef ESR_RDB_NO_POLL
+            seen = poll(item + num_clusters);
+#endif
+            if (lane == 0) {                  // ring position lives in lane 0
                 const RdbItem it = rdb_decode(R, item, rank);
-                if (it.layer > 0) {
-                    // layer-1 of the 3x3 tile neighbourhood must be in memory before this item's first load
-                    const uint32_t* f = R.flags + static_cast<size_t>(it.layer - 1) * R.spatial_tiles +
-                                        static_cast<size_t>(it.n) * R.tiles_per_img;
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int yy = it.ty + dy;
-                        if (yy < 0 || yy >= R.tiles_y) continue;
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int xx = it.tx + dx;
-                            if (xx < 0 || xx >= R.tiles_x) continue;
-                            const uint32_t* fp = f + yy * R.tiles_x + xx;
-                            for (uint32_t spin = 0; ld_acquire_u32(fp) < static_cast<uint32_t>(kEpiWarps); ++spin) {
-                                if (spin > (1u << 24)) { __trap(); }
-                            }
-                        }
-                    }
-                    fence_proxy_async_all();
-                }
                 const RdbLayerDev& Ly = R.layer[it.layer];
                 const int x0 = it.tx * kTileWOut - 1, y0 = it.ty * (NB * kBandRows) - 1;
                 for (int kb = 0; kb < Ly.nkb; ++kb) {
@@ -529,6 +549,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                     if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer (leader CTA only)
@@ -544,7 +565,8 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
             mbar_wait(w_ready, 0);
             const int per_chunk = R.nlayers * R.ppc;
             for (int item = cluster_id; item < R.total_items; item += num_clusters) {
-                const RdbLayerDev& Ly = R.layer[(item % per_chunk) / R.ppc];
+                const int c_ = static_cast<int>(__umulhi(static_cast<uint32_t>(item), R.m_per_chunk));
+                const RdbLayerDev& Ly = R.layer[__umulhi(static_cast<uint32_t>(item - c_ * per_chunk), R.m_ppc)];
                 mbar_wait(&acc_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t acc0 = tmem_base + as * (NB * kAccSlot);
@@ -591,6 +613,34 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
         }
+    } else if (warp == 2 + kEpiWarps) {
+        // ---------------------------------------------------------------- publisher (one thread per CTA)
+        // Waits until the eight epilogue warps have issued the stores of an item (mbarrier, release/acquire at CTA
+        // scope: cumulative), makes them visible GPU-wide and bumps the tile's counter.  The ~0.7 us of the GPU-scope
+        // fence is paid here, not by the epilogue warps.
+#ifdef ESR_RDB_NO_PUBLISHER
+        if (false) {
+#else
+        if (lane == 0) {
+#endif
+            uint32_t want = 0;
+            const uint32_t cnt_addr = smem_u32(stored_cnt);
+            for (int item = cluster_id; item < R.total_items; item += num_clusters) {
+                const RdbItem it = rdb_decode(R, item, rank);
+                want += kEpiWarps;
+                for (uint32_t spin = 0;; ++spin) {               // a counter, not an mbarrier: lagging behind cannot alias phases
+                    uint32_t v;
+                    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(cnt_addr) : "memory");
+                    if (v >= want) break;
+                    __nanosleep(200);                            // do not steal issue slots from the epilogue warps of this scheduler
+                    if (spin > (1u << 24)) { __trap(); }
+                }
+                if (it.ok && it.layer + 1 < R.nlayers) {
+                    __threadfence();
+                    atomicAdd(R.flags + static_cast<size_t>(it.layer) * R.spatial_tiles + it.gt, static_cast<uint32_t>(kEpiWarps));
+                }
+            }
+        }
     } else {
         // ---------------------------------------------------------------- epilogue (each CTA: its own tile)
         const int wq = warp & 3;
@@ -599,7 +649,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
         pdl_wait();
         {   // clear the counter third a later launch will use (nobody reads it during this launch)
             const int nwords = R.nlayers * R.spatial_tiles;
-            const int t = blockIdx.x * (kEpiWarps * 32) + (threadIdx.x - 64);
+            const int t = blockIdx.x * (kEpiWarps * 32) + (threadIdx.x - 64);   // epilogue threads are 64 .. 64 + 256
             for (int i = t; i < nwords; i += gridDim.x * kEpiWarps * 32) R.flags_zero[i] = 0u;
         }
         uint32_t as = 0, aphase = 0;
@@ -659,13 +709,21 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                 st_global_v8(o, *reinterpret_cast<const uint32_t(*)[8]>(&pk[0]));
                 st_global_v8(o + 16, *reinterpret_cast<const uint32_t(*)[8]>(&pk[8]));
             }
-            if (it.ok && it.layer + 1 < R.nlayers) {
-                // publish: this warp's part of (layer, tile) is stored
-                fence_proxy_async_all();
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(R.flags + static_cast<size_t>(it.layer) * R.spatial_tiles + it.gt, 1u);
-            }
+            // generic-proxy stores -> later TMA (async proxy) reads by other SMs: every writer fences the proxies, the
+            // publisher warp does the GPU-scope part
+#ifndef ESR_RDB_NO_SIGNAL
+#ifndef ESR_RDB_NO_PROXY_FENCE
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+            __syncwarp();
+#endif
+            if (lane == 0) asm volatile(
+#ifdef ESR_RDB_NO_SIGNAL
+                "red.relaxed.cta.shared::cta.add.u32 [%0], 1;"
+#else
+                "red.release.cta.shared::cta.add.u32 [%0], 1;"
+#endif
+                ::"r"(smem_u32(stored_cnt)) : "memory");
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
     }
@@ -733,7 +791,12 @@ int build_rdb_growth(const esr_rdb_growth_desc& d, RdbOp* op) {
     R.ppc = (R.tiles_c + 1) / 2;
     R.chunks = d.B / ic;
     R.total_items = R.chunks * R.nlayers * R.ppc;
+    const auto magic = [](int dd) { return static_cast<uint32_t>(((1ull << 32) + dd - 1) / dd); };
+    ESR_CHECK_ARG(static_cast<long long>(R.total_items) * R.nlayers * R.ppc < (1ll << 32) &&
+                  static_cast<long long>(R.spatial_tiles) * R.tiles_per_img < (1ll << 32), "rdb_growth: problem too large");
+    R.m_per_chunk = magic(R.nlayers * R.ppc); R.m_ppc = magic(R.ppc); R.m_tpi = magic(R.tiles_per_img); R.m_tx = magic(R.tiles_x);
     const size_t third = static_cast<size_t>(ESR_RDB_MAX_LAYERS) * R.spatial_tiles;
+    R.reverse = 0;                                        // set by the sequence builder (alternates launch by launch)
     R.flags = d.flags + third * d.flags_use;
     R.flags_zero = d.flags + third * d.flags_zero;
     constexpr int a_tile = (2 * kBandRows + 2) * kTileW * kRowBytes;
@@ -757,6 +820,7 @@ RdbOp* new_rdb_op(const esr_rdb_growth_desc& d, int* rc) {
     return op;
 }
 void delete_rdb_op(RdbOp* op) { delete op; }
+void rdb_op_set_reverse(RdbOp* op, int reverse) { op->R.reverse = reverse; }
 
 int launch_rdb_growth(const RdbOp& op, cudaStream_t stream, int use_pdl) {
     using namespace pair;
@@ -773,7 +837,7 @@ int launch_rdb_growth(const RdbOp& op, cudaStream_t stream, int use_pdl) {
     const int smem = 1024 + static_cast<int>(R.w_smem_bytes) + R.nstages * a_tile + 256 + ESR_RDB_MAX_LAYERS * 32 * 4;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(kRdbThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];

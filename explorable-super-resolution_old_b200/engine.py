@@ -270,8 +270,11 @@ class GPlan:
         self.y = torch.empty(B, eng.out_nc, H4, W4, **f32)
         self.seq = capi.lib().esr_seq_create()
         self.descs = []
-        # fused growth convs (conv 0..3 of every RDB in one persistent launch with tile-level dependencies)
-        self.fuse_rdb = eng.pair and not use_simt and os.environ.get("ESR_FUSE_RDB", "1") != "0"
+        # Fused growth convs (conv 0..3 of every RDB in one persistent launch with tile-level dependencies, csrc/
+        # conv3x3_tc2.cu).  Opt-in (ESR_FUSE_RDB=1): bit-identical, 78 % less DRAM traffic for those convs at 4-8 images
+        # per chunk, but with all four weight images resident only 4 A-ring stages fit and it measures 3 % slower
+        # than the separate launches at config 2.
+        self.fuse_rdb = eng.pair and not use_simt and os.environ.get("ESR_FUSE_RDB", "0") == "1"
         self.rdb_flags = torch.zeros(int(capi.lib().esr_rdb_growth_flag_words(B, hp, wp)), dtype=torch.int32, device=device) \
             if self.fuse_rdb else None
         self._record_forward(use_simt)
@@ -359,8 +362,11 @@ class GPlan:
                 xin = rin if d == 1 else self.T[d % 2]
                 pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
                 if self.fuse_rdb:
-                    self.ops.append(self._growth_desc([(eng.convs[pre + "%d.0" % i], NF + GC * i) for i in range(4)], b,
-                                                      self.E_lat, g, n_rdb))
+                    per = int(os.environ.get("ESR_RDB_LAYERS", 4))       # growth convs per fused launch (4, 2 or 1)
+                    groups = [list(range(i0, min(i0 + per, 4))) for i0 in range(0, 4, per)]
+                    for gi, grp in enumerate(groups):
+                        self.ops.append(self._growth_desc([(eng.convs[pre + "%d.0" % i], NF + GC * i) for i in grp], b,
+                                                          self.E_lat, g * len(groups) + gi, n_rdb * len(groups)))
                 else:
                     for i in range(4):
                         add(self._desc(pre + "%d.0" % i, hp, wp, b, self.E_lat, flags=L, out_bf16=b, out_choff=NF + GC * i))

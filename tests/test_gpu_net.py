@@ -124,6 +124,7 @@ def test_fused_growth_convs_bit_identical_to_separate_launches(cuda_device, monk
     netG = build_product_G(cuda_device, 2, "all_layers_HR_downscaled", wts)
     G = netG.generated_image_model
     monkeypatch.setenv("ESR_RDB_CHUNK", str(chunk))
+    monkeypatch.setenv("ESR_FUSE_RDB", "1")
     with torch.no_grad():
         fused = [netG(mi).clone() for _ in range(3)]
         assert list(G._plans.values())[-1].fuse_rdb
