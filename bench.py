@@ -267,12 +267,22 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    # conv-only timing inside the same regime (events around the recorded conv sequence)
+    # conv-only timing in the same regime as the step (CUDA-graph replay of the recorded conv sequence, events)
+    def convs_only():
+        for _i in range(BATCH // SUB):
+            plans[_i % NSTREAMS].run_convs()
+    conv_run = convs_only
+    if graph is not None:
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            convs_only()
+        conv_run = cg.replay
+    for _ in range(2):
+        conv_run()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
     for _ in range(args.steps):
-        for _i in range(BATCH // SUB):
-            plans[_i % NSTREAMS].run_convs()
+        conv_run()
     c1.record()
     torch.cuda.synchronize()
     conv_ms = c0.elapsed_time(c1) / args.steps
