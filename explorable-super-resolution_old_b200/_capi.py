@@ -15,7 +15,7 @@ KBLOCK_CH = 32
 CEM_MAX_TAPS = 64
 
 EPI_LRELU, EPI_RES1, EPI_RES2, EPI_ACCUM, EPI_MASK, EPI_F32_BLOCKED = 1, 2, 4, 8, 16, 32
-CONV_F16, EPI_OUT_F16 = 64, 128
+CONV_F16, EPI_OUT_F16, EPI_RES1_HILO = 64, 128, 256
 
 
 class KBlock(C.Structure):
@@ -45,6 +45,9 @@ class ConvDesc(C.Structure):
         ("tile_choff", C.c_int16 * MAX_COUT_TILES),
         ("no_accum_tiles", C.c_uint16), ("no_bf16_tiles", C.c_uint16), ("no_res_tiles", C.c_uint16),
         ("pair", C.c_uint16), ("gamma", C.c_float),
+        ("res1_hi", C.c_void_p), ("res1_hi_stride", C.c_int32), ("res1_hi_choff", C.c_int32),
+        ("res1_lo", C.c_void_p), ("res1_lo_stride", C.c_int32), ("res1_lo_choff", C.c_int32),
+        ("out_lo", C.c_void_p), ("out_lo_stride", C.c_int32), ("out_lo_choff", C.c_int32),
     ]
 
     def __init__(self, *a, **kw):

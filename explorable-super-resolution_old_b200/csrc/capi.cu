@@ -44,7 +44,7 @@ struct esr_seq {
 };
 
 extern "C" const char* esr_last_error(void) { return esr::g_error; }
-extern "C" int esr_abi_version(void) { return 1; }
+extern "C" int esr_abi_version(void) { return 2; }   // 2: pair weight layout / esr_rdb_growth_* / hi-lo trunk fields
 
 extern "C" int esr_device_check(int device) {
     cudaDeviceProp p;

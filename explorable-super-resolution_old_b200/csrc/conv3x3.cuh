@@ -102,6 +102,28 @@ __device__ __forceinline__ void ld_global_v8f_stream(const float* p, float* v) {
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }
+__device__ __forceinline__ void ld_global_v8u(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+// r[0..16) = hi + lo, two bf16 NHWC tensors (16 consecutive channels of one pixel each, 32-byte aligned)
+__device__ __forceinline__ void load16_hilo(const esr_conv_desc& d, size_t pix, int co0, float* r) {
+    uint32_t h[8], l[8];
+    ld_global_v8u(reinterpret_cast<const __nv_bfloat16*>(d.res1_hi) + pix * d.res1_hi_stride + d.res1_hi_choff + co0, h);
+    ld_global_v8u(reinterpret_cast<const __nv_bfloat16*>(d.res1_lo) + pix * d.res1_lo_stride + d.res1_lo_choff + co0, l);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {   // bf16 -> f32 is a 16-bit shift
+        r[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+        r[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void store16_lo(const esr_conv_desc& d, size_t pix, int co0, const float* v) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(bf16_lo_part(v[2 * i]), bf16_lo_part(v[2 * i + 1]));
+    st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + pix * d.out_lo_stride + d.out_lo_choff + co0, pk);
+}
 // 16 consecutive floats, 32-byte vector accesses when `wide` (address 32-byte aligned)
 __device__ __forceinline__ void load16f(const float* p, float* r, bool wide) {
     if (wide) { ld_global_v8f(p, r); ld_global_v8f(p + 8, r + 8); }
@@ -207,8 +229,12 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, i
         return;
     }
     if constexpr (MODE == kEpiRes) {
-        ld_global_v8f_stream(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
-        ld_global_v8f_stream(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
+        if (d.flags & ESR_EPI_RES1_HILO) {
+            load16_hilo(d, (static_cast<size_t>(n) * d.H + y) * d.W + x, co0, P.r1);
+        } else {
+            ld_global_v8f_stream(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
+            ld_global_v8f_stream(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
+        }
         if (d.flags & ESR_EPI_RES2) {
             ld_global_v8f_stream(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0), P.r2);
             ld_global_v8f_stream(d.res2 + f32_off(d, true, d.res2_stride, n, y, x, d.res2_choff + co0 + 8), P.r2 + 8);
@@ -218,6 +244,7 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, i
     const uint32_t flags = tile_flags(d, ct);
     const size_t pix = (static_cast<size_t>(n) * d.H + y) * d.W + x;
     if (flags & ESR_EPI_ACCUM) load16f_at(d, d.out_f32, d.out_f32_stride, d.out_f32_choff, n, y, x, co0, P.r1);
+    else if ((flags & ESR_EPI_RES1) && (flags & ESR_EPI_RES1_HILO)) load16_hilo(d, pix, co0, P.r1);
     else if (flags & ESR_EPI_RES1) load16f_at(d, d.res1, d.res1_stride, d.res1_choff, n, y, x, co0, P.r1);
     if (flags & ESR_EPI_RES2) load16f_at(d, d.res2, d.res2_stride, d.res2_choff, n, y, x, co0, P.r2);
     if (flags & ESR_EPI_MASK) {
@@ -254,8 +281,11 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = d.beta * v[i] + P.r2[i];
         }
-        st_global_v8f_stream(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), v);
-        st_global_v8f_stream(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
+        if (d.out_f32 != nullptr) {
+            st_global_v8f_stream(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), v);
+            st_global_v8f_stream(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
+        }
+        if (d.out_lo != nullptr) store16_lo(d, pix, co0, v);
         uint32_t pk[8];
         if (d.flags & ESR_EPI_OUT_F16) {
 #pragma unroll
@@ -361,6 +391,7 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
         for (int i = 0; i < 16; ++i) v[i] = d.beta * v[i] + P.r2[i];
     }
     if (d.out_f32 != nullptr) store16f_at(d, d.out_f32, d.out_f32_stride, d.out_f32_choff, n, y, x, co0, v);
+    if (d.out_lo != nullptr) store16_lo(d, pix, co0, v);
     if (d.out_nchw != nullptr) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -438,9 +469,10 @@ inline int classify_epilogue(const esr_conv_desc& d) {
     if ((f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == ESR_EPI_LRELU && bf_ok && d.out_f32 == nullptr && d.out_nchw == nullptr &&
         d.up == 1 && d.cout_tile == 32)
         return kEpiTrunk;
-    if ((f & ~static_cast<uint32_t>(ESR_EPI_RES2 | ESR_EPI_OUT_F16)) == (ESR_EPI_RES1 | ESR_EPI_F32_BLOCKED) && bf_ok && d.up == 1 &&
-        d.out_f32 != nullptr && d.out_nchw == nullptr && d.res1 != nullptr && (!(f & ESR_EPI_RES2) || d.res2 != nullptr))
-        return kEpiRes;      // blocked-layout alignment was validated (validate_conv_desc)
+    if ((f & ~static_cast<uint32_t>(ESR_EPI_RES2 | ESR_EPI_OUT_F16 | ESR_EPI_RES1_HILO)) == (ESR_EPI_RES1 | ESR_EPI_F32_BLOCKED) && bf_ok &&
+        d.up == 1 && (d.out_f32 != nullptr || d.out_lo != nullptr) && d.out_nchw == nullptr &&
+        ((f & ESR_EPI_RES1_HILO) || d.res1 != nullptr) && (!(f & ESR_EPI_RES2) || d.res2 != nullptr))
+        return kEpiRes;      // blocked-layout / pair alignment was validated (validate_conv_desc)
     if ((f & ~static_cast<uint32_t>(ESR_EPI_LRELU | ESR_EPI_OUT_F16 | ESR_EPI_F32_BLOCKED)) == 0 && bf_ok && d.out_f32 == nullptr &&
         d.out_nchw == nullptr)
         return kEpiAct;

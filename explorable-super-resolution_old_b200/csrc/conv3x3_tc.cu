@@ -359,12 +359,21 @@ int validate_conv_desc(const esr_conv_desc& d) {
     if (d.out_f32) ESR_CHECK_ARG(d.out_f32_stride % 4 == 0 && d.out_f32_choff % 4 == 0, "f32 output misaligned");
     if (d.flags & ESR_EPI_ACCUM) ESR_CHECK_ARG(d.out_f32 != nullptr, "ACCUM needs out_f32");
     if (d.flags & ESR_EPI_F32_BLOCKED) {
+        const bool r1f32 = (d.flags & ESR_EPI_RES1) && !(d.flags & ESR_EPI_RES1_HILO);
+        (void)r1f32;
         ESR_CHECK_ARG((d.out_f32 == nullptr || (d.out_f32_stride % 8 == 0 && d.out_f32_choff % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out_f32) & 31) == 0)) &&
                       (d.res1 == nullptr || (d.res1_stride % 8 == 0 && d.res1_choff % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res1) & 31) == 0)) &&
                       (d.res2 == nullptr || (d.res2_stride % 8 == 0 && d.res2_choff % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res2) & 31) == 0)),
                       "blocked f32 tensors need 8-channel multiples and 32-byte alignment");
     }
-    if (d.flags & ESR_EPI_RES1) ESR_CHECK_ARG(d.res1 && d.res1_stride % 4 == 0 && d.res1_choff % 4 == 0, "res1 misaligned");
+    const auto pair16 = [](const void* p, int stride, int choff) {
+        return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 31) == 0 && stride % 16 == 0 && choff % 16 == 0;
+    };
+    if ((d.flags & ESR_EPI_RES1) && (d.flags & ESR_EPI_RES1_HILO))
+        ESR_CHECK_ARG(pair16(d.res1_hi, d.res1_hi_stride, d.res1_hi_choff) && pair16(d.res1_lo, d.res1_lo_stride, d.res1_lo_choff),
+                      "res1_hi / res1_lo must be bf16 NHWC, 32-byte aligned, 16-channel multiples");
+    else if (d.flags & ESR_EPI_RES1) ESR_CHECK_ARG(d.res1 && d.res1_stride % 4 == 0 && d.res1_choff % 4 == 0, "res1 misaligned");
+    if (d.out_lo) ESR_CHECK_ARG(pair16(d.out_lo, d.out_lo_stride, d.out_lo_choff), "out_lo misaligned");
     if (d.flags & ESR_EPI_RES2) ESR_CHECK_ARG(d.res2 && d.res2_stride % 4 == 0 && d.res2_choff % 4 == 0, "res2 misaligned");
     if (d.flags & ESR_EPI_MASK) ESR_CHECK_ARG(d.mask && d.out_bf16 && d.up == 1 && d.mask_stride % 8 == 0 && d.mask_choff % 8 == 0, "mask misaligned");
     if (d.out_nchw) ESR_CHECK_ARG(d.cout_real > 0 && d.cout_real <= d.cout_tile * d.cout_tiles, "bad cout_real");

@@ -79,6 +79,7 @@ enum {
     ESR_EPI_MASK = 1u << 4,    /* bf16 output *= (mask > 0 ? 1 : slope) (LeakyReLU')     */
     ESR_EPI_F32_BLOCKED = 1u << 5, /* out_f32 / res1 / res2 use the blocked layout [B, C/8, H, W, 8] (coalesced
                                       32-byte accesses across the pixels of a warp) instead of NHWC; *_stride is C */
+    ESR_EPI_RES1_HILO = 1u << 8, /* with ESR_EPI_RES1: the residual is the bf16 pair res1_hi + res1_lo, not `res1` */
     ESR_CONV_F16 = 1u << 6,    /* MMA operands of this launch (every K block and the packed weights, term 2) are IEEE
                                   fp16 instead of bf16: the convs outside the residual-scaled trunk, whose operand
                                   rounding dominates the output error, 11 significant bits instead of 8 */
@@ -122,6 +123,16 @@ typedef struct esr_conv_desc {
     uint16_t pair;            /* != 0: wpack is in the pair layout (esr_pack_layout pair=1) and the launch runs on
                                  2-CTA clusters with tcgen05.mma.cta_group::2 (M = 256: one 4x32-pixel band per CTA) */
     float gamma;              /* res1 multiplier: v = alpha*v + gamma*res1 */
+    /* Residual trunk carried as a bf16 pair instead of fp32 (halves the trunk's HBM traffic inside a block chain):
+     * with ESR_EPI_RES1_HILO, res1 = bf16 res1_hi[..] + bf16 res1_lo[..] (NHWC, e.g. hi = channels 0..63 of the
+     * dense-block buffer the conv reads anyway, lo = the residue stored by the previous block); out_lo != NULL
+     * stores bf16(v - bf16(v)) next to the bf16 output (x = hi + lo keeps ~17 significant bits). */
+    const void* res1_hi;
+    int32_t res1_hi_stride, res1_hi_choff;
+    const void* res1_lo;
+    int32_t res1_lo_stride, res1_lo_choff;
+    void* out_lo;
+    int32_t out_lo_stride, out_lo_choff;
 } esr_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM kernel (the product path). */

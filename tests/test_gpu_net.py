@@ -136,6 +136,22 @@ def test_fused_growth_convs_bit_identical_to_separate_launches(cuda_device, monk
         assert torch.equal(f, ref)
 
 
+def test_hilo_trunk_matches_fp32_trunk(cuda_device, monkeypatch):
+    """ESR_TRUNK_HILO=1: the residual between the RDBs of an RRDB as a bf16 hi/lo pair (~17 significant bits)."""
+    wts = synth.make_weights("default", seed=6, nb=2)
+    lr, z = synth.make_inputs(2, 20, 33, seed=6)
+    mi = concat_latent(lr, z).to(cuda_device)
+    netG = build_product_G(cuda_device, 2, "all_layers_HR_downscaled", wts)
+    G = netG.generated_image_model
+    with torch.no_grad():
+        ref = netG(mi).clone()
+        monkeypatch.setenv("ESR_TRUNK_HILO", "1")
+        G._plans.clear()
+        out = netG(mi).clone()
+        assert list(G._plans.values())[-1].trunk_hilo
+    assert (out - ref).abs().max().item() < 2e-4
+
+
 def test_host_pipeline_matches_direct_call(cuda_device):
     """parallel.HostPipeline (chunked, copies overlapped with compute) returns what netG(x) returns."""
     from esr_b200.parallel import HostPipeline

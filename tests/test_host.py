@@ -124,7 +124,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "libesr_b200.so does not export %s" % name
     assert set(capi.SIGNATURES) <= declared
-    assert lib.esr_abi_version() == 1
+    assert lib.esr_abi_version() == 2
     assert ctypes.sizeof(capi.ConvDesc) % 8 == 0
     # host-only entry point: weight image layout needs no GPU
     kb = (capi.KBlock * capi.MAX_KBLOCKS)()
