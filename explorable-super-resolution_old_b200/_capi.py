@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libesr_b200.so")
+LIB_PATH = os.environ.get("ESR_LIB_PATH") or os.path.join(HERE, "libesr_b200.so")   # override: A/B timing of builds
 
 MAX_KBLOCKS = 24
 MAX_COUT_TILES = 8
