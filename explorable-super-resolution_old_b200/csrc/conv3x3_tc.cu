@@ -381,6 +381,7 @@ int validate_conv_desc(const esr_conv_desc& d) {
 }
 
 static unsigned long long* g_prof_buf = nullptr;
+unsigned long long* rdb_prof_buffer() { return g_prof_buf; }
 static int g_use_pdl = []() { const char* v = getenv("ESR_NO_PDL"); return (v && atoi(v)) ? 0 : 1; }();
 
 static bool f32_wide_ok(const float* p, int stride, int choff) {

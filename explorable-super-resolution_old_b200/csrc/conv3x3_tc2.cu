@@ -405,10 +405,14 @@ struct RdbLaunch {
     uint32_t m_per_chunk, m_ppc, m_tpi, m_tx;   // ceil(2^32 / d): n / d == __umulhi(n, m) for n * d < 2^32 (no XU divisions)
     int nstages;
     uint32_t w_smem_bytes;
+    unsigned long long* prof;               // optional [gridDim][16] role counters (-DESR_PROFILE_ROLES)
 };
 
 constexpr int kRdbStages = 10;
-constexpr int kRdbThreads = kNumThreads + 32;   // + one publisher warp (GPU-scope fence + counter bump, off the epilogue's path)
+constexpr int kRdbThreads = kNumThreads + 64;   // + publisher warp (GPU-scope fence + counter bump, off the epilogue's path)
+                                                // + second TMA producer warp (a producer thread needs ~450-700 clk per
+                                                //   K block: one alone cannot feed the 576-clk MMAs of a block)
+constexpr int kRdbProducerB = 3 + kEpiWarps;    // warp index of the second producer
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
@@ -490,9 +494,11 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
 
-    if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (one per CTA; whole warp polls)
-        if (elect_one()) {
+    if (warp == 0 || warp == kRdbProducerB) {
+        // ------------------------------------------------------------ TMA producers (two warps per CTA: K block q of the
+        // launch-wide sequence goes to producer q & 1; both walk all items and poll the dependency counters)
+        const uint32_t who = warp == 0 ? 0u : 1u;
+        if (who == 0 && elect_one()) {
             uint32_t wbytes = 0;
             for (int l = 0; l < R.nlayers; ++l) wbytes += R.layer[l].w_half_bytes;
             mbar_expect_tx_local(w_full, wbytes);
@@ -522,35 +528,51 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
             return ld_acquire_u32(R.flags + static_cast<size_t>(it.layer - 1) * R.spatial_tiles +
                                   static_cast<size_t>(it.n) * R.tiles_per_img + yy * R.tiles_x + xx);
         };
-        uint32_t stage = 0, phase = 0;
+        uint32_t q = 0;                                   // running K-block number (same in both producers)
         uint32_t seen = poll(cluster_id);
+        ESR_PROF(long long p_t0 = clock64(), p_poll = 0, p_wait = 0, p_items = 0, p_respin = 0;)
         for (int item = cluster_id; item < R.total_items; item += num_clusters) {
+            ESR_PROF(const long long pc0 = clock64(); ++p_items;)
 #ifndef ESR_RDB_NO_POLL
             for (uint32_t spin = 0; !__all_sync(0xffffffffu, seen >= static_cast<uint32_t>(kEpiWarps)); ++spin) {
                 if (spin > (1u << 24)) { __trap(); }
                 seen = poll(item);
+                ESR_PROF(++p_respin;)
             }
 #endif
+            ESR_PROF(p_poll += clock64() - pc0;)
             // (the generic->async proxy fence of this hand-over sits on the writer side, in publish(): a full proxy
             // fence here would also wait for this thread's TMA loads in flight and serialise the items)
 #ifndef ESR_RDB_NO_POLL
             seen = poll(item + num_clusters);
 #endif
-            if (lane == 0) {                  // ring position lives in lane 0
+            {
                 const RdbItem it = rdb_decode(R, item, rank);
                 const RdbLayerDev& Ly = R.layer[it.layer];
-                const int x0 = it.tx * kTileWOut - 1, y0 = it.ty * (NB * kBandRows) - 1;
-                for (int kb = 0; kb < Ly.nkb; ++kb) {
-                    const esr_kblock& K = Ly.kb[kb];
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                    if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
-                    tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, it.n);
-                    if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
+                if (lane == 0) {
+                    const int x0 = it.tx * kTileWOut - 1, y0 = it.ty * (NB * kBandRows) - 1;
+                    for (int kb = 0; kb < Ly.nkb; ++kb) {
+                        const uint32_t qk = q + kb;
+                        if ((qk & 1u) != who) continue;
+                        const uint32_t stage = qk % static_cast<uint32_t>(nstages);
+                        const uint32_t phase = (qk / static_cast<uint32_t>(nstages)) & 1u;
+                        const esr_kblock& K = Ly.kb[kb];
+                        ESR_PROF(const long long w0c = clock64();)
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ESR_PROF(p_wait += clock64() - w0c;)
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
+                        tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, it.n);
+                    }
                 }
+                q += Ly.nkb;
             }
             __syncwarp();
         }
+        ESR_PROF(if (R.prof && lane == 0 && who == 0) {
+            unsigned long long* o = R.prof + blockIdx.x * 16;
+            o[0] = clock64() - p_t0; o[1] = p_wait; o[2] = p_items; o[6] = p_poll; o[10] = p_respin;
+        })
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer (leader CTA only)
         if (rank != 0) {
@@ -561,13 +583,17 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
         } else if (elect_one()) {
             const uint32_t w_lo = smem_u32(s_w) >> 4, a_lo = smem_u32(s_a) >> 4;
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            ESR_PROF(long long m_t0 = clock64(), m_wacc = 0, m_wfull = 0;)
             mbar_wait(w_full, 0);
             mbar_wait(w_ready, 0);
+            ESR_PROF(const long long m_tw = clock64() - m_t0;)
             const int per_chunk = R.nlayers * R.ppc;
             for (int item = cluster_id; item < R.total_items; item += num_clusters) {
                 const int c_ = static_cast<int>(__umulhi(static_cast<uint32_t>(item), R.m_per_chunk));
                 const RdbLayerDev& Ly = R.layer[__umulhi(static_cast<uint32_t>(item - c_ * per_chunk), R.m_ppc)];
+                ESR_PROF(long long c0 = clock64();)
                 mbar_wait(&acc_empty[as], aphase ^ 1);
+                ESR_PROF(m_wacc += clock64() - c0;)
                 tc_fence_after();
                 const uint32_t acc0 = tmem_base + as * (NB * kAccSlot);
                 uint32_t nonfirst = 0;
@@ -575,7 +601,9 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                     const uint32_t masks = *reinterpret_cast<const uint32_t*>(&Ly.kb[kb].dy_mask);
                     const uint32_t dy_mask = masks & 0xff, slice_mask = (masks >> 8) & 0xff;
                     const uint32_t w0 = w_lo + ((Ly.w_smem_off + Ly.kb[kb].w_off) >> 4);
+                    ESR_PROF(c0 = clock64();)
                     mbar_wait(&full_bar[stage], phase);
+                    ESR_PROF(m_wfull += clock64() - c0;)
                     tc_fence_after();
                     const uint32_t a0 = a_lo + stage * (kATile >> 4);
                     if (dy_mask == 7u && slice_mask == 3u) {
@@ -612,6 +640,10 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                 umma_commit2(&acc_full[as]);
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
+            ESR_PROF(if (R.prof) {
+                unsigned long long* o = R.prof + blockIdx.x * 16;
+                o[3] = clock64() - m_t0; o[4] = m_wacc; o[5] = m_wfull; o[9] = m_tw;
+            })
         }
     } else if (warp == 2 + kEpiWarps) {
         // ---------------------------------------------------------------- publisher (one thread per CTA)
@@ -653,6 +685,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
             for (int i = t; i < nwords; i += gridDim.x * kEpiWarps * 32) R.flags_zero[i] = 0u;
         }
         uint32_t as = 0, aphase = 0;
+        ESR_PROF(long long e_t0 = clock64(), e_wait = 0, e_n = 0;)
         for (int item = cluster_id; item < R.total_items; item += num_clusters) {
             const RdbItem it = rdb_decode(R, item, rank);
             const RdbLayerDev& Ly = R.layer[it.layer];
@@ -666,7 +699,9 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
 #pragma unroll
                 for (int i = 0; i < 4; ++i) mk[i] = __ldg(m + i);
             }
+            ESR_PROF(const long long ec0 = clock64();)
             mbar_wait(&acc_full[as], aphase);
+            ESR_PROF(e_wait += clock64() - ec0; ++e_n;)
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * (NB * kAccSlot) + b * kAccSlot + (static_cast<uint32_t>(wq * 32) << 16);
             float vc[32];
@@ -726,6 +761,10 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                 ::"r"(smem_u32(stored_cnt)) : "memory");
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
+        ESR_PROF(if (R.prof && warp == 2 && lane == 1) {
+            unsigned long long* o = R.prof + blockIdx.x * 16;
+            o[7] = clock64() - e_t0; o[8] = e_wait; o[11] = e_n;
+        })
     }
 
     tc_fence_before();
@@ -741,6 +780,8 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
 int num_sms_cached();
 
 int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W, int box_rows);
+
+unsigned long long* rdb_prof_buffer();   // conv3x3_tc.cu (esr_debug_set_profile_buffer)
 
 struct RdbOp {
     alignas(64) CUtensorMap tm0;
@@ -797,6 +838,7 @@ int build_rdb_growth(const esr_rdb_growth_desc& d, RdbOp* op) {
     R.m_per_chunk = magic(R.nlayers * R.ppc); R.m_ppc = magic(R.ppc); R.m_tpi = magic(R.tiles_per_img); R.m_tx = magic(R.tiles_x);
     const size_t third = static_cast<size_t>(ESR_RDB_MAX_LAYERS) * R.spatial_tiles;
     R.reverse = 0;                                        // set by the sequence builder (alternates launch by launch)
+    R.prof = rdb_prof_buffer();
     R.flags = d.flags + third * d.flags_use;
     R.flags_zero = d.flags + third * d.flags_zero;
     constexpr int a_tile = (2 * kBandRows + 2) * kTileW * kRowBytes;
