@@ -100,6 +100,20 @@ def test_consistency_and_fp32_oracle_larger_image(cuda_device):
     assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB" % (err, p)
 
 
+def test_production_net_non_square_input(cuda_device):
+    """nb=23, 1x3x72x100 (non-square, not a multiple of the 8x30 tile): PSNR / max error vs the fp32 oracle."""
+    wts = synth.make_weights("default", seed=8)
+    lr, z = synth.make_inputs(1, 72, 100, seed=8)
+    mi = concat_latent(lr, z)
+    netG = build_product_G(cuda_device, 23, "all_layers_HR_downscaled", wts)
+    with torch.no_grad():
+        out = netG(mi.to(cuda_device)).cpu()
+        ref = GCEMOracle(wts).forward(mi)
+    err, p = (out - ref).abs().max().item(), psnr(out, ref)
+    assert out.shape == (1, 3, 288, 400)
+    assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB" % (err, p)
+
+
 def test_batch_shards_are_bit_identical(cuda_device):
     """batch sharding is exact - image i of a batch == the same image run alone."""
     wts = synth.make_weights("kaiming", seed=2, nb=2)
