@@ -29,6 +29,29 @@ with torch.no_grad():
     def d2h_sync(): host_out.copy_(netG(x), non_blocking=True)
     print('compute + same-stream D2H: %.2f ms' % timed(d2h_sync))
     print('H2D alone: %.2f ms   D2H alone: %.2f ms' % (timed(lambda: xs.copy_(host_in, non_blocking=True)), timed(lambda: host_out.copy_(x[:, :3].repeat(1, 1, 4, 4)[:16], non_blocking=True))))
+g0, out0 = netG.capture(x.clone(), slot=0)
+print('captured graph replay only: %.2f ms' % timed(g0.replay))
+g1, out1 = netG.capture(x.clone(), slot=1)
+def alt():
+    g0.replay(); g1.replay()
+print('two captured graphs alternating (2 buffer sets): %.2f ms per replay' % (timed(alt) / 2))
+s_out = torch.cuda.Stream()
+def replay_d2h():
+    g0.replay()
+    ev = torch.cuda.Event(); ev.record()
+    with torch.cuda.stream(s_out):
+        s_out.wait_event(ev)
+        host_out.copy_(out0, non_blocking=True)
+print('graph replay + D2H on side stream: %.2f ms' % timed(replay_d2h))
+torch.cuda.synchronize()
+s_in = torch.cuda.Stream()
+xs2 = [x.clone(), x.clone()]
+def h2d_replay():
+    with torch.cuda.stream(s_in):
+        xs2[0].copy_(host_in, non_blocking=True)
+    g0.replay()
+print('graph replay + concurrent H2D (other buffer): %.2f ms' % timed(h2d_replay))
+torch.cuda.synchronize()
 for g in (False, True):
     pipe = HostPipeline(netG, chunk=16, use_graph=g)
     def f(): pipe(host_in, host_out)
