@@ -414,9 +414,13 @@ constexpr int kRdbThreads = kNumThreads + 64;   // + publisher warp (GPU-scope f
                                                 //   K block: one alone cannot feed the 576-clk MMAs of a block)
 constexpr int kRdbProducerB = 3 + kEpiWarps;    // warp index of the second producer
 
+// Dependency counters are read with a RELAXED load: an acquire load blocks the producer warp until it returns
+// (~800 clk per item, on the path that feeds the MMAs).  Ordering is kept by construction instead: the publisher
+// makes the tile's stores visible at GPU scope (fence + proxy fence) before it bumps the counter, and the TMA
+// loads of the dependent item are only issued - control dependent - after the bumped value has been observed.
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -530,7 +534,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
         };
         uint32_t q = 0;                                   // running K-block number (same in both producers)
         uint32_t seen = poll(cluster_id);
-        ESR_PROF(long long p_t0 = clock64(), p_poll = 0, p_wait = 0, p_items = 0, p_respin = 0;)
+        ESR_PROF(long long p_t0 = clock64(), p_poll = 0, p_wait = 0, p_items = 0, p_respin = 0, p_issue = 0, p_sync = 0, p_poll2 = 0;)
         for (int item = cluster_id; item < R.total_items; item += num_clusters) {
             ESR_PROF(const long long pc0 = clock64(); ++p_items;)
 #ifndef ESR_RDB_NO_POLL
@@ -543,9 +547,11 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
             ESR_PROF(p_poll += clock64() - pc0;)
             // (the generic->async proxy fence of this hand-over sits on the writer side, in publish(): a full proxy
             // fence here would also wait for this thread's TMA loads in flight and serialise the items)
+            ESR_PROF(const long long pq0 = clock64();)
 #ifndef ESR_RDB_NO_POLL
             seen = poll(item + num_clusters);
 #endif
+            ESR_PROF(p_poll2 += clock64() - pq0;)
             {
                 const RdbItem it = rdb_decode(R, item, rank);
                 const RdbLayerDev& Ly = R.layer[it.layer];
@@ -559,19 +565,23 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                         const esr_kblock& K = Ly.kb[kb];
                         ESR_PROF(const long long w0c = clock64();)
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        ESR_PROF(p_wait += clock64() - w0c;)
+                        ESR_PROF(p_wait += clock64() - w0c; const long long i0c = clock64();)
                         const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
                         tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, it.n);
+                        ESR_PROF(p_issue += clock64() - i0c;)
                     }
                 }
                 q += Ly.nkb;
             }
+            ESR_PROF(const long long s0c = clock64();)
             __syncwarp();
+            ESR_PROF(p_sync += clock64() - s0c;)
         }
         ESR_PROF(if (R.prof && lane == 0 && who == 0) {
             unsigned long long* o = R.prof + blockIdx.x * 16;
             o[0] = clock64() - p_t0; o[1] = p_wait; o[2] = p_items; o[6] = p_poll; o[10] = p_respin;
+            o[12] = p_issue; o[13] = p_sync; o[14] = p_poll2;
         })
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer (leader CTA only)

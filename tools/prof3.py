@@ -31,6 +31,7 @@ lead = q[0::2].mean(0); allc = q.mean(0)
 print('fused growth launch, chunk %s: %.1f us event-timed (NOTE: standalone relaunch re-uses dirty counters: dependencies trivially met)' % (chunk, e0.elapsed_time(e1) * 1e3))
 print('  producer: total %.0f wait_empty %.0f poll %.0f respins %.0f items %.0f -> per item total %.0f wait_empty %.0f poll %.0f' % (
     allc[0], allc[1], allc[6], allc[10], allc[2], allc[0] / allc[2], allc[1] / allc[2], allc[6] / allc[2]))
+print('  producer A detail per item: issue(expect_tx+tma) %.0f  syncwarp %.0f  poll-next %.0f' % (allc[12] / allc[2], allc[13] / allc[2], allc[14] / allc[2]))
 print('  mma: total %.0f wait_acc_empty %.0f wait_full %.0f wait_w %.0f -> busy %.0f (per item %.0f)' % (
     lead[3], lead[4], lead[5], lead[9], lead[3] - lead[4] - lead[5] - lead[9], (lead[3] - lead[4] - lead[5] - lead[9]) / allc[2]))
 print('  epi(warp2): total %.0f wait_acc_full %.0f items %.0f -> per item total %.0f wait %.0f work %.0f' % (
