@@ -246,6 +246,10 @@ struct InvTaps {
     int n;
 };
 
+// NT = compile-time length of the (HH^T)^-1 factor (27 for the bicubic x4 configuration; 0 = run-time loops).  With
+// NT known the two separable passes are register tiled (4 outputs per thread share NT+3 loaded values) and fully
+// unrolled: 30 shared loads + 108 FMAs per 4 outputs instead of 4 x 27 x (constant load, shared load, FMA, loop).
+template <int NT>
 __global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__ CemTab T, const __grid_constant__ InvTaps K,
                                                          const float* __restrict__ d, const float* __restrict__ y,
                                                          float* __restrict__ out, int h, int w, int crop, int seg) {
@@ -257,11 +261,11 @@ __global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__
     const int jb = blockIdx.x * kStripCells - 2;                   // LR cell of lane 0
     const int j = jb + lane;
     const int ib = blockIdx.y * 4 * seg;                           // first LR row of the block
-    const int RB = 4 * seg, pad = K.n >> 1;
-    const int Re = RB + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad;
-    float* dt = sm;                                                // [Rd][Cd]  d, replicate clamped
-    float* hb = dt + Rd * Cd;                                      // [Rd][32]  horizontal pass
-    float* et = hb + Rd * 32;                                      // [Re][32]  e (zero outside the image)
+    const int RB = 4 * seg, nt = NT > 0 ? NT : K.n, pad = nt >> 1;
+    const int Re = RB + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad, Cds = (Cd + 3) & ~3;
+    float* dt = sm;                                                // [Rd][Cds]  d, replicate clamped
+    float* hb = dt + Rd * Cds;                                     // [Rd][32]   horizontal pass
+    float* et = hb + Rd * 32;                                      // [Re][32]   e (zero outside the image)
     const int i0 = ib + warp * seg, i1 = min(i0 + seg, h);
     const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w && 4 * j >= crop && 4 * j + 3 < W - crop;
     auto load_y = [&](int i, float4 (&b)[4]) {                     // the 4 HR rows of LR row i (base image)
@@ -277,39 +281,85 @@ __global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__
     load_y(i0, yc);                                                // HBM loads fly while the e tile is built
     load_y(i0 + 1, yn);
     const float* dp = d + static_cast<size_t>(plane) * h * w;
-    for (int idx = threadIdx.x; idx < Rd * Cd; idx += 128) {
-        const int r = idx / Cd, c = idx - r * Cd;
-        dt[idx] = __ldg(dp + static_cast<size_t>(clampi(ib - 2 - pad + r, 0, h - 1)) * w + clampi(jb - pad + c, 0, w - 1));
+    for (int r = warp; r < Rd; r += 4) {                           // a warp per tile row: no div / mod, one clamp per row
+        const float* row = dp + static_cast<size_t>(clampi(ib - 2 - pad + r, 0, h - 1)) * w;
+        for (int c = lane; c < Cd; c += 32) dt[r * Cds + c] = __ldg(row + clampi(jb - pad + c, 0, w - 1));
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < Rd * 32; idx += 128) {
-        const int r = idx >> 5, c = idx & 31;
-        const float* t = dt + r * Cd + c;
-        float acc = 0.f;
-        for (int k = 0; k < K.n; ++k) acc = fmaf(K.t[k], t[k], acc);
-        hb[idx] = acc;
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < Re * 32; idx += 128) {
-        const int r = idx >> 5, c = idx & 31;
-        const int ii = ib - 2 + r, jj = jb + c;
-        float acc = 0.f;
-        if (ii >= 0 && ii < h && jj >= 0 && jj < w) {
-            const float* t = hb + r * 32 + c;
-            for (int k = 0; k < K.n; ++k) acc = fmaf(K.t[k], t[k * 32], acc);
+    if constexpr (NT > 0) {
+        for (int task = threadIdx.x; task < Rd * 8; task += 128) {          // 4 consecutive columns per task
+            const int r = task >> 3, c4 = (task & 7) * 4;
+            const float4* src = reinterpret_cast<const float4*>(dt + r * Cds + c4);   // Cds % 4 == 0: 16-byte aligned
+            float v[NT + 5];
+#pragma unroll
+            for (int q = 0; q < (NT + 6) / 4; ++q) {
+                const float4 t4 = src[q];
+                v[4 * q] = t4.x;
+                if (4 * q + 1 < NT + 5) v[4 * q + 1] = t4.y;
+                if (4 * q + 2 < NT + 5) v[4 * q + 2] = t4.z;
+                if (4 * q + 3 < NT + 5) v[4 * q + 3] = t4.w;
+            }
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const float tk = K.t[k];
+                o0 = fmaf(tk, v[k], o0); o1 = fmaf(tk, v[k + 1], o1); o2 = fmaf(tk, v[k + 2], o2); o3 = fmaf(tk, v[k + 3], o3);
+            }
+            *reinterpret_cast<float4*>(hb + r * 32 + c4) = make_float4(o0, o1, o2, o3);
         }
-        et[idx] = acc;
+        __syncthreads();
+        for (int task = threadIdx.x; task < (Re >> 2) * 32; task += 128) {  // 4 consecutive rows per task (Re % 4 == 0)
+            const int r0 = (task >> 5) * 4, c = task & 31;
+            float v[NT + 3];
+#pragma unroll
+            for (int k = 0; k < NT + 3; ++k) v[k] = hb[(r0 + k) * 32 + c];
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const float tk = K.t[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o[q] = fmaf(tk, v[k + q], o[q]);
+            }
+            const int jj = jb + c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ii = ib - 2 + r0 + q;
+                et[(r0 + q) * 32 + c] = (ii >= 0 && ii < h && jj >= 0 && jj < w) ? o[q] : 0.f;
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < Rd * 32; idx += 128) {
+            const int r = idx >> 5, c = idx & 31;
+            const float* t = dt + r * Cds + c;
+            float acc = 0.f;
+            for (int k = 0; k < nt; ++k) acc = fmaf(K.t[k], t[k], acc);
+            hb[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < Re * 32; idx += 128) {
+            const int r = idx >> 5, c = idx & 31;
+            const int ii = ib - 2 + r, jj = jb + c;
+            float acc = 0.f;
+            if (ii >= 0 && ii < h && jj >= 0 && jj < w) {
+                const float* t = hb + r * 32 + c;
+                for (int k = 0; k < nt; ++k) acc = fmaf(K.t[k], t[k * 32], acc);
+            }
+            et[idx] = acc;
+        }
     }
     __syncthreads();
     if (i0 >= h) return;
     // horizontally upsampled e rows i-2 .. i+2 (4 HR phases each); et row index of LR row ii is ii - ib + 2
     float hu[5][4];
+    int lofs[5];                                                   // neighbour cells (edge lanes never write: clamped)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lofs[k] = min(max(lane + k - 2, 0), 31);
     auto hrow = [&](int ii, float (&o)[4]) {
         const float* e = et + (ii - ib + 2) * 32;
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
         for (int k = -2; k <= 2; ++k) {
-            const float n = e[min(max(lane + k, 0), 31)];
+            const float n = e[lofs[k + 2]];
             p0 = fmaf(T.up[0][k + 2], n, p0);
             p1 = fmaf(T.up[1][k + 2], n, p1);
             p2 = fmaf(T.up[2][k + 2], n, p2);
@@ -603,12 +653,18 @@ int cem_invup4(const esr_cem_filters& f, const float* d, const float* y, int pla
     K.n = f.n_inv;
     for (int i = 0; i < f.n_inv; ++i) K.t[i] = f.inv[i];
     const int seg = pick_seg(planes, h, w) > 16 ? 16 : pick_seg(planes, h, w), pad = f.n_inv / 2;   // <= 16: smem tile
-    const int Re = 4 * seg + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad;
-    const size_t sm = sizeof(float) * (static_cast<size_t>(Rd) * Cd + static_cast<size_t>(Rd) * 32 + static_cast<size_t>(Re) * 32);
-    int rc = set_smem(reinterpret_cast<const void*>(cem_invup4_kernel), sm);
-    if (rc) return rc;
+    const int Re = 4 * seg + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad, Cds = (Cd + 3) & ~3;
+    const size_t sm = sizeof(float) * (static_cast<size_t>(Rd) * Cds + static_cast<size_t>(Rd) * 32 + static_cast<size_t>(Re) * 32);
     dim3 grid(ceil_div(w, kStripCells), ceil_div(h, 4 * seg), planes);
-    cem_invup4_kernel<<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
+    if (f.n_inv == 27) {
+        int rc = set_smem(reinterpret_cast<const void*>(cem_invup4_kernel<27>), sm);
+        if (rc) return rc;
+        cem_invup4_kernel<27><<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
+    } else {
+        int rc = set_smem(reinterpret_cast<const void*>(cem_invup4_kernel<0>), sm);
+        if (rc) return rc;
+        cem_invup4_kernel<0><<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
+    }
     return check_launch("cem_invup4_kernel");
 }
 
