@@ -166,75 +166,94 @@ struct CemTab {            // polyphase tap tables, [phase][cell offset -2..2]
 
 // Vertical taps first: every HR row costs 20 FMAs into five float4 accumulators (LR rows I-2..I+2) and no
 // shuffles; the horizontal taps run once per LR row on the finished accumulator (20 FMAs for the cell's five
-// partial sums, which neighbours exchange with 4 shuffles).  Loads: a ring of three 4-row groups addressed
-// statically (the row loop is unrolled by 3), two groups (8 HR rows, 4 KiB per warp) in flight.
-__global__ void __launch_bounds__(128, 4) cem_down4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ y,
+// partial sums, which neighbours exchange with 4 shuffles).  Loads go through a per-warp shared-memory ring of
+// kDownGroups 4-row groups filled with cp.async (16 bytes per lane per row, each lane only ever reads its own
+// slots, so no barrier is needed): kDownGroups-1 groups = 12 HR rows (6 KiB per warp) are in flight without
+// costing registers, which is what this latency-bound kernel needs (28 warps per SM instead of 16).
+constexpr int kDownGroups = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ CemTab T, const float* __restrict__ y,
                                                         const float* __restrict__ x, float* __restrict__ out, int H,
                                                         int W, int seg) {
+    __shared__ float4 ring[4][kDownGroups][4][32];                  // [warp][group slot][HR row of the group][lane]
     const int h = H >> 2, w = W >> 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int plane = blockIdx.z;
     const int j = blockIdx.x * kStripCells - 2 + lane;             // LR cell of this lane
-    const int i0 = (blockIdx.y * 4 + warp) * seg;                   // seg is a multiple of 4
+    const int i0 = (blockIdx.y * 4 + warp) * seg;
     if (i0 >= h) return;
     const int i1 = min(i0 + seg, h);
     const float* yp = y + static_cast<size_t>(plane) * H * W;
-    const bool inside = j >= 0 && j < w;
-    const float* col = yp + (inside ? 4 * j : (j < 0 ? 0 : W - 1));   // replicate padding for cells outside the image
+    // cells outside the image replicate the edge pixel: fetch the edge cell, pick its outer element when read back
+    const int edge = j < 0 ? -1 : (j >= w ? 1 : 0);
+    const float* col = yp + 4 * min(max(j, 0), w - 1);
     const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w;
-    auto load_group = [&](int I, float4 (&g)[4]) {                  // the 4 HR rows of LR row I (replicate padded)
+    const int last = i1 + 1;                                        // LR row groups i0-2 .. i1+1 feed rows i0 .. i1-1
+    auto issue_group = [&](int I) {                                 // the 4 HR rows of LR row I (rows replicate padded)
+        if (I <= last) {
+            float4(*slot)[32] = ring[warp][(I - (i0 - 2)) % kDownGroups];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int r = min(max(4 * I + q, 0), H - 1);
-            const float* p = col + static_cast<size_t>(r) * W;
-            if (inside) g[q] = __ldg(reinterpret_cast<const float4*>(p));
-            else { const float e = __ldg(p); g[q] = make_float4(e, e, e, e); }
+            for (int q = 0; q < 4; ++q) {
+                const int r = min(max(4 * I + q, 0), H - 1);
+                cp_async16(&slot[q][lane], col + static_cast<size_t>(r) * W);
+            }
         }
+        cp_async_commit();                                          // (possibly empty) group: keeps the wait counts uniform
     };
     float4 acc[5];                                                  // LR rows I-2 .. I+2 (4 HR columns of the cell each)
 #pragma unroll
     for (int m = 0; m < 5; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 g[3][4];
-    load_group(i0 - 2, g[0]);
-    load_group(i0 - 1, g[1]);
-    const int last = i1 + 1;
-    for (int Ib = i0 - 2; Ib <= last; Ib += 3) {
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int I = Ib + u;
-            if (I > last) break;                                    // warp-uniform
-            if (I + 2 <= last) load_group(I + 2, g[(u + 2) % 3]);
+    for (int g = 0; g < kDownGroups - 1; ++g) issue_group(i0 - 2 + g);
+    for (int I = i0 - 2; I <= last; ++I) {
+        cp_async_wait<kDownGroups - 2>();                           // group I has landed (this thread's own copies)
+        const float4(*slot)[32] = ring[warp][(I - (i0 - 2)) % kDownGroups];
+        float4 c[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 c = g[u][q];
-#pragma unroll
-                for (int m = 0; m < 5; ++m) {                       // row 4I+q feeds LR row I-2+m with tap index 4-m
-                    const float wv = T.down_v[q][4 - m];
-                    acc[m].x = fmaf(wv, c.x, acc[m].x); acc[m].y = fmaf(wv, c.y, acc[m].y);
-                    acc[m].z = fmaf(wv, c.z, acc[m].z); acc[m].w = fmaf(wv, c.w, acc[m].w);
-                }
-            }
-            // LR row I-2 is complete: this cell's contribution to the output columns (own cell) - k, k = -2..2
-            const float4 a = acc[0];
-            float hsum = 0.f;
-#pragma unroll
-            for (int k = -2; k <= 2; ++k) {
-                float p = T.down_h[0][k + 2] * a.x;
-                p = fmaf(T.down_h[1][k + 2], a.y, p);
-                p = fmaf(T.down_h[2][k + 2], a.z, p);
-                p = fmaf(T.down_h[3][k + 2], a.w, p);
-                hsum += k == 0 ? p : __shfl_sync(0xffffffffu, p, lane + k);
-            }
-            const int i = I - 2;
-            if (i >= i0 && i < i1 && writer) {
-                const size_t o = (static_cast<size_t>(plane) * h + i) * w + j;
-                out[o] = x != nullptr ? x[o] - hsum : hsum;
-            }
-#pragma unroll
-            for (int m = 0; m < 4; ++m) acc[m] = acc[m + 1];
-            acc[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 4; ++q) {
+            c[q] = slot[q][lane];
+            if (edge < 0) c[q] = make_float4(c[q].x, c[q].x, c[q].x, c[q].x);
+            else if (edge > 0) c[q] = make_float4(c[q].w, c[q].w, c[q].w, c[q].w);
         }
+        issue_group(I + kDownGroups - 1);                           // refills the slot read one iteration ago
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {                           // row 4I+q feeds LR row I-2+m with tap index 4-m
+                const float wv = T.down_v[q][4 - m];
+                acc[m].x = fmaf(wv, c[q].x, acc[m].x); acc[m].y = fmaf(wv, c[q].y, acc[m].y);
+                acc[m].z = fmaf(wv, c[q].z, acc[m].z); acc[m].w = fmaf(wv, c[q].w, acc[m].w);
+            }
+        }
+        // LR row I-2 is complete: this cell's contribution to the output columns (own cell) - k, k = -2..2
+        const float4 a = acc[0];
+        float hsum = 0.f;
+#pragma unroll
+        for (int k = -2; k <= 2; ++k) {
+            float p = T.down_h[0][k + 2] * a.x;
+            p = fmaf(T.down_h[1][k + 2], a.y, p);
+            p = fmaf(T.down_h[2][k + 2], a.z, p);
+            p = fmaf(T.down_h[3][k + 2], a.w, p);
+            hsum += k == 0 ? p : __shfl_sync(0xffffffffu, p, lane + k);
+        }
+        const int i = I - 2;
+        if (i >= i0 && i < i1 && writer) {
+            const size_t o = (static_cast<size_t>(plane) * h + i) * w + j;
+            out[o] = x != nullptr ? x[o] - hsum : hsum;
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[m] = acc[m + 1];
+        acc[4] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    cp_async_wait<0>();
 }
 
 // out = crop(y + Up(K * d)) with the 27x27 (HH^T)^-1 correlation fused in: the block builds the tile of
