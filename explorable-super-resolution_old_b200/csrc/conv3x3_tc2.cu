@@ -543,6 +543,8 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
         ESR_PROF(long long p_t0 = clock64(), p_poll = 0, p_wait = 0, p_items = 0, p_respin = 0, p_issue = 0, p_sync = 0, p_poll2 = 0;)
         for (int item = cluster_id; item < R.total_items; item += num_clusters) {
             ESR_PROF(const long long pc0 = clock64(); ++p_items;)
+            ESR_PROF(const int tslot = (item - cluster_id) / num_clusters;
+                     if (R.prof && blockIdx.x == 0 && who == 0 && lane == 0 && tslot < 32) R.prof[148 * 16 + tslot * 8 + 0] = gtime_ns();)
 #ifndef ESR_RDB_NO_POLL
             for (uint32_t spin = 0; !__all_sync(0xffffffffu, seen >= static_cast<uint32_t>(kEpiWarps)); ++spin) {
                 if (spin > (1u << 24)) { __trap(); }
@@ -577,6 +579,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                         tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, it.n);
                         ESR_PROF(p_issue += clock64() - i0c;)
                     }
+                    ESR_PROF(if (R.prof && blockIdx.x == 0 && who == 0 && tslot < 32) R.prof[148 * 16 + tslot * 8 + 1] = gtime_ns();)
                 }
                 q += Ly.nkb;
             }
@@ -607,9 +610,9 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
             for (int item = cluster_id; item < R.total_items; item += num_clusters) {
                 const int c_ = static_cast<int>(__umulhi(static_cast<uint32_t>(item), R.m_per_chunk));
                 const RdbLayerDev& Ly = R.layer[__umulhi(static_cast<uint32_t>(item - c_ * per_chunk), R.m_ppc)];
-                ESR_PROF(long long c0 = clock64();)
+                ESR_PROF(long long c0 = clock64(); const int tslot = (item - cluster_id) / num_clusters;)
                 mbar_wait(&acc_empty[as], aphase ^ 1);
-                ESR_PROF(m_wacc += clock64() - c0;)
+                ESR_PROF(m_wacc += clock64() - c0; if (R.prof && blockIdx.x == 0 && tslot < 32) R.prof[148 * 16 + tslot * 8 + 2] = gtime_ns();)
                 tc_fence_after();
                 const uint32_t acc0 = tmem_base + as * (NB * kAccSlot);
                 uint32_t nonfirst = 0;
@@ -619,7 +622,9 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                     const uint32_t w0 = w_lo + ((Ly.w_smem_off + Ly.kb[kb].w_off) >> 4);
                     ESR_PROF(c0 = clock64();)
                     mbar_wait(&full_bar[stage], phase);
-                    ESR_PROF(m_wfull += clock64() - c0;)
+                    ESR_PROF(m_wfull += clock64() - c0;
+                             if (R.prof && blockIdx.x == 0 && tslot < 32 && kb == 0) R.prof[148 * 16 + tslot * 8 + 3] = gtime_ns();
+                             if (R.prof && blockIdx.x == 0 && tslot < 32 && kb == Ly.nkb - 1) R.prof[148 * 16 + tslot * 8 + 4] = gtime_ns();)
                     tc_fence_after();
                     const uint32_t a0 = a_lo + stage * (kATile >> 4);
                     if (dy_mask == 7u && slice_mask == 3u) {
@@ -715,9 +720,10 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
 #pragma unroll
                 for (int i = 0; i < 4; ++i) mk[i] = __ldg(m + i);
             }
-            ESR_PROF(const long long ec0 = clock64();)
+            ESR_PROF(const long long ec0 = clock64(); const int tslot = (item - cluster_id) / num_clusters;)
             mbar_wait(&acc_full[as], aphase);
-            ESR_PROF(e_wait += clock64() - ec0; ++e_n;)
+            ESR_PROF(e_wait += clock64() - ec0; ++e_n;
+                     if (R.prof && blockIdx.x == 0 && warp == 0 && lane == 1 && tslot < 32) R.prof[148 * 16 + tslot * 8 + 5] = gtime_ns();)
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * (NB * kAccSlot) + b * kAccSlot + (static_cast<uint32_t>(wq * 32) << 16);
             float vc[32];
@@ -762,6 +768,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
             }
             // generic-proxy stores -> later TMA (async proxy) reads by other SMs: every writer fences the proxies, the
             // publisher warp does the GPU-scope part
+            ESR_PROF(if (R.prof && blockIdx.x == 0 && warp == 0 && lane == 1 && tslot < 32) R.prof[148 * 16 + tslot * 8 + 6] = gtime_ns();)
 #ifndef ESR_RDB_NO_SIGNAL
 #ifndef ESR_RDB_NO_PROXY_FENCE
             asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -923,6 +930,8 @@ bool fill_launch_pair(ConvLaunch* L) {
     L->w_smem_bytes = (d.w_tile_bytes / 2 + 1023u) & ~1023u;
     const int room = pair::kSmemMax - 1024 - pair::kCtrlBytes - static_cast<int>(L->w_smem_bytes);
     int st = room / a_tile;
+    static const int cap = []() { const char* v = getenv("ESR_MAX_STAGES"); return v ? atoi(v) : 0; }();   // tuning aid
+    if (cap >= 2 && st > cap) st = cap;
     L->nstages = st > pair::kMaxStages ? pair::kMaxStages : st;
     return L->nstages >= 2;
 }

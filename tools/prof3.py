@@ -10,7 +10,7 @@ chunk = sys.argv[1] if len(sys.argv) > 1 else "8"
 os.environ["ESR_RDB_CHUNK"] = chunk
 l = capi.lib()
 l.esr_debug_set_profile_buffer.argtypes = [C.c_void_p]
-prof = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+prof = torch.zeros(148 * 16 + 32 * 8, dtype=torch.int64, device=dev)
 l.esr_debug_set_profile_buffer(C.c_void_p(prof.data_ptr()))
 netG = build_product_G(dev, 1, 'all_layers_HR_downscaled', synth.make_weights('default', seed=0, nb=1))
 G = netG.generated_image_model
@@ -26,7 +26,8 @@ with torch.no_grad():
         prof.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); capi.check(l.esr_rdb_growth_tc(C.byref(d), capi.stream_ptr())); e1.record(); torch.cuda.synchronize()
-q = prof.cpu().double()
+tr = prof[148 * 16:].cpu().view(32, 8).double()
+q = prof[:148 * 16].view(148, 16).cpu().double()
 lead = q[0::2].mean(0); allc = q.mean(0)
 print('fused growth launch, chunk %s: %.1f us event-timed (NOTE: standalone relaunch re-uses dirty counters: dependencies trivially met)' % (chunk, e0.elapsed_time(e1) * 1e3))
 print('  producer: total %.0f wait_empty %.0f poll %.0f respins %.0f items %.0f -> per item total %.0f wait_empty %.0f poll %.0f' % (
@@ -36,3 +37,8 @@ print('  mma: total %.0f wait_acc_empty %.0f wait_full %.0f wait_w %.0f -> busy 
     lead[3], lead[4], lead[5], lead[9], lead[3] - lead[4] - lead[5] - lead[9], (lead[3] - lead[4] - lead[5] - lead[9]) / allc[2]))
 print('  epi(warp2): total %.0f wait_acc_full %.0f items %.0f -> per item total %.0f wait %.0f work %.0f' % (
     allc[7], allc[8], allc[11], allc[7] / allc[11], allc[8] / allc[11], (allc[7] - allc[8]) / allc[11]))
+
+t0 = tr[0, 0]
+print('  trace of cluster 0 (us from its first item): item | producer: item start, loads issued | mma: acc free, first tile landed, last tile landed | epilogue: acc ready, stores issued')
+for i in range(20):
+    print('   %2d | %6.2f %6.2f | %6.2f %6.2f %6.2f | %6.2f %6.2f' % ((i,) + tuple(float((tr[i, k] - t0) / 1e3) for k in range(7))))
