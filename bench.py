@@ -175,12 +175,14 @@ def main():
     from esr_b200 import _capi as capi, cem as pcem, networks, synth
     capi.lib()                                                # fail loudly if the extension is missing
     opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 256}},
-           "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input="all_layers",
+           "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input=os.environ.get("ESR_BENCH_LATENT", "all_layers"),
                              latent_input_domain="HR_downscaled", latent_channels=3, norm_type=None, mode="CNA",
                              nf=64, nb=23, in_nc=3, out_nc=3, gc=32, scale=SF)}
     netG = networks.define_G(opt, CEM=pcem.CEMnet(pcem.Get_CEM_Config(SF)), num_latent_channels=3)
     sd = netG.state_dict()
-    sd.update({"generated_image_model." + k: v for k, v in synth.make_weights("default", seed=0).items()})
+    _lat = os.environ.get("ESR_BENCH_LATENT", "all_layers")      # "first_layer": experiment only (not BASELINE's config)
+    sd.update({"generated_image_model." + k: v for k, v in synth.make_weights(
+        "default", seed=0, latent_input=_lat + "_HR_downscaled").items()})
     netG.load_state_dict(sd)
     netG.to(dev).eval()
     for p in netG.parameters():
