@@ -20,7 +20,7 @@ CONV_F16, EPI_OUT_F16, EPI_RES1_HILO = 64, 128, 256
 
 class KBlock(C.Structure):
     _fields_ = [("src", C.c_int32), ("chan", C.c_int32), ("w_off", C.c_uint32), ("dy_mask", C.c_uint8),
-                ("slice_mask", C.c_uint8), ("n_dy", C.c_uint8), ("reserved", C.c_uint8)]
+                ("slice_mask", C.c_uint8), ("n_dy", C.c_uint8), ("half", C.c_uint8)]
 
 
 class TensorNHWC(C.Structure):

@@ -47,6 +47,11 @@ __host__ __device__ inline uint32_t sw64_offset(uint32_t n, uint32_t k) {
     return n * 64u + ((((k >> 3) ^ (n >> 1)) & 3u) << 4) + (k & 7u) * 2u;
 }
 
+// Same for a [rows x 16ch] SWIZZLE_32B slab (32-byte rows): the 16-byte chunk bit is XORed with address bit 7.
+__host__ __device__ inline uint32_t sw32_offset(uint32_t n, uint32_t k) {
+    return n * 32u + ((((k >> 3) ^ (n >> 2)) & 1u) << 4) + (k & 7u) * 2u;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&p);

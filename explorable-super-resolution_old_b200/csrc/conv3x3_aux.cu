@@ -35,9 +35,10 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
             const uint16_t* src = reinterpret_cast<const uint16_t*>(d.src[K.src].ptr);
             const int sc = d.src[K.src].channels;
             int wi = 0;
+            const int half_k0 = K.half ? ((K.slice_mask & 1) ? 0 : 16) : 0;     // lean block: its 16-channel slice
             for (int dy = 0; dy < 3; ++dy) {
                 if (!((K.dy_mask >> dy) & 1)) continue;
-                const uint8_t* wslab = wt + K.w_off + static_cast<size_t>(wi) * slab_rows * kRowBytes;
+                const uint8_t* wslab = wt + K.w_off + static_cast<size_t>(wi) * slab_rows * (K.half ? 32 : kRowBytes);
                 ++wi;
                 const int yy = y + dy - 1;
                 if (yy < 0 || yy >= d.H) continue;
@@ -52,7 +53,8 @@ __global__ void conv3x3_simt_kernel(const __grid_constant__ ConvLaunch L) {
                         for (int i = 0; i < 16; ++i) {
                             const int nrow = dx * CT + col0 + i;
                             const uint16_t w = *reinterpret_cast<const uint16_t*>(
-                                wslab + (nrow / slab_rows) * half_bytes + sw64_offset(nrow % slab_rows, k));
+                                wslab + (nrow / slab_rows) * half_bytes +
+                                (K.half ? sw32_offset(nrow % slab_rows, k - half_k0) : sw64_offset(nrow % slab_rows, k)));
                             v[i] = fmaf(av, operand_value(w, f16), v[i]);
                         }
                     }
@@ -113,8 +115,14 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
         }
         const uint16_t val = operand_bits(w, slot.term);
         const int slab_rows = a.pair ? N / 2 : N;            // pair layout: rows [r*N/2, (r+1)*N/2) live in CTA r's half image
-        uint8_t* dst = a.out + static_cast<size_t>(ct) * a.w_tile_bytes + (n / slab_rows) * (a.w_tile_bytes / 2) + K.w_off +
-                       static_cast<size_t>(wi) * slab_rows * kRowBytes + sw64_offset(n % slab_rows, k);
+        uint8_t* dst = a.out + static_cast<size_t>(ct) * a.w_tile_bytes + (n / slab_rows) * (a.w_tile_bytes / 2) + K.w_off;
+        if (K.half) {                                        // lean block: [rows x 16 ch] slabs, SWIZZLE_32B, one slice
+            const int k0 = (K.slice_mask & 1) ? 0 : 16;
+            if (k < k0 || k >= k0 + 16) continue;
+            dst += static_cast<size_t>(wi) * slab_rows * 32 + sw32_offset(n % slab_rows, k - k0);
+        } else {
+            dst += static_cast<size_t>(wi) * slab_rows * kRowBytes + sw64_offset(n % slab_rows, k);
+        }
         *reinterpret_cast<uint16_t*>(dst) = val;
     }
     const int nb = a.cout_tiles * CT;
@@ -195,7 +203,12 @@ extern "C" int64_t esr_pack_layout(int32_t cout_tile, int32_t cout_tiles, int32_
     for (int i = 0; i < num_kblocks; ++i) {
         kblocks[i].n_dy = static_cast<uint8_t>(__builtin_popcount(kblocks[i].dy_mask & 7));
         kblocks[i].w_off = off;
-        off += kblocks[i].n_dy * 3u * cout_tile * esr::kRowBytes / (pair ? 2u : 1u);
+        if (kblocks[i].half && !(pair && (kblocks[i].dy_mask & 7) == 2 && (kblocks[i].slice_mask == 1 || kblocks[i].slice_mask == 2))) {
+            esr::set_error("esr_pack_layout: K block %d: `half` needs pair mode, dy_mask 0b010 and a single slice", i);
+            return ESR_ERR_INVALID;
+        }
+        off += kblocks[i].n_dy * 3u * cout_tile * (kblocks[i].half ? 32u : static_cast<uint32_t>(esr::kRowBytes)) / (pair ? 2u : 1u);
+        off = (off + 511u) & ~511u;                              // slabs of lean blocks are 1.5 KiB: keep every block 512-byte aligned
     }
     if (pair) off *= 2;                                      // two half images per cout tile
     if (w_tile_bytes) *w_tile_bytes = off;

@@ -310,7 +310,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 [B,H,W,C] seen as a 4-D tensor (C, W, H, B); box = 32 ch x 32 px x 10 rows.
-int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W, int box_rows) {
+// lean != 0: 16-channel / 32-byte rows, SWIZZLE_32B (the lean latent blocks, esr_kblock.half)
+int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W, int box_rows, int lean) {
     EncodeTiledFn enc = get_encode_fn();
     if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ESR_ERR_CUDA; }
     ESR_CHECK_ARG(t.ptr != nullptr && t.channels >= kKB && t.channels % 8 == 0,
@@ -320,10 +321,11 @@ int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H,
                                 static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(t.channels) * 2, static_cast<cuuint64_t>(W) * t.channels * 2,
                                    static_cast<cuuint64_t>(H) * W * t.channels * 2};
-    const cuuint32_t box[4] = {kKB, kTileW, static_cast<cuuint32_t>(box_rows), 1};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(lean ? 16 : kKB), kTileW, static_cast<cuuint32_t>(box_rows), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(t.ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, lean ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r)); return ESR_ERR_CUDA; }
     return ESR_OK;
@@ -350,8 +352,11 @@ int validate_conv_desc(const esr_conv_desc& d) {
         ESR_CHECK_ARG((k.dy_mask & 7) != 0 && (k.slice_mask & 3) != 0 && k.n_dy == __builtin_popcount(k.dy_mask & 7),
                       "kblock %d: bad masks", i);
         ESR_CHECK_ARG(k.w_off % 512 == 0 &&
-                      k.w_off + k.n_dy * 3u * d.cout_tile * kRowBytes / (d.pair ? 2u : 1u) <= d.w_tile_bytes / (d.pair ? 2u : 1u),
+                      k.w_off + k.n_dy * 3u * d.cout_tile * (k.half ? 32u : static_cast<uint32_t>(kRowBytes)) / (d.pair ? 2u : 1u) <=
+                          d.w_tile_bytes / (d.pair ? 2u : 1u),
                       "kblock %d: weight slab outside tile image", i);
+        ESR_CHECK_ARG(!k.half || (d.pair && k.src == 1 && (k.dy_mask & 7) == 2 && (k.slice_mask == 1 || k.slice_mask == 2)),
+                      "kblock %d: a lean (half) block needs pair mode, source 1, the centre tap and one slice", i);
     }
     ESR_CHECK_ARG(d.up == 1 || d.up == 2, "up must be 1 or 2");
     if (d.out_bf16) ESR_CHECK_ARG(d.out_bf16_stride % 8 == 0 && d.out_bf16_choff % 8 == 0 &&
@@ -476,10 +481,17 @@ int build_conv_launch(const esr_conv_desc& d, CUtensorMap* tm0, CUtensorMap* tm1
         ESR_CHECK_ARG(fill_launch_pair(L), "pair mode: weights (%u B per cout tile) leave no room for the A-tile ring", d.w_tile_bytes);
         box_rows = L->pair_nb * kBandRows + 2;
     }
-    rc = make_act_tensor_map(tm0, d.src[0], d.B, d.H, d.W, box_rows);
+    rc = make_act_tensor_map(tm0, d.src[0], d.B, d.H, d.W, box_rows, 0);
     if (rc != ESR_OK) return rc;
     if (d.src[1].ptr != nullptr) {
-        rc = make_act_tensor_map(tm1, d.src[1], d.B, d.H, d.W, box_rows);
+        // lean latent blocks: source 1 is loaded without halo rows, 16 channels wide (all or none of its blocks)
+        int lean = -1;
+        for (int i = 0; i < d.num_kblocks; ++i)
+            if (d.kblocks[i].src == 1) {
+                ESR_CHECK_ARG(lean < 0 || lean == (d.kblocks[i].half ? 1 : 0), "source 1: lean and full K blocks cannot be mixed");
+                lean = d.kblocks[i].half ? 1 : 0;
+            }
+        rc = make_act_tensor_map(tm1, d.src[1], d.B, d.H, d.W, lean == 1 ? box_rows - 2 : box_rows, lean == 1);
         if (rc != ESR_OK) return rc;
     } else {
         *tm1 = *tm0;

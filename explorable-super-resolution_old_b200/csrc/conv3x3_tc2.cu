@@ -49,6 +49,8 @@ constexpr int kTmemCols = 512;
 constexpr int kCtrlBytes = 256 + 256;              // barriers + tmem slot, 64 floats of bias
 constexpr int kSmemMax = 227 * 1024;
 constexpr uint32_t kDescHi = ((8u * kRowBytes) >> 4) | (1u << 14) | (4u << 29);
+// lean blocks: 32-byte rows, SBO = 256 B, SWIZZLE_32B (layout code 6)
+constexpr uint32_t kDescHiLean = ((8u * 32u) >> 4) | (1u << 14) | (6u << 29);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -107,15 +109,19 @@ __device__ __forceinline__ void tmem_relinquish2() {
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_issue2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_issue2_hi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
         "setp.ne.b32 p, %5, 0;\n\t"
         "mov.b64 da, {%1, %3};\n\t"
         "mov.b64 db, {%2, %3};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n"
-        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void umma_issue2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    umma_issue2_hi(tmem_d, a_lo, b_lo, kDescHi, idesc, accumulate);
 }
 // arrives on the barrier at this offset in BOTH CTAs once all prior MMAs of the pair have completed
 __device__ __forceinline__ void umma_commit2(uint64_t* bar) {
@@ -136,6 +142,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     constexpr int NB = CT == 32 ? 2 : 1;           // bands per CTA tile
     constexpr int kRows = NB * kBandRows + 2;      // halo rows per A tile
     constexpr int kATile = kRows * kTileW * kRowBytes;
+    constexpr int kLeanTile = NB * kBandRows * kTileW * 32;   // lean latent tile: no halo rows, 32-byte rows
+    constexpr uint32_t kLeanRow16 = (kTileW * 32) >> 4;
     constexpr int kAccSlot = CT == 32 ? 128 : 256; // TMEM columns per band accumulator
     // operand format bits: a_format [7,10) and b_format [10,13) are 1 for bf16, 0 for fp16
     const uint32_t kIdesc = idesc_bf16_m256(N) & ((L.d.flags & ESR_CONV_F16) ? ~((1u << 7) | (1u << 10)) : ~0u);
@@ -222,11 +230,17 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                     // only the leader arrives, expecting both CTAs' tiles; the peer's bytes may be credited before
                     // that (a transiently negative tx-count is legal), never to an older phase: the peer issues
                     // only after its copy of the multicast "stage free" commit
-                    if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
-                    if (L.a_stream && K.src == 0)
-                        tma_load_4d_pair_hint(s_a + stage * kATile, &tmap0, lead_full, K.chan, x0, y0, n, stream_policy);
-                    else
-                        tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
+                    if (K.half) {                   // lean latent block: centre rows only, 16 channels (SWIZZLE_32B)
+                        if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kLeanTile);
+                        tma_load_4d_pair(s_a + stage * kATile, &tmap1, lead_full, K.chan + ((K.slice_mask & 1) ? 0 : 16), x0,
+                                         y0 + 1, n);
+                    } else {
+                        if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
+                        if (L.a_stream && K.src == 0)
+                            tma_load_4d_pair_hint(s_a + stage * kATile, &tmap0, lead_full, K.chan, x0, y0, n, stream_policy);
+                        else
+                            tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
+                    }
                     if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
             }
@@ -267,7 +281,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                     ESR_PROF(m_wfull += clock64() - c0; if (first_full && L.prof) { L.prof[blockIdx.x * 16 + 10] = gtime_ns(); first_full = false; })
                     tc_fence_after();
                     const uint32_t a0 = a_lo + stage * (kATile >> 4);
-                    if (dy_mask == 7u && slice_mask == 3u) {
+                    if (masks >> 24) {                // lean latent block: one K=16 MMA per band, SWIZZLE_32B operands
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+                            umma_issue2_hi(acc0 + b * kAccSlot, a0 + (b * kBandRows) * kLeanRow16, w0, kDescHiLean, kIdesc, nonfirst);
+                    } else if (dy_mask == 7u && slice_mask == 3u) {
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
@@ -457,6 +475,8 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                           const __grid_constant__ RdbLaunch R) {
     constexpr int CT = 32, N = 96, NB = 2;
     constexpr int kATile = (NB * kBandRows + 2) * kTileW * kRowBytes;   // 20 KiB
+    constexpr int kLeanTile = NB * kBandRows * kTileW * 32;             // 8 KiB
+    constexpr uint32_t kLeanRow16 = (kTileW * 32) >> 4;
     constexpr int kAccSlot = 128;
     constexpr uint32_t kIdesc = idesc_bf16_m256(N);
     constexpr uint32_t kARow16 = (kTileW * kRowBytes) >> 4;
@@ -575,8 +595,14 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         ESR_PROF(p_wait += clock64() - w0c; const long long i0c = clock64();)
                         const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                        if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
-                        tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, it.n);
+                        if (K.half) {                 // lean latent block: centre rows only, 16 channels (SWIZZLE_32B)
+                            if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kLeanTile);
+                            tma_load_4d_pair(s_a + stage * kATile, &tmap1, lead_full, K.chan + ((K.slice_mask & 1) ? 0 : 16), x0,
+                                             y0 + 1, it.n);
+                        } else {
+                            if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
+                            tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, it.n);
+                        }
                         ESR_PROF(p_issue += clock64() - i0c;)
                     }
                     ESR_PROF(if (R.prof && blockIdx.x == 0 && who == 0 && tslot < 32) R.prof[148 * 16 + tslot * 8 + 1] = gtime_ns();)
@@ -627,7 +653,11 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
                              if (R.prof && blockIdx.x == 0 && tslot < 32 && kb == Ly.nkb - 1) R.prof[148 * 16 + tslot * 8 + 4] = gtime_ns();)
                     tc_fence_after();
                     const uint32_t a0 = a_lo + stage * (kATile >> 4);
-                    if (dy_mask == 7u && slice_mask == 3u) {
+                    if (masks >> 24) {                // lean latent block: one K=16 MMA per band, SWIZZLE_32B operands
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+                            umma_issue2_hi(acc0 + b * kAccSlot, a0 + (b * kBandRows) * kLeanRow16, w0, kDescHiLean, kIdesc, nonfirst);
+                    } else if (dy_mask == 7u && slice_mask == 3u) {
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
@@ -802,7 +832,7 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
 
 int num_sms_cached();
 
-int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W, int box_rows);
+int make_act_tensor_map(CUtensorMap* tm, const esr_tensor_nhwc& t, int B, int H, int W, int box_rows, int lean);
 
 unsigned long long* rdb_prof_buffer();   // conv3x3_tc.cu (esr_debug_set_profile_buffer)
 
@@ -837,7 +867,9 @@ int build_rdb_growth(const esr_rdb_growth_desc& d, RdbOp* op) {
             const esr_kblock& kb = s.kblocks[k];
             ESR_CHECK_ARG((kb.src == 0 || (kb.src == 1 && d.src[1].ptr)) && kb.chan >= 0 && kb.chan % 8 == 0 &&
                           kb.chan + kKB <= d.src[kb.src].channels && (kb.dy_mask & 7) && (kb.slice_mask & 3) && kb.w_off % 512 == 0 &&
-                          kb.w_off + kb.n_dy * 48u * kRowBytes <= D.w_half_bytes, "rdb_growth: bad K block %d of layer %d", k, l);
+                          kb.w_off + kb.n_dy * 48u * (kb.half ? 32u : static_cast<uint32_t>(kRowBytes)) <= D.w_half_bytes &&
+                          (!kb.half || (kb.src == 1 && (kb.dy_mask & 7) == 2 && (kb.slice_mask == 1 || kb.slice_mask == 2))),
+                          "rdb_growth: bad K block %d of layer %d", k, l);
             D.kb[k] = kb;
         }
         woff += (D.w_half_bytes + 1023u) & ~1023u;
@@ -870,9 +902,19 @@ int build_rdb_growth(const esr_rdb_growth_desc& d, RdbOp* op) {
     int st = room / a_tile;
     R.nstages = st > kRdbStages ? kRdbStages : st;
     ESR_CHECK_ARG(R.nstages >= 2, "rdb_growth: weights (%u B per CTA) leave no room for the A-tile ring", R.w_smem_bytes);
-    int rc = make_act_tensor_map(&op->tm0, d.src[0], d.B, d.H, d.W, 2 * kBandRows + 2);
+    int rc = make_act_tensor_map(&op->tm0, d.src[0], d.B, d.H, d.W, 2 * kBandRows + 2, 0);
     if (rc != ESR_OK) return rc;
-    if (d.src[1].ptr != nullptr) return make_act_tensor_map(&op->tm1, d.src[1], d.B, d.H, d.W, 2 * kBandRows + 2);
+    if (d.src[1].ptr != nullptr) {
+        int lean = -1;
+        for (int l = 0; l < d.num_layers; ++l)
+            for (int k = 0; k < d.layers[l].num_kblocks; ++k)
+                if (d.layers[l].kblocks[k].src == 1) {
+                    const int h = d.layers[l].kblocks[k].half ? 1 : 0;
+                    ESR_CHECK_ARG(lean < 0 || lean == h, "rdb_growth: lean and full K blocks of source 1 cannot be mixed");
+                    lean = h;
+                }
+        return make_act_tensor_map(&op->tm1, d.src[1], d.B, d.H, d.W, lean == 1 ? 2 * kBandRows : 2 * kBandRows + 2, lean == 1);
+    }
     op->tm1 = op->tm0;
     return ESR_OK;
 }

@@ -28,6 +28,7 @@ from . import _capi as capi
 from ._capi import KBlock, ConvDesc, WRow, WSlot, XSlot, RdbGrowthDesc
 
 DY_ALL, DY_CENTRE = 0b111, 0b010
+LEAN_LATENT = os.environ.get("ESR_LEAN_LATENT", "1") != "0"   # 0: load the latent rows as full 32-channel halo tiles (A/B timing)
 NF, GC = 64, 32
 
 
@@ -47,9 +48,14 @@ class PackedConv:
         self.nkb = len(kblocks)
         assert self.nkb <= capi.MAX_KBLOCKS, name
         self.kblocks = (KBlock * capi.MAX_KBLOCKS)()
-        for i, (src, chan, dy_mask, slice_mask) in enumerate(kblocks):
+        # lean latent blocks (esr_kblock.half): every block of source 1 is centre tap + one 16-channel slice; pair only
+        src1 = [kbt for kbt in kblocks if kbt[0] == 1]
+        lean = bool(self.pair and LEAN_LATENT and src1 and all(k[2] == DY_CENTRE and k[3] in (1, 2) for k in src1))
+        for i, kbt in enumerate(kblocks):
+            src, chan, dy_mask, slice_mask = kbt[:4]
             self.kblocks[i].src, self.kblocks[i].chan = src, chan
             self.kblocks[i].dy_mask, self.kblocks[i].slice_mask = dy_mask, slice_mask
+            self.kblocks[i].half = 1 if (lean and src == 1) else 0
         wtb = C.c_uint32(0)
         total = capi.lib().esr_pack_layout(cout_tile, self.cout_tiles, self.pair, self.nkb, self.kblocks, C.byref(wtb))
         if total < 0:

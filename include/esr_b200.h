@@ -63,7 +63,11 @@ typedef struct esr_kblock {
                            sources that were pre-expanded over dy */
     uint8_t slice_mask; /* bit s: channels [16s,16s+16) of the block are used */
     uint8_t n_dy;       /* popcount(dy_mask) */
-    uint8_t reserved;
+    uint8_t half;       /* != 0 (pair launches only): lean block for the row-expanded latent - centre tap, one 16-channel
+                           slice (dy_mask == 0b010, slice_mask == 0b01 or 0b10).  Its activation tile is loaded without
+                           halo rows as 16-channel / 32-byte rows (SWIZZLE_32B): 8 KiB instead of 20 KiB per 8x32-pixel
+                           tile, and its weight slabs are packed as [rows x 16 ch] in the same swizzle.  Every block of
+                           source 1 of a launch must then be lean. */
 } esr_kblock;
 
 typedef struct esr_tensor_nhwc {

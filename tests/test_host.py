@@ -93,7 +93,8 @@ def test_engine_layout_arithmetic():
         assert e.convs[name].cout == co
     assert e.flops_per_lr_pixel() == 2 * 18316944               # 36.634 MFLOP per LR pixel
     c0 = e.convs["model.1.sub.0.RDB1.convs.0.0"]
-    assert (c0.nkb, c0.cout_tiles, c0.w_tile_bytes) == (3, 1, 2 * 18432 + 6144)
+    assert (c0.nkb, c0.cout_tiles, c0.w_tile_bytes) == (3, 1, 2 * 18432 + 3072)      # lean latent block: 16-channel slabs
+    assert [k.half for k in list(c0.kblocks)[:3]] == [0, 0, 1]
     c4 = e.convs["model.1.sub.0.RDB1.convs.4.0"]
     assert (c4.nkb, c4.cout_tile, c4.cout_tiles, c4.pair) == (7, 64, 1, 1) and c4.w_tile_bytes // 2 <= 124 * 1024
     # outer convs, default mode: fp16 operands, one term (2 main K blocks + the fp16 latent slice)
