@@ -151,12 +151,18 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     constexpr uint32_t kWSlab16 = ((N / 2) * kRowBytes) >> 4;     // this CTA's half of one [N x 32ch] slab
     const esr_conv_desc& d = L.d;
     const int nstages = L.nstages;
+    // The lean latent block (last in the list) rides in the stage of the last main block: its 2 MMAs per band would
+    // otherwise pay a whole stage turn-over (barrier wait + commit, ~250 clk of MMA-thread time for 96 clk of tensor
+    // work - removing the latent blocks altogether made the step 10 % faster, shrinking their tiles did nothing).
+    const bool attach = d.num_kblocks >= 2 && d.kblocks[d.num_kblocks - 1].half != 0;
+    const int nkb = attach ? d.num_kblocks - 1 : d.num_kblocks;          // stages per tile
+    const int stage_bytes = kATile + (attach ? kLeanTile : 0);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_w = smem;
     uint8_t* s_a = smem + L.w_smem_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + nstages * kATile);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + nstages * stage_bytes);
     uint64_t* full_bar = bars;                      // waited in the leader only
     uint64_t* empty_bar = bars + kMaxStages;
     uint64_t* acc_full = bars + 2 * kMaxStages;
@@ -196,7 +202,6 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     ESR_PROF(if (L.prof && threadIdx.x == 0) L.prof[blockIdx.x * 16 + 13] = gtime_ns();)
     pdl_launch_dependents();
 
-    const int nkb = d.num_kblocks;
     const int tiles_per_img = L.tiles_x * L.tiles_y;
 
     if (warp == kProducerWarp) {
@@ -230,16 +235,21 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                     // only the leader arrives, expecting both CTAs' tiles; the peer's bytes may be credited before
                     // that (a transiently negative tx-count is legal), never to an older phase: the peer issues
                     // only after its copy of the multicast "stage free" commit
-                    if (K.half) {                   // lean latent block: centre rows only, 16 channels (SWIZZLE_32B)
+                    uint8_t* dst = s_a + stage * stage_bytes;
+                    if (K.half) {                   // lean latent block on its own (no main block before it)
                         if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kLeanTile);
-                        tma_load_4d_pair(s_a + stage * kATile, &tmap1, lead_full, K.chan + ((K.slice_mask & 1) ? 0 : 16), x0,
-                                         y0 + 1, n);
+                        tma_load_4d_pair(dst, &tmap1, lead_full, K.chan + ((K.slice_mask & 1) ? 0 : 16), x0, y0 + 1, n);
                     } else {
-                        if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * kATile);
+                        const bool with_lean = attach && kb == nkb - 1;
+                        if (rank == 0) mbar_expect_tx_local(&full_bar[stage], 2 * (kATile + (with_lean ? kLeanTile : 0)));
                         if (L.a_stream && K.src == 0)
-                            tma_load_4d_pair_hint(s_a + stage * kATile, &tmap0, lead_full, K.chan, x0, y0, n, stream_policy);
+                            tma_load_4d_pair_hint(dst, &tmap0, lead_full, K.chan, x0, y0, n, stream_policy);
                         else
-                            tma_load_4d_pair(s_a + stage * kATile, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
+                            tma_load_4d_pair(dst, K.src == 0 ? &tmap0 : &tmap1, lead_full, K.chan, x0, y0, n);
+                        if (with_lean) {            // centre rows only, 16 channels (SWIZZLE_32B), same stage / barrier
+                            const esr_kblock& Kl = d.kblocks[nkb];
+                            tma_load_4d_pair(dst + kATile, &tmap1, lead_full, Kl.chan + ((Kl.slice_mask & 1) ? 0 : 16), x0, y0 + 1, n);
+                        }
                     }
                     if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
@@ -280,7 +290,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                     mbar_wait(&full_bar[stage], phase);
                     ESR_PROF(m_wfull += clock64() - c0; if (first_full && L.prof) { L.prof[blockIdx.x * 16 + 10] = gtime_ns(); first_full = false; })
                     tc_fence_after();
-                    const uint32_t a0 = a_lo + stage * (kATile >> 4);
+                    const uint32_t a0 = a_lo + stage * (stage_bytes >> 4);
                     if (masks >> 24) {                // lean latent block: one K=16 MMA per band, SWIZZLE_32B operands
 #pragma unroll
                         for (int b = 0; b < NB; ++b)
@@ -313,6 +323,12 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                         }
                     }
                     nonfirst = 1;
+                    if (attach && kb == nkb - 1) {   // the latent rows, loaded behind this block's tile
+                        const uint32_t wl = w_lo + (d.kblocks[nkb].w_off >> 4);
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+                            umma_issue2_hi(acc0 + b * kAccSlot, a0 + (kATile >> 4) + (b * kBandRows) * kLeanRow16, wl, kDescHiLean, kIdesc, 1u);
+                    }
                     umma_commit2(&empty_bar[stage]);
                     if (++stage == static_cast<uint32_t>(nstages)) { stage = 0; phase ^= 1; }
                 }
@@ -964,7 +980,8 @@ int launch_rdb_growth(const RdbOp& op, cudaStream_t stream, int use_pdl) {
 bool fill_launch_pair(ConvLaunch* L) {
     const esr_conv_desc& d = L->d;
     const int nb = d.cout_tile == 32 ? 2 : 1;
-    const int a_tile = (nb * kBandRows + 2) * kTileW * kRowBytes;
+    const bool attach = d.num_kblocks >= 2 && d.kblocks[d.num_kblocks - 1].half != 0;
+    const int a_tile = (nb * kBandRows + 2) * kTileW * kRowBytes + (attach ? nb * kBandRows * kTileW * 32 : 0);
     L->pair_nb = nb;
     L->tiles_y = ceil_div(d.H, nb * kBandRows);
     L->spatial_tiles = d.B * L->tiles_x * L->tiles_y;
@@ -996,7 +1013,8 @@ int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLa
         attr_set = true;
     }
     const int nb = L.d.cout_tile == 32 ? 2 : 1;
-    const int a_tile = (nb * kBandRows + 2) * kTileW * kRowBytes;
+    const bool attach = L.d.num_kblocks >= 2 && L.d.kblocks[L.d.num_kblocks - 1].half != 0;
+    const int a_tile = (nb * kBandRows + 2) * kTileW * kRowBytes + (attach ? nb * kBandRows * kTileW * 32 : 0);
     const int num_pairs = (L.spatial_tiles + 1) / 2;
     int per_ct = (num_sms_cached() / 2) / L.d.cout_tiles;       // clusters per cout tile
     if (per_ct > num_pairs) per_ct = num_pairs;
