@@ -91,6 +91,13 @@ class CemFilters(C.Structure):
                 ("ds", C.c_float * CEM_MAX_TAPS), ("inv", C.c_float * CEM_MAX_TAPS)]
 
 
+class CemFilters2d(C.Structure):
+    _fields_ = [("sf", C.c_int32), ("pre", C.c_int32), ("n_ds", C.c_int32), ("n_inv", C.c_int32),
+                ("ds", C.c_void_p), ("inv", C.c_void_p)]
+
+
+CEM2D_MAX_SIDE = 63
+
 # name -> (restype, argtypes); every symbol include/esr_b200.h declares
 _i32, _i64, _vp, _f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
 SIGNATURES = {
@@ -116,6 +123,11 @@ SIGNATURES = {
     "esr_cem_upscale": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "esr_cem_project": (C.c_int, [C.POINTER(CemFilters), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esr_cem_project_bwd": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "esr_cem2d_downscale": (C.c_int, [C.POINTER(CemFilters2d), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_cem2d_inv_hth": (C.c_int, [C.POINTER(CemFilters2d), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_cem2d_upscale": (C.c_int, [C.POINTER(CemFilters2d), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "esr_cem2d_project": (C.c_int, [C.POINTER(CemFilters2d), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "esr_cem2d_project_bwd": (C.c_int, [C.POINTER(CemFilters2d), _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esr_seq_create": (_vp, []),
     "esr_seq_destroy": (None, [_vp]),
     "esr_seq_add_conv": (C.c_int, [_vp, C.POINTER(ConvDesc), _i32]),
@@ -169,6 +181,42 @@ def stream_ptr():
 
 def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class CemFilterBank2D:
+    """General (non-separable) CEM filters: the 2-D taps live in device memory, uploaded once per
+    device on first use (esr_cem_filters2d carries device pointers)."""
+
+    def __init__(self, sf, pre, ds_2d, inv_2d):
+        import numpy as np
+        self.sf, self.pre = int(sf), int(pre)
+        self.ds = np.ascontiguousarray(ds_2d, dtype=np.float32)
+        self.inv = np.ascontiguousarray(inv_2d, dtype=np.float32)
+        for name, k in (("ds_kernel", self.ds), ("inv_hTh", self.inv)):
+            if k.ndim != 2 or k.shape[0] != k.shape[1] or k.shape[0] % 2 == 0 or k.shape[0] > CEM2D_MAX_SIDE:
+                raise EsrError("%s of shape %s: the 2-D stencil path needs a square, odd-sided filter of at most %d taps a side"
+                               % (name, k.shape, CEM2D_MAX_SIDE))
+        self._per_device = {}
+
+    def on(self, device_index):
+        import torch
+        if device_index not in self._per_device:
+            dev = torch.device("cuda", device_index)
+            ds, inv = torch.from_numpy(self.ds).to(dev), torch.from_numpy(self.inv).to(dev)
+            f = CemFilters2d()
+            f.sf, f.pre, f.n_ds, f.n_inv = self.sf, self.pre, self.ds.shape[0], self.inv.shape[0]
+            f.ds, f.inv = ds.data_ptr(), inv.data_ptr()
+            self._per_device[device_index] = (f, ds, inv)
+        return self._per_device[device_index][0]
+
+
+def cem_call(op, filters, *args):
+    """Runs CEM operator `op` ('downscale', 'inv_hth', 'upscale', 'project', 'project_bwd') on the current
+    device with either the separable (esr_cem_*) or the general 2-D (esr_cem2d_*) filters."""
+    if isinstance(filters, CemFilterBank2D):
+        import torch
+        return check(getattr(lib(), "esr_cem2d_" + op)(filters.on(torch.cuda.current_device()), *args))
+    return check(getattr(lib(), "esr_cem_" + op)(filters, *args))
 
 
 def cem_filters_struct(sf, pre, ds_1d, inv_1d):

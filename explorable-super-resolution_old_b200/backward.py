@@ -326,8 +326,8 @@ def generator_backward(ctx, g):
         if ctx.cem_filters is not None:
             n = B * eng.out_nc * (H4 * W4 + H4 * plan.wp + 2 * plan.hp * plan.wp)
             ws = torch.empty(n, dtype=torch.float32, device=g.device)
-            capi.check(capi.lib().esr_cem_project_bwd(ctx.cem_filters, capi.ptr(g), B, eng.out_nc, H4, W4, sf * ctx.margin,
-                                                      capi.ptr(bp.g_y), capi.ptr(ws), capi.stream_ptr()))
+            capi.cem_call("project_bwd", ctx.cem_filters, capi.ptr(g), B, eng.out_nc, H4, W4, sf * ctx.margin,
+                          capi.ptr(bp.g_y), capi.ptr(ws), capi.stream_ptr())
             g_y = bp.g_y
         else:
             g_y = g

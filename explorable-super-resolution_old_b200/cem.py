@@ -5,7 +5,8 @@
 
 The fixed filters are derived once at construction time in float64 numpy (init-time host code,
 codes/CEM/CEMnet.py:105-126 and codes/CEM/imresize_CEM.py:18-94); for the default bicubic
-kernel they are rank-1, and the CUDA kernels consume their 1-D factors.
+kernel (and a mildly blurred one) they are rank-1 and the CUDA kernels consume their 1-D factors;
+estimated / user-supplied kernels and strong blurs run the general 2-D stencils (csrc/cem2d.cu).
 """
 import collections
 
@@ -47,12 +48,94 @@ def default_ds_kernel_1d(sf):
     return (up[::-1] / sf).astype(np.float32)
 
 
+def _conv2_full(a, b):
+    out = np.zeros((a.shape[0] + b.shape[0] - 1, a.shape[1] + b.shape[1] - 1))
+    for i in range(b.shape[0]):
+        for j in range(b.shape[1]):
+            out[i:i + a.shape[0], j:j + a.shape[1]] += b[i, j] * a
+    return out
+
+
+def _gaussian_2d(sigma):
+    """Normalised isotropic Gaussian holding 99% of its 1-D mass (imresize_CEM.py:101-109):
+    half width = ceil(-ppf(0.005) * sigma), ppf(0.005) of the unit normal = -2.5758293035489004."""
+    half = int(np.ceil(2.5758293035489004 * sigma))
+    g = np.exp(-0.5 * (np.arange(-half, half + 1) / sigma) ** 2)
+    g2 = np.outer(g, g)
+    return g2 / g2.sum()
+
+
+def _rint(v):
+    return int(np.round(v))
+
+
+def _center_mass(k, sf):
+    """Re-centre a user-supplied (already rot180'd) kernel on its centre of mass by zero padding,
+    then trim it to the frame holding 99% of its root-energy, keeping a side the x`sf` polyphase
+    split accepts (imresize_CEM.py:114-160)."""
+    if k.ndim != 2 or k.shape[0] != k.shape[1]:
+        raise ValueError("Currently supporting only square kernels")
+    n = k.shape[0]
+    cols, rows = np.meshgrid(np.arange(n), np.arange(n))
+    # first moments in flipped coordinates, 1-based (what conv2(grid, k, 'valid') + 1 evaluates)
+    gx = float(np.sum(cols[::-1, ::-1] * k)) + 1
+    gy = float(np.sum(rows[::-1, ::-1] * k)) + 1
+    pad = {"x": 2 * (n / 2 - gx), "y": 2 * (n / 2 - gy)}
+    before = {a: max(0.0, -pad[a]) for a in pad}
+    after = {a: max(0.0, pad[a]) for a in pad}
+    extra = float(np.round(abs(pad["y"])) - np.round(abs(pad["x"])))   # > 0: x needs more zeros to stay square
+    if extra != 0:
+        grow = "x" if extra > 0 else "y"
+        # the rounding of the two pads decides which side takes the odd zero
+        lean_after = (np.round(after[grow]) - after[grow]) - (np.round(before[grow]) - before[grow]) > 0
+        lo, hi = int(np.floor(abs(extra) / 2)), int(np.ceil(abs(extra) / 2))
+        before[grow] = _rint(before[grow]) + (lo if lean_after else hi)
+        after[grow] = _rint(after[grow]) + (hi if lean_after else lo)
+    k = np.pad(k, ((_rint(before["y"]), _rint(after["y"])), (_rint(before["x"]), _rint(after["x"]))), mode="constant")
+    if k.shape[0] != k.shape[1]:
+        raise ValueError("re-centring the kernel left it non-square")
+    n = k.shape[0]
+    total = np.sqrt(np.sum(k ** 2))
+    frames = [1.0] + [np.sqrt(np.sum(k[f:-f, f:-f] ** 2)) / total for f in range(1, int(np.ceil(n / 2)))]
+    below = [f for f, e in enumerate(frames) if e < 0.99]
+    if not below:
+        raise ValueError("kernel too concentrated to trim (no frame holds < 99% of its energy)")
+    cut = [below[0], below[0]]
+    side = 0
+    while (n - sum(cut) - 1 + (sf + 1) % 2) % sf != 0:
+        cut[side] -= 1
+        side ^= 1
+    if min(cut) <= 0:
+        raise ValueError("kernel support too small to trim to a x%d-compatible size" % sf)
+    k = k[cut[0]:n - cut[1], cut[0]:n - cut[1]]
+    return k / np.sum(k)
+
+
+def _upscale_kernel(sf, upscale_kernel):
+    """imresize(None, [sf, sf], return_upscale_kernel=True, kernel=...) (imresize_CEM.py:18-47)."""
+    pre, post = sampling_phase(sf)
+    pad_front, pad_back = max(0, post - pre), max(0, pre - post)   # compensates the uneven phase of even factors
+    if isinstance(upscale_kernel, np.ndarray):
+        if abs(1 - np.sum(upscale_kernel)) >= np.finfo(np.float32).eps:
+            raise ValueError("Supplied non-default kernel does not sum to 1")
+        k = _center_mass(np.rot90(upscale_kernel.astype(np.float64), 2), sf) * sf ** 2
+        if (k.shape[0] + pad_front + pad_back - 1) % sf != 0:
+            raise ValueError("Convolution-invalidated size should be an integer multiplication of the scale factor")
+    else:
+        w = _cubic_weights_1d(sf)
+        k = np.outer(w, w)
+        if upscale_kernel is not None and "blurry_cubic" in upscale_kernel:
+            k = _conv2_full(k, _gaussian_2d(float(upscale_kernel[len("blurry_cubic_"):])))
+    return np.pad(k, ((pad_front, pad_back), (pad_front, pad_back)), mode="constant")
+
+
 def Return_kernel(ds_factor, upscale_kernel=None):
-    if upscale_kernel is not None and not (isinstance(upscale_kernel, str) and upscale_kernel in ("cubic", "reset_2_default")):
-        raise NotImplementedError("non-default CEM kernels (blurry_cubic / estimated, imresize_CEM.py:22-42) need the "
-                                  "non-separable stencil path, which is not built yet (SURVEY.md §8f rank 2)")
-    d = default_ds_kernel_1d(int(ds_factor)).astype(np.float64)
-    return np.outer(d, d).astype(np.float32)
+    """ds_kernel (CEMnet.py:218-219).  upscale_kernel: None / 'cubic' / 'reset_2_default' (bicubic),
+    'blurry_cubic_<sigma>', or a square ndarray downscaling kernel summing to 1."""
+    sf = int(ds_factor)
+    if isinstance(upscale_kernel, str) and not any(w in upscale_kernel for w in ("cubic", "reset_2_default")):
+        raise ValueError("unknown CEM kernel %r" % (upscale_kernel,))
+    return (np.rot90(_upscale_kernel(sf, upscale_kernel), 2) / sf ** 2).astype(np.float32)
 
 
 def _response_margin(resp, limit):
@@ -65,14 +148,6 @@ def _response_margin(resp, limit):
     col = np.flatnonzero(bad[:n // 2, n // 2])
     row = np.flatnonzero(bad[n // 2, :n // 2])
     return int(max(col[-1] + 1, row[-1] + 1))
-
-
-def _conv2_full(a, b):
-    out = np.zeros((a.shape[0] + b.shape[0] - 1, a.shape[1] + b.shape[1] - 1))
-    for i in range(b.shape[0]):
-        for j in range(b.shape[1]):
-            out[i:i + a.shape[0], j:j + a.shape[1]] += b[i, j] * a
-    return out
 
 
 def _conv2_same_ones(n, k):
@@ -91,14 +166,15 @@ def Get_CEM_Config(sf):
     return config
 
 
-def _rank1_factor(k2d, what):
+def _rank1_factor(k2d):
+    """f with k2d == outer(f, f) to 1e-6 of its peak, or None when the filter is not symmetric rank-1."""
     u, s, vt = np.linalg.svd(k2d.astype(np.float64))
     f = u[:, 0] * np.sqrt(s[0])
     g = vt[0] * np.sqrt(s[0])
     if f[np.argmax(np.abs(f))] < 0:
         f, g = -f, -g
     if np.abs(np.outer(f, g) - k2d).max() > 1e-6 * np.abs(k2d).max() or np.abs(f - g).max() > 1e-6 * np.abs(f).max():
-        raise NotImplementedError("%s is not a symmetric rank-1 filter; the general 2-D stencil path is not built yet" % what)
+        return None
     return 0.5 * (f + g)
 
 
@@ -119,9 +195,16 @@ class CEMnet:
         self.invalidity_margins_LR = 2 * self.ds_kernel_invalidity_half_size_LR + self.inv_hTh_invalidity_half_size
         self.invalidity_margins_HR = self.ds_factor * self.invalidity_margins_LR
         self.pre_stride, self.post_stride = sampling_phase(sf)
-        self._ds_1d = _rank1_factor(self.ds_kernel, "ds_kernel")
-        self._inv_1d = _rank1_factor(self.inv_hTh, "inv_hTh")
-        self._filters = capi.cem_filters_struct(sf, self.pre_stride, self._ds_1d, self._inv_1d)
+        # rank-1 symmetric filters (bicubic, mildly blurred bicubic) take the separable kernels; anything else
+        # (estimated kernels, strong blur: the magnitude clamp of inv_hTh is not separable) the 2-D stencils
+        self._ds_1d = _rank1_factor(self.ds_kernel)
+        self._inv_1d = _rank1_factor(self.inv_hTh)
+        self.separable = (self._ds_1d is not None and self._inv_1d is not None
+                          and max(len(self._ds_1d), len(self._inv_1d)) <= capi.CEM_MAX_TAPS)
+        if self.separable:
+            self._filters = capi.cem_filters_struct(sf, self.pre_stride, self._ds_1d, self._inv_1d)
+        else:
+            self._filters = capi.CemFilterBank2D(sf, self.pre_stride, self.ds_kernel, self.inv_hTh)
 
     def _ds_margin(self, sf, limit):
         # downscaling a constant image with zero padding: imresize(ones, 1/sf, use_zero_padding=True)
@@ -211,17 +294,17 @@ class Filter_Layer(nn.Module):
             raise NotImplementedError("standalone CEM operators are forward-only; gradients flow through CEM_PyTorch.forward")
         x = _require_cuda_f32(x, "CEM " + self._op)
         B, Cc, H, W = x.shape
-        sf, l = self._f.sf, capi.lib()
+        sf = self._f.sf
         with torch.cuda.device(x.device):
             if self._op == "down":
                 out = torch.empty(B, Cc, H // sf, W // sf, device=x.device, dtype=torch.float32)
-                capi.check(l.esr_cem_downscale(self._f, capi.ptr(x), B, Cc, H, W, capi.ptr(out), capi.stream_ptr()))
+                capi.cem_call("downscale", self._f, capi.ptr(x), B, Cc, H, W, capi.ptr(out), capi.stream_ptr())
             elif self._op == "up":
                 out = torch.empty(B, Cc, H * sf, W * sf, device=x.device, dtype=torch.float32)
-                capi.check(l.esr_cem_upscale(self._f, capi.ptr(x), B, Cc, H, W, capi.ptr(out), capi.stream_ptr()))
+                capi.cem_call("upscale", self._f, capi.ptr(x), B, Cc, H, W, capi.ptr(out), capi.stream_ptr())
             else:
                 out = torch.empty_like(x)
-                capi.check(l.esr_cem_inv_hth(self._f, capi.ptr(x), B, Cc, H, W, capi.ptr(out), capi.stream_ptr()))
+                capi.cem_call("inv_hth", self._f, capi.ptr(x), B, Cc, H, W, capi.ptr(out), capi.stream_ptr())
         return out
 
 
@@ -238,8 +321,8 @@ class _CemProject(torch.autograd.Function):
         out = torch.empty(B, Cc, H - 2 * crop, W - 2 * crop, device=y.device, dtype=torch.float32)
         ws = torch.empty(2 * B * Cc * (H // sf) * (W // sf), device=y.device, dtype=torch.float32)
         with torch.cuda.device(y.device):
-            capi.check(capi.lib().esr_cem_project(filters, capi.ptr(y), capi.ptr(x), B, Cc, H, W, crop, capi.ptr(out),
-                                                  capi.ptr(ws), capi.stream_ptr()))
+            capi.cem_call("project", filters, capi.ptr(y), capi.ptr(x), B, Cc, H, W, crop, capi.ptr(out), capi.ptr(ws),
+                          capi.stream_ptr())
         ctx.filters, ctx.crop, ctx.shape = filters, crop, (B, Cc, H, W)
         return out
 
@@ -252,8 +335,8 @@ class _CemProject(torch.autograd.Function):
         n = B * Cc * (H * W + H * (W // sf) + 2 * (H // sf) * (W // sf))
         ws = torch.empty(n, device=g.device, dtype=torch.float32)
         with torch.cuda.device(g.device):
-            capi.check(capi.lib().esr_cem_project_bwd(ctx.filters, capi.ptr(g), B, Cc, H, W, ctx.crop, capi.ptr(gy),
-                                                      capi.ptr(ws), capi.stream_ptr()))
+            capi.cem_call("project_bwd", ctx.filters, capi.ptr(g), B, Cc, H, W, ctx.crop, capi.ptr(gy), capi.ptr(ws),
+                          capi.stream_ptr())
         return gy, None, None, None
 
 

@@ -591,6 +591,13 @@ __global__ void cem_pad_zero_kernel(const float* __restrict__ g, float* __restri
     }
 }
 
+int cem_pad_zero(const float* g, float* out, int planes, int H, int W, int crop, cudaStream_t s) {
+    const size_t want = (static_cast<size_t>(planes) * H * W + 255) / 256;
+    const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+    cem_pad_zero_kernel<<<grid, 256, 0, s>>>(g, out, planes, H, W, crop);
+    return check_launch("cem_pad_zero_kernel");
+}
+
 static int launch_adj1d(Adj1dArgs& a, cudaStream_t s) {
     const size_t total = static_cast<size_t>(a.planes) * a.other * a.nout;
     const size_t want = (total + 255) / 256;
@@ -746,12 +753,7 @@ extern "C" int esr_cem_project_bwd(const esr_cem_filters* f, const float* g_out,
     float* tA = Gp + nHR;                                              // [planes,H,w]
     float* tB = tA + static_cast<size_t>(planes) * H * w;              // [planes,h,w]
     float* tC = tB + static_cast<size_t>(planes) * h * w;              // [planes,h,w]
-    {
-        const size_t want = (nHR + 255) / 256;
-        const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
-        cem_pad_zero_kernel<<<grid, 256, 0, s>>>(g_out, Gp, planes, H, W, crop);
-        if ((rc = check_launch("cem_pad_zero_kernel"))) return rc;
-    }
+    if ((rc = cem_pad_zero(g_out, Gp, planes, H, W, crop, s))) return rc;
     Adj1dArgs a;
     // Up^T: Up = correlate(u = sf*ds) over the replicate-padded zero-stuffed image; sample at sf*i+pre.
     for (int t = 0; t < f->n_ds; ++t) a.taps[t] = f->ds[t] * sf;

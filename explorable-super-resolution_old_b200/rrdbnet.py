@@ -138,9 +138,8 @@ class _GeneratorFn(torch.autograd.Function):
                 out = torch.empty(B, y.size(1), y.size(2) - 2 * crop, y.size(3) - 2 * crop, device=x.device,
                                   dtype=torch.float32)
                 ws = torch.empty(2 * B * y.size(1) * plan.hp * plan.wp, device=x.device, dtype=torch.float32)
-                capi.check(capi.lib().esr_cem_project(cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, y.size(1),
-                                                      y.size(2), y.size(3), crop, capi.ptr(out), capi.ptr(ws),
-                                                      capi.stream_ptr()))
+                capi.cem_call("project", cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, y.size(1), y.size(2),
+                              y.size(3), crop, capi.ptr(out), capi.ptr(ws), capi.stream_ptr())
         ctx.plan, ctx.cem_filters, ctx.margin, ctx.net = plan, cem_filters, margin, net
         return out
 
@@ -173,8 +172,8 @@ def capture_inference(net, x_static, margin, cem_filters, slot=0):
         if cem_filters is None:
             out.copy_(y)
         else:
-            capi.check(capi.lib().esr_cem_project(cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, onc, H4, W4, crop,
-                                                  capi.ptr(out), capi.ptr(ws), capi.stream_ptr()))
+            capi.cem_call("project", cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, onc, H4, W4, crop, capi.ptr(out),
+                          capi.ptr(ws), capi.stream_ptr())
     with torch.cuda.device(x_static.device):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -18,6 +18,8 @@
  *   esr_cem_upscale       Upscale_OP                    CEM/CEMnet.py:153-159
  *   esr_cem_project       CEM_PyTorch.forward :183-190  (out = y + Up(K*(x - Down y)), crop)
  *   esr_cem_project_bwd   its adjoint w.r.t. y (autograd in the reference, Z_optimization.py:633)
+ *   esr_cem2d_*           the same five operators for non-default kernels (imresize_CEM.py:22-42),
+ *                         whose filters are not rank-1
  *
  * Conventions: every function returns 0 on success or a negative esr_status and
  * records a message readable through esr_last_error() (thread-local).  No
@@ -293,6 +295,33 @@ int esr_cem_project(const esr_cem_filters* f, const float* y, const float* x, in
  * replicate-padding folds.  workspace: B*C*(H*W + H*(W/sf) + 2*(H/sf)*(W/sf)) floats. */
 int esr_cem_project_bwd(const esr_cem_filters* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
                         int32_t crop, float* g_y, float* workspace, void* stream);
+
+/* ------------------------------------------------- CEM, general (non-separable) filters
+ * The reference accepts any square downscaling kernel (imresize_CEM.py:22-32: an estimated /
+ * user-supplied ndarray, re-centred by Center_Mass) and `blurry_cubic_<sigma>` (:37-41); for those
+ * ds_kernel and / or inv_hTh (whose Fourier-domain magnitude clamp, CEMnet.py:112, is not
+ * separable) are not rank-1 and the operators run as direct 2-D stencils.  Same semantics,
+ * workspace sizes and argument order as the esr_cem_* entry points above.
+ *   ds  : DEVICE pointer, n_ds*n_ds floats row-major  == CEMnet.ds_kernel   (CEMnet.py:22)
+ *   inv : DEVICE pointer, n_inv*n_inv floats row-major == CEMnet.inv_hTh    (CEMnet.py:105-126)
+ * n_ds, n_inv odd, <= ESR_CEM2D_MAX_SIDE. */
+#define ESR_CEM2D_MAX_SIDE 63
+typedef struct esr_cem_filters2d {
+    int32_t sf, pre, n_ds, n_inv;
+    const float* ds;
+    const float* inv;
+} esr_cem_filters2d;
+
+int esr_cem2d_downscale(const esr_cem_filters2d* f, const float* y, int32_t B, int32_t C, int32_t H, int32_t W,
+                        float* out, void* stream);
+int esr_cem2d_inv_hth(const esr_cem_filters2d* f, const float* x, int32_t B, int32_t C, int32_t h, int32_t w,
+                      float* out, void* stream);
+int esr_cem2d_upscale(const esr_cem_filters2d* f, const float* x, int32_t B, int32_t C, int32_t h, int32_t w,
+                      float* out, void* stream);
+int esr_cem2d_project(const esr_cem_filters2d* f, const float* y, const float* x, int32_t B, int32_t C, int32_t H,
+                      int32_t W, int32_t crop, float* out, float* workspace, void* stream);
+int esr_cem2d_project_bwd(const esr_cem_filters2d* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
+                          int32_t crop, float* g_y, float* workspace, void* stream);
 
 /* Debug aid (tools/prof.py): per-CTA role cycle counters of later tcgen05 conv launches, when the
  * library was built with -DESR_PROFILE_ROLES.  buf: [148][16] uint64 device memory or NULL. */

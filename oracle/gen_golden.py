@@ -40,11 +40,88 @@ def build_ref_G(CEMnet, networks, nb, latent_input, kind, seed):
     return netG, cem
 
 
+def aniso_kernel(n, theta, s1, s2, shift=(0.0, 0.0)):
+    """Anisotropic, off-centre Gaussian: a stand-in for an estimated (KernelGAN-style) downscaling kernel."""
+    yy, xx = np.mgrid[:n, :n] - (n - 1) / 2
+    xx, yy = xx - shift[0], yy - shift[1]
+    a = (np.cos(theta) * xx + np.sin(theta) * yy) / s1
+    b = (-np.sin(theta) * xx + np.cos(theta) * yy) / s2
+    k = np.exp(-0.5 * (a * a + b * b))
+    return k / k.sum()
+
+
+NONDEFAULT_CASES = [  # name, sf, kernel, with operator outputs
+    ("blur1_x4", 4, "blurry_cubic_1", True),        # still rank-1: separable kernels, longer taps
+    ("blur2_x4", 4, "blurry_cubic_2", True),        # inv_hTh not rank-1 (magnitude clamp active)
+    ("blur07_x2", 2, "blurry_cubic_0.7", False),
+    ("blur1_x3", 3, "blurry_cubic_1", False),
+    ("aniso13_x4", 4, aniso_kernel(13, 0.6, 3.0, 1.5), True),
+    ("aniso17s_x4", 4, aniso_kernel(17, 0.6, 3.0, 1.5, (1.3, -0.8)), False),
+    ("aniso15_x2", 2, aniso_kernel(15, 0.3, 2.0, 1.0, (0.4, 1.2)), True),
+    ("aniso15_x3", 3, aniso_kernel(15, 1.1, 2.5, 1.2, (-1.0, 0.6)), True),
+    ("aniso21s_x4", 4, aniso_kernel(21, 2.0, 4.0, 2.5, (2.2, 1.7)), False),
+    # SRRaGAN_model.py:63-65: estimated kernels are inverted with lower_magnitude_bound = 0.1
+    ("aniso13_x4_lmb01", 4, aniso_kernel(13, 0.6, 3.0, 1.5), False),
+]
+
+
+def gen_nondefault(CEMnet):
+    """Non-default CEM kernels (imresize_CEM.py:22-42): derived filters, operator outputs, projection and its
+    gradient, from the unmodified reference."""
+    import CEM.imresize_CEM as im
+
+    class Stub(torch.nn.Module):
+        num_latent_channels, upscale = 3, 4
+
+        def forward(self, x):
+            return self.y
+
+    out = {}
+    rng = np.random.default_rng(21)
+    for name, sf, kernel, with_ops in NONDEFAULT_CASES:
+        im.imresize.kernels = {}
+        conf = CEMnet.Get_CEM_Config(sf)
+        if name.endswith("_lmb01"):
+            conf.lower_magnitude_bound = 0.1
+        cem = CEMnet.CEMnet(conf, upscale_kernel=kernel)
+        out[name + "_sf"] = np.array(sf)
+        out[name + "_lmb"] = np.array(conf.lower_magnitude_bound)
+        out[name + "_kernel"] = np.array(kernel) if isinstance(kernel, str) else kernel
+        out[name + "_ds_kernel"] = cem.ds_kernel.astype(np.float32)
+        out[name + "_inv_hTh"] = cem.inv_hTh.astype(np.float64)
+        out[name + "_margins"] = np.array([cem.invalidity_margins_LR, cem.invalidity_margins_HR,
+                                           cem.ds_kernel_invalidity_half_size_LR, cem.inv_hTh_invalidity_half_size])
+        print(name, cem.ds_kernel.shape, cem.inv_hTh.shape, out[name + "_margins"])
+        if not with_ops:
+            continue
+        stub = Stub()
+        wrapped = cem.WrapArchitecture_PyTorch(stub)
+        h, w = 11, 14
+        y = torch.from_numpy(rng.random((1, 3, sf * h, sf * w), dtype=np.float32))
+        x = torch.from_numpy(rng.random((1, 3, h, w), dtype=np.float32))
+        stub.y = y
+        wrapped.train(True)
+        with torch.no_grad():
+            ops = dict(y=y.numpy(), x=x.numpy(), down=wrapped.DownscaleOP(y).numpy(), up=wrapped.Upscale_OP(x).numpy(),
+                       inv=wrapped.Conv_LR_with_Inv_hTh_OP(x).numpy(), project=wrapped(x).numpy())
+        yg = y.clone().requires_grad_(True)
+        stub.y = yg
+        g = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32))
+        (wrapped(x) * g).sum().backward()
+        ops["grad_g"], ops["grad_y"] = g.numpy(), yg.grad.numpy()
+        out.update({name + "_" + k: v for k, v in ops.items()})
+    im.imresize.kernels = {}
+    np.savez_compressed(os.path.join(OUT, "cem_nondefault.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     CEMnet, networks, arch, zopt = ref_shims.load_reference()
     import CEM.imresize_CEM as im
+
+    if "nondefault" in sys.argv[1:]:      # only the non-default-kernel fixture
+        return gen_nondefault(CEMnet)
 
     # 1. filters --------------------------------------------------------------------------
     filt = {}
@@ -161,6 +238,9 @@ def main():
         zres[name + "_Z"] = Z.numpy()
         print(name, opt.loss_values)
     np.savez_compressed(os.path.join(OUT, "zopt.npz"), **zres)
+
+    # 5. non-default CEM kernels -----------------------------------------------------------
+    gen_nondefault(CEMnet)
 
 
 if __name__ == "__main__":

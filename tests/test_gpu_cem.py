@@ -83,3 +83,140 @@ def test_ops_match_oracle_and_consistency(cuda_device, sf, shape):
             stub.y = stub.y + y.to(cuda_device)
             out12 = w(x.to(cuda_device))
         assert (out12 - out - out2).abs().max().item() <= 2e-5
+
+
+# ------------------------------------------------------------------ non-default kernels (csrc/cem2d.cu)
+NONDEFAULT_OP_CASES = ["blur1_x4", "blur2_x4", "aniso13_x4", "aniso15_x2", "aniso15_x3"]
+
+
+def _kernel_of(g, name):
+    k = g[name + "_kernel"]
+    return str(k) if k.dtype.kind in "US" else k
+
+
+def _stub_wrapped(net, sf, dev, train=True):
+    class Stub(torch.nn.Module):
+        num_latent_channels, upscale = 3, sf
+
+        def forward(self, x):
+            return self.y
+    stub = Stub()
+    return net.WrapArchitecture_PyTorch(stub).to(dev).train(train), stub
+
+
+def _tol(net):
+    """fp32 accumulation through K = inv_hTh: rounding of the O(1) operands is amplified by ||K||_1 (15 for the
+    mild kernels, 220 for blurry_cubic_2, whose inverse is ill conditioned by construction)."""
+    return 1e-5 + 3e-7 * float(np.abs(net.inv_hTh).sum())
+
+
+def _oracle_of(net):
+    sf = int(net.ds_factor)
+    return CEMOracle(sf, filters=dict(ds_kernel=net.ds_kernel, inv_hTh=net.inv_hTh, margin_LR=int(net.invalidity_margins_LR),
+                                      margin_HR=int(net.invalidity_margins_HR)))
+
+
+@pytest.mark.parametrize("name", NONDEFAULT_OP_CASES)
+def test_nondefault_ops_match_reference_golden(golden, cuda_device, name):
+    """blurry_cubic_<sigma> and ndarray kernels against the unmodified reference (ops, projection, its gradient)."""
+    g = golden("cem_nondefault")
+    sf = int(g[name + "_sf"])
+    net = pcem.CEMnet(pcem.Get_CEM_Config(sf), upscale_kernel=_kernel_of(g, name))
+    w, stub = _stub_wrapped(net, sf, cuda_device)
+    y, x = torch.from_numpy(g[name + "_y"]).to(cuda_device), torch.from_numpy(g[name + "_x"]).to(cuda_device)
+    with torch.no_grad():
+        np.testing.assert_allclose(w.DownscaleOP(y).cpu().numpy(), g[name + "_down"], atol=1e-5)
+        np.testing.assert_allclose(w.Upscale_OP(x).cpu().numpy(), g[name + "_up"], atol=1e-5)
+        np.testing.assert_allclose(w.Conv_LR_with_Inv_hTh_OP(x).cpu().numpy(), g[name + "_inv"], atol=_tol(net))
+        stub.y = y
+        np.testing.assert_allclose(w(x).cpu().numpy(), g[name + "_project"], atol=_tol(net))
+    yg = y.clone().requires_grad_(True)
+    stub.y = yg
+    (w(x) * torch.from_numpy(g[name + "_grad_g"]).to(cuda_device)).sum().backward()
+    np.testing.assert_allclose(yg.grad.cpu().numpy(), g[name + "_grad_y"], atol=_tol(net))
+
+
+@pytest.mark.parametrize("name,shape,crop", [("aniso17s_x4", (2, 3, 37, 45), 0), ("aniso17s_x4", (1, 3, 70, 33), 8),
+                                             ("blur2_x4", (1, 2, 40, 77), 12), ("aniso15_x3", (1, 3, 35, 67), 6),
+                                             ("aniso15_x2", (3, 1, 64, 31), 2), ("aniso21s_x4", (1, 3, 5, 3), 0)])
+def test_nondefault_project_and_adjoint_match_oracle(golden, cuda_device, name, shape, crop):
+    """Ragged sizes (tiles cut by the image edge, images narrower than the stencils), cropped output, and the
+    exact adjoint including the replicate-padding folds, against the oracle's autograd."""
+    g = golden("cem_nondefault")
+    sf = int(g[name + "_sf"])
+    net = pcem.CEMnet(pcem.Get_CEM_Config(sf), upscale_kernel=_kernel_of(g, name))
+    assert not net.separable
+    ora = _oracle_of(net)
+    gen = torch.Generator().manual_seed(3)
+    B, Cc, h, w_ = shape
+    y = torch.rand(B, Cc, sf * h, sf * w_, generator=gen)
+    x = torch.rand(B, Cc, h, w_, generator=gen)
+
+    def tile3(k):  # the oracle's depthwise weights are built for 3 planes; rebuild for Cc
+        return k[:1].repeat(Cc, 1, 1, 1)
+    ora.w_inv, ora.w_down, ora.w_up = tile3(ora.w_inv), tile3(ora.w_down), tile3(ora.w_up)
+    ora._dw = lambda t, wt, pad: torch.nn.functional.conv2d(torch.nn.functional.pad(t, (pad,) * 4, mode="replicate"), wt, groups=Cc)
+    yo = y.clone().requires_grad_(True)
+    ref = ora.project(yo, x)
+    ref = ref[:, :, crop:ref.size(2) - crop, crop:ref.size(3) - crop]
+    gout = torch.randn(ref.shape, generator=gen)
+    (ref * gout).sum().backward()
+    yd = y.to(cuda_device).requires_grad_(True)
+    out = pcem._CemProject.apply(yd, x.to(cuda_device), net._filters, crop)
+    (out * gout.to(cuda_device)).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), atol=_tol(net))
+    np.testing.assert_allclose(yd.grad.cpu().numpy(), yo.grad.numpy(), atol=_tol(net) * max(1.0, yo.grad.abs().max().item() / 4))
+
+
+def test_stencil_path_equals_separable_path(cuda_device):
+    """The default bicubic filters pushed through the general 2-D stencils give what the rank-1 kernels give
+    (forward, every operator, and the adjoint), at a size with many tiles per plane."""
+    from esr_b200 import _capi as capi
+    net = pcem.CEMnet(pcem.Get_CEM_Config(4))
+    bank = capi.CemFilterBank2D(4, net.pre_stride, net.ds_kernel, net.inv_hTh)
+    gen = torch.Generator().manual_seed(5)
+    y = torch.rand(2, 3, 512, 384, generator=gen).to(cuda_device)
+    x = torch.rand(2, 3, 128, 96, generator=gen).to(cuda_device)
+    gout = torch.randn(2, 3, 512 - 80, 384 - 80, generator=gen).to(cuda_device)
+    res = []
+    for f in (net._filters, bank):
+        yd = y.clone().requires_grad_(True)
+        out = pcem._CemProject.apply(yd, x, f, 40)
+        (out * gout).sum().backward()
+        ops = [pcem.Filter_Layer(net.inv_hTh, op, f).to(cuda_device)(t) for op, t in (("down", y), ("up", x), ("inv", x))]
+        res.append([out.detach(), yd.grad] + ops)
+    for a, b in zip(*res):
+        assert (a - b).abs().max().item() <= 2e-5 * max(1.0, a.abs().max().item())
+
+
+def test_generator_with_estimated_kernel_matches_oracle(golden, cuda_device):
+    """G + CEM built on a user-supplied kernel, eval mode (pre-padding by that kernel's own margins), forward and
+    the Z gradient: the whole drop-in path with a non-default CEM."""
+    from esr_b200 import networks, synth
+    from oracle.rrdbnet import GCEMOracle
+    from oracle.cem_ops import concat_latent
+    g = golden("cem_nondefault")
+    net = pcem.CEMnet(pcem.Get_CEM_Config(4), upscale_kernel=g["aniso13_x4_kernel"])
+    opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 256}},
+           "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input="all_layers", latent_input_domain="HR_downscaled",
+                             latent_channels=3, norm_type=None, mode="CNA", nf=64, nb=1, in_nc=3, out_nc=3, gc=32, scale=4)}
+    netG = networks.define_G(opt, CEM=net, num_latent_channels=3).to(cuda_device).eval()
+    wts = synth.make_weights("default", seed=9, nb=1, latent_input="all_layers_HR_downscaled")
+    sd = netG.state_dict()
+    sd.update({"generated_image_model." + k: v for k, v in wts.items()})
+    netG.load_state_dict(sd)
+    for p in netG.parameters():
+        p.requires_grad_(False)
+    lr, z = synth.make_inputs(1, 9, 11, seed=9)
+    ora = GCEMOracle(wts, nb=1, cem=_oracle_of(net))
+    zo = z.clone().requires_grad_(True)
+    ref = ora.forward(concat_latent(lr, zo))
+    gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (ref * gout).sum().backward()
+    zd = z.to(cuda_device).requires_grad_(True)
+    out = netG(concat_latent(lr.to(cuda_device), zd))
+    assert out.shape == ref.shape
+    (out * gout.to(cuda_device)).sum().backward()
+    assert (out.detach().cpu() - ref.detach()).abs().max().item() <= 1e-2
+    gz, gr = zd.grad.cpu(), zo.grad
+    assert float((gz - gr).norm() / gr.norm()) < 4e-2 and float((gz * gr).sum() / (gz.norm() * gr.norm())) > 0.999

@@ -33,11 +33,6 @@ def test_product_filters_match_oracle_and_golden(golden, sf):
     np.testing.assert_allclose(np.outer(c._inv_1d, c._inv_1d), o["inv_hTh"], atol=2e-6)
 
 
-def test_non_default_kernel_is_loud():
-    with pytest.raises(NotImplementedError):
-        pcem.CEMnet(pcem.Get_CEM_Config(4), upscale_kernel=np.ones((5, 5)) / 25)
-
-
 def test_state_dict_contract():
     """Key names, order and shapes of the reference module tree, 17 060 948 + 3 921 parameters."""
     netG = networks.define_G(make_opt(), CEM=pcem.CEMnet(pcem.Get_CEM_Config(4)), num_latent_channels=3)
