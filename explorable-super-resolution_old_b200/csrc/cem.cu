@@ -194,16 +194,26 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
     const float* yp = y + static_cast<size_t>(plane) * H * W;
     // cells outside the image replicate the edge pixel: fetch the edge cell, pick its outer element when read back
     const int edge = j < 0 ? -1 : (j >= w ? 1 : 0);
+    const bool strip_has_edge = blockIdx.x == 0 || (blockIdx.x + 1) * kStripCells + 2 > w;   // warp-uniform
     const float* col = yp + 4 * min(max(j, 0), w - 1);
     const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w;
     const int last = i1 + 1;                                        // LR row groups i0-2 .. i1+1 feed rows i0 .. i1-1
+    const uint32_t ring_base = static_cast<uint32_t>(__cvta_generic_to_shared(&ring[warp][0][0][lane]));
+    constexpr uint32_t kRowBytes = 32 * sizeof(float4), kGroupBytes = 4 * kRowBytes;
     auto issue_group = [&](int I) {                                 // the 4 HR rows of LR row I (rows replicate padded)
         if (I <= last) {
-            float4(*slot)[32] = ring[warp][(I - (i0 - 2)) % kDownGroups];
+            const uint32_t dst = ring_base + static_cast<uint32_t>((I - (i0 - 2)) % kDownGroups) * kGroupBytes;
+            if (I >= 0 && I < h) {                                  // interior group: one row pointer, no clamps
+                const float* src = col + static_cast<size_t>(4 * I) * W;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int r = min(max(4 * I + q, 0), H - 1);
-                cp_async16(&slot[q][lane], col + static_cast<size_t>(r) * W);
+                for (int q = 0; q < 4; ++q)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * kRowBytes), "l"(src + static_cast<size_t>(q) * W) : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = min(max(4 * I + q, 0), H - 1);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * kRowBytes), "l"(col + static_cast<size_t>(r) * W) : "memory");
+                }
             }
         }
         cp_async_commit();                                          // (possibly empty) group: keeps the wait counts uniform
@@ -218,10 +228,13 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
         const float4(*slot)[32] = ring[warp][(I - (i0 - 2)) % kDownGroups];
         float4 c[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            c[q] = slot[q][lane];
-            if (edge < 0) c[q] = make_float4(c[q].x, c[q].x, c[q].x, c[q].x);
-            else if (edge > 0) c[q] = make_float4(c[q].w, c[q].w, c[q].w, c[q].w);
+        for (int q = 0; q < 4; ++q) c[q] = slot[q][lane];
+        if (strip_has_edge) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (edge < 0) c[q] = make_float4(c[q].x, c[q].x, c[q].x, c[q].x);
+                else if (edge > 0) c[q] = make_float4(c[q].w, c[q].w, c[q].w, c[q].w);
+            }
         }
         issue_group(I + kDownGroups - 1);                           // refills the slot read one iteration ago
 #pragma unroll
@@ -268,8 +281,8 @@ struct InvTaps {
 // NT = compile-time length of the (HH^T)^-1 factor (27 for the bicubic x4 configuration; 0 = run-time loops).  With
 // NT known the two separable passes are register tiled (4 outputs per thread share NT+3 loaded values) and fully
 // unrolled: 30 shared loads + 108 FMAs per 4 outputs instead of 4 x 27 x (constant load, shared load, FMA, loop).
-template <int NT>
-__global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__ CemTab T, const __grid_constant__ InvTaps K,
+template <int NT, int MINB>
+__global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_constant__ CemTab T, const __grid_constant__ InvTaps K,
                                                          const float* __restrict__ d, const float* __restrict__ y,
                                                          float* __restrict__ out, int h, int w, int crop, int seg) {
     extern __shared__ float sm[];
@@ -287,13 +300,16 @@ __global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__
     float* et = hb + Rd * 32;                                      // [Re][32]   e (zero outside the image)
     const int i0 = ib + warp * seg, i1 = min(i0 + seg, h);
     const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w && 4 * j >= crop && 4 * j + 3 < W - crop;
+    // running pointers: LR row i's first HR row in y / out (one add per row instead of a 64-bit multiply per access)
+    const int Wq = W >> 2;
+    const float4* ybase = reinterpret_cast<const float4*>(y + static_cast<size_t>(plane) * H * W) + j;
     auto load_y = [&](int i, float4 (&b)[4]) {                     // the 4 HR rows of LR row i (base image)
+        const float4* p = ybase + static_cast<size_t>(4 * i) * Wq;
+        const bool rows_in = writer && i < i1 && 4 * i >= crop && 4 * i + 3 < H - crop;   // crop % 4 == 0: all or nothing
 #pragma unroll
         for (int psi = 0; psi < 4; ++psi) {
-            const int Y = 4 * i + psi;
             b[psi] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (writer && i < i1 && Y >= crop && Y < H - crop)
-                b[psi] = __ldg(reinterpret_cast<const float4*>(y + (static_cast<size_t>(plane) * H + Y) * W) + j);
+            if (rows_in) b[psi] = __ldg(p + psi * Wq);
         }
     };
     float4 yc[4], yn[4];
@@ -302,8 +318,13 @@ __global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__
     const float* dp = d + static_cast<size_t>(plane) * h * w;
     for (int r = warp; r < Rd; r += 4) {                           // a warp per tile row: no div / mod, one clamp per row
         const float* row = dp + static_cast<size_t>(clampi(ib - 2 - pad + r, 0, h - 1)) * w;
-        for (int c = lane; c < Cd; c += 32) dt[r * Cds + c] = __ldg(row + clampi(jb - pad + c, 0, w - 1));
+        for (int c = lane; c < Cd; c += 32)                        // cp.async: the whole tile is in flight at once
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dt + r * Cds + c))),
+                         "l"(row + clampi(jb - pad + c, 0, w - 1))
+                         : "memory");
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     if constexpr (NT > 0) {
         for (int task = threadIdx.x; task < Rd * 8; task += 128) {          // 4 consecutive columns per task
@@ -392,21 +413,19 @@ __global__ void __launch_bounds__(128) cem_invup4_kernel(const __grid_constant__
         hrow(i + 2, hu[4]);
         float4 yn2[4];
         load_y(i + 2, yn2);
-        if (writer) {
+        if (writer && 4 * i >= crop && 4 * i + 3 < H - crop) {     // crop % 4 == 0: an LR row is kept or cropped whole
+            float4* op = reinterpret_cast<float4*>(out + (static_cast<size_t>(plane) * Ho + (4 * i - crop)) * Wo + (4 * j - crop));
+            const int Woq = Wo >> 2;
 #pragma unroll
             for (int psi = 0; psi < 4; ++psi) {
-                const int Y = 4 * i + psi;
-                if (Y < crop || Y >= H - crop) continue;
-                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 r = yc[psi];
 #pragma unroll
                 for (int kv = 0; kv < 5; ++kv) {
                     const float wv = T.up[psi][kv];
                     r.x = fmaf(wv, hu[kv][0], r.x); r.y = fmaf(wv, hu[kv][1], r.y);
                     r.z = fmaf(wv, hu[kv][2], r.z); r.w = fmaf(wv, hu[kv][3], r.w);
                 }
-                const float4 b = yc[psi];
-                r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
-                *reinterpret_cast<float4*>(out + (static_cast<size_t>(plane) * Ho + (Y - crop)) * Wo + (4 * j - crop)) = r;
+                op[psi * Woq] = r;
             }
         }
 #pragma unroll
@@ -483,16 +502,31 @@ __global__ void __launch_bounds__(128) cem_up4_kernel(const __grid_constant__ Ce
     }
 }
 
-// LR rows per warp of the streaming kernels: long segments amortise the 4-row (down) / 30-row (d tile) halos,
-// short ones keep >= 16 warps per SM in flight on small problems (config 4: 3 planes of 512 x 512 cells).
-static int pick_seg(int planes, int h, int w) {
-    static const int forced = []() { const char* v = getenv("ESR_CEM_SEG"); return v ? atoi(v) : 0; }();   // tuning aid
-    if (forced == 8 || forced == 16 || forced == 32) return forced;
+// LR rows per warp (`seg`) of the streaming kernels.  A block covers 4*seg LR rows of a strip and pays a fixed
+// halo on top (Down: 4 LR-row groups of loads + FMAs; K+Up: the 26 extra rows of its d / e tiles, worth ~1.2 rows of
+// streaming), so long segments amortise the halo, but the last block row of a plane is padded up to 4*seg rows and
+// small problems need >= 4 blocks (16 warps) per SM to hide latency.  Cost model fitted to a sweep on B200
+// (tools/cem_seg_sweep.py; config 4: 3 planes of 512^2 cells, config 2: 48 planes of 148^2):
+//   cost(seg) = ceil(h / 4seg) * (seg + halo) / min(1, blocks / (148 * 4)).
+static int pick_seg(int planes, int h, int w, const char* env_name, int max_seg, float halo) {
+    if (const char* v = getenv(env_name)) {                       // tuning aid
+        const int forced = atoi(v);
+        if (forced >= 2 && forced <= max_seg) return forced;
+    }
     const long strips = ceil_div(w, kStripCells);
-    for (int seg = 32; seg > 8; seg >>= 1)
-        if (strips * ceil_div(h, seg) * planes >= 148L * 16) return seg;
-    return 8;
+    int best = 8;
+    float best_cost = 3.4e38f;
+    for (int seg = 6; seg <= max_seg; ++seg) {
+        const int block_rows = ceil_div(h, 4 * seg);
+        const float blocks = static_cast<float>(strips * block_rows * planes);
+        const float fill = blocks / (148.f * 4.f);
+        const float cost = block_rows * (seg + halo) / (fill < 1.f ? fill : 1.f);
+        if (cost < best_cost) { best_cost = cost; best = seg; }
+    }
+    return best;
 }
+static int pick_seg_down(int planes, int h, int w) { return pick_seg(planes, h, w, "ESR_CEM_SEG_DOWN", 16, 4.f); }
+static int pick_seg_up(int planes, int h, int w) { return pick_seg(planes, h, w, "ESR_CEM_SEG_UP", 16, 1.2f); }
 
 static bool fast4_ok(const esr_cem_filters& f, int H, int W, int crop, const void* a, const void* b, const void* c) {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -637,7 +671,7 @@ int cem_down(const esr_cem_filters& f, const float* y, const float* x, int plane
              cudaStream_t s) {
     ESR_CHECK_ARG(H % f.sf == 0 && W % f.sf == 0, "HR size %dx%d not divisible by %d", H, W, f.sf);
     if (fast4_ok(f, H, W, 0, y, nullptr, nullptr)) {
-        const int seg = pick_seg(planes, H / 4, W / 4);
+        const int seg = pick_seg_down(planes, H / 4, W / 4);
         dim3 grid(ceil_div(W / 4, kStripCells), ceil_div(ceil_div(H / 4, seg), 4), planes);
         cem_down4_kernel<<<grid, 128, 0, s>>>(make_tab(f), y, x, out, H, W, seg);
         return check_launch("cem_down4_kernel");
@@ -678,19 +712,20 @@ int cem_invup4(const esr_cem_filters& f, const float* d, const float* y, int pla
     InvTaps K;
     K.n = f.n_inv;
     for (int i = 0; i < f.n_inv; ++i) K.t[i] = f.inv[i];
-    const int seg = pick_seg(planes, h, w) > 16 ? 16 : pick_seg(planes, h, w), pad = f.n_inv / 2;   // <= 16: smem tile
+    const int seg = pick_seg_up(planes, h, w), pad = f.n_inv / 2;   // <= 16: smem tile
     const int Re = 4 * seg + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad, Cds = (Cd + 3) & ~3;
     const size_t sm = sizeof(float) * (static_cast<size_t>(Rd) * Cds + static_cast<size_t>(Rd) * 32 + static_cast<size_t>(Re) * 32);
     dim3 grid(ceil_div(w, kStripCells), ceil_div(h, 4 * seg), planes);
-    if (f.n_inv == 27) {
-        int rc = set_smem(reinterpret_cast<const void*>(cem_invup4_kernel<27>), sm);
+    auto launch = [&](auto kern) -> int {
+        int rc = set_smem(reinterpret_cast<const void*>(kern), sm);
         if (rc) return rc;
-        cem_invup4_kernel<27><<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
-    } else {
-        int rc = set_smem(reinterpret_cast<const void*>(cem_invup4_kernel<0>), sm);
-        if (rc) return rc;
-        cem_invup4_kernel<0><<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
-    }
+        kern<<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
+        return ESR_OK;
+    };
+    int rc;
+    if (f.n_inv == 27) rc = launch(cem_invup4_kernel<27, 4>);      // 5 blocks / SM (96 registers) measured 7-19 % slower
+    else rc = launch(cem_invup4_kernel<0, 4>);
+    if (rc) return rc;
     return check_launch("cem_invup4_kernel");
 }
 
