@@ -162,6 +162,11 @@ struct CemTab {            // polyphase tap tables, [phase][cell offset -2..2]
     float down_h[4][5];    // down: weight of element e of cell j+c for output column j
     float down_v[4][5];    // down: weight of HR row 4I+q for output row I-m, index [q][m+2]
     float up[4][5];        // up: weight of cell j+c for HR phase phi (same table for rows)
+    // packed-fp32 (FFMA2) operand forms of the same numbers
+    float2 down_v2[4][5];  // (down_v, down_v)
+    float2 up_v2[4][5];    // (up, up)
+    float2 up_h01[5];      // (up[0][c], up[1][c])
+    float2 up_h23[5];      // (up[2][c], up[3][c])
 };
 
 // Vertical taps first: every HR row costs 20 FMAs into five float4 accumulators (LR rows I-2..I+2) and no
@@ -218,12 +223,19 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
         }
         cp_async_commit();                                          // (possibly empty) group: keeps the wait counts uniform
     };
-    float4 acc[5];                                                  // LR rows I-2 .. I+2 (4 HR columns of the cell each)
+    float2 acc_lo[5], acc_hi[5];                                    // LR rows I-2 .. I+2 (4 HR columns of the cell each)
 #pragma unroll
-    for (int m = 0; m < 5; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < 5; ++m) acc_lo[m] = acc_hi[m] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int g = 0; g < kDownGroups - 1; ++g) issue_group(i0 - 2 + g);
+    const float* xcol = x != nullptr ? x + static_cast<size_t>(plane) * h * w + j : nullptr;
+    auto load_x = [&](int i) {                                      // LR image sample of output row i (0 where unused)
+        return (xcol != nullptr && writer && i >= i0 && i < i1) ? __ldg(xcol + static_cast<size_t>(i) * w) : 0.f;
+    };
+    float x_next = 0.f;                                             // fetched one iteration before its row completes
     for (int I = i0 - 2; I <= last; ++I) {
+        const float x_cur = x_next;
+        x_next = load_x(I - 1);
         cp_async_wait<kDownGroups - 2>();                           // group I has landed (this thread's own copies)
         const float4(*slot)[32] = ring[warp][(I - (i0 - 2)) % kDownGroups];
         float4 c[4];
@@ -241,13 +253,13 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
         for (int q = 0; q < 4; ++q) {
 #pragma unroll
             for (int m = 0; m < 5; ++m) {                           // row 4I+q feeds LR row I-2+m with tap index 4-m
-                const float wv = T.down_v[q][4 - m];
-                acc[m].x = fmaf(wv, c[q].x, acc[m].x); acc[m].y = fmaf(wv, c[q].y, acc[m].y);
-                acc[m].z = fmaf(wv, c[q].z, acc[m].z); acc[m].w = fmaf(wv, c[q].w, acc[m].w);
+                const float2 wv = T.down_v2[q][4 - m];              // packed fp32: two FFMA2 instead of four FFMA
+                acc_lo[m] = __ffma2_rn(wv, make_float2(c[q].x, c[q].y), acc_lo[m]);
+                acc_hi[m] = __ffma2_rn(wv, make_float2(c[q].z, c[q].w), acc_hi[m]);
             }
         }
         // LR row I-2 is complete: this cell's contribution to the output columns (own cell) - k, k = -2..2
-        const float4 a = acc[0];
+        const float4 a = make_float4(acc_lo[0].x, acc_lo[0].y, acc_hi[0].x, acc_hi[0].y);
         float hsum = 0.f;
 #pragma unroll
         for (int k = -2; k <= 2; ++k) {
@@ -260,11 +272,11 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
         const int i = I - 2;
         if (i >= i0 && i < i1 && writer) {
             const size_t o = (static_cast<size_t>(plane) * h + i) * w + j;
-            out[o] = x != nullptr ? x[o] - hsum : hsum;
+            out[o] = x != nullptr ? x_cur - hsum : hsum;
         }
 #pragma unroll
-        for (int m = 0; m < 4; ++m) acc[m] = acc[m + 1];
-        acc[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < 4; ++m) { acc_lo[m] = acc_lo[m + 1]; acc_hi[m] = acc_hi[m + 1]; }
+        acc_lo[4] = acc_hi[4] = make_float2(0.f, 0.f);
     }
     cp_async_wait<0>();
 }
@@ -275,6 +287,7 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
 // e tile (no shuffles), a rolling 5-row window for the vertical taps, y and out as coalesced float4 rows.
 struct InvTaps {
     float t[ESR_CEM_MAX_TAPS];
+    float2 t2[ESR_CEM_MAX_TAPS];   // (t, t): FFMA2 operand form
     int n;
 };
 
@@ -312,14 +325,17 @@ __global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_cons
             if (rows_in) b[psi] = __ldg(p + psi * Wq);
         }
     };
-    float4 yc[4], yn[4];
+    float4 yc[4], yn[4], yn2[4];                                   // three LR rows (12 HR rows, 6 KiB per warp) in flight
     load_y(i0, yc);                                                // HBM loads fly while the e tile is built
     load_y(i0 + 1, yn);
+    load_y(i0 + 2, yn2);
     const float* dp = d + static_cast<size_t>(plane) * h * w;
     for (int r = warp; r < Rd; r += 4) {                           // a warp per tile row: no div / mod, one clamp per row
         const float* row = dp + static_cast<size_t>(clampi(ib - 2 - pad + r, 0, h - 1)) * w;
+        float* drow = NT > 0 ? dt + (r >> 1) * Cds * 2 + (r & 1) : dt + r * Cds;   // NT > 0: row pairs interleaved
+        const int cstep = NT > 0 ? 2 : 1;
         for (int c = lane; c < Cd; c += 32)                        // cp.async: the whole tile is in flight at once
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dt + r * Cds + c))),
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(drow + c * cstep))),
                          "l"(row + clampi(jb - pad + c, 0, w - 1))
                          : "memory");
     }
@@ -327,44 +343,51 @@ __global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_cons
     cp_async_wait<0>();
     __syncthreads();
     if constexpr (NT > 0) {
-        for (int task = threadIdx.x; task < Rd * 8; task += 128) {          // 4 consecutive columns per task
-            const int r = task >> 3, c4 = (task & 7) * 4;
-            const float4* src = reinterpret_cast<const float4*>(dt + r * Cds + c4);   // Cds % 4 == 0: 16-byte aligned
-            float v[NT + 5];
+        // horizontal pass: 2 rows x 2 columns per task.  The d tile is stored with row pairs interleaved
+        // (dt[(r/2)*Cds + col][r&1]), so one 16-byte load brings two columns of both rows as two aligned register
+        // pairs and every tap is one packed FMA per output column: 14 LDS.128 + 54 FFMA2 per 4 outputs.
+        for (int task = threadIdx.x; task < (Rd >> 1) * 16; task += 128) {
+            const int rp = task >> 4, c = (task & 15) * 2;
+            const float4* src = reinterpret_cast<const float4*>(dt + (rp * Cds + c) * 2);
+            float2 v[NT + 1];                                               // v[k] = (d[2rp][c+k], d[2rp+1][c+k])
 #pragma unroll
-            for (int q = 0; q < (NT + 6) / 4; ++q) {
+            for (int q = 0; q < (NT + 1) / 2; ++q) {
                 const float4 t4 = src[q];
-                v[4 * q] = t4.x;
-                if (4 * q + 1 < NT + 5) v[4 * q + 1] = t4.y;
-                if (4 * q + 2 < NT + 5) v[4 * q + 2] = t4.z;
-                if (4 * q + 3 < NT + 5) v[4 * q + 3] = t4.w;
+                v[2 * q] = make_float2(t4.x, t4.y);
+                v[2 * q + 1] = make_float2(t4.z, t4.w);
             }
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+            float2 o0 = make_float2(0.f, 0.f), o1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
-                const float tk = K.t[k];
-                o0 = fmaf(tk, v[k], o0); o1 = fmaf(tk, v[k + 1], o1); o2 = fmaf(tk, v[k + 2], o2); o3 = fmaf(tk, v[k + 3], o3);
+                const float2 tk = K.t2[k];
+                o0 = __ffma2_rn(tk, v[k], o0);
+                o1 = __ffma2_rn(tk, v[k + 1], o1);
             }
-            *reinterpret_cast<float4*>(hb + r * 32 + c4) = make_float4(o0, o1, o2, o3);
+            *reinterpret_cast<float2*>(hb + (2 * rp) * 32 + c) = make_float2(o0.x, o1.x);
+            *reinterpret_cast<float2*>(hb + (2 * rp + 1) * 32 + c) = make_float2(o0.y, o1.y);
         }
         __syncthreads();
-        for (int task = threadIdx.x; task < (Re >> 2) * 32; task += 128) {  // 4 consecutive rows per task (Re % 4 == 0)
-            const int r0 = (task >> 5) * 4, c = task & 31;
-            float v[NT + 3];
+        for (int task = threadIdx.x; task < (Re >> 2) * 16; task += 128) {  // 4 rows (Re % 4 == 0) x 2 columns per task
+            const int r0 = (task >> 4) * 4, c = (task & 15) * 2;
+            float2 v[NT + 3];                                               // column pairs: packed fp32 FMAs
 #pragma unroll
-            for (int k = 0; k < NT + 3; ++k) v[k] = hb[(r0 + k) * 32 + c];
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < NT + 3; ++k) v[k] = *reinterpret_cast<const float2*>(hb + (r0 + k) * 32 + c);
+            float2 o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
-                const float tk = K.t[k];
+                const float2 tk = K.t2[k];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) o[q] = fmaf(tk, v[k + q], o[q]);
+                for (int q = 0; q < 4; ++q) o[q] = __ffma2_rn(tk, v[k + q], o[q]);
             }
             const int jj = jb + c;
+            const bool in0 = jj >= 0 && jj < w, in1 = jj + 1 >= 0 && jj + 1 < w;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int ii = ib - 2 + r0 + q;
-                et[(r0 + q) * 32 + c] = (ii >= 0 && ii < h && jj >= 0 && jj < w) ? o[q] : 0.f;
+                const bool rin = ii >= 0 && ii < h;
+                *reinterpret_cast<float2*>(et + (r0 + q) * 32 + c) = make_float2(rin && in0 ? o[q].x : 0.f, rin && in1 ? o[q].y : 0.f);
             }
         }
     } else {
@@ -390,50 +413,47 @@ __global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_cons
     __syncthreads();
     if (i0 >= h) return;
     // horizontally upsampled e rows i-2 .. i+2 (4 HR phases each); et row index of LR row ii is ii - ib + 2
-    float hu[5][4];
+    float2 hu01[5], hu23[5];                                       // HR phases (0,1) and (2,3) of each row
     int lofs[5];                                                   // neighbour cells (edge lanes never write: clamped)
 #pragma unroll
     for (int k = 0; k < 5; ++k) lofs[k] = min(max(lane + k - 2, 0), 31);
-    auto hrow = [&](int ii, float (&o)[4]) {
+    auto hrow = [&](int ii, float2& o01, float2& o23) {
         const float* e = et + (ii - ib + 2) * 32;
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = -2; k <= 2; ++k) {
-            const float n = e[lofs[k + 2]];
-            p0 = fmaf(T.up[0][k + 2], n, p0);
-            p1 = fmaf(T.up[1][k + 2], n, p1);
-            p2 = fmaf(T.up[2][k + 2], n, p2);
-            p3 = fmaf(T.up[3][k + 2], n, p3);
+        for (int k = 0; k < 5; ++k) {
+            const float n = e[lofs[k]];
+            const float2 n2 = make_float2(n, n);
+            p01 = __ffma2_rn(T.up_h01[k], n2, p01);
+            p23 = __ffma2_rn(T.up_h23[k], n2, p23);
         }
-        o[0] = p0; o[1] = p1; o[2] = p2; o[3] = p3;
+        o01 = p01; o23 = p23;
     };
 #pragma unroll
-    for (int kv = 0; kv < 4; ++kv) hrow(i0 - 2 + kv, hu[kv]);
+    for (int kv = 0; kv < 4; ++kv) hrow(i0 - 2 + kv, hu01[kv], hu23[kv]);
     for (int i = i0; i < i1; ++i) {
-        hrow(i + 2, hu[4]);
-        float4 yn2[4];
-        load_y(i + 2, yn2);
+        hrow(i + 2, hu01[4], hu23[4]);
+        float4 yn3[4];
+        load_y(i + 3, yn3);
         if (writer && 4 * i >= crop && 4 * i + 3 < H - crop) {     // crop % 4 == 0: an LR row is kept or cropped whole
             float4* op = reinterpret_cast<float4*>(out + (static_cast<size_t>(plane) * Ho + (4 * i - crop)) * Wo + (4 * j - crop));
             const int Woq = Wo >> 2;
 #pragma unroll
             for (int psi = 0; psi < 4; ++psi) {
-                float4 r = yc[psi];
+                float2 r01 = make_float2(yc[psi].x, yc[psi].y), r23 = make_float2(yc[psi].z, yc[psi].w);
 #pragma unroll
                 for (int kv = 0; kv < 5; ++kv) {
-                    const float wv = T.up[psi][kv];
-                    r.x = fmaf(wv, hu[kv][0], r.x); r.y = fmaf(wv, hu[kv][1], r.y);
-                    r.z = fmaf(wv, hu[kv][2], r.z); r.w = fmaf(wv, hu[kv][3], r.w);
+                    const float2 wv = T.up_v2[psi][kv];
+                    r01 = __ffma2_rn(wv, hu01[kv], r01);
+                    r23 = __ffma2_rn(wv, hu23[kv], r23);
                 }
-                op[psi * Woq] = r;
+                op[psi * Woq] = make_float4(r01.x, r01.y, r23.x, r23.y);
             }
         }
 #pragma unroll
-        for (int kv = 0; kv < 4; ++kv)
+        for (int kv = 0; kv < 4; ++kv) { hu01[kv] = hu01[kv + 1]; hu23[kv] = hu23[kv + 1]; }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hu[kv][q] = hu[kv + 1][q];
-#pragma unroll
-        for (int psi = 0; psi < 4; ++psi) { yc[psi] = yn[psi]; yn[psi] = yn2[psi]; }
+        for (int psi = 0; psi < 4; ++psi) { yc[psi] = yn[psi]; yn[psi] = yn2[psi]; yn2[psi] = yn3[psi]; }
     }
 }
 
@@ -507,8 +527,8 @@ __global__ void __launch_bounds__(128) cem_up4_kernel(const __grid_constant__ Ce
 // streaming), so long segments amortise the halo, but the last block row of a plane is padded up to 4*seg rows and
 // small problems need >= 4 blocks (16 warps) per SM to hide latency.  Cost model fitted to a sweep on B200
 // (tools/cem_seg_sweep.py; config 4: 3 planes of 512^2 cells, config 2: 48 planes of 148^2):
-//   cost(seg) = ceil(h / 4seg) * (seg + halo) / min(1, blocks / (148 * 4)).
-static int pick_seg(int planes, int h, int w, const char* env_name, int max_seg, float halo) {
+//   cost(seg) = ceil(h / 4seg) * (seg + halo) / min(1, blocks / (148 * 4)) * ceil(waves) / waves.
+static int pick_seg(int planes, int h, int w, const char* env_name, int max_seg, float halo, int blocks_per_sm) {
     if (const char* v = getenv(env_name)) {                       // tuning aid
         const int forced = atoi(v);
         if (forced >= 2 && forced <= max_seg) return forced;
@@ -520,13 +540,15 @@ static int pick_seg(int planes, int h, int w, const char* env_name, int max_seg,
         const int block_rows = ceil_div(h, 4 * seg);
         const float blocks = static_cast<float>(strips * block_rows * planes);
         const float fill = blocks / (148.f * 4.f);
-        const float cost = block_rows * (seg + halo) / (fill < 1.f ? fill : 1.f);
+        float cost = block_rows * (seg + halo) / (fill < 1.f ? fill : 1.f);
+        const float waves = blocks / (148.f * blocks_per_sm);     // a partly filled last wave costs a whole one (ncu: 38 %
+        if (waves > 1.f) cost *= ceilf(waves) / waves;            // of K+Up's time had most SMs idle at 1.06 waves)
         if (cost < best_cost) { best_cost = cost; best = seg; }
     }
     return best;
 }
-static int pick_seg_down(int planes, int h, int w) { return pick_seg(planes, h, w, "ESR_CEM_SEG_DOWN", 16, 4.f); }
-static int pick_seg_up(int planes, int h, int w) { return pick_seg(planes, h, w, "ESR_CEM_SEG_UP", 16, 1.2f); }
+static int pick_seg_down(int planes, int h, int w) { return pick_seg(planes, h, w, "ESR_CEM_SEG_DOWN", 16, 4.f, 6); }
+static int pick_seg_up(int planes, int h, int w) { return pick_seg(planes, h, w, "ESR_CEM_SEG_UP", 16, 1.2f, 4); }
 
 static bool fast4_ok(const esr_cem_filters& f, int H, int W, int crop, const void* a, const void* b, const void* c) {
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -545,6 +567,15 @@ static CemTab make_tab(const esr_cem_filters& f) {
             const int tu = 4 * k + pad + pre - p;        // up: 4j+p + t - pad - pre = 4(j+k)
             T.up[p][k + 2] = (tu >= 0 && tu < nt) ? f.ds[tu] * f.sf : 0.f;
         }
+    for (int p = 0; p < 4; ++p)
+        for (int c = 0; c < 5; ++c) {
+            T.down_v2[p][c] = make_float2(T.down_v[p][c], T.down_v[p][c]);
+            T.up_v2[p][c] = make_float2(T.up[p][c], T.up[p][c]);
+        }
+    for (int c = 0; c < 5; ++c) {
+        T.up_h01[c] = make_float2(T.up[0][c], T.up[1][c]);
+        T.up_h23[c] = make_float2(T.up[2][c], T.up[3][c]);
+    }
     return T;
 }
 
@@ -711,7 +742,7 @@ int cem_invup4(const esr_cem_filters& f, const float* d, const float* y, int pla
                cudaStream_t s) {
     InvTaps K;
     K.n = f.n_inv;
-    for (int i = 0; i < f.n_inv; ++i) K.t[i] = f.inv[i];
+    for (int i = 0; i < f.n_inv; ++i) { K.t[i] = f.inv[i]; K.t2[i] = make_float2(f.inv[i], f.inv[i]); }
     const int seg = pick_seg_up(planes, h, w), pad = f.n_inv / 2;   // <= 16: smem tile
     const int Re = 4 * seg + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad, Cds = (Cd + 3) & ~3;
     const size_t sm = sizeof(float) * (static_cast<size_t>(Rd) * Cds + static_cast<size_t>(Rd) * 32 + static_cast<size_t>(Re) * 32);

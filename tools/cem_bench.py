@@ -13,13 +13,26 @@ l = capi.lib()
 def run():
     capi.check(l.esr_cem_project(f, capi.ptr(y), capi.ptr(x), B, C, H, W, 0, capi.ptr(out), capi.ptr(ws), capi.stream_ptr()))
 for _ in range(3): run()
-ts = []
-for _ in range(10):
-    flush.zero_()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); run(); e1.record(); torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-t = sorted(ts)[len(ts) // 2]
+flush2 = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+def median_time(clean):
+    ts = []
+    for _ in range(15):
+        flush.zero_()
+        if clean:                 # evict the flush's dirty lines too: the timed kernels then start cold AND clean
+            flush2.view(torch.int64).sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+t = median_time(False)
+t_clean = median_time(True)
+# back-to-back without flush (warm L2), many launches per event pair: no event quantisation
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50): run()
+e1.record(); torch.cuda.synchronize()
+t_warm = e0.elapsed_time(e1) / 50
+print(json.dumps({"cold_after_write_flush_us": 1e3 * t, "cold_after_write_then_read_flush_us": 1e3 * t_clean, "warm_back_to_back_us": 1e3 * t_warm}))
 byts = 4 * 3 * (2 * H * W + H * W // 16)
 peak = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs'] if os.path.exists('MEASURED_PEAKS.json') else 6650.0
 print(json.dumps({"cem_2048": {"ms": t, "algorithmic_GBs": byts / t / 1e6, "frac_of_hbm_peak": byts / t / 1e6 / peak, "Mpix_s": H * W / t / 1e3, "l2": "flushed between iterations (256 MiB memset)"}}))
