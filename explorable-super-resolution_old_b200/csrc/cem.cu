@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
     const int plane = blockIdx.z;
     const int j = blockIdx.x * kStripCells - 2 + lane;             // LR cell of this lane
     const int i0 = (blockIdx.y * 4 + warp) * seg;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched K+Up may start its prologue early
     if (i0 >= h) return;
     const int i1 = min(i0 + seg, h);
     const float* yp = y + static_cast<size_t>(plane) * H * W;
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_cons
     load_y(i0, yc);                                                // HBM loads fly while the e tile is built
     load_y(i0 + 1, yn);
     load_y(i0 + 2, yn2);
+    asm volatile("griddepcontrol.wait;" ::: "memory");             // d comes from the Down launch just before (PDL)
     const float* dp = d + static_cast<size_t>(plane) * h * w;
     for (int r = warp; r < Rd; r += 4) {                           // a warp per tile row: no div / mod, one clamp per row
         const float* row = dp + static_cast<size_t>(clampi(ib - 2 - pad + r, 0, h - 1)) * w;
@@ -739,7 +741,7 @@ int cem_up(const esr_cem_filters& f, const float* x, const float* y, int planes,
 
 // Fused (HH^T)^-1 + Up + residual add, x4 only; d = x - Down(y).
 int cem_invup4(const esr_cem_filters& f, const float* d, const float* y, int planes, int h, int w, int crop, float* out,
-               cudaStream_t s) {
+               cudaStream_t s, bool after_down) {
     InvTaps K;
     K.n = f.n_inv;
     for (int i = 0; i < f.n_inv; ++i) { K.t[i] = f.inv[i]; K.t2[i] = make_float2(f.inv[i], f.inv[i]); }
@@ -747,10 +749,23 @@ int cem_invup4(const esr_cem_filters& f, const float* d, const float* y, int pla
     const int Re = 4 * seg + 4, Rd = Re + 2 * pad, Cd = 32 + 2 * pad, Cds = (Cd + 3) & ~3;
     const size_t sm = sizeof(float) * (static_cast<size_t>(Rd) * Cds + static_cast<size_t>(Rd) * 32 + static_cast<size_t>(Re) * 32);
     dim3 grid(ceil_div(w, kStripCells), ceil_div(h, 4 * seg), planes);
+    // Programmatic dependent launch on the Down kernel that produced d: the blocks become resident while Down's last
+    // blocks drain, issue their y prefetch, and only then wait for d (griddepcontrol.wait in the kernel).
     auto launch = [&](auto kern) -> int {
         int rc = set_smem(reinterpret_cast<const void*>(kern), sm);
         if (rc) return rc;
-        kern<<<grid, 128, sm, s>>>(make_tab(f), K, d, y, out, h, w, crop, seg);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = sm;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = after_down ? 1 : 0;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, make_tab(f), K, d, y, out, h, w, crop, seg);
+        if (e != cudaSuccess) { set_error("cem_invup4_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
         return ESR_OK;
     };
     int rc;
@@ -800,7 +815,7 @@ extern "C" int esr_cem_project(const esr_cem_filters* f, const float* y, const f
     float* e = workspace + static_cast<size_t>(planes) * h * w;
     if ((rc = cem_down(*f, y, x, planes, H, W, d, s))) return rc;
     if (fast4_ok(*f, H, W, crop, y, out, d) && ((W - 2 * crop) % 4 == 0))
-        return cem_invup4(*f, d, y, planes, h, w, crop, out, s);          // two launches: Down, then K + Up + add
+        return cem_invup4(*f, d, y, planes, h, w, crop, out, s, true);    // two launches: Down, then K + Up + add
     if ((rc = cem_inv(*f, d, planes, h, w, e, s))) return rc;
     return cem_up(*f, e, y, planes, h, w, crop, 1.f, out, s);
 }
