@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
                                                         const float* __restrict__ x, float* __restrict__ out, int H,
                                                         int W, int seg) {
     __shared__ float4 ring[4][kDownGroups][4][32];                  // [warp][group slot][HR row of the group][lane]
+    __shared__ float xring[4][kDownGroups][32];                     // x of the LR row that group completes (row I-2)
     const int h = H >> 2, w = W >> 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int plane = blockIdx.z;
@@ -206,9 +207,14 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
     const int last = i1 + 1;                                        // LR row groups i0-2 .. i1+1 feed rows i0 .. i1-1
     const uint32_t ring_base = static_cast<uint32_t>(__cvta_generic_to_shared(&ring[warp][0][0][lane]));
     constexpr uint32_t kRowBytes = 32 * sizeof(float4), kGroupBytes = 4 * kRowBytes;
+    const float* xcol = x != nullptr ? x + static_cast<size_t>(plane) * h * w + j : nullptr;
+    const uint32_t xring_base = static_cast<uint32_t>(__cvta_generic_to_shared(&xring[warp][0][lane]));
     auto issue_group = [&](int I) {                                 // the 4 HR rows of LR row I (rows replicate padded)
         if (I <= last) {
-            const uint32_t dst = ring_base + static_cast<uint32_t>((I - (i0 - 2)) % kDownGroups) * kGroupBytes;
+            const uint32_t gslot = static_cast<uint32_t>((I - (i0 - 2)) % kDownGroups);
+            const uint32_t dst = ring_base + gslot * kGroupBytes;
+            if (xcol != nullptr && writer && I - 2 >= i0 && I - 2 < i1)   // same depth of prefetch as the HR rows
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(xring_base + gslot * 128u), "l"(xcol + static_cast<size_t>(I - 2) * w) : "memory");
             if (I >= 0 && I < h) {                                  // interior group: one row pointer, no clamps
                 const float* src = col + static_cast<size_t>(4 * I) * W;
 #pragma unroll
@@ -229,16 +235,10 @@ __global__ void __launch_bounds__(128) cem_down4_kernel(const __grid_constant__ 
     for (int m = 0; m < 5; ++m) acc_lo[m] = acc_hi[m] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int g = 0; g < kDownGroups - 1; ++g) issue_group(i0 - 2 + g);
-    const float* xcol = x != nullptr ? x + static_cast<size_t>(plane) * h * w + j : nullptr;
-    auto load_x = [&](int i) {                                      // LR image sample of output row i (0 where unused)
-        return (xcol != nullptr && writer && i >= i0 && i < i1) ? __ldg(xcol + static_cast<size_t>(i) * w) : 0.f;
-    };
-    float x_next = 0.f;                                             // fetched one iteration before its row completes
     for (int I = i0 - 2; I <= last; ++I) {
-        const float x_cur = x_next;
-        x_next = load_x(I - 1);
         cp_async_wait<kDownGroups - 2>();                           // group I has landed (this thread's own copies)
         const float4(*slot)[32] = ring[warp][(I - (i0 - 2)) % kDownGroups];
+        const float x_cur = xring[warp][(I - (i0 - 2)) % kDownGroups][lane];   // only meaningful where it was fetched
         float4 c[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[q] = slot[q][lane];
@@ -317,19 +317,22 @@ __global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_cons
     // running pointers: LR row i's first HR row in y / out (one add per row instead of a 64-bit multiply per access)
     const int Wq = W >> 2;
     const float4* ybase = reinterpret_cast<const float4*>(y + static_cast<size_t>(plane) * H * W) + j;
+    // y is fetched three LR rows (12 HR rows, 6 KiB per warp) ahead into four register buffers that take turns
+    // (the streaming loop is unrolled by four): no register copies, so no instruction waits on the newest load.
+    auto rows_kept = [&](int i) { return writer && i < i1 && 4 * i >= crop && 4 * i + 3 < H - crop; };   // crop % 4 == 0
     auto load_y = [&](int i, float4 (&b)[4]) {                     // the 4 HR rows of LR row i (base image)
-        const float4* p = ybase + static_cast<size_t>(4 * i) * Wq;
-        const bool rows_in = writer && i < i1 && 4 * i >= crop && 4 * i + 3 < H - crop;   // crop % 4 == 0: all or nothing
+        if (rows_kept(i)) {
+            const float4* p = ybase + static_cast<size_t>(4 * i) * Wq;
 #pragma unroll
-        for (int psi = 0; psi < 4; ++psi) {
-            b[psi] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rows_in) b[psi] = __ldg(p + psi * Wq);
+            for (int psi = 0; psi < 4; ++psi) b[psi] = __ldg(p + psi * Wq);
         }
     };
-    float4 yc[4], yn[4], yn2[4];                                   // three LR rows (12 HR rows, 6 KiB per warp) in flight
-    load_y(i0, yc);                                                // HBM loads fly while the e tile is built
-    load_y(i0 + 1, yn);
-    load_y(i0 + 2, yn2);
+    float4 yb0[4], yb1[4], yb2[4], yb3[4];
+#pragma unroll
+    for (int psi = 0; psi < 4; ++psi) yb0[psi] = yb1[psi] = yb2[psi] = yb3[psi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    load_y(i0, yb0);                                               // HBM loads fly while the e tile is built
+    load_y(i0 + 1, yb1);
+    load_y(i0 + 2, yb2);
     asm volatile("griddepcontrol.wait;" ::: "memory");             // d comes from the Down launch just before (PDL)
     const float* dp = d + static_cast<size_t>(plane) * h * w;
     for (int r = warp; r < Rd; r += 4) {                           // a warp per tile row: no div / mod, one clamp per row
@@ -433,16 +436,15 @@ __global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_cons
     };
 #pragma unroll
     for (int kv = 0; kv < 4; ++kv) hrow(i0 - 2 + kv, hu01[kv], hu23[kv]);
-    for (int i = i0; i < i1; ++i) {
+    auto step = [&](int i, const float4 (&cur)[4], float4 (&fill)[4]) {   // emits LR row i from `cur`, refills `fill` with row i+3
         hrow(i + 2, hu01[4], hu23[4]);
-        float4 yn3[4];
-        load_y(i + 3, yn3);
-        if (writer && 4 * i >= crop && 4 * i + 3 < H - crop) {     // crop % 4 == 0: an LR row is kept or cropped whole
+        load_y(i + 3, fill);
+        if (rows_kept(i)) {
             float4* op = reinterpret_cast<float4*>(out + (static_cast<size_t>(plane) * Ho + (4 * i - crop)) * Wo + (4 * j - crop));
             const int Woq = Wo >> 2;
 #pragma unroll
             for (int psi = 0; psi < 4; ++psi) {
-                float2 r01 = make_float2(yc[psi].x, yc[psi].y), r23 = make_float2(yc[psi].z, yc[psi].w);
+                float2 r01 = make_float2(cur[psi].x, cur[psi].y), r23 = make_float2(cur[psi].z, cur[psi].w);
 #pragma unroll
                 for (int kv = 0; kv < 5; ++kv) {
                     const float2 wv = T.up_v2[psi][kv];
@@ -454,8 +456,15 @@ __global__ void __launch_bounds__(128, MINB) cem_invup4_kernel(const __grid_cons
         }
 #pragma unroll
         for (int kv = 0; kv < 4; ++kv) { hu01[kv] = hu01[kv + 1]; hu23[kv] = hu23[kv + 1]; }
-#pragma unroll
-        for (int psi = 0; psi < 4; ++psi) { yc[psi] = yn[psi]; yn[psi] = yn2[psi]; yn2[psi] = yn3[psi]; }
+    };
+    for (int i = i0; i < i1; i += 4) {
+        step(i, yb0, yb3);
+        if (i + 1 >= i1) break;
+        step(i + 1, yb1, yb0);
+        if (i + 2 >= i1) break;
+        step(i + 2, yb2, yb1);
+        if (i + 3 >= i1) break;
+        step(i + 3, yb3, yb2);
     }
 }
 
