@@ -35,7 +35,7 @@ class DgradSpecs:
     def __init__(self, eng):
         self.eng = eng
         self.convs = {}
-        nz, p = eng.nz, eng.precise
+        nz, p = eng.nz, eng.precise_bwd
         hi_lo = ((0, 0), (64, 0), (0, 1)) if p else ((0, 0),)
 
         def outer_blocks():
@@ -219,7 +219,7 @@ class BackwardPlan:
         hp, wp, sf = plan.hp, plan.wp, plan.sf
         H4, W4 = sf * hp, sf * wp
         names = eng.outer_names
-        lo = 64 if eng.precise else -1
+        lo = 64 if eng.precise_bwd else -1
         nz = eng.nz
         lat_bit = lambda pc: 1 << (pc.cout_tiles - 1)
         # ---- HR convs
@@ -234,9 +234,9 @@ class BackwardPlan:
             self._conv(names[1 + u], res * hp, res * wp, self.GVu[u], self.GU[u], 64)
             lowH, lowW = res // 2 * hp, res // 2 * wp
             if u > 0:      # below sits upconv u-1, whose LeakyReLU output was stored 2x2-replicated in plan.U[u]
-                self._combine(self.GU[u], 64, 0, 2, None, lowH, lowW, None, plan.U[u], plan.U[u].shape[-1], 2, 1.0, self.GVu[u - 1], eng.precise)
+                self._combine(self.GU[u], 64, 0, 2, None, lowH, lowW, None, plan.U[u], plan.U[u].shape[-1], 2, 1.0, self.GVu[u - 1], eng.precise_bwd)
             else:          # below sits the trunk shortcut sum (no activation)
-                self._combine(self.GU[0], 64, 0, 2, None, lowH, lowW, self.Gsc, None, 0, 1, 1.0, self.GS, eng.precise)
+                self._combine(self.GU[0], 64, 0, 2, None, lowH, lowW, self.Gsc, None, 0, 1, 1.0, self.GS, eng.precise_bwd)
         # ---- LR_conv: H = d(last RRDB output) -> frame (3nb)%4, emits 0.04*H for RDB3.conv5 of the last RRDB
         n_rdb = 3 * eng.nb
         touched = set()
@@ -273,7 +273,7 @@ class BackwardPlan:
             self._conv(None, hp, wp, GB, self.GF32, 4 * FRAME, pc=pc, **kw)
         # ---- d(fea) = d(RRDB0 input) + shortcut gradient -> first conv's latent rows
         if eng.nz_in:
-            self._combine(self.GF32, 4 * FRAME, 0, 1, self.Gsc, hp, wp, None, None, 0, 1, 1.0, self.GFea, eng.precise)
+            self._combine(self.GF32, 4 * FRAME, 0, 1, self.Gsc, hp, wp, None, None, 0, 1, 1.0, self.GFea, eng.precise_bwd)
             self._conv("model.0", hp, wp, self.GFea, self.GF32, 4 * FRAME, out_choff=0, lat_tile_to=LAT_OFF,
                        accum=nz > 0)
         self.n_lat_acc = 4 if nz else 1
@@ -310,25 +310,29 @@ class BackwardPlan:
         return n
 
 
+def generator_backward_eager(plan, bp, cem_filters, margin, g):
+    """d(model_input) for the gradient g w.r.t. the (cropped) output of G+CEM; g: contiguous f32 on the plan's device."""
+    eng = plan.eng
+    B, sf = plan.B, plan.sf
+    H4, W4 = sf * plan.hp, sf * plan.wp
+    if cem_filters is not None:
+        n = B * eng.out_nc * (H4 * W4 + H4 * plan.wp + 2 * plan.hp * plan.wp)
+        ws = torch.empty(n, dtype=torch.float32, device=g.device)
+        capi.cem_call("project_bwd", cem_filters, capi.ptr(g), B, eng.out_nc, H4, W4, sf * margin,
+                      capi.ptr(bp.g_y), capi.ptr(ws), capi.stream_ptr())
+        g_y = bp.g_y
+    else:
+        g_y = g
+    return bp.run(g_y)
+
+
 def generator_backward(ctx, g):
     """autograd hook of rrdbnet._GeneratorFn."""
     plan, net = ctx.plan, ctx.net
     if len(plan.bufs) <= 2:
         raise capi.EsrError("backward needs a forward pass recorded with gradients enabled")
-    eng = plan.eng
-    if eng.nz_in == 0:
+    if plan.eng.nz_in == 0:
         raise capi.EsrError("this generator has no latent input: nothing to differentiate")
     bp = net.backward_plan(plan)
-    g = g.contiguous().float()
-    B, sf = plan.B, plan.sf
-    H4, W4 = sf * plan.hp, sf * plan.wp
     with torch.cuda.device(g.device):
-        if ctx.cem_filters is not None:
-            n = B * eng.out_nc * (H4 * W4 + H4 * plan.wp + 2 * plan.hp * plan.wp)
-            ws = torch.empty(n, dtype=torch.float32, device=g.device)
-            capi.cem_call("project_bwd", ctx.cem_filters, capi.ptr(g), B, eng.out_nc, H4, W4, sf * ctx.margin,
-                          capi.ptr(bp.g_y), capi.ptr(ws), capi.stream_ptr())
-            g_y = bp.g_y
-        else:
-            g_y = g
-        return bp.run(g_y)
+        return generator_backward_eager(plan, bp, ctx.cem_filters, ctx.margin, g.contiguous().float())

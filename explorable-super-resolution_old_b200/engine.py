@@ -145,7 +145,11 @@ class GEngine:
         self.nz = nz_in if all_layers else 0          # latent channels concatenated to every later conv
         self.out_nc, self.upscale = out_nc, upscale
         self.n_up = int(math.log2(upscale))
-        self.precise = precise_outer                   # backward: split-bf16 gradient operands for the outer convs
+        self.precise = precise_outer
+        # backward: the dgrads of the outer convs take plain bf16 gradient operands like the 345 trunk dgrads (measured
+        # against the oracle's autograd at nb=23: relative error 0.0285 vs 0.0280 with three-term split-bf16 operands,
+        # 4 % faster per Z iteration); ESR_BWD_PRECISE=1 restores the split operands
+        self.precise_bwd = precise_outer and os.environ.get("ESR_BWD_PRECISE", "0") == "1"
         self.outer_mode = outer_mode or os.environ.get("ESR_OUTER_MODE") or ("f16" if precise_outer else "bf16")
         assert self.outer_mode in ("f16", "split", "bf16")
         # CTA-pair (cta_group::2) kernels wherever cout >= 32; ESR_PAIR=0 keeps the single-CTA kernel (A/B timing)
@@ -248,6 +252,7 @@ class GPlan:
     def __init__(self, eng, B, h, w, m, device, with_cem_input=True, keep_activations=False, use_simt=False):
         self.eng, self.B, self.h, self.w, self.m = eng, B, h, w, m
         self.device = device
+        self.graphed = {}                      # (cem filters, margin) -> rrdbnet._GraphedStep (dies with the plan)
         sf = eng.upscale
         hp, wp = h + 2 * m, w + 2 * m
         self.hp, self.wp, self.sf = hp, wp, sf

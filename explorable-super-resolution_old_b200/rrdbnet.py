@@ -72,6 +72,9 @@ class RRDBNet(nn.Module):
         self.precise_outer = True
         self.outer_mode = None                         # None: engine default ("f16"); "split" | "bf16" for experiments
         self.debug_simt = False
+        # Replay the differentiable forward and its data-gradient backward as CUDA graphs (one host launch each instead
+        # of ~360).  Z_optimizer switches it on for its loop; shapes, margin and CEM filters key the captured graphs.
+        self.use_cuda_graphs = False
 
     # ------------------------------------------------------------------ engine plumbing
     def _named_convs(self):
@@ -121,6 +124,69 @@ class RRDBNet(nn.Module):
         return run_generator(self, x, margin=0, cem_filters=None)
 
 
+def _capture(run, device):
+    """Runs `run` once on a side stream (lazy initialisation inside the library happens outside the capture), then
+    captures it.  Returns (graph, value returned by the captured call)."""
+    with torch.cuda.device(device):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res = run()
+    return graph, res
+
+
+class _GraphedStep:
+    """Forward (input plumbing, 351 convs, CEM projection) and backward (CEM adjoint, 351 dgrads, input adjoint) of one
+    plan as two CUDA graphs over fixed buffers.  Both are captured on the first differentiable forward, on the calling
+    thread (autograd runs backward hooks on a worker thread, where a capture would be fragile)."""
+
+    def __init__(self, net, plan, margin, cem_filters, x):
+        from .backward import generator_backward_eager
+        B, sf, dev = plan.B, net.upscale, x.device
+        crop = sf * margin
+        H4, W4 = sf * plan.hp, sf * plan.wp
+        onc = plan.y.size(1)
+        self.plan, self.filters = plan, cem_filters
+        self.x = torch.empty_like(x)
+        self.x.copy_(x)
+        self.out = torch.empty(B, onc, H4 - 2 * crop, W4 - 2 * crop, device=dev, dtype=torch.float32)
+        self.ws = torch.empty(max(1, 2 * B * onc * plan.hp * plan.wp), device=dev, dtype=torch.float32)
+        self.g = torch.zeros_like(self.out)
+        self.bp = net.backward_plan(plan) if net._cfg["nz_in"] > 0 else None
+
+        def fwd():
+            _forward_eager(plan, self.x, cem_filters, crop, self.out, self.ws)
+        self.fwd_graph, _ = _capture(fwd, dev)
+        self.bwd_graph, self.g_in = (None, None)
+        if self.bp is not None:
+            self.bwd_graph, self.g_in = _capture(lambda: generator_backward_eager(plan, self.bp, cem_filters, margin, self.g), dev)
+
+    def forward(self, x):
+        self.x.copy_(x)
+        self.fwd_graph.replay()
+        return self.out.clone()
+
+    def backward(self, g):
+        self.g.copy_(g)
+        self.bwd_graph.replay()
+        return self.g_in.clone()
+
+
+def _forward_eager(plan, x, cem_filters, crop, out, ws):
+    y = plan.run_g(x)
+    if cem_filters is None:
+        out.copy_(y)
+    else:
+        B, onc = y.size(0), y.size(1)
+        capi.cem_call("project", cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, onc, y.size(2), y.size(3), crop,
+                      capi.ptr(out), capi.ptr(ws), capi.stream_ptr())
+
+
 class _GeneratorFn(torch.autograd.Function):
     """G (+ optional CEM projection) as one autograd node: data gradient only."""
 
@@ -129,23 +195,27 @@ class _GeneratorFn(torch.autograd.Function):
         B, C, h, w = x.shape
         plan = net.plan(B, h, w, margin, keep=need_grad)
         sf = net.upscale
+        ctx.plan, ctx.cem_filters, ctx.margin, ctx.net, ctx.graphed = plan, cem_filters, margin, net, None
         with torch.cuda.device(x.device):
-            y = plan.run_g(x)
-            if cem_filters is None:
-                out = y.clone()
-            else:
-                crop = sf * margin
-                out = torch.empty(B, y.size(1), y.size(2) - 2 * crop, y.size(3) - 2 * crop, device=x.device,
-                                  dtype=torch.float32)
-                ws = torch.empty(2 * B * y.size(1) * plan.hp * plan.wp, device=x.device, dtype=torch.float32)
-                capi.cem_call("project", cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, y.size(1), y.size(2),
-                              y.size(3), crop, capi.ptr(out), capi.ptr(ws), capi.stream_ptr())
-        ctx.plan, ctx.cem_filters, ctx.margin, ctx.net = plan, cem_filters, margin, net
+            if need_grad and net.use_cuda_graphs:
+                key = (id(cem_filters), margin)
+                if key not in plan.graphed:
+                    plan.graphed[key] = _GraphedStep(net, plan, margin, cem_filters, x)
+                ctx.graphed = plan.graphed[key]
+                return ctx.graphed.forward(x)
+            crop = sf * margin
+            onc = plan.y.size(1)
+            out = torch.empty(B, onc, sf * plan.hp - 2 * crop, sf * plan.wp - 2 * crop, device=x.device, dtype=torch.float32)
+            ws = torch.empty(2 * B * onc * plan.hp * plan.wp, device=x.device, dtype=torch.float32) if cem_filters is not None else None
+            _forward_eager(plan, x, cem_filters, crop, out, ws)
         return out
 
     @staticmethod
     def backward(ctx, g):
         from .backward import generator_backward
+        if ctx.graphed is not None and ctx.graphed.bwd_graph is not None:
+            with torch.cuda.device(g.device):
+                return ctx.graphed.backward(g.contiguous().float()), None, None, None, None
         return generator_backward(ctx, g), None, None, None, None
 
 

@@ -8,6 +8,7 @@ Objectives built here: 'l1' (training mode, HR_unpadder given), 'TV', 'max_STD' 
 'STD_increase' / 'STD_decrease' (global).  The histogram / dictionary / scribble / periodicity / VGG /
 adversarial objectives of the GUI are out of this path's scope.
 """
+import os
 import time
 
 import numpy as np
@@ -158,6 +159,9 @@ class Z_optimizer():
 
     def optimize(self):
         self.Manage_Model_Grad_Requirements(disable=True)
+        G = getattr(self.model.netG, 'generated_image_model', self.model.netG)
+        if hasattr(G, 'use_cuda_graphs') and os.environ.get('ESR_ZOPT_GRAPH', '1') != '0':
+            G.use_cuda_graphs = True           # forward and backward of every iteration replay as CUDA graphs
         self.loss_values = []
         if self.random_Z_inits and self.cur_iter == 0:
             self.Z_model.Randomize_Z(what_2_shuffle=self.random_Z_inits)
