@@ -138,6 +138,8 @@ class GEngine:
     def __init__(self, nb, nz_in, all_layers, out_nc=3, in_nc=3, upscale=4, precise_outer=True, pair=True,
                  outer_mode=None):
         if upscale not in (2, 4):
+            # x3: the reference's own RRDBNet cannot be constructed for upscale=3 (architecture.py:144 concatenates a
+            # list with the nn.Sequential its x3 upsampler is: TypeError), so there is nothing to be a drop-in for
             raise NotImplementedError("upscale %d: only x2 / x4 (nearest x2 upconv stages) are built" % upscale)
         if in_nc != 3 or out_nc > 16:
             raise NotImplementedError("in_nc must be 3 and out_nc <= 16")

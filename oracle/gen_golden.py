@@ -19,20 +19,20 @@ from esr_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def make_opt(nb, latent_input, is_train=False, patch=256):
+def make_opt(nb, latent_input, is_train=False, patch=256, sf=4):
     return {"gpu_ids": None, "is_train": is_train, "datasets": {"train": {"patch_size": patch}},
             "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input=latent_input,
                               latent_input_domain="HR_downscaled", latent_channels=3, norm_type=None, mode="CNA",
-                              nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=4)}
+                              nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=sf)}
 
 
-def build_ref_G(CEMnet, networks, nb, latent_input, kind, seed):
+def build_ref_G(CEMnet, networks, nb, latent_input, kind, seed, sf=4):
     import CEM.imresize_CEM as im
     im.imresize.kernels = {}
-    cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(4))
-    netG = networks.define_G(make_opt(nb, latent_input), CEM=cem, num_latent_channels=0 if latent_input == "None" else 3)
+    cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(sf))
+    netG = networks.define_G(make_opt(nb, latent_input, sf=sf), CEM=cem, num_latent_channels=0 if latent_input == "None" else 3)
     li = None if latent_input == "None" else latent_input + "_HR_downscaled"
-    w = synth.make_weights(kind, seed=seed, nb=nb, latent_input=li)
+    w = synth.make_weights(kind, seed=seed, nb=nb, latent_input=li, upscale=sf)
     sd = netG.state_dict()
     assert [k for k in sd if "Filter" not in k] == ["generated_image_model." + k for k in w]
     sd.update({"generated_image_model." + k: v for k, v in w.items()})
@@ -114,6 +114,28 @@ def gen_nondefault(CEMnet):
     np.savez_compressed(os.path.join(OUT, "cem_nondefault.npz"), **out)
 
 
+def gen_x2(CEMnet, networks):
+    """x2 generator + CEM (one nearest-x2 upconv stage, architecture.py:140-146; the reference's x3 branch cannot be
+    constructed): outputs in eval (pre-padded) and train mode, and the Z gradient through the reference's autograd."""
+    out = {}
+    for name, nb, kind, seed, B, h, w, train in (("x2_nb2_eval", 2, "default", 6, 1, 12, 10, False),
+                                                 ("x2_nb1_train", 1, "kaiming", 8, 2, 9, 14, True)):
+        netG, _ = build_ref_G(CEMnet, networks, nb, "all_layers", kind, seed, sf=2)
+        netG.train(train)
+        for p in netG.parameters():
+            p.requires_grad = False
+        lr, z = synth.make_inputs(B, h, w, sf=2, seed=seed)
+        zg = z.clone().requires_grad_(True)
+        res = netG(torch.cat([zg.contiguous().view(B, 12, h, w), lr], 1))
+        g = torch.from_numpy(np.random.default_rng(seed).standard_normal(tuple(res.shape)).astype(np.float32))
+        (res * g).sum().backward()
+        out[name + "_out"], out[name + "_gout"], out[name + "_gz"] = res.detach().numpy(), g.numpy(), zg.grad.numpy()
+        out[name + "_cfg"] = np.array([nb, seed, B, h, w, int(train)])
+        out[name + "_kind"] = np.array(kind)
+        print(name, tuple(res.shape), float(res.abs().max()), float(zg.grad.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "g_cem_x2.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -122,6 +144,8 @@ def main():
 
     if "nondefault" in sys.argv[1:]:      # only the non-default-kernel fixture
         return gen_nondefault(CEMnet)
+    if "x2" in sys.argv[1:]:              # only the x2 fixture
+        return gen_x2(CEMnet, networks)
 
     # 1. filters --------------------------------------------------------------------------
     filt = {}
@@ -241,6 +265,9 @@ def main():
 
     # 5. non-default CEM kernels -----------------------------------------------------------
     gen_nondefault(CEMnet)
+
+    # 6. x2 generator ------------------------------------------------------------------------
+    gen_x2(CEMnet, networks)
 
 
 if __name__ == "__main__":

@@ -189,3 +189,23 @@ def test_no_cpu_fallback():
     lr, z = synth.make_inputs(1, 8, 8)
     with pytest.raises(Exception):
         netG(concat_latent(lr, z))
+
+
+@pytest.mark.parametrize("name", ["x2_nb2_eval", "x2_nb1_train"])
+def test_x2_generator_matches_reference_golden(golden, cuda_device, name):
+    """x2 generator + x2 CEM against the unmodified reference: output (max error <= 1e-2, PSNR >= 50 dB) and the Z
+    gradient of its autograd (bf16 dgrad operands: a few per cent)."""
+    g = golden("g_cem_x2")
+    nb, seed, B, h, w, train = [int(v) for v in g[name + "_cfg"]]
+    wts = synth.make_weights(str(g[name + "_kind"]), seed=seed, nb=nb, upscale=2)
+    lr, z = synth.make_inputs(B, h, w, sf=2, seed=seed)
+    netG = build_product_G(cuda_device, nb, "all_layers_HR_downscaled", wts, train=bool(train), sf=2)
+    zp = z.clone().to(cuda_device).requires_grad_(True)
+    out = netG(concat_latent(lr.to(cuda_device), zp, sf=2))
+    ref = torch.from_numpy(g[name + "_out"])
+    assert out.shape == ref.shape
+    assert (out.detach().cpu() - ref).abs().max().item() <= 1e-2
+    assert psnr(out.detach().cpu(), ref) >= 50.0
+    (out * torch.from_numpy(g[name + "_gout"]).to(cuda_device)).sum().backward()
+    got, gz = zp.grad.cpu(), torch.from_numpy(g[name + "_gz"])
+    assert float((got - gz).norm() / gz.norm()) < 4e-2 and float((got * gz).sum() / (got.norm() * gz.norm())) > 0.999

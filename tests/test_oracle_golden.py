@@ -85,3 +85,21 @@ def test_param_count_and_flops():
         res = 1 if k.startswith(("model.0", "model.1")) else (4 if k.startswith("model.2") else 16)
         macs += 9 * co * ci * res
     assert macs == 18316944
+
+
+X2_CASES = ["x2_nb2_eval", "x2_nb1_train"]
+
+
+@pytest.mark.parametrize("name", X2_CASES)
+def test_x2_generator_matches_reference(golden, name):
+    """x2 (one nearest-x2 upconv stage): forward and the Z gradient of the reference's autograd."""
+    g = golden("g_cem_x2")
+    nb, seed, B, h, w, train = [int(v) for v in g[name + "_cfg"]]
+    wts = synth.make_weights(str(g[name + "_kind"]), seed=seed, nb=nb, upscale=2)
+    lr, z = synth.make_inputs(B, h, w, sf=2, seed=seed)
+    ora = GCEMOracle(wts, sf=2, pre_pad=not train, nb=nb)
+    zg = z.clone().requires_grad_(True)
+    out = ora.forward(concat_latent(lr, zg, sf=2))
+    np.testing.assert_allclose(out.detach().numpy(), g[name + "_out"], atol=2e-5)
+    (out * torch.from_numpy(g[name + "_gout"])).sum().backward()
+    np.testing.assert_allclose(zg.grad.numpy(), g[name + "_gz"], atol=2e-5)
