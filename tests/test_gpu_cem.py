@@ -220,3 +220,70 @@ def test_generator_with_estimated_kernel_matches_oracle(golden, cuda_device):
     assert (out.detach().cpu() - ref.detach()).abs().max().item() <= 1e-2
     gz, gr = zd.grad.cpu(), zo.grad
     assert float((gz - gr).norm() / gr.norm()) < 4e-2 and float((gz * gr).sum() / (gz.norm() * gr.norm())) > 0.999
+
+
+def _estimated_kernel_G(golden, dev, nb=1, seed=9):
+    from esr_b200 import networks, synth
+    g = golden("cem_nondefault")
+    conf = pcem.Get_CEM_Config(4)
+    conf.lower_magnitude_bound = 0.1                     # what the reference sets for estimated kernels
+    net = pcem.CEMnet(conf, upscale_kernel=g["aniso13_x4_kernel"])
+    opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 256}},
+           "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input="all_layers", latent_input_domain="HR_downscaled",
+                             latent_channels=3, norm_type=None, mode="CNA", nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=4)}
+    netG = networks.define_G(opt, CEM=net, num_latent_channels=3).to(dev).eval()
+    wts = synth.make_weights("default", seed=seed, nb=nb, latent_input="all_layers_HR_downscaled")
+    sd = netG.state_dict()
+    sd.update({"generated_image_model." + k: v for k, v in wts.items()})
+    netG.load_state_dict(sd)
+    for p in netG.parameters():
+        p.requires_grad_(False)
+    return netG, net
+
+
+def test_z_optimizer_with_estimated_kernel(golden, cuda_device):
+    """The Z-optimisation loop through a CEM built on an estimated kernel: the captured graphs (which then contain the
+    2-D stencil kernels and their adjoint) reproduce the eager loop's loss trajectory, and the loss goes down."""
+    from esr_b200 import synth
+    from esr_b200.z_optimization import Z_optimizer, SRModelShim
+    losses = {}
+    for mode in ("eager", "graph"):
+        netG, net = _estimated_kernel_G(golden, cuda_device)
+        assert not net.separable
+        lr, z0 = synth.make_inputs(1, 8, 9, seed=5)
+        model = SRModelShim(netG)
+        data = {"LR": lr.to(cuda_device), "Z": (0.5 * z0).to(cuda_device)}
+        model.feed_data(data)
+        with torch.no_grad():
+            model.fake_H = netG(model.model_input)
+        opt = Z_optimizer(objective="TV", Z_size=[32, 36], model=model, Z_range=1.0, max_iters=4, data=data, initial_LR=0.1,
+                          batch_size=1)
+        if mode == "eager":
+            import os
+            os.environ["ESR_ZOPT_GRAPH"] = "0"
+        try:
+            opt.optimize()
+        finally:
+            if mode == "eager":
+                del os.environ["ESR_ZOPT_GRAPH"]
+        assert netG.generated_image_model.use_cuda_graphs == (mode == "graph")
+        losses[mode] = np.array(opt.loss_values)
+    np.testing.assert_allclose(losses["graph"], losses["eager"], rtol=1e-4)
+    assert losses["graph"][-1] < losses["graph"][0]
+
+
+def test_host_pipeline_with_estimated_kernel(golden, cuda_device):
+    """Serving path (captured inference graph, copy streams) with 2-D CEM filters equals the direct call."""
+    from esr_b200 import synth
+    from esr_b200.parallel import HostPipeline
+    from oracle.cem_ops import concat_latent
+    netG, net = _estimated_kernel_G(golden, cuda_device)
+    lr, z = synth.make_inputs(3, 12, 10, seed=2)
+    mi = concat_latent(lr, z).contiguous()
+    with torch.no_grad():
+        ref = netG(mi.to(cuda_device)).cpu()
+    host_in, host_out = mi.pin_memory(), torch.empty_like(ref).pin_memory()
+    pipe = HostPipeline(netG, chunk=2)
+    pipe(host_in, host_out)
+    pipe.wait()
+    assert torch.equal(host_out, ref)
