@@ -89,11 +89,12 @@ def oracle_step_seconds(n_images, h, w, threads):
     return time.perf_counter() - t0
 
 
-def conv_traffic():
-    """DRAM bytes (read + write) of the 351 conv launches of one step, from the committed ncu capture."""
+def conv_traffic(key="conv_dram_bytes_per_step"):
+    """DRAM bytes (read + write) of the 351 conv launches of one step (or, with another key, of the CEM projection at
+    config 4), from the committed ncu captures."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)["conv_dram_bytes_per_step"]
+            return json.load(f)[key]
     except Exception:
         return None
 
@@ -126,8 +127,10 @@ def cem_standalone(dev, pk):
     t = sorted(ts)[len(ts) // 2]
     byts = 4 * C * (2 * H * W + H * W // (SF * SF))           # read y, read x, write out = 24.75 B / HR px
     return {"bound": "hbm", "achieved": byts / t / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": byts / t / 1e6 / pk["hbm"],
-            "kernel": "cem_down4_kernel + cem_invup4_kernel (2 launches), 1x3x2048x2048 output, %.1f us, algorithmic %.1f MB; "
-                      "L2 flushed between iterations" % (t * 1e3, byts / 1e6), "traffic": None}
+            "kernel": "cem_down4_kernel + cem_invup4_kernel (2 launches, the second a programmatic dependent of the first), "
+                      "1x3x2048x2048 output, %.1f us, algorithmic %.1f MB; L2 flushed between iterations; traffic = DRAM bytes "
+                      "of both launches (ncu, cold cache per launch, profiles/)" % (t * 1e3, byts / 1e6),
+            "traffic": conv_traffic("cem_cfg4_dram_bytes")}
 
 
 def run_reference(args):
