@@ -22,11 +22,13 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 constexpr int DT_R = 8, DT_C = 32;
 
 // out = (x ? x - Down(y) : Down(y)),  y: [P,H,W]  out/x: [P,H/sf,W/sf]   (P = B*C planes)
+template <int SF>
 __global__ void __launch_bounds__(256) cem_down_kernel(const __grid_constant__ esr_cem_filters f,
                                                        const float* __restrict__ y, const float* __restrict__ x,
                                                        float* __restrict__ out, int H, int W) {
     extern __shared__ float sm[];
-    const int sf = f.sf, nt = f.n_ds, pad = f.n_ds / 2;
+    constexpr int sf = SF;
+    const int nt = f.n_ds, pad = f.n_ds / 2;
     const int h = H / sf, w = W / sf;
     const int plane = blockIdx.z;
     const int i0 = blockIdx.y * DT_R, j0 = blockIdx.x * DT_C;
@@ -97,19 +99,41 @@ __global__ void __launch_bounds__(256) cem_inv_kernel(const __grid_constant__ es
 // -------------------------------------------------------------------------- Up
 // out[Y-crop, X-crop] = (y ? y[Y,X] : 0) + sign * sum_{ty,tx} u[ty] u[tx] z[clamp(Y+ty-pad), clamp(X+tx-pad)],
 // z = x zero-stuffed at phase pre.  Block: UT_R x UT_C LR cells -> (UT_R*sf) x (UT_C*sf) HR pixels.
+// SF is a template parameter (divisions by it become multiplies); away from the border only every SF-th tap meets a
+// sample, so the interior walks its phase's taps directly; within pad pixels of the border the replicate padding of
+// the zero-stuffed image breaks the phase pattern and every tap is tested.
 constexpr int UT_R = 8, UT_C = 32;
+template <int SF>
+__device__ __forceinline__ float up_taps_1d(const float* __restrict__ u, int nt, int pad, int pre, int P, int L,
+                                            const float* __restrict__ src, int src_stride, int cell0) {
+    // sum_t u[t] * z[clamp(P + t - pad, 0, L-1)] along one axis; src[(cell - cell0) * src_stride] = sample of LR cell
+    float acc = 0.f;
+    if (P >= pad && P + (nt - 1 - pad) <= L - 1) {
+        const int t0 = ((pre + pad - P) % SF + SF) % SF;
+        const float* s = src + ((P + t0 - pad - pre) / SF - cell0) * src_stride;
+        for (int t = t0; t < nt; t += SF, s += src_stride) acc = fmaf(u[t] * SF, *s, acc);
+    } else {
+        for (int t = 0; t < nt; ++t) {
+            const int q = clampi(P + t - pad, 0, L - 1) - pre;
+            if (q >= 0 && q % SF == 0) acc = fmaf(u[t] * SF, src[(q / SF - cell0) * src_stride], acc);
+        }
+    }
+    return acc;
+}
+
+template <int SF>
 __global__ void __launch_bounds__(256) cem_up_kernel(const __grid_constant__ esr_cem_filters f,
                                                      const float* __restrict__ x, const float* __restrict__ y,
                                                      float* __restrict__ out, int h, int w, int crop, float sign) {
     extern __shared__ float sm[];
-    const int sf = f.sf, nt = f.n_ds, pad = nt / 2, pre = f.pre;
-    const int H = h * sf, W = w * sf;
+    const int nt = f.n_ds, pad = nt / 2, pre = f.pre;
+    const int H = h * SF, W = w * SF;
     const int plane = blockIdx.z;
     const int I0 = blockIdx.y * UT_R, J0 = blockIdx.x * UT_C;
-    const int ext = (nt - 1) / sf + 2;                  // LR halo cells needed on each side (conservative)
+    const int ext = (nt - 1) / SF + 2;                  // LR halo cells needed on each side (conservative)
     const int rows_in = UT_R + 2 * ext, cols_in = UT_C + 2 * ext;
     float* tile = sm;                                   // x[I0-ext .., J0-ext ..] (zero outside)
-    float* hbuf = sm + rows_in * cols_in;               // [rows_in][UT_C*sf] horizontally upsampled
+    float* hbuf = sm + rows_in * cols_in;               // [rows_in][UT_C*SF] horizontally upsampled
     const float* xp = x + static_cast<size_t>(plane) * h * w;
     for (int idx = threadIdx.x; idx < rows_in * cols_in; idx += blockDim.x) {
         const int r = idx / cols_in, c = idx - r * cols_in;
@@ -117,33 +141,19 @@ __global__ void __launch_bounds__(256) cem_up_kernel(const __grid_constant__ esr
         tile[idx] = (rr >= 0 && rr < h && cc >= 0 && cc < w) ? __ldg(xp + static_cast<size_t>(rr) * w + cc) : 0.f;
     }
     __syncthreads();
-    const int wc = UT_C * sf;
+    constexpr int wc = UT_C * SF, hr = UT_R * SF;
     for (int idx = threadIdx.x; idx < rows_in * wc; idx += blockDim.x) {
         const int r = idx / wc, cx = idx - r * wc;
-        const int X = J0 * sf + cx;
-        float acc = 0.f;
-        if (X < W) {
-            for (int t = 0; t < nt; ++t) {
-                const int m = clampi(X + t - pad, 0, W - 1);   // replicate pad of the stuffed image
-                const int q = m - pre;
-                if (q >= 0 && q % sf == 0) acc = fmaf(f.ds[t] * sf, tile[r * cols_in + (q / sf - (J0 - ext))], acc);
-            }
-        }
-        hbuf[idx] = acc;
+        const int X = J0 * SF + cx;
+        hbuf[idx] = X < W ? up_taps_1d<SF>(f.ds, nt, pad, pre, X, W, tile + r * cols_in, 1, J0 - ext) : 0.f;
     }
     __syncthreads();
     const int Hout = H - 2 * crop, Wout = W - 2 * crop;
-    const int hr = UT_R * sf;
     for (int idx = threadIdx.x; idx < hr * wc; idx += blockDim.x) {
         const int ry = idx / wc, cx = idx - ry * wc;
-        const int Y = I0 * sf + ry, X = J0 * sf + cx;
+        const int Y = I0 * SF + ry, X = J0 * SF + cx;
         if (Y < crop || Y >= H - crop || X < crop || X >= W - crop) continue;
-        float acc = 0.f;
-        for (int t = 0; t < nt; ++t) {
-            const int m = clampi(Y + t - pad, 0, H - 1);
-            const int q = m - pre;
-            if (q >= 0 && q % sf == 0) acc = fmaf(f.ds[t] * sf, hbuf[(q / sf - (I0 - ext)) * wc + cx], acc);
-        }
+        const float acc = up_taps_1d<SF>(f.ds, nt, pad, pre, Y, H, hbuf + cx, wc, I0 - ext);
         const size_t o = (static_cast<size_t>(plane) * Hout + (Y - crop)) * Wout + (X - crop);
         const float base = y != nullptr ? __ldg(y + (static_cast<size_t>(plane) * H + Y) * W + X) : 0.f;
         out[o] = base + sign * acc;
@@ -719,11 +729,14 @@ int cem_down(const esr_cem_filters& f, const float* y, const float* x, int plane
         return check_launch("cem_down4_kernel");
     }
     const size_t sm = down_smem(f);
-    int rc = set_smem(reinterpret_cast<const void*>(cem_down_kernel), sm);
-    if (rc) return rc;
     dim3 grid(ceil_div(W / f.sf, DT_C), ceil_div(H / f.sf, DT_R), planes);
-    cem_down_kernel<<<grid, 256, sm, s>>>(f, y, x, out, H, W);
-    return check_launch("cem_down_kernel");
+    auto launch = [&](auto kern) -> int {
+        int rc = set_smem(reinterpret_cast<const void*>(kern), sm);
+        if (rc) return rc;
+        kern<<<grid, 256, sm, s>>>(f, y, x, out, H, W);
+        return check_launch("cem_down_kernel");
+    };
+    return f.sf == 2 ? launch(cem_down_kernel<2>) : f.sf == 3 ? launch(cem_down_kernel<3>) : launch(cem_down_kernel<4>);
 }
 int cem_inv(const esr_cem_filters& f, const float* x, int planes, int h, int w, float* out, cudaStream_t s) {
     const size_t sm = inv_smem(f);
@@ -741,11 +754,14 @@ int cem_up(const esr_cem_filters& f, const float* x, const float* y, int planes,
         return check_launch("cem_up4_kernel");
     }
     const size_t sm = up_smem(f);
-    int rc = set_smem(reinterpret_cast<const void*>(cem_up_kernel), sm);
-    if (rc) return rc;
     dim3 grid(ceil_div(w, UT_C), ceil_div(h, UT_R), planes);
-    cem_up_kernel<<<grid, 256, sm, s>>>(f, x, y, out, h, w, crop, sign);
-    return check_launch("cem_up_kernel");
+    auto launch = [&](auto kern) -> int {
+        int rc = set_smem(reinterpret_cast<const void*>(kern), sm);
+        if (rc) return rc;
+        kern<<<grid, 256, sm, s>>>(f, x, y, out, h, w, crop, sign);
+        return check_launch("cem_up_kernel");
+    };
+    return f.sf == 2 ? launch(cem_up_kernel<2>) : f.sf == 3 ? launch(cem_up_kernel<3>) : launch(cem_up_kernel<4>);
 }
 
 // Fused (HH^T)^-1 + Up + residual add, x4 only; d = x - Down(y).
