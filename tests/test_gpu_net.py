@@ -114,6 +114,27 @@ def test_production_net_non_square_input(cuda_device):
     assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB" % (err, p)
 
 
+def test_full_size_batch_config2_properties(cuda_device):
+    """BASELINE config 2 at full size (16 x 3x128x128 LR, eval / pre-pad): size-independent properties over the whole
+    batch - CEM consistency of every image, image k of the batch == the same image run alone (bit for bit) - and
+    PSNR / max error of one image against the fp32 oracle (the oracle takes seconds per image at this size)."""
+    wts = synth.make_weights("default", seed=0)
+    lr, z = synth.make_inputs(16, 128, 128, seed=21)
+    mi = concat_latent(lr, z)
+    netG = build_product_G(cuda_device, 23, "all_layers_HR_downscaled", wts)
+    with torch.no_grad():
+        out = netG(mi.to(cuda_device))
+        res = (netG.DownscaleOP(out).cpu() - lr).abs()[:, :, 3:-3, 3:-3]
+        alone = netG(mi[9:10].contiguous().to(cuda_device))
+    assert out.shape == (16, 3, 512, 512)
+    assert res.amax(dim=(1, 2, 3)).max().item() <= 1e-4
+    assert torch.equal(alone[0], out[9])
+    with torch.no_grad():
+        ref = GCEMOracle(wts).forward(mi[4:5])
+    err, p = (out[4:5].cpu() - ref).abs().max().item(), psnr(out[4:5].cpu(), ref)
+    assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB" % (err, p)
+
+
 def test_batch_shards_are_bit_identical(cuda_device):
     """batch sharding is exact - image i of a batch == the same image run alone."""
     wts = synth.make_weights("kaiming", seed=2, nb=2)
