@@ -80,3 +80,21 @@ def test_kernel_argument_errors():
         capi.CemFilterBank2D(4, 1, np.zeros((65, 65), np.float32), np.zeros((5, 5), np.float32))
     with pytest.raises(capi.EsrError):
         capi.CemFilterBank2D(4, 1, np.zeros((9, 9), np.float32), np.zeros((6, 6), np.float32))
+
+
+def test_c_abi_rejects_bad_2d_filters_before_any_launch():
+    """esr_cem2d_* validate the filter descriptor first (no CUDA call has happened yet): even / oversized sides, null
+    tap pointers and unsupported scale factors come back as an error code with a message, on a box without a GPU too."""
+    import ctypes as C
+    l = capi.lib()
+    buf = (C.c_float * 16)()
+    addr = C.cast(buf, C.c_void_p).value
+    for sf, n_ds, n_inv, ds, inv, needle in ((4, 8, 5, addr, addr, "ds kernel side"), (4, 9, 65, addr, addr, "inv_hTh side"),
+                                             (4, 9, 5, 0, addr, "null"), (5, 9, 5, addr, addr, "scale factor")):
+        f = capi.CemFilters2d()
+        f.sf, f.pre, f.n_ds, f.n_inv, f.ds, f.inv = sf, 1, n_ds, n_inv, ds, inv
+        rc = l.esr_cem2d_downscale(f, addr, 1, 1, 8, 8, addr, None)
+        assert rc < 0
+        assert needle in l.esr_last_error().decode()
+        with pytest.raises(capi.EsrError):
+            capi.check(l.esr_cem2d_project_bwd(f, addr, 1, 1, 8, 8, 0, addr, addr, None))
