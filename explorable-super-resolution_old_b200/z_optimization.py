@@ -162,6 +162,13 @@ class Z_optimizer():
         G = getattr(self.model.netG, 'generated_image_model', self.model.netG)
         if hasattr(G, 'use_cuda_graphs') and os.environ.get('ESR_ZOPT_GRAPH', '1') != '0':
             G.use_cuda_graphs = True           # forward and backward of every iteration replay as CUDA graphs
+        # With a fixed iteration count nothing inside the loop needs a loss value on the host, so the per-iteration
+        # .item() reads of the reference loop (Z_optimization.py:620-634) are deferred to one read after the last
+        # iteration: the host queues iteration k+1 while the GPU runs iteration k.  loss_values / latest_Z_loss_values
+        # hold plain floats when optimize() returns, as in the reference.  The convergence mode (max_iters < 0) and
+        # loggers read every value as they go.
+        defer = self.max_iters > 0 and self.loggers is None and os.environ.get('ESR_ZOPT_DEFER_READS', '1') != '0'
+        pending_latest = None
         self.loss_values = []
         if self.random_Z_inits and self.cur_iter == 0:
             self.Z_model.Randomize_Z(what_2_shuffle=self.random_Z_inits)
@@ -201,12 +208,20 @@ class Z_optimizer():
                     logger.print_format_results('val', {'epoch': 0, 'iters': z_iter, 'time': time.time(), 'model': '',
                                                         'lr': cur_LR, 'Z_loss': cur_value}, dont_print=True)
             if not self.model_training:
-                self.latest_Z_loss_values = [val.item() for val in Z_loss]
+                if defer:
+                    pending_latest = Z_loss.detach()
+                else:
+                    self.latest_Z_loss_values = [val.item() for val in Z_loss]
             Z_loss = Z_loss.mean()
             Z_loss.backward()                                                # data gradient back to Z
-            self.loss_values.append(Z_loss.item())
+            self.loss_values.append(Z_loss.detach() if defer else Z_loss.item())
             self.optimizer.step()
             z_iter += 1
+        if defer:
+            if self.loss_values:
+                self.loss_values = torch.stack(self.loss_values).cpu().tolist()
+            if pending_latest is not None:
+                self.latest_Z_loss_values = pending_latest.cpu().tolist()
         if not self.model_training:
             print('Final STDs: ', ['%.3e' % (val.item()) for val in self.Masked_STD(first_image_only=False).mean(0)])
         self.cur_iter = z_iter + 1
