@@ -230,3 +230,22 @@ def test_x2_generator_matches_reference_golden(golden, cuda_device, name):
     (out * torch.from_numpy(g[name + "_gout"]).to(cuda_device)).sum().backward()
     got, gz = zp.grad.cpu(), torch.from_numpy(g[name + "_gz"])
     assert float((got - gz).norm() / gz.norm()) < 4e-2 and float((got * gz).sum() / (got.norm() * gz.norm())) > 0.999
+
+
+def test_pretrained_checkpoint_without_latent_is_reproduced(cuda_device):
+    """base_model.py:126-136: a generator without Z loaded into the Z-conditioned one (zero weights for the new input
+    channels) must output what the original does, whatever Z is - until the Z weights are trained."""
+    from esr_b200 import checkpoint
+    from tests.test_checkpoint import esrgan_style_checkpoint, make_opt
+    ckpt, plain_w = esrgan_style_checkpoint(nb=2, seed=12)
+    lat = networks.define_G(make_opt(nb=2), CEM=pcem.CEMnet(pcem.Get_CEM_Config(4)), num_latent_channels=3)
+    checkpoint.load_network(ckpt, lat, latent_input="all_layers_HR_downscaled", num_latent_channels=3)
+    lat = lat.to(cuda_device).eval()
+    plain = build_product_G(cuda_device, 2, None, plain_w)
+    lr, z = synth.make_inputs(1, 18, 14, seed=12)
+    with torch.no_grad():
+        a = lat(concat_latent(lr, z).to(cuda_device))
+        b = lat(concat_latent(lr, -z).to(cuda_device))
+        ref = plain(lr.to(cuda_device))
+    assert torch.equal(a, b)
+    assert (a - ref).abs().max().item() <= 1e-5
