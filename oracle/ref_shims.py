@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE, build-container only: /root/reference does not exist on the
 GPU box, so nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` calls this
 module.  It is used by ``oracle/gen_golden.py`` to produce the committed fixtures
-and by ``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent).
+and by ``tests/test_checkpoint.py::test_matches_reference_loader`` (skipped when the reference is absent).
 
 The shims only repair imports that broke with newer library versions or that
 assume a CUDA device; no reference source is modified or copied.
