@@ -17,6 +17,8 @@ Host-side only (state_dict surgery); nothing here touches the GPU.
 """
 import collections
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -62,6 +64,8 @@ def load_network(load_path, network, strict=False, optimizer=None, CEM_arch=True
     """base_model.py:100-111.  load_path: a file path or an already loaded checkpoint object."""
     if isinstance(network, nn.DataParallel):
         network = network.module
+    if isinstance(load_path, os.PathLike):
+        load_path = os.fspath(load_path)
     loaded = torch.load(load_path, map_location=map_location) if isinstance(load_path, (str, bytes)) or hasattr(load_path, "read") \
         else load_path
     if 'optimizer_state_dict' in loaded:

@@ -1,10 +1,18 @@
-"""`import models.networks as networks` -> B200 generator factory (reference: codes/models/networks.py)."""
-from esr_b200.networks import define_G, init_weights, weights_init_kaiming  # noqa: F401
+"""`import models.networks as networks`: the reference's factories (define_D, define_F, ... codes/models/networks.py)
+with ``define_G`` / ``init_weights`` / ``weights_init_kaiming`` (:28-102) replaced by the B200 generator factory."""
+from ._shadow_loader import reexport as _reexport
 
+try:
+    _reference = _reexport(__name__, globals())
+except Exception as _e:      # the reference's own module failed to import (missing third-party package): generator only
+    _reference, _reference_error = None, _e
+from esr_b200.networks import define_G, init_weights, weights_init_kaiming  # noqa: E402,F401
 
-def define_D(*a, **kw):
-    raise NotImplementedError("the discriminator / GAN training step is outside the built hot path (SURVEY.md §8f)")
+if _reference is None:
+    def define_D(*a, **kw):
+        raise NotImplementedError("models.networks.define_D: the reference tree is not importable here and the "
+                                  "discriminator is outside this package's hot path")
 
-
-def define_F(*a, **kw):
-    raise NotImplementedError("the VGG feature extractor is outside the built hot path (SURVEY.md §8f)")
+    def define_F(*a, **kw):
+        raise NotImplementedError("models.networks.define_F: the reference tree is not importable here and the VGG "
+                                  "feature extractor is outside this package's hot path")

@@ -419,12 +419,13 @@ void fill_launch(ConvLaunch* L, const esr_conv_desc& d) {
 int num_sms_cached();
 static int num_sms() { return num_sms_cached(); }
 int num_sms_cached() {
-    static int n = 0;
+    static std::atomic<int> per_dev[64];                  // zero-initialised; keyed by device ordinal
+    const int dev = current_device_ordinal();
+    int n = per_dev[dev].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        per_dev[dev].store(n, std::memory_order_relaxed);
     }
     return n;
 }
@@ -441,13 +442,11 @@ int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLau
         {conv3x3_tc_kernel<32, kEpiGeneric>, conv3x3_tc_kernel<32, kEpiTrunk>, conv3x3_tc_kernel<32, kEpiRes>,
          conv3x3_tc_kernel<32, kEpiAct>, conv3x3_tc_kernel<32, kEpiGeneric>, conv3x3_tc_kernel<32, kEpiMask>,
          conv3x3_tc_kernel<32, kEpiDx0>}};
-    static bool attr_set = false;
-    if (!attr_set) {
+    ESR_ONCE_PER_DEVICE(
         for (int a = 0; a < 2; ++a)
             for (int b = 0; b < 7; ++b)
                 ESR_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr_set = true;
-    }
+    );
     ESR_CHECK_ARG(L.nstages >= 2, "conv weights (%u B per cout tile) leave no room for the A-tile ring", L.d.w_tile_bytes);
     // every CTA owns one cout tile: grid is a multiple of cout_tiles, at most one CTA per SM
     int per_ct = num_sms() / L.d.cout_tiles;

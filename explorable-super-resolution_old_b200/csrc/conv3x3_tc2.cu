@@ -441,7 +441,7 @@ struct RdbLaunch {
     uint32_t* flags;                        // [nlayers][spatial_tiles] counters of this launch
     uint32_t* flags_zero;                   // same size, cleared for a later launch
     int reverse;                            // walk chunks and tiles last-to-first (alternates launch by launch: L2 reuse)
-    uint32_t m_per_chunk, m_ppc, m_tpi, m_tx;   // ceil(2^32 / d): n / d == __umulhi(n, m) for n * d < 2^32 (no XU divisions)
+    uint32_t m_per_chunk, m_ppc, m_tpi, m_tx;   // ceil(2^32 / d): n / d == __umulhi(n, m) for n * d < 2^32 (no XU divisions); 0 for d == 1
     int nstages;
     uint32_t w_smem_bytes;
     unsigned long long* prof;               // optional [gridDim][16] role counters (-DESR_PROFILE_ROLES)
@@ -466,21 +466,27 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct RdbItem { int layer, n, ty, tx, gt; bool ok; };
+// n / d through the precomputed magic m = ceil(2^32 / d).  d == 1 has no 32-bit magic (2^32 wraps to 0, and
+// __umulhi(n, 0) would be 0 instead of n - the round-1 fault on plans with one tile column / one pair per chunk):
+// the host stores 0 for it and the division is the identity.
+__device__ __forceinline__ int fast_div(int n, uint32_t m) {
+    return m == 0u ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), m));
+}
 __device__ __forceinline__ RdbItem rdb_decode(const RdbLaunch& R, int item, uint32_t rank) {
     const int per_chunk = R.nlayers * R.ppc;
-    int c = static_cast<int>(__umulhi(static_cast<uint32_t>(item), R.m_per_chunk));
+    int c = fast_div(item, R.m_per_chunk);
     const int rem = item - c * per_chunk;
     RdbItem it;
-    it.layer = static_cast<int>(__umulhi(static_cast<uint32_t>(rem), R.m_ppc));
+    it.layer = fast_div(rem, R.m_ppc);
     int p = rem - it.layer * R.ppc;
     if (R.reverse) { c = R.chunks - 1 - c; p = R.ppc - 1 - p; }
     int tl = 2 * p + static_cast<int>(rank);
     it.ok = tl < R.tiles_c;
     if (!it.ok) tl = R.tiles_c - 1;                                 // odd tail: duplicate tile, nothing stored
     it.gt = c * R.tiles_c + tl;
-    it.n = static_cast<int>(__umulhi(static_cast<uint32_t>(it.gt), R.m_tpi));
+    it.n = fast_div(it.gt, R.m_tpi);
     const int r = it.gt - it.n * R.tiles_per_img;
-    it.ty = static_cast<int>(__umulhi(static_cast<uint32_t>(r), R.m_tx));
+    it.ty = fast_div(r, R.m_tx);
     it.tx = r - it.ty * R.tiles_x;
     return it;
 }
@@ -650,8 +656,8 @@ conv3x3_rdb_growth_kernel(const __grid_constant__ CUtensorMap tmap0, const __gri
             ESR_PROF(const long long m_tw = clock64() - m_t0;)
             const int per_chunk = R.nlayers * R.ppc;
             for (int item = cluster_id; item < R.total_items; item += num_clusters) {
-                const int c_ = static_cast<int>(__umulhi(static_cast<uint32_t>(item), R.m_per_chunk));
-                const RdbLayerDev& Ly = R.layer[__umulhi(static_cast<uint32_t>(item - c_ * per_chunk), R.m_ppc)];
+                const int c_ = fast_div(item, R.m_per_chunk);
+                const RdbLayerDev& Ly = R.layer[fast_div(item - c_ * per_chunk, R.m_ppc)];
                 ESR_PROF(long long c0 = clock64(); const int tslot = (item - cluster_id) / num_clusters;)
                 mbar_wait(&acc_empty[as], aphase ^ 1);
                 ESR_PROF(m_wacc += clock64() - c0; if (R.prof && blockIdx.x == 0 && tslot < 32) R.prof[148 * 16 + tslot * 8 + 2] = gtime_ns();)
@@ -903,7 +909,8 @@ int build_rdb_growth(const esr_rdb_growth_desc& d, RdbOp* op) {
     R.ppc = (R.tiles_c + 1) / 2;
     R.chunks = d.B / ic;
     R.total_items = R.chunks * R.nlayers * R.ppc;
-    const auto magic = [](int dd) { return static_cast<uint32_t>(((1ull << 32) + dd - 1) / dd); };
+    // ceil(2^32 / d); d == 1 would need 2^32 itself: stored as 0 = "identity" (fast_div)
+    const auto magic = [](int dd) { return dd <= 1 ? 0u : static_cast<uint32_t>(((1ull << 32) + dd - 1) / dd); };
     ESR_CHECK_ARG(static_cast<long long>(R.total_items) * R.nlayers * R.ppc < (1ll << 32) &&
                   static_cast<long long>(R.spatial_tiles) * R.tiles_per_img < (1ll << 32), "rdb_growth: problem too large");
     R.m_per_chunk = magic(R.nlayers * R.ppc); R.m_ppc = magic(R.ppc); R.m_tpi = magic(R.tiles_per_img); R.m_tx = magic(R.tiles_x);
@@ -947,12 +954,10 @@ void rdb_op_set_reverse(RdbOp* op, int reverse) { op->R.reverse = reverse; }
 
 int launch_rdb_growth(const RdbOp& op, cudaStream_t stream, int use_pdl) {
     using namespace pair;
-    static bool attr_set = false;
-    if (!attr_set) {
+    ESR_ONCE_PER_DEVICE(
         ESR_CUDA(cudaFuncSetAttribute(conv3x3_rdb_growth_kernel<kEpiTrunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         ESR_CUDA(cudaFuncSetAttribute(conv3x3_rdb_growth_kernel<kEpiMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr_set = true;
-    }
+    );
     const pair::RdbLaunch& R = op.R;
     constexpr int a_tile = (2 * kBandRows + 2) * kTileW * kRowBytes;
     int clusters = num_sms_cached() / 2;
@@ -1005,13 +1010,11 @@ int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLa
         {conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiRes>,
          conv3x3_tc2_kernel<64, kEpiAct>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>,
          conv3x3_tc2_kernel<64, kEpiGeneric>}};
-    static bool attr_set = false;
-    if (!attr_set) {
+    ESR_ONCE_PER_DEVICE(
         for (int a = 0; a < 2; ++a)
             for (int b = 0; b < 7; ++b)
                 ESR_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr_set = true;
-    }
+    );
     const int nb = L.d.cout_tile == 32 ? 2 : 1;
     const bool attach = L.d.num_kblocks >= 2 && L.d.kblocks[L.d.num_kblocks - 1].half != 0;
     const int a_tile = (nb * kBandRows + 2) * kTileW * kRowBytes + (attach ? nb * kBandRows * kTileW * 32 : 0);

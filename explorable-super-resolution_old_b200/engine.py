@@ -291,9 +291,10 @@ class GPlan:
         # conv3x3_tc2.cu).  Opt-in (ESR_FUSE_RDB=1): bit-identical, 78 % less DRAM traffic for those convs at 4-8 images
         # per chunk, but with all four weight images resident only 4 A-ring stages fit and it measures 3 % slower
         # than the separate launches at config 2.
-        # Not below 32 x 32 padded pixels: a 12 x 14 plan makes the fused launch fault (illegal address; validated envelope
-        # is 36 x 40 and up, tools/fuse_probe.py) - such plans keep the separate launches.
-        self.fuse_rdb = eng.pair and not use_simt and os.environ.get("ESR_FUSE_RDB", "0") == "1" and hp >= 32 and wp >= 32
+        # (Round 1 kept plans below 32 x 32 padded pixels on separate launches because a 12 x 14 plan faulted: the item
+        # decode divided by 1 through a magic number that had wrapped to 0 - fixed in csrc/conv3x3_tc2.cu: fast_div -
+        # so every plan size takes the fused launch now; tests/test_gpu_net.py covers 12x14, 22x24, 33x35.)
+        self.fuse_rdb = eng.pair and not use_simt and os.environ.get("ESR_FUSE_RDB", "0") == "1"
         self.rdb_flags = torch.zeros(int(capi.lib().esr_rdb_growth_flag_words(B, hp, wp)), dtype=torch.int32, device=device) \
             if self.fuse_rdb else None
         self._record_forward(use_simt)

@@ -48,9 +48,10 @@ class HostPipeline:
     def __init__(self, netG, chunk=16, use_graph=True):
         self.netG, self.chunk = netG, chunk
         self.use_graph = use_graph                                         # replay the chunk's forward as a CUDA graph
-        self._graphs = {}                                                  # (slot, rows) -> (graph, static output)
+        self._graphs = {}                                                  # (slot, rows, input shape, module state) -> (graph, static output)
         self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
         self._x, self._free, self._k = [None, None], [None, None], 0     # two device staging slots for the inputs
+        self._down = [None, None]                                          # per slot: download of the chunk that last used it
         self._live = []                                                    # outputs whose download is still in flight
         self._done = None
 
@@ -74,6 +75,10 @@ class HostPipeline:
                 x.copy_(host_in[lo:hi], non_blocking=True)
                 up.record(self.s_in)
             cur.wait_event(up)
+            # the captured graph writes ONE static output buffer per slot: chunk k+2 must not overwrite it while chunk
+            # k's device->host copy (on s_out) is still reading it
+            if self._down[slot] is not None:
+                cur.wait_event(self._down[slot])
             out = self._forward(slot, x)
             done = torch.cuda.Event()
             done.record(cur)
@@ -84,15 +89,21 @@ class HostPipeline:
                 host_out[lo:hi].copy_(out, non_blocking=True)
                 down.record(self.s_out)
             self._live = [(o, e) for (o, e) in self._live if not e.query()] + [(out, down)]
-            self._done = down
+            self._done = self._down[slot] = down
         return host_out
 
     def _forward(self, slot, x):
         """netG(x) for the staging slot: through the module's captured inference graph when it offers one
         (CEM_PyTorch.capture: fixed input slot, fixed output buffer), else the eager module call."""
         if self.use_graph and hasattr(self.netG, "capture"):
-            key = (slot, x.size(0))
+            # a captured graph bakes in the packed weights, the margin (train / eval) and the geometry: key on all of
+            # them, so load_state_dict, a weight update or a train()/eval() flip re-captures instead of replaying stale state
+            state = tuple((p.data_ptr(), p._version) for p in self.netG.parameters())
+            key = (slot, tuple(x.shape), x.data_ptr(), bool(getattr(self.netG, "pre_pad", False)), state)
             if key not in self._graphs:
+                for old in [k for k in self._graphs if k[0] == slot and k[1] == key[1]]:
+                    torch.cuda.current_stream().synchronize()              # nothing may still be replaying the stale graph
+                    del self._graphs[old]
                 self._graphs[key] = self.netG.capture(x, slot=slot) or False
             ent = self._graphs[key]
             if ent:

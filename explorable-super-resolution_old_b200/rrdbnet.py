@@ -188,7 +188,14 @@ def _forward_eager(plan, x, cem_filters, crop, out, ws):
 
 
 class _GeneratorFn(torch.autograd.Function):
-    """G (+ optional CEM projection) as one autograd node: data gradient only."""
+    """G (+ optional CEM projection) as one autograd node: data gradient only.
+
+    The activations the backward needs (the sign of the 279 LeakyReLU outputs) stay in the plan's buffers, which are
+    shared by every forward of the same geometry: each differentiable forward stamps the plan, and a backward whose
+    stamp is no longer the plan's latest raises instead of silently differentiating through another input's
+    activations (two forwards before one backward, or a second backward after another forward).  The gradient is
+    defined for the latent channels only: the LR channels of d(model_input) are zero (the reference's Z optimisation
+    never asks for them, Z_optimization.py:545-553)."""
 
     @staticmethod
     def forward(ctx, x, net, margin, cem_filters, need_grad):
@@ -196,6 +203,9 @@ class _GeneratorFn(torch.autograd.Function):
         plan = net.plan(B, h, w, margin, keep=need_grad)
         sf = net.upscale
         ctx.plan, ctx.cem_filters, ctx.margin, ctx.net, ctx.graphed = plan, cem_filters, margin, net, None
+        if need_grad:
+            plan.fwd_stamp = getattr(plan, "fwd_stamp", 0) + 1
+        ctx.stamp = getattr(plan, "fwd_stamp", 0)
         with torch.cuda.device(x.device):
             if need_grad and net.use_cuda_graphs:
                 key = (id(cem_filters), margin)
@@ -213,6 +223,9 @@ class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         from .backward import generator_backward
+        if getattr(ctx.plan, "fwd_stamp", 0) != ctx.stamp:
+            raise capi.EsrError("backward through a generator forward whose activations were overwritten by a later "
+                                "differentiable forward of the same shape (call backward before the next forward)")
         if ctx.graphed is not None and ctx.graphed.bwd_graph is not None:
             with torch.cuda.device(g.device):
                 return ctx.graphed.backward(g.contiguous().float()), None, None, None, None
@@ -269,7 +282,16 @@ def run_generator(net, x, margin, cem_filters):
         raise ValueError("expected %d input channels (Z.view(B,%d,h,w) ++ LR), got %d" % (nz_in * sf * sf + 3, nz_in * sf * sf, x.size(1)))
     need_grad = torch.is_grad_enabled() and x.requires_grad
     if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
-        raise NotImplementedError("weight gradients (GAN training step) are not built; freeze the generator "
-                                  "(Z_optimizer does, Z_optimization.py:545-553) or run under torch.no_grad()")
+        if need_grad:
+            raise NotImplementedError("weight gradients through this autograd node are not built; freeze the generator "
+                                      "(Z_optimizer does, Z_optimization.py:545-553), run under torch.no_grad(), or use "
+                                      "training.generator_step for the explicit weight-gradient path")
+        # a plain netG(x) right after define_G (parameters still require grad, input does not): forward only, like the
+        # reference's output values; no graph is recorded, so a later .backward() on it raises in autograd itself
+        if not getattr(net, "_warned_fwd_only", False):
+            net._warned_fwd_only = True
+            import warnings
+            warnings.warn("RRDBNet: parameters require grad but no weight-gradient graph is recorded by forward(); "
+                          "running forward-only")
     xc = x.contiguous().float()
     return _GeneratorFn.apply(xc, net, margin, cem_filters, need_grad)

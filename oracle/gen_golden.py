@@ -136,6 +136,108 @@ def gen_x2(CEMnet, networks):
     np.savez_compressed(os.path.join(OUT, "g_cem_x2.npz"), **out)
 
 
+class RefModel:
+    """Minimal stand-in for SRRaGANModel (codes/models/SRRaGAN_model.py:249-302 restated): only what Z_optimizer touches."""
+
+    def __init__(self, netG):
+        self.netG, self.num_latent_channels, self.opt = netG, 3, {"scale": 4}
+
+    def ConcatLatent(self, LR_image, latent_input):
+        if LR_image.size()[2:] != latent_input.size()[2:]:
+            latent_input = latent_input.contiguous().view([latent_input.size(0), latent_input.size(1) * 16] + list(LR_image.size()[2:]))
+        self.model_input = torch.cat([latent_input, LR_image], dim=1)
+
+    def GetLatent(self):
+        latent = 1 * self.model_input[:, :-3, ...]
+        return latent.view([latent.size(0), 3] + [4 * v for v in latent.size()[2:]])
+
+    def feed_data(self, data, need_HR=True):
+        self.var_L = data["LR"]
+        self.ConcatLatent(self.var_L, data["Z"])
+
+
+ZOPT2_CASES = [  # name, objective, max_iters, masks, batch
+    ("max_std", "max_STD", 4, False, 1),          # Z_optimization.py:426-435, :603-607, 'max' sign flip :618
+    ("min_std", "min_STD", 3, False, 1),
+    ("std_increase", "STD_increase", 4, False, 1),   # additive increment data['STD_increment'] (:431-435)
+    ("std_decrease_mult", "STD_decrease", 3, False, 1),   # STD_increment None: multiplicative 1/1.05 (:433)
+    ("tv_converge", "TV", -3, False, 1),          # max_iters < 0: relative-decrease stop rule, cap 5*|max_iters| (:564-571)
+    ("tv_masked", "TV", 4, True, 1),              # image_mask + Z_mask (:347-355; Optimizable_Z mask blend :300-303)
+    ("tv_batch2", "TV", 3, False, 2),             # batch_size 2: per-image losses (latest_Z_loss_values), mean for Adam
+]
+
+
+def zopt2_masks(h4, w4):
+    """Deterministic image / Z masks of the masked case (both HR sized, as GUI.py builds them)."""
+    im = np.zeros((h4, w4), dtype=np.float32)
+    im[h4 // 4:3 * h4 // 4, w4 // 8:5 * w4 // 8] = 1
+    zm = np.zeros((h4, w4), dtype=np.float32)
+    zm[h4 // 8:7 * h4 // 8, :3 * w4 // 4] = 1
+    return im, zm
+
+
+def gen_zopt2(CEMnet, networks, zopt):
+    """More of the reference's Z_optimizer on the built objectives: STD objectives, convergence mode, masks, batch 2."""
+    zres = {}
+    for name, objective, max_iters, masked, bs in ZOPT2_CASES:
+        netG, cem = build_ref_G(CEMnet, networks, 2, "all_layers", "default", 5)
+        netG.train(False)
+        lr, z0 = synth.make_inputs(1, 8, 8, seed=5)
+        lr = lr.repeat(bs, 1, 1, 1)
+        model = RefModel(netG)
+        data = {"LR": lr, "Z": (0.5 * z0).repeat(bs, 1, 1, 1)}
+        if "increase" in objective or "decrease" in objective:
+            data["STD_increment"] = None if name.endswith("_mult") else 0.02
+        model.feed_data(data)
+        with torch.no_grad():
+            model.fake_H = netG(model.model_input)
+        kw = {}
+        if masked:
+            im, zm = zopt2_masks(32, 32)
+            kw = dict(image_mask=im, Z_mask=zm, initial_Z=0.5 * z0)
+        opt = zopt.Z_optimizer(objective=objective, Z_size=[32, 32], model=model, Z_range=1.0, max_iters=max_iters, data=data,
+                               initial_LR=0.1, batch_size=bs, **kw)
+        if bs > 1:       # pin the per-image initial Z (the reference would draw it with torch's RNG, :559-560)
+            opt.random_Z_inits = False
+            z_init = torch.from_numpy(np.random.default_rng(17).standard_normal((bs, 3, 32, 32)).astype(np.float32)) * 0.3
+            opt.Z_model.Z.data.copy_(z_init)
+            zres[name + "_Zinit"] = z_init.numpy()
+        Z = opt.optimize()
+        zres[name + "_loss"] = np.array(opt.loss_values, dtype=np.float64)
+        zres[name + "_latest"] = np.array(opt.latest_Z_loss_values, dtype=np.float64)
+        zres[name + "_Z"] = Z.numpy()
+        zres[name + "_cur_iter"] = np.array(opt.cur_iter)
+        zres[name + "_initial_STD"] = opt.initial_STD.numpy()
+        print(name, opt.loss_values, opt.cur_iter)
+    np.savez_compressed(os.path.join(OUT, "zopt2.npz"), **zres)
+
+
+CFG3_WINDOWS = [(0, 0), (464, 464), (928, 928), (0, 928)]      # top-left corners of the stored 96 x 96 HR windows
+CFG3_WIN = 96
+
+
+def gen_cfg3(CEMnet, networks):
+    """BASELINE config 3 at its own size: the production generator (nb = 23, default init) + CEM, eval mode, one
+    1x3x256x256 LR image; output and dL/dZ of the reference's autograd for L = sum(out * g).  Only windows of the two
+    1x3x1024x1024 tensors are stored (borders, centre) plus whole-tensor norms."""
+    netG, _ = build_ref_G(CEMnet, networks, 23, "all_layers", "default", 0)
+    netG.train(False)
+    for p in netG.parameters():
+        p.requires_grad = False
+    lr, z = synth.make_inputs(1, 256, 256, seed=33)
+    zg = z.clone().requires_grad_(True)
+    res = netG(torch.cat([zg.contiguous().view(1, 48, 256, 256), lr], 1))
+    g = torch.from_numpy(np.random.default_rng(33).standard_normal(tuple(res.shape)).astype(np.float32))
+    (res * g).sum().backward()
+    out = {"cfg": np.array([23, 0, 33, 256, 256]), "out_norm": np.array(float(res.detach().double().norm())),
+           "gz_norm": np.array(float(zg.grad.double().norm())), "out_mean": np.array(float(res.detach().double().mean()))}
+    for k, (y0, x0) in enumerate(CFG3_WINDOWS):
+        out["out_%d" % k] = res.detach()[0, :, y0:y0 + CFG3_WIN, x0:x0 + CFG3_WIN].numpy()
+        out["gz_%d" % k] = zg.grad[0, :, y0:y0 + CFG3_WIN, x0:x0 + CFG3_WIN].numpy()
+    print("cfg3", tuple(res.shape), out["out_norm"], out["gz_norm"])
+    np.savez_compressed(os.path.join(OUT, "cfg3.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -146,6 +248,10 @@ def main():
         return gen_nondefault(CEMnet)
     if "x2" in sys.argv[1:]:              # only the x2 fixture
         return gen_x2(CEMnet, networks)
+    if "zopt2" in sys.argv[1:]:           # only the extra Z_optimizer trajectories
+        return gen_zopt2(CEMnet, networks, zopt)
+    if "cfg3" in sys.argv[1:]:            # only the config-3-size output / gradient windows (about a minute, ~20 GB)
+        return gen_cfg3(CEMnet, networks)
 
     # 1. filters --------------------------------------------------------------------------
     filt = {}
@@ -213,26 +319,6 @@ def main():
     np.savez_compressed(os.path.join(OUT, "g_cem.npz"), **out)
 
     # 4. Z optimisation through the reference's Z_optimizer --------------------------------
-    class RefModel:
-        """Minimal stand-in for SRRaGANModel (codes/models/SRRaGAN_model.py:249-302 restated):
-        only what Z_optimizer touches."""
-
-        def __init__(self, netG):
-            self.netG, self.num_latent_channels, self.opt = netG, 3, {"scale": 4}
-
-        def ConcatLatent(self, LR_image, latent_input):
-            if LR_image.size()[2:] != latent_input.size()[2:]:
-                latent_input = latent_input.contiguous().view([latent_input.size(0), latent_input.size(1) * 16] + list(LR_image.size()[2:]))
-            self.model_input = torch.cat([latent_input, LR_image], dim=1)
-
-        def GetLatent(self):
-            latent = 1 * self.model_input[:, :-3, ...]
-            return latent.view([latent.size(0), 3] + [4 * v for v in latent.size()[2:]])
-
-        def feed_data(self, data, need_HR=True):
-            self.var_L = data["LR"]
-            self.ConcatLatent(self.var_L, data["Z"])
-
     zres = {}
     for name, objective, train_mode in (("tv_eval", "TV", False), ("l1_train", "l1", True)):
         netG, cem = build_ref_G(CEMnet, networks, 2, "all_layers", "default", 5)
@@ -268,6 +354,10 @@ def main():
 
     # 6. x2 generator ------------------------------------------------------------------------
     gen_x2(CEMnet, networks)
+
+    # 7. more Z_optimizer paths, config-3-size gradient ----------------------------------------
+    gen_zopt2(CEMnet, networks, zopt)
+    gen_cfg3(CEMnet, networks)
 
 
 if __name__ == "__main__":

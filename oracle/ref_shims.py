@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE, build-container only: /root/reference does not exist on the
 GPU box, so nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` calls this
-module.  It is used by ``oracle/gen_golden.py`` to produce the committed fixtures
+module with /root/reference (the vendored copy of oracle/vendor_ref.py is what the GPU box sees).  It is used by ``oracle/gen_golden.py`` to produce the committed fixtures
 and by ``tests/test_checkpoint.py::test_matches_reference_loader`` (skipped when the reference is absent).
 
 The shims only repair imports that broke with newer library versions or that
@@ -12,7 +12,11 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ESR_REFERENCE_ROOT", "/root/reference/codes")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "codes")   # oracle/vendor_ref.py (GPU box)
+REF_ROOT = os.environ.get("ESR_REFERENCE_ROOT") or \
+    ("/root/reference/codes" if os.path.isdir("/root/reference/codes/CEM") else _VENDORED)
+COMPAT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                          "explorable-super-resolution_old_b200", "compat")
 
 
 def available():
@@ -26,8 +30,10 @@ def _stub(name, **attrs):
     return sys.modules[name]
 
 
-def install():
-    """Make ``import CEM.CEMnet``, ``models.networks``, ``Z_optimization`` work."""
+def install(compat_first=False):
+    """Make ``import CEM.CEMnet``, ``models.networks``, ``Z_optimization`` work.  compat_first: put this package's
+    import-path shims AHEAD of the reference (the drop-in configuration of INTEGRATION.md): the reference's callers
+    then run on the B200 implementations of the hot path."""
     if not available():
         raise RuntimeError("reference tree not found at %s" % REF_ROOT)
     import numpy as np
@@ -57,6 +63,10 @@ def install():
             _stub(name)
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
+    if compat_first:
+        if COMPAT_DIR in sys.path:
+            sys.path.remove(COMPAT_DIR)
+        sys.path.insert(sys.path.index(REF_ROOT), COMPAT_DIR)
 
 
 class _CpuDeviceTorch:

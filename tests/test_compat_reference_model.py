@@ -1,0 +1,123 @@
+"""The module-level drop-in boundary: with ``compat/`` ahead of the reference's
+``codes/`` on sys.path, the reference's OWN ``SRRaGANModel`` (codes/models/SRRaGAN_model.py:30-71, base_model.py:10-17)
+is constructed from its shipped ``options/test/GUI_esrgan.json`` and ends up driving this package's generator.
+
+Runs in a subprocess (the import order of ``models`` / ``CEM`` must not leak into the other tests).  The reference is
+taken from /root/reference (build container) or from oracle/_ref (the vendored copy on the GPU box); skipped when
+neither exists."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import json, os, sys, tempfile
+sys.path.insert(0, %(root)r)
+import torch
+from oracle import ref_shims
+ref_shims.install(compat_first=True)
+import options.options as option
+import models
+from models import create_model
+import models.networks, models.modules.architecture, CEM.CEMnet, Z_optimization
+from esr_b200 import synth, cem as pcem, rrdbnet, networks as pnet
+use_gpu = %(gpu)r and torch.cuda.is_available()
+res = {}
+res["networks_file"] = models.networks.__file__
+res["srragan_file"] = __import__("models.SRRaGAN_model", fromlist=["x"]).__file__
+res["base_model_file"] = __import__("models.base_model", fromlist=["x"]).__file__
+res["loss_file"] = __import__("models.modules.loss", fromlist=["x"]).__file__
+res["has_define_D"] = hasattr(models.networks, "define_D") and hasattr(models.modules.architecture, "Discriminator_VGG_128")
+assert models.modules.architecture.RRDBNet is rrdbnet.RRDBNet and CEM.CEMnet.CEMnet is pcem.CEMnet
+opt = option.parse(os.path.join(ref_shims.REF_ROOT, "options", "test", "GUI_esrgan.json"), is_train=False)
+tmp = tempfile.mkdtemp()
+opt["path"]["models"] = os.path.join(tmp, "models"); os.makedirs(opt["path"]["models"])
+opt["path"]["log"] = tmp
+opt["gpu_ids"] = [0] if use_gpu else None
+nb = %(nb)d
+opt["network_G"]["nb"] = nb
+opt = option.dict_to_nonedict(opt)
+# a checkpoint in the public ESRGAN naming (RDB1.conv1.0.weight ...): the reference's positional loader must map it
+w = synth.make_weights("kaiming", seed=9, nb=nb)
+ck = {}
+for k, v in w.items():
+    k2 = k
+    for i in range(5):
+        k2 = k2.replace("convs.%%d.0" %% i, "conv%%d.0" %% (i + 1))
+    ck[k2] = v
+torch.save(ck, os.path.join(opt["path"]["models"], "7_G.pth"))
+model = create_model(opt)
+res["model_class"] = type(model).__module__ + "." + type(model).__name__
+G = model.netG.module if hasattr(model.netG, "module") else model.netG
+res["netG_class"] = type(G).__module__ + "." + type(G).__name__
+res["gen_class"] = type(G.generated_image_model).__module__ + "." + type(G.generated_image_model).__name__
+sd = G.state_dict()
+res["weights_loaded"] = all(torch.equal(sd["generated_image_model." + k].cpu(), v) for k, v in w.items())
+res["state"] = [model.device.type, bool(model.is_train), model.num_latent_channels, model.gradient_step_num]
+lr, z = synth.make_inputs(1, 12, 10, seed=9)
+model.feed_data({"LR": lr, "Z": z}, need_HR=False)
+res["model_input"] = list(model.model_input.shape)
+if use_gpu:
+    from oracle.rrdbnet import GCEMOracle
+    model.test()
+    ref = GCEMOracle(w, nb=nb).forward(model.model_input.cpu())
+    res["test_err"] = float((model.fake_H.cpu() - ref).abs().max())
+    data = {"LR": lr, "Z": 0.5 * z}
+    model.feed_data(data, need_HR=False); model.test()
+    zo = Z_optimization.Z_optimizer(objective="TV", Z_size=[48, 40], model=model, Z_range=1.0, max_iters=3, data=data, initial_LR=0.1, batch_size=1)
+    zo.optimize()
+    res["tv_losses"] = [float(v) for v in zo.loss_values]
+    res["zopt_class"] = type(zo).__module__
+else:
+    try:
+        model.test()
+        res["cpu_raises"] = False
+    except Exception as e:
+        res["cpu_raises"] = type(e).__name__
+print("RESULT " + json.dumps(res))
+'''
+
+
+def _run(gpu, nb):
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("reference tree not available (neither /root/reference nor oracle/_ref)")
+    p = subprocess.run([sys.executable, "-c", SCRIPT % dict(root=ROOT, gpu=gpu, nb=nb)], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + "\n" + p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[len("RESULT "):]), ref_shims.REF_ROOT
+
+
+def _check_common(res, ref_root):
+    compat = os.path.join(ROOT, "explorable-super-resolution_old_b200", "compat")
+    assert res["networks_file"].startswith(compat)
+    for k in ("srragan_file", "base_model_file", "loss_file"):          # the reference's own files, not shims
+        assert os.path.realpath(res[k]).startswith(os.path.realpath(ref_root)), (k, res[k])
+    assert res["has_define_D"]
+    assert res["model_class"] == "models.SRRaGAN_model.SRRaGANModel"
+    assert res["netG_class"].endswith("cem.CEM_PyTorch") and res["gen_class"].endswith("rrdbnet.RRDBNet")
+    assert res["weights_loaded"], "the reference's positional checkpoint loader did not fill the B200 generator"
+    assert res["model_input"] == [1, 51, 12, 10]
+    assert res["state"][1:] == [False, 3, 7]
+
+
+def test_reference_model_constructs_on_compat_cpu():
+    res, ref_root = _run(gpu=False, nb=23)
+    _check_common(res, ref_root)
+    assert res["state"][0] == "cpu"
+    assert res["cpu_raises"] == "EsrError", "no CPU fallback: model.test() on CPU must raise (got %r)" % res["cpu_raises"]
+
+
+@pytest.mark.gpu
+def test_reference_model_runs_on_b200(cuda_device):
+    """model.test() and Z_optimizer('TV') of the reference's SRRaGANModel through this package's kernels."""
+    res, ref_root = _run(gpu=True, nb=2)
+    _check_common(res, ref_root)
+    assert res["state"][0] == "cuda"
+    assert res["test_err"] <= 1e-2
+    assert res["zopt_class"].endswith("z_optimization") and len(res["tv_losses"]) == 3 and res["tv_losses"][-1] < res["tv_losses"][0]

@@ -85,3 +85,30 @@ def test_graph_replay_matches_eager(cuda_device):
         # and with it the last bits, varies from run to run (eager included)
         assert (ge - gg).abs().max().item() <= 1e-5 * ge.abs().max().item()
     assert not torch.equal(res["graph"][0][0], res["graph"][1][0])
+
+
+def test_config3_size_output_and_gradient_match_reference(golden, cuda_device):
+    """BASELINE config 3 at its own size (1x3x256x256 LR, nb = 23, eval mode): output and dL/dZ against windows of
+    the unmodified reference's result (tests/golden/cfg3.npz, oracle/gen_golden.py: gen_cfg3), plus whole-tensor
+    norms.  Tolerances: PSNR >= 50 dB / max error <= 1e-2 on the output (north_star), relative error < 5 % and cosine
+    > 0.999 on the gradient (bf16 dgrad operands through 351 layers)."""
+    g = golden("cfg3")
+    nb, wseed, seed, h, w = [int(v) for v in g["cfg"]]
+    wts = synth.make_weights("default", seed=wseed, nb=nb)
+    lr, z = synth.make_inputs(1, h, w, seed=seed)
+    netG = build_product_G(cuda_device, nb, "all_layers_HR_downscaled", wts)
+    zp = z.clone().to(cuda_device).requires_grad_(True)
+    out = netG(concat_latent(lr.to(cuda_device), zp))
+    gout = torch.from_numpy(np.random.default_rng(seed).standard_normal(tuple(out.shape)).astype(np.float32))
+    (out * gout.to(cuda_device)).sum().backward()
+    o, gz = out.detach().cpu(), zp.grad.cpu()
+    assert abs(float(o.double().norm()) / float(g["out_norm"]) - 1) < 1e-3
+    assert abs(float(gz.double().norm()) / float(g["gz_norm"]) - 1) < 5e-2
+    from tests.helpers import psnr
+    for k, (y0, x0) in enumerate([(0, 0), (464, 464), (928, 928), (0, 928)]):
+        ro, rg = torch.from_numpy(g["out_%d" % k]), torch.from_numpy(g["gz_%d" % k])
+        wo, wg = o[0, :, y0:y0 + 96, x0:x0 + 96], gz[0, :, y0:y0 + 96, x0:x0 + 96]
+        assert (wo - ro).abs().max().item() <= 1e-2 and psnr(wo, ro) >= 50.0, "output window %d" % k
+        rel = _rel(wg, rg)
+        cos = float((wg * rg).sum() / (wg.norm() * rg.norm()))
+        assert rel < 5e-2 and cos > 0.999, "gradient window %d: relative error %g, cosine %g" % (k, rel, cos)

@@ -148,15 +148,20 @@ def test_batch_shards_are_bit_identical(cuda_device):
             assert torch.equal(one[0], full[i])
 
 
-@pytest.mark.parametrize("B,h,w,chunk", [(1, 16, 20, 0), (8, 30, 41, 4), (6, 24, 70, 2), (3, 52, 33, 1)])
-def test_fused_growth_convs_bit_identical_to_separate_launches(cuda_device, monkeypatch, B, h, w, chunk):
+@pytest.mark.parametrize("B,h,w,chunk,train", [(1, 16, 20, 0, False), (8, 30, 41, 4, False), (6, 24, 70, 2, False),
+                                               (3, 52, 33, 1, False),
+                                               # unpadded (train-mode) plans with one tile column / one tile pair per
+                                               # chunk: the sizes the round-1 fused launch faulted on (divisor-1 magic)
+                                               (1, 12, 14, 0, True), (1, 22, 24, 0, True), (1, 33, 35, 0, True),
+                                               (2, 8, 8, 1, True), (1, 4, 30, 0, True)])
+def test_fused_growth_convs_bit_identical_to_separate_launches(cuda_device, monkeypatch, B, h, w, chunk, train):
     """conv 0..3 of every RDB as ONE persistent launch with tile-level dependencies (esr_rdb_growth_tc) against the
     same convs as four launches: several chunks, several tiles per cluster, odd tile counts; run twice (the flag
     thirds rotate and are cleared by the launches themselves)."""
     wts = synth.make_weights("default", seed=5, nb=2)
     lr, z = synth.make_inputs(B, h, w, seed=5)
     mi = concat_latent(lr, z).to(cuda_device)
-    netG = build_product_G(cuda_device, 2, "all_layers_HR_downscaled", wts)
+    netG = build_product_G(cuda_device, 2, "all_layers_HR_downscaled", wts, train=train)
     G = netG.generated_image_model
     monkeypatch.setenv("ESR_RDB_CHUNK", str(chunk))
     monkeypatch.setenv("ESR_FUSE_RDB", "1")

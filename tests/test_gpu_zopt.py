@@ -54,3 +54,58 @@ def test_unbuilt_objective_is_loud(cuda_device):
     netG, model, data = _setup(cuda_device, train_mode=False)
     with pytest.raises(NotImplementedError):
         Z_optimizer(objective="hist", Z_size=[32, 32], model=model, Z_range=1.0, max_iters=4, data=data, initial_LR=0.1)
+
+
+# ------------------------------------------------------------------ more of the reference's Z_optimizer (zopt2.npz)
+def _masks(h4, w4):
+    """Same deterministic masks as oracle/gen_golden.py: zopt2_masks."""
+    im = np.zeros((h4, w4), dtype=np.float32)
+    im[h4 // 4:3 * h4 // 4, w4 // 8:5 * w4 // 8] = 1
+    zm = np.zeros((h4, w4), dtype=np.float32)
+    zm[h4 // 8:7 * h4 // 8, :3 * w4 // 4] = 1
+    return im, zm
+
+
+ZOPT2 = [("max_std", "max_STD", 4, False, 1), ("min_std", "min_STD", 3, False, 1), ("std_increase", "STD_increase", 4, False, 1),
+         ("std_decrease_mult", "STD_decrease", 3, False, 1), ("tv_converge", "TV", -3, False, 1), ("tv_masked", "TV", 4, True, 1),
+         ("tv_batch2", "TV", 3, False, 2)]
+
+
+@pytest.mark.parametrize("name,objective,max_iters,masked,bs", ZOPT2)
+def test_more_objectives_and_modes_match_reference(golden, cuda_device, name, objective, max_iters, masked, bs):
+    """STD objectives (Z_optimization.py:426-435, :603-607), the convergence mode (max_iters < 0, :564-571), image / Z
+    masks (:347-355, :300-303) and batch_size 2 against trajectories recorded from the reference's own Z_optimizer."""
+    g = golden("zopt2")
+    dev = cuda_device
+    wts = synth.make_weights("default", seed=5, nb=2)
+    netG = build_product_G(dev, 2, "all_layers_HR_downscaled", wts, train=False)
+    lr, z0 = synth.make_inputs(1, 8, 8, seed=5)
+    model = SRModelShim(netG)
+    data = {"LR": lr.repeat(bs, 1, 1, 1).to(dev), "Z": (0.5 * z0).repeat(bs, 1, 1, 1).to(dev)}
+    if "increase" in objective or "decrease" in objective:
+        data["STD_increment"] = None if name.endswith("_mult") else 0.02
+    model.feed_data(data)
+    with torch.no_grad():
+        model.fake_H = netG(model.model_input)
+    kw = {}
+    if masked:
+        im, zm = _masks(32, 32)
+        kw = dict(image_mask=im, Z_mask=zm, initial_Z=(0.5 * z0).to(dev))
+    opt = Z_optimizer(objective=objective, Z_size=[32, 32], model=model, Z_range=1.0, max_iters=max_iters, data=data,
+                      initial_LR=0.1, batch_size=bs, **kw)
+    np.testing.assert_allclose(opt.initial_STD.cpu().numpy(), g[name + "_initial_STD"], rtol=2e-3)
+    if bs > 1:
+        opt.random_Z_inits = False
+        opt.Z_model.Z.data.copy_(torch.from_numpy(g[name + "_Zinit"]).to(dev))
+    Z = opt.optimize()
+    ref = g[name + "_loss"]
+    assert len(opt.loss_values) == len(ref), "stop rule: %d iterations, the reference ran %d" % (len(opt.loss_values), len(ref))
+    # squared STD differences are tiny numbers formed by cancellation: looser relative bound there
+    rtol = 3e-2 if ("increase" in objective or "decrease" in objective) else 3e-3
+    np.testing.assert_allclose(np.array(opt.loss_values), ref, rtol=rtol)
+    np.testing.assert_allclose(np.array(opt.latest_Z_loss_values), g[name + "_latest"], rtol=rtol)
+    assert opt.cur_iter == int(g[name + "_cur_iter"])
+    assert float((Z.cpu() - torch.from_numpy(g[name + "_Z"])).abs().mean()) < 2e-2
+    if masked:           # outside the Z mask the control signal must stay what it was (Optimizable_Z's mask blend)
+        keep = torch.from_numpy(1 - _masks(32, 32)[1]).bool()
+        assert float((Z.cpu()[0, :, keep] - (0.5 * z0)[0, :, keep]).abs().max()) < 1e-5
