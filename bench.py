@@ -2,11 +2,14 @@
 """Benchmark of the RRDBNet(+Z) -> CEM hot path (BASELINE.json metric: x4 SR output Mpix/s).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores (oracle port)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own modules on the host cores
+  python bench.py --scaling strong ...                     # config 2 as BASELINE states it: ONE batch of 16 split over the ranks
 
 One "step" = one G+CEM forward over a batch of 16 synthetic 3x128x128 LR images + random Z in eval mode
 (CEM pre-pad by 10 px), BASELINE config 2.  N > 1: one process per GPU (torchrun), every rank runs its own
-batch of 16 (batch sharding, no data-path collective: images are independent), scaling = weak.
+batch of 16 (batch sharding, no data-path collective: images are independent), scaling = weak; the same line carries
+a "strong" object (the one batch of 16 split 16/N per rank, timed in the same run) and --scaling strong makes that the
+headline value.
 """
 import argparse
 import contextlib
@@ -73,19 +76,39 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def oracle_step_seconds(n_images, h, w, threads):
-    """Reference algorithm (CPU oracle, fp32) on `n_images` images of the workload; returns seconds."""
+def reference_forward_fn(n_images, h, w, threads):
+    """(callable running one forward of the workload over n_images images on the host cores, kind).  kind "reference":
+    the UNMODIFIED reference's own define_G -> CEM_PyTorch(RRDBNet) modules (from /root/reference in the build
+    container, from the vendored oracle/_ref on the GPU box); "port": the oracle restatement, when neither exists."""
     from esr_b200 import synth
+    from oracle import ref_shims
     from oracle.cem_ops import concat_latent
-    from oracle.rrdbnet import GCEMOracle
     torch.set_num_threads(threads)
-    wts = synth.make_weights("default", seed=0)
     lr, z = synth.make_inputs(n_images, h, w, seed=0)
-    net = GCEMOracle(wts)
     mi = concat_latent(lr, z)
+    if ref_shims.available() and os.environ.get("ESR_BENCH_REF_PORT", "0") != "1":
+        import contextlib as _c, io as _io
+        with _c.redirect_stdout(_io.StringIO()):
+            CEMnet, networks, _, _ = ref_shims.load_reference()
+            netG, _ = ref_shims.build_ref_G(CEMnet, networks, 23, "all_layers", "default", 0)
+        netG.train(False)                                          # eval: CEM pre-pads by 10 px (CEMnet.py:192-194)
+
+        def fwd():
+            with torch.no_grad():
+                return netG(mi)
+        return fwd, "reference"
+    from oracle.rrdbnet import GCEMOracle
+    net = GCEMOracle(synth.make_weights("default", seed=0))
+
+    def fwd_port():
+        with torch.no_grad():
+            return net.forward(mi)
+    return fwd_port, "port"
+
+
+def timed(fn):
     t0 = time.perf_counter()
-    with torch.no_grad():
-        net.forward(mi)
+    fn()
     return time.perf_counter() - t0
 
 
@@ -133,26 +156,181 @@ def cem_standalone(dev, pk):
             "traffic": conv_traffic("cem_cfg4_dram_bytes")}
 
 
+def workload_config(world, per_rank, graph=True, sub=None, nstreams=1):
+    return {"workload": WORKLOAD, "global_batch": per_rank * world, "parallelism": "batch shard x%d" % world,
+            "l2": "per-step working set (~4.5 GB of activations) >> 126 MB L2, no flush needed",
+            "cuda_graph": graph, "images_per_pass": sub if sub is not None else per_rank, "passes_in_flight": nstreams}
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path on this box's host cores, all threads.  One step = a bounded
+    sample of the workload (REF_SAMPLE of its 16 images, same image size / mode), so that --steps K --warmup W ends
+    within minutes; `steps` and `ms_per_step` are what was really run and timed, `value` the sample's throughput."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_img = 4
-    for _ in range(max(args.warmup, 0) and 1):
-        oracle_step_seconds(n_img, 32, 32, cores)            # warm the thread pool / allocator, small
-    times = [oracle_step_seconds(n_img, LR_H, LR_W, cores) for _ in range(max(1, min(args.steps, 3)))]
-    t = min(times)
+    n_img = int(os.environ.get("ESR_BENCH_REF_IMAGES", 1))
+    fwd, kind = reference_forward_fn(n_img, LR_H, LR_W, cores)
+    budget = float(os.environ.get("ESR_BENCH_REF_BUDGET_S", 150))
+    t_first = timed(fwd)                                            # also the warm-up (thread pool, allocator)
+    warm = max(0, min(args.warmup, int(budget * 0.2 / max(t_first, 1e-3))) - 1)
+    for _ in range(warm):
+        fwd()
+    steps = max(1, min(args.steps, int(budget * 0.8 / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fwd()
+    t = (time.perf_counter() - t0) / steps
     mpix = n_img * SF * SF * LR_H * LR_W / 1e6 / t
-    sample = "%d of %d images of the batch per step (3x%dx%d LR each, eval/pre-pad), best of %d" % (
-        n_img, BATCH, LR_H, LR_W, len(times))
+    sample = "%d of the %d images of the batch per step (3x%dx%d LR each, eval/pre-pad, fp32), %d steps timed after %d warm-up " \
+             "passes, %s" % (n_img, BATCH, LR_H, LR_W, steps, warm + 1,
+                             "the reference's own nn.Modules" if kind == "reference" else "oracle port (reference tree absent)")
     line = {"impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3 * BATCH / n_img,
+            "steps": steps, "warmup": warm + 1, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": dict(workload_config(1, BATCH), sample_images_per_step=n_img),
+            "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+class StepRunner:
+    """G+CEM forward of `per_rank` resident images through the recorded launch sequence (inputs already in HBM)."""
+
+    def __init__(self, netG, dev, per_rank, seed, use_graph=True):
+        from esr_b200 import _capi as capi, synth
+        self.capi, self.netG, self.G, self.dev, self.n = capi, netG, netG.generated_image_model, dev, per_rank
+        lr, z = synth.make_inputs(per_rank, LR_H, LR_W, seed=seed)
+        self.host_in = torch.cat([z.contiguous().view(per_rank, 16 * 3, LR_H, LR_W), lr], 1).contiguous().pin_memory()
+        self.x_dev = self.host_in.to(dev)
+        self.host_out = torch.empty(per_rank, 3, SF * LR_H, SF * LR_W).pin_memory()
+        self.SUB = min(int(os.environ.get("ESR_SUBBATCH", per_rank)), per_rank)     # images per pass through the layers
+        self.NSTREAMS = int(os.environ.get("ESR_STREAMS", 1))                       # sub-batches in flight
+        assert per_rank % self.SUB == 0 and (per_rank // self.SUB) % self.NSTREAMS == 0
+        self.plans = [self.G.plan(self.SUB, LR_H, LR_W, MARGIN, keep=False, slot=i) for i in range(self.NSTREAMS)]
+        plan = self.plans[0]
+        self.filters = netG._filters
+        self.out_dev = torch.empty(per_rank, 3, SF * LR_H, SF * LR_W, device=dev)
+        self.wss = [torch.empty(2 * self.SUB * 3 * plan.hp * plan.wp, device=dev) for _ in range(self.NSTREAMS)]
+        self.side = [torch.cuda.Stream() for _ in range(self.NSTREAMS)] if self.NSTREAMS > 1 else []
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self.H4, self.W4 = SF * plan.hp, SF * plan.wp
+        self.launches_per_fwd = plan.launches_per_forward(with_cem=True)
+        self.graph = self.conv_graph = None
+        for _ in range(3):
+            self.step()
+        torch.cuda.synchronize()
+        self.step(record=True)                       # per-phase split (untimed iteration)
+        torch.cuda.synchronize()
+        ev = self.ev
+        self.phases = {"prep": ev[0].elapsed_time(ev[1]), "convs": ev[1].elapsed_time(ev[2]), "cem": ev[2].elapsed_time(ev[3])}
+        if use_graph:
+            self.graph = self._capture(self.step)
+            self.conv_graph = self._capture(self.convs_only)
+        self.run = self.graph.replay if self.graph is not None else self.step
+        self.conv_run = self.conv_graph.replay if self.conv_graph is not None else self.convs_only
+
+    def _capture(self, fn):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        for _ in range(2):
+            g.replay()
+        return g
+
+    def convs_only(self):
+        for i in range(self.n // self.SUB):
+            self.plans[i % self.NSTREAMS].run_convs()
+
+    def step(self, record=False):
+        capi, l, ev = self.capi, self.capi.lib(), self.ev
+        main = torch.cuda.current_stream()
+        for s_ in self.side:
+            s_.wait_stream(main)
+        for k, i0 in enumerate(range(0, self.n, self.SUB)):
+            first = i0 == 0
+            pl, w_ = self.plans[k % self.NSTREAMS], self.wss[k % self.NSTREAMS]
+            with torch.cuda.stream(self.side[k % self.NSTREAMS]) if self.side else contextlib.nullcontext():
+                if record and first:
+                    ev[0].record()
+                pl.run_prep(self.x_dev[i0:i0 + self.SUB])
+                if record and first:
+                    ev[1].record()
+                pl.run_convs()
+                if record and first:
+                    ev[2].record()
+                capi.check(l.esr_cem_project(self.filters, capi.ptr(pl.y), capi.ptr(pl.lr_pad), self.SUB, 3, self.H4, self.W4,
+                                             SF * MARGIN, capi.ptr(self.out_dev[i0:i0 + self.SUB]), capi.ptr(w_), capi.stream_ptr()))
+                if record and first:
+                    ev[3].record()
+        for s_ in self.side:
+            main.wait_stream(s_)
+
+    def timed_steps(self, steps, barrier):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.run()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps
+
+    def conv_share(self, rounds):
+        """Share of the step spent in the 351 conv launches: step and conv-only graphs replayed ALTERNATELY in one
+        window (same clocks, same thermal state), each replay bracketed by events; returns sum(conv) / sum(step)."""
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(rounds)]
+        for a, b, c in evs:
+            a.record()
+            self.run()
+            b.record()
+            self.conv_run()
+            c.record()
+        torch.cuda.synchronize()
+        ts, tc = sum(a.elapsed_time(b) for a, b, _ in evs), sum(b.elapsed_time(c) for _, b, c in evs)
+        return tc / ts, ts / rounds, tc / rounds
+
+    def release(self):
+        self.graph = self.conv_graph = self.plans = self.wss = self.out_dev = None
+        self.G._plans.clear()
+        torch.cuda.empty_cache()
+
+
+def config1_latency(netG, dev):
+    """BASELINE config 1 (1x3x64x64 LR, eval/pre-pad) as a latency: one CUDA-graph replay of the whole forward, L2 warm,
+    median of 20 (361 launches for 0.16 ms of ideal math - a launch-overhead measurement)."""
+    from esr_b200 import synth
+    from esr_b200.rrdbnet import capture_inference
+    lr, z = synth.make_inputs(1, 64, 64, seed=1)
+    x = torch.cat([z.contiguous().view(1, 48, 64, 64), lr], 1).contiguous().to(dev)
+    G = netG.generated_image_model
+    graph, out = capture_inference(G, x, MARGIN, netG._filters, slot=7)
+    for _ in range(3):
+        graph.replay()
+    ts = []
+    for _ in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    t = sorted(ts)[len(ts) // 2]
+    plan = G.plan(1, 64, 64, MARGIN, keep=False, slot=7)
+    n_launch = plan.launches_per_forward(with_cem=True)
+    flops = G.engine().flops_per_lr_pixel() * (64 + 2 * MARGIN) ** 2
+    res = {"config": "1x3x64x64 LR + Z, eval/pre-pad (BASELINE config 1), CUDA-graph replay", "latency_us": t * 1e3,
+           "launches": n_launch, "us_per_launch": t * 1e3 / n_launch, "output_mpix_per_s": 16 * 64 * 64 / 1e6 / (t * 1e-3),
+           "algorithmic_tflops": flops / (t * 1e-3) / 1e12}
+    del graph
+    G._plans.clear()
+    return res
 
 
 def main():
@@ -161,6 +339,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 16 images per rank (default); strong: BASELINE config 2's one batch of 16 split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-zopt", action="store_true")
@@ -176,6 +356,7 @@ def main():
     torch.cuda.set_device(dev)
 
     from esr_b200 import _capi as capi, cem as pcem, networks, synth
+    from esr_b200.parallel import shard_range
     capi.lib()                                                # fail loudly if the extension is missing
     opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 256}},
            "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input=os.environ.get("ESR_BENCH_LATENT", "all_layers"),
@@ -191,47 +372,6 @@ def main():
     for p in netG.parameters():
         p.requires_grad_(False)
     G = netG.generated_image_model
-    lr, z = synth.make_inputs(BATCH, LR_H, LR_W, seed=rank)
-    host_in = torch.cat([z.contiguous().view(BATCH, 16 * 3, LR_H, LR_W), lr], 1).contiguous().pin_memory()
-    x_dev = host_in.to(dev)
-    host_out = torch.empty(BATCH, 3, SF * LR_H, SF * LR_W).pin_memory()
-
-    SUB = int(os.environ.get("ESR_SUBBATCH", BATCH))       # images per pass through the layer sequence
-    NSTREAMS = int(os.environ.get("ESR_STREAMS", 1))        # sub-batches in flight (each on its own stream / buffers)
-    assert BATCH % SUB == 0 and (BATCH // SUB) % NSTREAMS == 0
-    plans = [G.plan(SUB, LR_H, LR_W, MARGIN, keep=False, slot=i) for i in range(NSTREAMS)]
-    plan = plans[0]
-    filters = netG._filters
-    out_dev = torch.empty(BATCH, 3, SF * LR_H, SF * LR_W, device=dev)
-    wss = [torch.empty(2 * SUB * 3 * plan.hp * plan.wp, device=dev) for _ in range(NSTREAMS)]
-    ws = wss[0]
-    side = [torch.cuda.Stream() for _ in range(NSTREAMS)] if NSTREAMS > 1 else []
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    H4, W4 = SF * plan.hp, SF * plan.wp
-
-    def step(record=False):
-        l = capi.lib()
-        main = torch.cuda.current_stream()
-        for s_ in side:
-            s_.wait_stream(main)
-        for k, i0 in enumerate(range(0, BATCH, SUB)):
-            first = i0 == 0
-            pl, w_ = plans[k % NSTREAMS], wss[k % NSTREAMS]
-            with torch.cuda.stream(side[k % NSTREAMS]) if side else contextlib.nullcontext():
-                if record and first:
-                    ev[0].record()
-                pl.run_prep(x_dev[i0:i0 + SUB])
-                if record and first:
-                    ev[1].record()
-                pl.run_convs()
-                if record and first:
-                    ev[2].record()
-                capi.check(l.esr_cem_project(filters, capi.ptr(pl.y), capi.ptr(pl.lr_pad), SUB, 3, H4, W4, SF * MARGIN,
-                                             capi.ptr(out_dev[i0:i0 + SUB]), capi.ptr(w_), capi.stream_ptr()))
-                if record and first:
-                    ev[3].record()
-        for s_ in side:
-            main.wait_stream(s_)
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,67 +379,35 @@ def main():
             torch.distributed.barrier()
             torch.cuda.synchronize()
 
-    launches_per_fwd = plan.launches_per_forward(with_cem=True)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    # per-phase split (untimed iteration) for the roofline of the dominant kernel
-    step(record=True)
-    torch.cuda.synchronize()
-    t_prep, t_conv, t_cem = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
 
-    graph = None
-    if not args.no_graph:
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            step()
-        torch.cuda.current_stream().wait_stream(s)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step()
-        for _ in range(2):
-            graph.replay()
-    run = graph.replay if graph is not None else step
+    strong_n = shard_range(BATCH, rank, world)
+    strong_n = strong_n[1] - strong_n[0]                       # images of the ONE batch of 16 that this rank owns
+    per_rank = BATCH if args.scaling == "weak" else strong_n
+    assert per_rank >= 1, "more ranks than images"
+    warmup = max(args.warmup, 3)
 
+    runner = StepRunner(netG, dev, per_rank, seed=rank, use_graph=not args.no_graph)
+    for _ in range(warmup):
+        runner.run()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        run()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    # conv-only timing in the same regime as the step (CUDA-graph replay of the recorded conv sequence, events)
-    def convs_only():
-        for _i in range(BATCH // SUB):
-            plans[_i % NSTREAMS].run_convs()
-    conv_run = convs_only
-    if graph is not None:
-        cg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cg):
-            convs_only()
-        conv_run = cg.replay
-    for _ in range(2):
-        conv_run()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for _ in range(args.steps):
-        conv_run()
-    c1.record()
-    torch.cuda.synchronize()
-    conv_ms = c0.elapsed_time(c1) / args.steps
+    ms = runner.timed_steps(args.steps, barrier)
+    share, _, _ = runner.conv_share(max(5, min(args.steps, 20)))
+    conv_ms = ms * share
 
     # end to end through the public module API with host buffers: netG(...) on pinned host input, result copied
-    # back to pinned host memory; parallel.HostPipeline overlaps the PCIe copies of one half batch with the
-    # other half's compute (both copies of every step are inside the timed region)
+    # back to pinned host memory; parallel.HostPipeline overlaps the PCIe copies with compute (both copies of every step
+    # are inside the timed region)
     from esr_b200.parallel import HostPipeline
     pipe = HostPipeline(netG, chunk=int(os.environ.get("ESR_E2E_CHUNK", BATCH)))
 
     def e2e_step():
-        pipe(host_in, host_out)
+        pipe(runner.host_in, runner.host_out)
     for _ in range(max(args.warmup, 4)):                      # the caching allocator settles after a few calls
         e2e_step()
     pipe.wait()
@@ -315,14 +423,54 @@ def main():
     e2e_ms = f0.elapsed_time(f1) / n_e2e
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    h2d, d2h = runner.host_in.numel() * 4, runner.host_out.numel() * 4
+    launches_per_fwd, SUB, NSTREAMS, phases = runner.launches_per_fwd, runner.SUB, runner.NSTREAMS, runner.phases
+    graph_used = runner.graph is not None
+    del pipe
+    runner.release()
+
+    # BASELINE config 2 exactly as stated: the ONE batch of 16 images split over the ranks (16 / 8 / 4 / 2 per rank)
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        r2 = StepRunner(netG, dev, strong_n, seed=100 + rank, use_graph=not args.no_graph)
+        for _ in range(warmup):
+            r2.run()
+        s_ms = r2.timed_steps(args.steps, barrier)
+        r2.release()
+        s_ms, = max_over_ranks([s_ms])
+        strong = {"value": BATCH * SF * SF * LR_H * LR_W / 1e6 / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms,
+                  "images_per_rank": strong_n, "global_batch": BATCH, "scaling": "strong",
+                  "note": "BASELINE config 2's single batch of 16 split over the ranks, no data-path collective"}
+
+    # One config-3-sized image (1x3x256x256 LR) across the ranks by halo-overlapped tiles (parallel.run_tiled, halo 16)
+    tiled = None
+    if not args.no_zopt:
+        from esr_b200.parallel import run_tiled
+        grid = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
+        lr_t, z_t = synth.make_inputs(1, 256, 256, seed=5)
+        mi_t = torch.cat([z_t.contiguous().view(1, 48, 256, 256), lr_t], 1).contiguous().to(dev)
+        for _ in range(3):
+            run_tiled(netG, mi_t, tiles=grid, halo=16)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_t = 5
+        t0e.record()
+        for _ in range(n_t):
+            run_tiled(netG, mi_t, tiles=grid, halo=16)
+        t1e.record()
+        barrier()
+        t_ms, = max_over_ranks([t0e.elapsed_time(t1e) / n_t])
+        tiled = {"config": "1x3x256x256 LR + Z, eval/pre-pad, %d x %d tiles with a 16 px halo over %d rank(s), outputs "
+                           "all-gathered (module call per rank, not graph-captured)" % (grid[0], grid[1], world),
+                 "ms": t_ms, "output_mpix_per_s": 16 * 256 * 256 / 1e6 / (t_ms * 1e-3)}
+        del mi_t
+        G._plans.clear()
+        torch.cuda.empty_cache()
 
     # BASELINE config 3: Z optimisation, 1x3x256x256 LR, objective 'TV', Adam lr 0.1 (rank 0 only, bounded)
     zopt = None
     if rank == 0 and not args.no_zopt:
         from esr_b200.z_optimization import Z_optimizer, SRModelShim
-        del plan, plans, out_dev, ws, wss
-        G._plans.clear()
-        torch.cuda.empty_cache()
         zh = 256
         lr3, z3 = synth.make_inputs(1, zh, zh, seed=3)
         model = SRModelShim(netG)
@@ -349,46 +497,60 @@ def main():
         zopt = {"config": "1x3x256x256 LR, objective TV, Adam lr 0.1, eval/pre-pad (BASELINE config 3)",
                 "iters_per_s": 1e3 / z_ms, "ms_per_iter": z_ms, "iters_timed": n_it, "loss_first_last": [zo.loss_values[0], zo.loss_values[-1]],
                 "algorithmic_tflops": zflops / (z_ms * 1e-3) / 1e12}
+        del zo, model
+        G._plans.clear()
+        G._bplans.clear()
+        torch.cuda.empty_cache()
 
-    t = torch.tensor([ms, e2e_ms, conv_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, e2e_ms, conv_ms = [float(v) for v in t.cpu()]
-    out_mpix = BATCH * SF * SF * LR_H * LR_W / 1e6
+    ms, e2e_ms, conv_ms = max_over_ranks([ms, e2e_ms, conv_ms])
+    n_total = per_rank * world if args.scaling == "weak" else BATCH
+    out_mpix = n_total * SF * SF * LR_H * LR_W / 1e6              # whole job, all ranks
     pk = peaks()
-    flops = G.engine().flops_per_lr_pixel() * BATCH * (LR_H + 2 * MARGIN) * (LR_W + 2 * MARGIN)
+    flops = G.engine().flops_per_lr_pixel() * per_rank * (LR_H + 2 * MARGIN) * (LR_W + 2 * MARGIN)
     achieved = flops / (conv_ms * 1e-3) / 1e12
     line = {
-        "metric": METRIC, "value": world * out_mpix / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": out_mpix / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16 MMA operands, fp32 accumulate/trunk/CEM", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "batch shard x%d" % world,
-                   "l2": "per-step working set (~4.5 GB of activations) >> 126 MB L2, no flush needed",
-                   "cuda_graph": graph is not None, "images_per_pass": SUB, "passes_in_flight": NSTREAMS},
-        "e2e": {"value": world * out_mpix / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
-        "gpu_launches": args.steps * (BATCH // SUB) * launches_per_fwd,
+        "config": workload_config(world, per_rank if args.scaling == "weak" else BATCH // world, graph_used, SUB, NSTREAMS),
+        "e2e": {"value": out_mpix / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": args.steps * (per_rank // SUB) * launches_per_fwd,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16"], "traffic": conv_traffic(), "peak_source": pk["src"] + " sustained bf16",
-                     "kernel": "conv3x3 tcgen05 kernels: pair::conv3x3_tc2_kernel (cta_group::2) x350 + conv3x3_tc_kernel x1 "
-                               "= 351 launches/step, %.3f ms/step; algorithmic %.1f GFLOP/step; traffic = DRAM bytes of "
-                               "those 351 launches per step (ncu, profiles/)" % (conv_ms, flops / 1e9),
+                     "kernel": "conv3x3 tcgen05 kernels (pair::conv3x3_tc2_kernel / conv3x3_rdb_growth_kernel, cta_group::2, + "
+                               "conv3x3_tc_kernel for the last conv): %.3f ms of the %.3f ms step (share %.4f from step and "
+                               "conv-only graphs replayed alternately in one window); algorithmic %.1f GFLOP/step; traffic = DRAM "
+                               "bytes of those launches per step (ncu, profiles/)" % (conv_ms, ms, share, flops / 1e9),
                      "frac_of_burst_peak": achieved / pk["bf16_burst"]},
-        "phases_ms": {"prep": t_prep, "convs": t_conv, "cem": t_cem},
+        "phases_ms": phases,
         "clocks": sampler.summary(),
     }
+    if args.scaling == "strong":
+        line["config"]["global_batch"] = BATCH
+    if strong is not None:
+        line["strong"] = strong
+    if tiled is not None:
+        line["tiled"] = tiled
     if zopt is not None:
         line["zopt"] = zopt
     if rank == 0 and not args.no_zopt:
         line["cem_roofline"] = cem_standalone(dev, pk)
+        line["config1"] = config1_latency(netG, dev)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            oracle_step_seconds(1, 32, 32, cores)
-            tc = oracle_step_seconds(BATCH, LR_H, LR_W, cores)
-            line["cpu_baseline"] = {"value": BATCH * SF * SF * LR_H * LR_W / 1e6 / tc, "unit": UNIT, "cores": cores,
-                                    "kind": "port", "sample": "one full step: the 16 images (3x128x128 LR, eval/pre-pad) as one "
-                                                              "batch through the fp32 oracle port, 1 pass, %.1f s" % tc}
+            n_img = int(os.environ.get("ESR_BENCH_CPU_IMAGES", 8))
+            fwd, kind = reference_forward_fn(n_img, LR_H, LR_W, cores)
+            small, _ = reference_forward_fn(1, 32, 32, cores) if kind == "port" else (None, None)
+            if small is not None:
+                small()
+            tc = timed(fwd)
+            line["cpu_baseline"] = {"value": n_img * SF * SF * LR_H * LR_W / 1e6 / tc, "unit": UNIT, "cores": cores,
+                                    "kind": kind, "sample": "%d of the step's 16 images (3x128x128 LR, eval/pre-pad) as one batch "
+                                                            "through %s, fp32, 1 pass, %.1f s" % (
+                                                                n_img, "the reference's own modules (oracle/_ref)" if kind == "reference"
+                                                                else "the oracle port", tc)}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

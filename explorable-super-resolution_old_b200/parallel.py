@@ -119,3 +119,77 @@ class HostPipeline:
     def wait(self):
         if self._done is not None:
             self._done.synchronize()
+
+
+# ------------------------------------------------------------------------------------------ tile sharding (B = 1)
+def tile_windows(h, w, tiles_y, tiles_x, halo):
+    """Splits an h x w LR image into tiles_y x tiles_x output tiles and gives every tile an input window of ONE common
+    size that contains the tile plus at least `halo` LR pixels on every side that is not an image border (windows of
+    border tiles are shifted inwards instead of shrunk, so all windows can run as one batch).
+    Returns (win_h, win_w, [(y0, x0, oy0, oy1, ox0, ox1)]): window origin and the tile's rows / columns, LR pixels."""
+    assert tiles_y >= 1 and tiles_x >= 1 and halo >= 0
+    ys = [shard_range(h, i, tiles_y) for i in range(tiles_y)]
+    xs = [shard_range(w, i, tiles_x) for i in range(tiles_x)]
+    win_h = min(h, max(b - a for a, b in ys) + (2 * halo if tiles_y > 1 else 0))
+    win_w = min(w, max(b - a for a, b in xs) + (2 * halo if tiles_x > 1 else 0))
+    wins = []
+    for (a, b) in ys:
+        y0 = min(max(a - halo, 0), h - win_h)
+        assert (y0 <= a - halo or y0 == 0) and (y0 + win_h >= b + halo or y0 + win_h == h)
+        for (c, d) in xs:
+            x0 = min(max(c - halo, 0), w - win_w)
+            assert (x0 <= c - halo or x0 == 0) and (x0 + win_w >= d + halo or x0 + win_w == w)
+            wins.append((y0, x0, a, b, c, d))
+    return win_h, win_w, wins
+
+
+def run_tiled(netG, model_input, tiles, halo=16, sf=4, nz=3, gather=True):
+    """One large image across the ranks by halo-overlapped spatial tiles (BASELINE north_star "by batch or
+    image tiles (halo-overlapped, no NCCL needed for inference)").  The reference's own precedent is the GUI's crop to
+    the edited bounding box + 30 px (codes/GUI.py:1530-1544).
+
+    model_input: [1, 16*nz+3, h, w] packed [Z.view, LR] (SRRaGAN_model.py:249-255).  Every tile's window is cut out of the
+    un-viewed Z ([1,nz,4h,4w]) and of the LR image, re-packed, and this rank's windows run through netG as ONE batch;
+    each output is cropped to its tile and written into the [1,3,4h,4w] result.  Unlike batch sharding this is an
+    approximation: a pixel closer than the network's effective receptive field to a tile border sees replicate padding
+    instead of its true neighbours.  With a halo of 16 LR px the difference is below the parity tolerance for the
+    random-init weights of the tests (tests/test_gpu_net.py::test_tile_sharding_error_vs_halo); trained checkpoints
+    need their halo re-measured.  With gather=True every rank returns the full image (one all_gather of the 3-channel
+    tiles); otherwise tiles owned by other ranks are left zero."""
+    assert model_input.dim() == 4 and model_input.size(0) == 1, "run_tiled shards ONE image; use run_sharded for batches"
+    _, C, h, w = model_input.shape
+    assert C == nz * sf * sf + 3
+    tiles_y, tiles_x = tiles
+    win_h, win_w, wins = tile_windows(h, w, tiles_y, tiles_x, halo)
+    rank, world = (dist.get_rank(), dist.get_world_size()) if (dist.is_available() and dist.is_initialized()) else (0, 1)
+    lo, hi = shard_range(len(wins), rank, world)
+    z_hr = model_input[:, :nz * sf * sf].contiguous().view(1, nz, sf * h, sf * w) if nz else None
+    lr = model_input[:, -3:]
+    batch = []
+    for (y0, x0, *_r) in wins[lo:hi]:
+        parts = []
+        if nz:
+            zc = z_hr[:, :, sf * y0:sf * (y0 + win_h), sf * x0:sf * (x0 + win_w)].contiguous()
+            parts.append(zc.view(1, nz * sf * sf, win_h, win_w))
+        parts.append(lr[:, :, y0:y0 + win_h, x0:x0 + win_w])
+        batch.append(torch.cat(parts, 1))
+    mine = None
+    if batch:
+        with torch.no_grad():
+            mine = netG(torch.cat(batch, 0).contiguous())
+    per = max(b - a for a, b in [shard_range(len(wins), r, world) for r in range(world)])
+    if world > 1 and gather:
+        buf = model_input.new_zeros((per, 3, sf * win_h, sf * win_w))
+        if mine is not None:
+            buf[:mine.size(0)] = mine
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        outs = [(r, parts[r]) for r in range(world)]
+    else:
+        outs = [(rank, mine)] if mine is not None else []
+    full = model_input.new_zeros((1, 3, sf * h, sf * w))
+    for r, t in outs:
+        rlo, rhi = shard_range(len(wins), r, world)
+        for k, (y0, x0, a, b, c, d) in enumerate(wins[rlo:rhi]):
+            full[0, :, sf * a:sf * b, sf * c:sf * d] = t[k, :, sf * (a - y0):sf * (b - y0), sf * (c - x0):sf * (d - x0)]
+    return full

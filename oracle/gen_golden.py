@@ -19,25 +19,7 @@ from esr_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def make_opt(nb, latent_input, is_train=False, patch=256, sf=4):
-    return {"gpu_ids": None, "is_train": is_train, "datasets": {"train": {"patch_size": patch}},
-            "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input=latent_input,
-                              latent_input_domain="HR_downscaled", latent_channels=3, norm_type=None, mode="CNA",
-                              nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=sf)}
-
-
-def build_ref_G(CEMnet, networks, nb, latent_input, kind, seed, sf=4):
-    import CEM.imresize_CEM as im
-    im.imresize.kernels = {}
-    cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(sf))
-    netG = networks.define_G(make_opt(nb, latent_input, sf=sf), CEM=cem, num_latent_channels=0 if latent_input == "None" else 3)
-    li = None if latent_input == "None" else latent_input + "_HR_downscaled"
-    w = synth.make_weights(kind, seed=seed, nb=nb, latent_input=li, upscale=sf)
-    sd = netG.state_dict()
-    assert [k for k in sd if "Filter" not in k] == ["generated_image_model." + k for k in w]
-    sd.update({"generated_image_model." + k: v for k, v in w.items()})
-    netG.load_state_dict(sd)
-    return netG, cem
+make_opt, build_ref_G = ref_shims.make_opt, ref_shims.build_ref_G
 
 
 def aniso_kernel(n, theta, s1, s2, shift=(0.0, 0.0)):

@@ -95,3 +95,26 @@ def load_reference():
     if not torch.cuda.is_available():
         zopt.torch = _CpuDeviceTorch(torch)
     return CEMnet, networks, arch, zopt
+
+
+def make_opt(nb, latent_input, is_train=False, patch=256, sf=4):
+    return {"gpu_ids": None, "is_train": is_train, "datasets": {"train": {"patch_size": patch}},
+            "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input=latent_input,
+                              latent_input_domain="HR_downscaled", latent_channels=3, norm_type=None, mode="CNA",
+                              nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=sf)}
+
+
+def build_ref_G(CEMnet, networks, nb, latent_input, kind, seed, sf=4):
+    """The reference's define_G -> CEM_PyTorch(RRDBNet) on CPU with the synthetic weights of esr_b200.synth."""
+    import CEM.imresize_CEM as im
+    from esr_b200 import synth
+    im.imresize.kernels = {}
+    cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(sf))
+    netG = networks.define_G(make_opt(nb, latent_input, sf=sf), CEM=cem, num_latent_channels=0 if latent_input == "None" else 3)
+    li = None if latent_input == "None" else latent_input + "_HR_downscaled"
+    w = synth.make_weights(kind, seed=seed, nb=nb, latent_input=li, upscale=sf)
+    sd = netG.state_dict()
+    assert [k for k in sd if "Filter" not in k] == ["generated_image_model." + k for k in w]
+    sd.update({"generated_image_model." + k: v for k, v in w.items()})
+    netG.load_state_dict(sd)
+    return netG, cem

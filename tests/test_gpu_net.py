@@ -176,6 +176,31 @@ def test_fused_growth_convs_bit_identical_to_separate_launches(cuda_device, monk
         assert torch.equal(f, ref)
 
 
+def test_tile_sharding_error_vs_halo(cuda_device):
+    """parallel.run_tiled: a 1x3x96x96 image as 2 x 2 halo-overlapped tiles through the production net
+    against the same image run whole.  The error falls with the halo; at 16 LR px it is far below the parity
+    tolerance (the survey's fp32 probe: <= 1e-6; here bf16 activations can flip a rounding, hence 1e-3) and the
+    stitched image still meets PSNR >= 50 dB / 1e-2 against the fp32 oracle."""
+    from esr_b200.parallel import run_tiled
+    wts = synth.make_weights("default", seed=0)
+    lr, z = synth.make_inputs(1, 96, 96, seed=14)
+    mi = concat_latent(lr, z).to(cuda_device)
+    netG = build_product_G(cuda_device, 23, "all_layers_HR_downscaled", wts)
+    with torch.no_grad():
+        whole = netG(mi)
+    errs = {}
+    for halo in (2, 8, 16):
+        tiled = run_tiled(netG, mi, tiles=(2, 2), halo=halo)
+        assert tiled.shape == whole.shape
+        errs[halo] = (tiled - whole).abs().max().item()
+    assert errs[16] <= 1e-3 and errs[16] <= errs[2], errs
+    assert errs[2] > errs[16] or errs[2] < 1e-6, errs
+    with torch.no_grad():
+        ref = GCEMOracle(wts).forward(mi.cpu())
+    err, p = (tiled.cpu() - ref).abs().max().item(), psnr(tiled.cpu(), ref)
+    assert err <= 1e-2 and p >= 50.0, "max|err| %g, PSNR %.1f dB" % (err, p)
+
+
 def test_hilo_trunk_matches_fp32_trunk(cuda_device, monkeypatch):
     """ESR_TRUNK_HILO=1: the residual between the RDBs of an RRDB as a bf16 hi/lo pair (~17 significant bits)."""
     wts = synth.make_weights("default", seed=6, nb=2)
