@@ -91,6 +91,7 @@ def reference_forward_fn(n_images, h, w, threads):
         with _c.redirect_stdout(_io.StringIO()):
             CEMnet, networks, _, _ = ref_shims.load_reference()
             netG, _ = ref_shims.build_ref_G(CEMnet, networks, 23, "all_layers", "default", 0)
+        netG = netG.cpu().float()                                  # the reference builds its CEM filters on the GPU when one exists
         netG.train(False)                                          # eval: CEM pre-pads by 10 px (CEMnet.py:192-194)
 
         def fwd():

@@ -59,14 +59,14 @@ sd = G.state_dict()
 res["weights_loaded"] = all(torch.equal(sd["generated_image_model." + k].cpu(), v) for k, v in w.items())
 res["state"] = [model.device.type, bool(model.is_train), model.num_latent_channels, model.gradient_step_num]
 lr, z = synth.make_inputs(1, 12, 10, seed=9)
-model.feed_data({"LR": lr, "Z": z}, need_HR=False)
+model.feed_data({"LR": lr, "Z": z.to(model.device)}, need_HR=False)
 res["model_input"] = list(model.model_input.shape)
 if use_gpu:
     from oracle.rrdbnet import GCEMOracle
     model.test()
     ref = GCEMOracle(w, nb=nb).forward(model.model_input.cpu())
     res["test_err"] = float((model.fake_H.cpu() - ref).abs().max())
-    data = {"LR": lr, "Z": 0.5 * z}
+    data = {"LR": lr, "Z": (0.5 * z).to(model.device)}
     model.feed_data(data, need_HR=False); model.test()
     zo = Z_optimization.Z_optimizer(objective="TV", Z_size=[48, 40], model=model, Z_range=1.0, max_iters=3, data=data, initial_LR=0.1, batch_size=1)
     zo.optimize()

