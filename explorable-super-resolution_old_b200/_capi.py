@@ -113,6 +113,7 @@ SIGNATURES = {
     "esr_expand_rows_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32,
                                       _vp, _vp]),
     "esr_debug_set_profile_buffer": (None, [_vp]),
+    "esr_debug_cem_timeout": (C.c_int, [C.POINTER(C.c_uint32)]),
     "esr_grad_combine": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32,
                                    _i32, _i32, _f, _f, _vp, _i32, _i32, _i32, _vp]),
     "esr_g_input_prep": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

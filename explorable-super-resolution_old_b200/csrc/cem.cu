@@ -9,9 +9,14 @@
 //
 // All three filters of the default (bicubic) configuration are rank-1, so every operator
 // runs as a horizontal pass into shared memory followed by a vertical pass.
+#include <cuda.h>
+
+#include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "esr_common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace esr {
 
@@ -600,6 +605,489 @@ static CemTab make_tab(const esr_cem_filters& f) {
     return T;
 }
 
+// ===================================================================== x4 projection, round 2: TMA-fed streaming kernels
+// Same two-launch structure (Down, then K + Up + add as a programmatic dependent), same arithmetic as the kernels above,
+// but (a) every HR row of y reaches a warp through its own ring of TMA tile loads (cp.async.bulk.tensor, one
+// instruction per 4-row group issued by one lane, completion on an mbarrier) instead of 128 per-lane cp.async / LDG
+// with address arithmetic, eight groups (32 HR rows, 16 KiB per warp) in flight without costing registers;
+// (b) persistent CTAs, one per SM, that walk a list of equal work items sized by a cost model so that the last wave is
+// full (ncu on the round-1 kernels: SMs active 67 % / 79 % of the time - ramp, 3.08 blocks per SM, tail);
+// (c) structurally zero filter taps are skipped (16 of the 20 polyphase slots of the bicubic x4 kernel are non-zero)
+// and the rolling accumulator windows rotate by renaming (the row loop is unrolled by five) instead of register copies.
+// Border handling: TMA fills columns outside the image with zeros; the lanes holding such cells take the replicated
+// edge value from the lane that owns the edge cell (one shuffle per row, only in strips that touch a border); row
+// groups above / below the image are fetched as four single-row boxes at clamped coordinates.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+int num_sms_cached();
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+template <int V> using IC = std::integral_constant<int, V>;
+
+// A ring wait that never completes is a protocol bug.  Instead of trapping (which kills the context and says nothing)
+// the streaming kernels record where it happened and carry on with whatever is in the slot: the launch ends, results
+// are wrong, and esr_debug_cem_timeout() reports {code, block, warp, group}.
+__device__ unsigned int g_cem_timeout[4];
+__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity, unsigned code, unsigned n) {
+    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+        if (it > (1u << 20)) {
+            if (atomicCAS(&g_cem_timeout[0], 0u, code) == 0u) {
+                g_cem_timeout[1] = blockIdx.x; g_cem_timeout[2] = threadIdx.x; g_cem_timeout[3] = n;
+            }
+            return;
+        }
+    }
+}
+
+constexpr int kAW = 16;                         // Down: warps per CTA (each an independent streaming unit; with 8 the kernel was
+                                                // latency bound: issue slots 41 % busy, mostly "wait" stalls, ncu r02)
+constexpr int kAD = 4;                          // ring stages per warp, one 4-row group each (16 warps x 4 x 2 KiB in flight)
+constexpr int kAStage = 4 * 512 + 256;          // 4 HR rows x 32 cells x 16 B, then 36 x values of the LR row it completes (cells j0-4 ..:
+                                                // a TMA box must start on a 16-byte boundary, j0-2 does not)
+constexpr uint32_t kAXBytes = 36 * 4;
+constexpr uint32_t kAllTaps = 0xfffffu;
+
+struct Down4Args {
+    const float* x;
+    float* out;
+    int H, W, h, w;
+    int strips, nseg, seg, items;
+    int dbg;                                    // ESR_CEM_DBGA bisect bits: 1 no x TMA, 2 single-row boxes only, 4 no negative column start
+};
+
+// VMASK / HMASK: bit (p*5 + c) set <=> T.down_v[p][c] / T.down_h[p][c] may be non-zero (host checked)
+template <uint32_t VMASK, uint32_t HMASK>
+__global__ void __launch_bounds__(kAW * 32, 1)
+cem_down4s_kernel(const __grid_constant__ CUtensorMap tmY4, const __grid_constant__ CUtensorMap tmY1,
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CemTab T, const __grid_constant__ Down4Args A) {
+    extern __shared__ uint8_t sm_raw[];
+    uint8_t* sm = sm_raw + ((128u - (smem_u32(sm_raw) & 127u)) & 127u);     // 128-byte aligned, still a shared-space pointer
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform: the ring, item and
+                                                                                       // TMA operands live in uniform registers
+    uint8_t* ring = sm + warp * (kAD * kAStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kAW * kAD * kAStage) + warp * kAD;
+    if (lane == 0) {
+        for (int s = 0; s < kAD; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    pdl_launch_dependents();                                       // the K + Up launch may take the SMs this grid leaves
+    const int h = A.h, w = A.w, H = A.H;
+    uint32_t cnt = 0;                                              // groups consumed so far: stage = cnt % kAD, parity = (cnt / kAD) & 1
+    for (int item = blockIdx.x * kAW + warp; item < A.items; item += gridDim.x * kAW) {
+        const int strip = item % A.strips;
+        const int t = item / A.strips;
+        const int sg = t % A.nseg, plane = t / A.nseg;
+        const int j0 = strip * kStripCells, j = j0 - 2 + lane;
+        const int i0 = sg * A.seg, i1 = min(i0 + A.seg, h);
+        if (i0 >= h) continue;
+        const int ngroups = i1 - i0 + 4;                           // LR row groups i0-2 .. i1+1 feed rows i0 .. i1-1
+        const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w;
+        const bool edge_l = j0 == 0, edge_r = j0 + kStripCells + 2 > w;            // warp-uniform
+        const int lane_last = w - 1 - (j0 - 2);                                    // lane of the last cell (edge_r strips)
+        auto issue = [&](int n, uint32_t slot) {                                   // lane 0 only
+            const int I = i0 - 2 + n;
+            uint8_t* dst = ring + slot * kAStage;
+            const bool want_x = A.x != nullptr && I - 2 >= i0 && I - 2 < i1 && !(A.dbg & 1);
+            mbar_expect_tx(&bars[slot], 2048u + (want_x ? kAXBytes : 0u));
+            const int c0 = (A.dbg & 4) ? max(4 * (j0 - 2), 0) : 4 * (j0 - 2);
+            if (I >= 0 && I < h && !(A.dbg & 2)) {
+                tma_load_3d(dst, &tmY4, &bars[slot], c0, 4 * I, plane);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    tma_load_3d(dst + q * 512, &tmY1, &bars[slot], c0, min(max(4 * I + q, 0), H - 1), plane);
+            }
+            if (want_x) tma_load_3d(dst + 2048, &tmX, &bars[slot], j0 - 4, I - 2, plane);
+        };
+        if (elect_one()) {
+            const int npre = ngroups < kAD ? ngroups : kAD;
+            for (int n = 0; n < npre; ++n) issue(n, (cnt + n) % kAD);
+        }
+        float2 acc_lo[5], acc_hi[5];
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc_lo[m] = acc_hi[m] = make_float2(0.f, 0.f);
+        // group n of the item (LR row group I = i0-2+n); R = n % 5 is the rotation of the accumulator window:
+        // LR row I-2+m lives in slot (m + R) % 5
+        auto body = [&](auto Rc, int n) {
+            constexpr int R = decltype(Rc)::value;
+            const uint32_t g = cnt + n, slot = g % kAD;
+            ring_wait(&bars[slot], (g / kAD) & 1u, 1u, static_cast<unsigned>(n));
+            const uint8_t* st = ring + slot * kAStage;
+            float4 c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = reinterpret_cast<const float4*>(st + q * 512)[lane];
+            const float x_cur = reinterpret_cast<const float*>(st + 2048)[lane + 2];
+            __syncwarp();                                          // every lane has its values: the slot may be refilled
+            if (n + kAD < ngroups && elect_one()) issue(n + kAD, slot);
+            if (edge_l || edge_r) {                                // replicate the edge pixel into the cells outside the image
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float first = __shfl_sync(0xffffffffu, c[q].x, 2);
+                    const float last = __shfl_sync(0xffffffffu, c[q].w, lane_last & 31);
+                    if (j < 0) c[q] = make_float4(first, first, first, first);
+                    else if (j >= w) c[q] = make_float4(last, last, last, last);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {                      // row 4I+q feeds LR row I-2+m with table entry [q][4-m]
+                    if (!((VMASK >> (q * 5 + 4 - m)) & 1u)) continue;
+                    const float2 wv = T.down_v2[q][4 - m];
+                    acc_lo[(m + R) % 5] = __ffma2_rn(wv, make_float2(c[q].x, c[q].y), acc_lo[(m + R) % 5]);
+                    acc_hi[(m + R) % 5] = __ffma2_rn(wv, make_float2(c[q].z, c[q].w), acc_hi[(m + R) % 5]);
+                }
+            }
+            // LR row I-2 is complete (if it belongs to the item: the first four groups only warm the window up):
+            // this cell's contribution to the output columns (own cell) - k, k = -2..2
+            const int i = i0 - 4 + n;                              // = I - 2
+            if (i < i0) { acc_lo[R % 5] = acc_hi[R % 5] = make_float2(0.f, 0.f); return; }
+            const float a0 = acc_lo[R % 5].x, a1 = acc_lo[R % 5].y, a2 = acc_hi[R % 5].x, a3 = acc_hi[R % 5].y;
+            float hsum = 0.f;
+#pragma unroll
+            for (int k = -2; k <= 2; ++k) {
+                float p = 0.f;
+                if ((HMASK >> (0 * 5 + k + 2)) & 1u) p = T.down_h[0][k + 2] * a0;
+                if ((HMASK >> (1 * 5 + k + 2)) & 1u) p = fmaf(T.down_h[1][k + 2], a1, p);
+                if ((HMASK >> (2 * 5 + k + 2)) & 1u) p = fmaf(T.down_h[2][k + 2], a2, p);
+                if ((HMASK >> (3 * 5 + k + 2)) & 1u) p = fmaf(T.down_h[3][k + 2], a3, p);
+                hsum += k == 0 ? p : __shfl_sync(0xffffffffu, p, (lane + k) & 31);
+            }
+            if (i < i1 && writer) {
+                const size_t o = (static_cast<size_t>(plane) * h + i) * w + j;
+                A.out[o] = A.x != nullptr ? x_cur - hsum : hsum;
+            }
+            acc_lo[R % 5] = acc_hi[R % 5] = make_float2(0.f, 0.f);   // becomes LR row I+3 of the next group
+        };
+        for (int n = 0; n < ngroups; n += 5) {
+            body(IC<0>{}, n);
+            if (n + 1 < ngroups) body(IC<1>{}, n + 1);
+            if (n + 2 < ngroups) body(IC<2>{}, n + 2);
+            if (n + 3 < ngroups) body(IC<3>{}, n + 3);
+            if (n + 4 < ngroups) body(IC<4>{}, n + 4);
+        }
+        cnt += ngroups;
+    }
+}
+
+// ---- K + Up + add.  CTA = 4 * NS warps = NS strips (28 cells each) x 4 row quarters; the CTA builds e = K * d for its
+// rows +-2 and 32 * NS columns in shared memory (same two register-tiled separable passes as cem_invup4_kernel), then
+// every warp streams its rows with y arriving through a per-warp TMA ring (28 cells = 448 B per row, only what it writes).
+// NS = 1 with several CTAs per SM balances best (one CTA of 8 warps per SM: 120 items on 148 SMs at config 4, latency
+// bound with 2 warps per scheduler, ncu r02).
+constexpr int kBD = 4;                          // ring stages per warp
+constexpr int kBStage = 4 * 448;
+constexpr int kBMaxRows = 128;                  // LR rows per CTA item
+
+struct InvUp4Args {
+    const float* d;
+    float* out;
+    int h, w, crop;
+    int pairs, nbrow, rb, seg, items;           // strip pairs per plane, block rows per plane, rows per block, rows per warp
+};
+
+template <int NT, int NS>
+__global__ void __launch_bounds__(NS * 128, NS == 1 ? 4 : 1)
+cem_invup4s_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CemTab T, const __grid_constant__ InvTaps K,
+                   const __grid_constant__ InvUp4Args A) {
+    extern __shared__ uint8_t sm_raw[];
+    uint8_t* smb = sm_raw + ((128u - (smem_u32(sm_raw) & 127u)) & 127u);    // 128-byte aligned, still a shared-space pointer
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+    constexpr int kBW = 4 * NS, kBCE = 32 * NS;
+    const int sx = warp % NS, sy = warp / NS;
+    constexpr int pad = NT >> 1;
+    const int h = A.h, w = A.w, crop = A.crop;
+    const int H = h << 2, W = w << 2, Ho = H - 2 * crop, Wo = W - 2 * crop, Woq = Wo >> 2;
+    const int RB = A.rb, Re = RB + 4, Rd = Re + 2 * pad;
+    constexpr int Cd = kBCE + 2 * pad, Cds = (Cd + 3) & ~3;
+    uint8_t* ring = smb + warp * (kBD * kBStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smb + kBW * kBD * kBStage) + warp * kBD;
+    float* dt = reinterpret_cast<float*>(smb + kBW * kBD * kBStage + 256);     // [Rd][Cds] d, replicate clamped, row pairs interleaved
+    float* hb = dt + ((Rd + 1) & ~1) * Cds;                                    // [Rd][64] horizontal pass
+    float* et = dt;                                                            // [Re][64] e (zero outside the image); aliases dt
+    if (lane == 0) {
+        for (int s = 0; s < kBD; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    uint32_t cnt = 0;
+    bool waited = false;
+    int lofs[5];                                                   // neighbour cells in the e tile (edge lanes never write: clamped)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lofs[k] = min(max(lane + k - 2, 0), 31) + sx * kStripCells;
+    for (int item = blockIdx.x; item < A.items; item += gridDim.x) {
+        const int pr = item % A.pairs;
+        const int t = item / A.pairs;
+        const int br = t % A.nbrow, plane = t / A.nbrow;
+        const int jb = pr * (NS * kStripCells) - 2;                 // LR cell of column 0 of the e tile
+        const int ib = br * RB;                                    // first LR row of the block
+        const int jw = jb + sx * kStripCells, j = jw + lane;       // this warp's strip: lane l holds cell jw + l
+        const int i0 = ib + sy * A.seg, i1 = min(min(i0 + A.seg, ib + RB), h);
+        const bool writer = lane >= 2 && lane < 2 + kStripCells && j < w && 4 * j >= crop && 4 * j + 3 < W - crop;
+        // rows this warp really emits (crop % 4 == 0): [ia, ie)
+        const int ia = max(i0, crop >> 2), ie = min(i1, (H - crop) >> 2);
+        const int ngroups = ie > ia ? ie - ia : 0;
+        const bool strip_live = jw + 2 < w;                        // the strip holds at least one image column
+        auto issue = [&](int n, uint32_t slot) {                   // lane 0: the 4 HR rows of LR row ia + n, cells jw+2 .. jw+29
+            mbar_expect_tx(&bars[slot], static_cast<uint32_t>(kBStage));
+            tma_load_3d(ring + slot * kBStage, &tmY, &bars[slot], 4 * (jw + 2), 4 * (ia + n), plane);
+        };
+        const int live_groups = strip_live ? ngroups : 0;
+        if (elect_one()) {
+            const int npre = live_groups < kBD ? live_groups : kBD;
+            for (int n = 0; n < npre; ++n) issue(n, (cnt + n) % kBD);
+        }
+        if (!waited) { pdl_wait(); waited = true; }                // d comes from the Down launch just before (PDL)
+        // ---- d tile: rows ib-2-pad .. , columns jb-pad .. (replicate clamped), whole tile in flight at once
+        const float* dp = A.d + static_cast<size_t>(plane) * h * w;
+        for (int r = warp; r < Rd; r += kBW) {
+            const float* row = dp + static_cast<size_t>(clampi(ib - 2 - pad + r, 0, h - 1)) * w;
+            float* drow = dt + (r >> 1) * Cds * 2 + (r & 1);
+            for (int c = lane; c < Cd; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(drow + c * 2)), "l"(row + clampi(jb - pad + c, 0, w - 1)) : "memory");
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // ---- horizontal pass: 2 rows x 2 columns per task (one 16-byte load = two columns of both rows)
+        for (int task = threadIdx.x; task < ((Rd + 1) >> 1) * (kBCE / 2); task += kBW * 32) {
+            const int rp = task / (kBCE / 2), c = (task % (kBCE / 2)) * 2;
+            const float4* src = reinterpret_cast<const float4*>(dt + (rp * Cds + c) * 2);
+            float2 v[NT + 1];
+#pragma unroll
+            for (int q = 0; q < (NT + 1) / 2; ++q) {
+                const float4 t4 = src[q];
+                v[2 * q] = make_float2(t4.x, t4.y);
+                v[2 * q + 1] = make_float2(t4.z, t4.w);
+            }
+            float2 o0 = make_float2(0.f, 0.f), o1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const float2 tk = K.t2[k];
+                o0 = __ffma2_rn(tk, v[k], o0);
+                o1 = __ffma2_rn(tk, v[k + 1], o1);
+            }
+            *reinterpret_cast<float2*>(hb + (2 * rp) * kBCE + c) = make_float2(o0.x, o1.x);
+            *reinterpret_cast<float2*>(hb + (2 * rp + 1) * kBCE + c) = make_float2(o0.y, o1.y);
+        }
+        __syncthreads();                                           // dt is dead from here on: et may overwrite it
+        // ---- vertical pass: 4 rows x 2 columns per task
+        for (int task = threadIdx.x; task < (Re >> 2) * (kBCE / 2); task += kBW * 32) {
+            const int r0 = (task / (kBCE / 2)) * 4, c = (task % (kBCE / 2)) * 2;
+            float2 v[NT + 3];
+#pragma unroll
+            for (int k = 0; k < NT + 3; ++k) v[k] = *reinterpret_cast<const float2*>(hb + (r0 + k) * kBCE + c);
+            float2 o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const float2 tk = K.t2[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o[q] = __ffma2_rn(tk, v[k + q], o[q]);
+            }
+            const int jj = jb + c;
+            const bool in0 = jj >= 0 && jj < w, in1 = jj + 1 >= 0 && jj + 1 < w;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ii = ib - 2 + r0 + q;
+                const bool rin = ii >= 0 && ii < h;
+                *reinterpret_cast<float2*>(et + (r0 + q) * kBCE + c) = make_float2(rin && in0 ? o[q].x : 0.f, rin && in1 ? o[q].y : 0.f);
+            }
+        }
+        __syncthreads();
+        // ---- streaming: horizontally upsampled e rows i-2 .. i+2 in a rotating window, vertical taps, y +, crop
+        if (live_groups > 0) {
+            float2 hu01[5], hu23[5];
+            auto hrow = [&](int ii, float2& o01, float2& o23) {   // et row index of LR row ii is ii - ib + 2
+                const float* e = et + (ii - ib + 2) * kBCE;
+                float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float nb = e[lofs[k]];
+                    const float2 n2 = make_float2(nb, nb);
+                    p01 = __ffma2_rn(T.up_h01[k], n2, p01);
+                    p23 = __ffma2_rn(T.up_h23[k], n2, p23);
+                }
+                o01 = p01; o23 = p23;
+            };
+#pragma unroll
+            for (int kv = 0; kv < 4; ++kv) hrow(ia - 2 + kv, hu01[kv], hu23[kv]);
+            float4* obase = reinterpret_cast<float4*>(A.out + (static_cast<size_t>(plane) * Ho + (4 * ia - crop)) * Wo + (4 * j - crop));
+            // row n of the warp (LR row ia + n); window slot of LR row i-2+kv is (kv + R) % 5, R = n % 5
+            auto body = [&](auto Rc, int n) {
+                constexpr int R = decltype(Rc)::value;
+                const int i = ia + n;
+                hrow(i + 2, hu01[(4 + R) % 5], hu23[(4 + R) % 5]);
+                const uint32_t g = cnt + n, slot = g % kBD;
+                ring_wait(&bars[slot], (g / kBD) & 1u, 2u, static_cast<unsigned>(n));
+                float4 yv[4];
+                const float4* sp = reinterpret_cast<const float4*>(ring + slot * kBStage) + min(max(lane - 2, 0), kStripCells - 1);
+#pragma unroll
+                for (int psi = 0; psi < 4; ++psi) yv[psi] = sp[psi * (kStripCells)];
+                __syncwarp();
+                if (n + kBD < live_groups && elect_one()) issue(n + kBD, slot);
+                if (writer) {
+                    float4* op = obase + static_cast<size_t>(4 * n) * Woq;
+#pragma unroll
+                    for (int psi = 0; psi < 4; ++psi) {
+                        float2 r01 = make_float2(yv[psi].x, yv[psi].y), r23 = make_float2(yv[psi].z, yv[psi].w);
+#pragma unroll
+                        for (int kv = 0; kv < 5; ++kv) {
+                            const float2 wv = T.up_v2[psi][kv];
+                            r01 = __ffma2_rn(wv, hu01[(kv + R) % 5], r01);
+                            r23 = __ffma2_rn(wv, hu23[(kv + R) % 5], r23);
+                        }
+                        op[psi * Woq] = make_float4(r01.x, r01.y, r23.x, r23.y);
+                    }
+                }
+            };
+            for (int n = 0; n < live_groups; n += 5) {
+                body(IC<0>{}, n);
+                if (n + 1 < live_groups) body(IC<1>{}, n + 1);
+                if (n + 2 < live_groups) body(IC<2>{}, n + 2);
+                if (n + 3 < live_groups) body(IC<3>{}, n + 3);
+                if (n + 4 < live_groups) body(IC<4>{}, n + 4);
+            }
+            cnt += live_groups;
+        }
+        __syncthreads();                                           // the next item overwrites dt / hb / et
+    }
+    if (!waited) pdl_wait();
+}
+
+static int make_plane_map(CUtensorMap* tm, const float* base, int planes, int rows, int cols, int box_cols, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ESR_ERR_CUDA; }
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 4, static_cast<cuuint64_t>(rows) * cols * 4};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (CEM plane map) failed with CUresult %d", static_cast<int>(r)); return ESR_ERR_CUDA; }
+    return ESR_OK;
+}
+
+// rows per work item minimising  ceil(items / units) * (rows + halo)  for `columns` independent columns of `h` rows on
+// `units` parallel workers (items = columns * ceil(h / rows)); rows <= max_rows
+static int pick_rows(long columns, int h, long units, float halo, int max_rows, int granule) {
+    int best = granule;
+    float best_cost = 3.4e38f;
+    for (int rows = granule; rows <= max_rows; rows += granule) {
+        const long items = columns * ceil_div(h, rows);
+        const float cost = static_cast<float>((items + units - 1) / units) * (rows + halo);
+        if (cost < best_cost - 1e-3f) { best_cost = cost; best = rows; }
+        if (rows >= h) break;
+    }
+    return best;
+}
+
+static bool stream4_ok(const esr_cem_filters& f, int H, int W, int crop, const void* y, const void* x, const void* out, const void* d) {
+    static const bool off = []() { const char* v = getenv("ESR_CEM_V1"); return v && atoi(v); }();     // A/B timing: round-1 kernels
+    const int w = W / 4;
+    return !off && f.n_inv == 27 && fast4_ok(f, H, W, crop, y, out, d) && (W - 2 * crop) % 4 == 0 && w % 4 == 0 && x != nullptr &&
+           (reinterpret_cast<uintptr_t>(x) & 15) == 0 && H >= 8 && W >= 8;
+}
+
+// Down as the TMA streaming kernel; d = x - Down(y)
+static int cem_down4s(const esr_cem_filters& f, const float* y, const float* x, int planes, int H, int W, float* out, cudaStream_t s) {
+    const CemTab T = make_tab(f);
+    uint32_t vmask = 0, hmask = 0;
+    for (int p = 0; p < 4; ++p)
+        for (int c = 0; c < 5; ++c) {
+            if (T.down_v[p][c] != 0.f) vmask |= 1u << (p * 5 + c);
+            if (T.down_h[p][c] != 0.f) hmask |= 1u << (p * 5 + c);
+        }
+    Down4Args A;
+    A.x = x; A.out = out; A.H = H; A.W = W; A.h = H / 4; A.w = W / 4;
+    A.dbg = []() { const char* v = getenv("ESR_CEM_DBGA"); return v ? atoi(v) : 0; }();
+    A.strips = ceil_div(A.w, kStripCells);
+    const int sms = num_sms_cached();
+    A.seg = pick_rows(static_cast<long>(A.strips) * planes, A.h, static_cast<long>(sms) * kAW, 4.f, 1 << 20, 1);
+    A.nseg = ceil_div(A.h, A.seg);
+    A.items = planes * A.nseg * A.strips;
+    CUtensorMap tmY4, tmY1, tmX;
+    int rc;
+    if ((rc = make_plane_map(&tmY4, y, planes, H, W, 128, 4))) return rc;
+    if ((rc = make_plane_map(&tmY1, y, planes, H, W, 128, 1))) return rc;
+    if ((rc = make_plane_map(&tmX, x, planes, A.h, A.w, 36, 1))) return rc;
+    const int smem = 128 + kAW * kAD * kAStage + kAW * kAD * 8;
+    const int grid = std::min(sms, ceil_div(A.items, kAW));   // one CTA of kAW warps per SM
+    // the bicubic x4 table (sampling phase 1): taps [0][0], [0][1]; [2][4], [3][4] and one more are structurally zero
+    constexpr uint32_t kBicV = 0xfffffu & ~((1u << (0 * 5 + 0)) | (1u << (1 * 5 + 0)) | (1u << (2 * 5 + 4)) | (1u << (3 * 5 + 4)));
+    auto launch = [&](auto kern) -> int {
+        ESR_ONCE_PER_DEVICE(ESR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)););
+        kern<<<grid, kAW * 32, smem, s>>>(tmY4, tmY1, tmX, T, A);
+        return check_launch("cem_down4s_kernel");
+    };
+    if ((vmask & ~kBicV) == 0 && (hmask & ~kBicV) == 0) return launch(cem_down4s_kernel<kBicV, kBicV>);
+    return launch(cem_down4s_kernel<kAllTaps, kAllTaps>);
+}
+
+static int cem_invup4s(const esr_cem_filters& f, const float* d, const float* y, int planes, int h, int w, int crop, float* out,
+                       cudaStream_t s) {
+    InvTaps K;
+    K.n = f.n_inv;
+    for (int i = 0; i < f.n_inv; ++i) { K.t[i] = f.inv[i]; K.t2[i] = make_float2(f.inv[i], f.inv[i]); }
+    InvUp4Args A;
+    A.d = d; A.out = out; A.h = h; A.w = w; A.crop = crop;
+    constexpr int NS = 1, kBW = 4 * NS, kBCE = 32 * NS;
+    A.pairs = ceil_div(w, NS * kStripCells);
+    const int sms = num_sms_cached();
+    constexpr int NT = 27, pad = NT / 2, Cds = (kBCE + 2 * pad + 3) & ~3;
+    auto smem_for = [&](int rb) {
+        const int RdE = (rb + 4 + 2 * pad + 1) & ~1;
+        return 128 + kBW * kBD * kBStage + 256 + 4 * (RdE * Cds + RdE * kBCE);
+    };
+    // rows per CTA item: a multiple of 16 (4 warps x 4-row tasks); the K pass of an item costs about 0.42 rows of
+    // streaming per row plus a fixed ~7 rows (its 30 halo rows); CTAs per SM follow from the item's shared memory
+    int best = 16;
+    float best_cost = 3.4e38f;
+    for (int rb = 16; rb <= kBMaxRows; rb += 16) {
+        const int per_sm = std::max(1, std::min(NS == 1 ? 4 : 1, (225 * 1024) / (smem_for(rb) + 1024)));
+        const long units = static_cast<long>(sms) * per_sm, items = static_cast<long>(A.pairs) * planes * ceil_div(h, rb);
+        const float cost = static_cast<float>((items + units - 1) / units) * (rb + 6.f) * per_sm;   // time ~ rounds x item x CTAs sharing the SM
+        if (cost < best_cost - 1e-3f) { best_cost = cost; best = rb; }
+        if (rb >= h) break;
+    }
+    A.rb = best;
+    A.seg = A.rb / 4;
+    A.nbrow = ceil_div(h, A.rb);
+    A.items = planes * A.nbrow * A.pairs;
+    CUtensorMap tmY;
+    int rc;
+    if ((rc = make_plane_map(&tmY, y, planes, 4 * h, 4 * w, 4 * kStripCells, 4))) return rc;
+    const int smem = smem_for(A.rb);
+    const int per_sm = std::max(1, std::min(NS == 1 ? 4 : 1, (225 * 1024) / (smem + 1024)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(std::min(sms * per_sm, A.items));
+    cfg.blockDim = dim3(kBW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ESR_ONCE_PER_DEVICE(ESR_CUDA(cudaFuncSetAttribute(cem_invup4s_kernel<27, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)););
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, cem_invup4s_kernel<27, NS>, tmY, make_tab(f), K, A);
+    if (e != cudaSuccess) { set_error("cem_invup4s_kernel launch failed: %s", cudaGetErrorString(e)); return ESR_ERR_CUDA; }
+    return check_launch("cem_invup4s_kernel");
+}
+
 // ----------------------------------------------------------------- adjoint (backward)
 // Every CEM operator is, per axis, F: out[a] = sum_t taps[t] * src[clamp(sa*a + off + t - pad, 0, Ls-1)]
 // (src = the image for Down / K, the zero-stuffed image for Up).  The kernel below evaluates the
@@ -804,6 +1292,14 @@ int cem_invup4(const esr_cem_filters& f, const float* d, const float* y, int pla
 
 using namespace esr;
 
+extern "C" int esr_debug_cem_timeout(uint32_t* out4) {
+    if (out4 == nullptr) { set_error("null pointer"); return ESR_ERR_INVALID; }
+    unsigned int zero[4] = {0, 0, 0, 0};
+    ESR_CUDA(cudaMemcpyFromSymbol(out4, g_cem_timeout, sizeof(zero)));
+    ESR_CUDA(cudaMemcpyToSymbol(g_cem_timeout, zero, sizeof(zero)));
+    return ESR_OK;
+}
+
 extern "C" int esr_cem_downscale(const esr_cem_filters* f, const float* y, int32_t B, int32_t C, int32_t H, int32_t W,
                                  float* out, void* stream) {
     int rc = check_filters(f);
@@ -838,6 +1334,12 @@ extern "C" int esr_cem_project(const esr_cem_filters* f, const float* y, const f
     const int h = H / f->sf, w = W / f->sf, planes = B * C;
     float* d = workspace;
     float* e = workspace + static_cast<size_t>(planes) * h * w;
+    if (stream4_ok(*f, H, W, crop, y, x, out, d)) {                         // round-2 TMA streaming kernels
+        static const int dbg = []() { const char* v = getenv("ESR_CEM_DEBUG"); return v ? atoi(v) : 0; }();   // 1: new Down only, 2: new K+Up only
+        if ((rc = dbg == 2 ? cem_down(*f, y, x, planes, H, W, d, s) : cem_down4s(*f, y, x, planes, H, W, d, s))) return rc;
+        if (dbg == 1) return cem_invup4(*f, d, y, planes, h, w, crop, out, s, false);
+        return cem_invup4s(*f, d, y, planes, h, w, crop, out, s);
+    }
     if ((rc = cem_down(*f, y, x, planes, H, W, d, s))) return rc;
     if (fast4_ok(*f, H, W, crop, y, out, d) && ((W - 2 * crop) % 4 == 0))
         return cem_invup4(*f, d, y, planes, h, w, crop, out, s, true);    // two launches: Down, then K + Up + add

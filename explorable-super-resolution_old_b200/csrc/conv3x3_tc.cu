@@ -297,7 +297,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {          // also used by csrc/cem.cu (fp32 plane maps of the CEM streaming kernels)
     static EncodeTiledFn fn = nullptr;
     if (fn == nullptr) {
         void* p = nullptr;

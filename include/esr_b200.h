@@ -323,6 +323,10 @@ int esr_cem2d_project(const esr_cem_filters2d* f, const float* y, const float* x
 int esr_cem2d_project_bwd(const esr_cem_filters2d* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
                           int32_t crop, float* g_y, float* workspace, void* stream);
 
+/* Debug aid: the x4 CEM streaming kernels record a ring wait that never completed instead of trapping;
+ * out4 = {code (0 = none, 1 = Down, 2 = K+Up), block, thread, group}; reading clears it. */
+int esr_debug_cem_timeout(uint32_t* out4);
+
 /* Debug aid (tools/prof.py): per-CTA role cycle counters of later tcgen05 conv launches, when the
  * library was built with -DESR_PROFILE_ROLES.  buf: [148][16] uint64 device memory or NULL. */
 void esr_debug_set_profile_buffer(void* buf);

@@ -32,6 +32,18 @@ e0.record()
 for _ in range(50): run()
 e1.record(); torch.cuda.synchronize()
 t_warm = e0.elapsed_time(e1) / 50
+# steady state on inputs larger than L2: six (y, x, out) sets = 624 MB take turns, 60 calls back to back, one event pair
+sets = [(torch.rand(B, C, H, W, device=dev), torch.rand(B, C, H // 4, W // 4, device=dev), torch.empty(B, C, H, W, device=dev)) for _ in range(6)]
+def run_set(k):
+    yy, xx, oo = sets[k % 6]
+    capi.check(l.esr_cem_project(f, capi.ptr(yy), capi.ptr(xx), B, C, H, W, 0, capi.ptr(oo), capi.ptr(ws), capi.stream_ptr()))
+for k in range(6): run_set(k)
+torch.cuda.synchronize()
+e0.record()
+for k in range(60): run_set(k)
+e1.record(); torch.cuda.synchronize()
+t_rot = e0.elapsed_time(e1) / 60
+print(json.dumps({"rotating_sets_back_to_back_us": 1e3 * t_rot, "v1_kernels": os.environ.get("ESR_CEM_V1", "0")}))
 print(json.dumps({"cold_after_write_flush_us": 1e3 * t, "cold_after_write_then_read_flush_us": 1e3 * t_clean, "warm_back_to_back_us": 1e3 * t_warm}))
 byts = 4 * 3 * (2 * H * W + H * W // 16)
 peak = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs'] if os.path.exists('MEASURED_PEAKS.json') else 6650.0
