@@ -727,8 +727,6 @@ cem_down4s_kernel(const __grid_constant__ CUtensorMap tmY4, const __grid_constan
 #pragma unroll
             for (int q = 0; q < 4; ++q) c[q] = reinterpret_cast<const float4*>(st + q * 512)[lane];
             const float x_cur = reinterpret_cast<const float*>(st + 2048)[lane + 2];
-            __syncwarp();                                          // every lane has its values: the slot may be refilled
-            if (n + kAD < ngroups && elect_one()) issue(n + kAD, slot);
             if (edge_l || edge_r) {                                // replicate the edge pixel into the cells outside the image
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -748,6 +746,9 @@ cem_down4s_kernel(const __grid_constant__ CUtensorMap tmY4, const __grid_constan
                     acc_hi[(m + R) % 5] = __ffma2_rn(wv, make_float2(c[q].z, c[q].w), acc_hi[(m + R) % 5]);
                 }
             }
+            // the slot's values have been consumed by the FMAs above (data dependence, not just issue order): refill it
+            __syncwarp();
+            if (n + kAD < ngroups && elect_one()) issue(n + kAD, slot);
             // LR row I-2 is complete (if it belongs to the item: the first four groups only warm the window up):
             // this cell's contribution to the output columns (own cell) - k, k = -2..2
             const int i = i0 - 4 + n;                              // = I - 2
@@ -936,8 +937,6 @@ cem_invup4s_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
                 const float4* sp = reinterpret_cast<const float4*>(ring + slot * kBStage) + min(max(lane - 2, 0), kStripCells - 1);
 #pragma unroll
                 for (int psi = 0; psi < 4; ++psi) yv[psi] = sp[psi * (kStripCells)];
-                __syncwarp();
-                if (n + kBD < live_groups && elect_one()) issue(n + kBD, slot);
                 if (writer) {
                     float4* op = obase + static_cast<size_t>(4 * n) * Woq;
 #pragma unroll
@@ -952,6 +951,12 @@ cem_invup4s_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
                         op[psi * Woq] = make_float4(r01.x, r01.y, r23.x, r23.y);
                     }
                 }
+                // refill only after the values read from the slot have been USED (the FMAs above depend on them): a
+                // __syncwarp() right after the loads only orders their issue, and with 12 warps per SM queueing on the
+                // shared-memory pipe a refill from L2 was seen landing under loads still in flight (config-2 shape, 3 CTAs
+                // per SM: sporadic wrong rows; never with one CTA per SM)
+                __syncwarp();
+                if (n + kBD < live_groups && elect_one()) issue(n + kBD, slot);
             };
             for (int n = 0; n < live_groups; n += 5) {
                 body(IC<0>{}, n);
@@ -1073,7 +1078,8 @@ static int cem_invup4s(const esr_cem_filters& f, const float* d, const float* y,
     const int smem = smem_for(A.rb);
     const int per_sm = std::max(1, std::min(NS == 1 ? 4 : 1, (225 * 1024) / (smem + 1024)));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(std::min(sms * per_sm, A.items));
+    static const int dbgb = []() { const char* v = getenv("ESR_CEM_DBGB"); return v ? atoi(v) : 0; }();   // bisect: 1 one item per CTA, 2 one CTA per SM
+    cfg.gridDim = dim3((dbgb & 1) ? A.items : std::min(sms * ((dbgb & 2) ? 1 : per_sm), A.items));
     cfg.blockDim = dim3(kBW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;

@@ -287,3 +287,28 @@ def test_host_pipeline_with_estimated_kernel(golden, cuda_device):
     pipe(host_in, host_out)
     pipe.wait()
     assert torch.equal(host_out, ref)
+
+
+def test_projection_config2_shape_many_ctas_per_sm(cuda_device):
+    """16 x 3 planes of 592^2 cropped by 40 (the CEM call inside BASELINE config 2): 864 work items on co-resident CTAs.
+    Regression test of a shared-memory ring race in the TMA streaming kernels (a refill landing under loads that had
+    been issued but not performed: sporadic wrong rows, only with several CTAs per SM) - three runs, each against the
+    CPU oracle through the C ABI."""
+    import ctypes as C
+    from esr_b200 import _capi as capi
+    f = pcem.CEMnet(pcem.Get_CEM_Config(4))._filters
+    B, Cc, H, W, crop = 16, 3, 592, 592, 40
+    g = torch.Generator().manual_seed(5)
+    y, x = torch.rand(B, Cc, H, W, generator=g), torch.rand(B, Cc, H // 4, W // 4, generator=g)
+    ref = CEMOracle(4).project(y, x)[:, :, crop:-crop, crop:-crop]
+    yd, xd = y.to(cuda_device), x.to(cuda_device)
+    ws = torch.empty(2 * B * Cc * (H // 4) * (W // 4), device=cuda_device)
+    for _ in range(3):
+        out = torch.full((B, Cc, H - 2 * crop, W - 2 * crop), float("nan"), device=cuda_device)
+        capi.check(capi.lib().esr_cem_project(f, capi.ptr(yd), capi.ptr(xd), B, Cc, H, W, crop, capi.ptr(out), capi.ptr(ws),
+                                              capi.stream_ptr()))
+        torch.cuda.synchronize()
+        rec = (C.c_uint32 * 4)()
+        capi.check(capi.lib().esr_debug_cem_timeout(rec))
+        assert list(rec) == [0, 0, 0, 0], "ring wait timed out: %s" % list(rec)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-5)
