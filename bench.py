@@ -349,6 +349,73 @@ def config1_latency(netG, dev):
     return res
 
 
+def run_train_g(args):
+    """Generator half of BASELINE config 5: batch 16 x 3x32x32 LR (128x128 HR patches) per rank, train mode (no CEM pad),
+    L1 pixel loss on fake_H, explicit data + weight gradients, bucketed NCCL all-reduce of the 68 MB gradient under the
+    weight-gradient kernels, torch Adam on the fp32 master weights.  Metric: HR patches per second, whole job."""
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    from esr_b200 import _capi as capi, cem as pcem, networks, synth
+    from esr_b200.training import GeneratorTrainer
+    capi.lib()
+    opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 128}},
+           "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input="all_layers", latent_input_domain="HR_downscaled",
+                             latent_channels=3, norm_type=None, mode="CNA", nf=64, nb=23, in_nc=3, out_nc=3, gc=32, scale=SF)}
+    netG = networks.define_G(opt, CEM=pcem.CEMnet(pcem.Get_CEM_Config(SF)), num_latent_channels=3)
+    sd = netG.state_dict()
+    sd.update({"generated_image_model." + k: v for k, v in synth.make_weights("kaiming", seed=0).items()})
+    netG.load_state_dict(sd)
+    netG.to(dev).train()
+    trainer = GeneratorTrainer(netG)
+    G = netG.generated_image_model
+    optim = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    Bp, hl = 16, 32
+    lr, z = synth.make_inputs(Bp, hl, hl, seed=rank)
+    mi = torch.cat([z.contiguous().view(Bp, 48, hl, hl), lr], 1).contiguous().to(dev)
+    target = torch.rand(Bp, 3, SF * hl, SF * hl, generator=torch.Generator().manual_seed(rank)).to(dev)
+
+    def step():
+        fake = trainer.forward(mi)
+        loss = (fake - target).abs().mean()
+        loss.backward()
+        trainer.backward(fake.grad)
+        optim.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        l0 = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        l1 = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.cpu())
+    if rank == 0:
+        flops = 3 * G.engine().flops_per_lr_pixel() * Bp * hl * hl          # forward + data gradient + weight gradient
+        print(json.dumps({"metric": "generator training step, 128x128 HR patches/s (RRDBNet+CEM, L1 pixel loss)", "value": world * Bp / (ms * 1e-3),
+                          "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MMA operands, fp32 master weights",
+                          "data": "synthetic", "config": {"workload": "BASELINE config 5, generator half: 16 x 3x32x32 LR per rank, train mode",
+                                                          "global_batch": Bp * world, "parallelism": "data parallel x%d, bucketed NCCL all-reduce (AVG) of %.1f MB of gradients" % (world, trainer.grad_bytes() / 1e6)},
+                          "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "loss_first_last": [float(l0), float(l1)]}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -357,12 +424,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 16 images per rank (default); strong: BASELINE config 2's one batch of 16 split over the ranks")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train_g"],
+                    help="infer: BASELINE config 2 (default, the headline metric); train_g: the generator half of config 5's "
+                         "training step (forward, data + weight gradients, NCCL gradient all-reduce, Adam), 16 x 32x32 LR patches per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-zopt", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train_g":
+        return run_train_g(args)
 
     rank, local_rank, world = dist_env()
     if world > 1:

@@ -98,6 +98,21 @@ class CemFilters2d(C.Structure):
 
 CEM2D_MAX_SIDE = 63
 
+class WgradItem(C.Structure):            # esr_wgrad_item
+    _fields_ = [("x", C.c_void_p), ("g", C.c_void_p), ("dw", C.c_void_p),
+                ("x_stride", C.c_int32), ("x_c0", C.c_int32), ("x_f16", C.c_int32),
+                ("g_stride", C.c_int32), ("g_c0", C.c_int32), ("cout", C.c_int32),
+                ("n_co", C.c_int32), ("n_ci", C.c_int32), ("cin_total", C.c_int32), ("ci0", C.c_int32),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("tile_begin", C.c_int32), ("tile_end", C.c_int32)]
+
+
+class WgradSmallItem(C.Structure):       # esr_wgrad_small_item
+    _fields_ = [("g", C.c_void_p), ("s", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p),
+                ("g_stride", C.c_int32), ("g_c0", C.c_int32), ("cout", C.c_int32), ("n_co", C.c_int32),
+                ("s_channels", C.c_int32), ("s_c0", C.c_int32), ("n_c", C.c_int32),
+                ("cin_total", C.c_int32), ("ci0", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/esr_b200.h declares
 _i32, _i64, _vp, _f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
 SIGNATURES = {
@@ -114,6 +129,13 @@ SIGNATURES = {
                                       _vp, _vp]),
     "esr_debug_set_profile_buffer": (None, [_vp]),
     "esr_debug_cem_timeout": (C.c_int, [C.POINTER(C.c_uint32)]),
+    "esr_wgrad16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "esr_wgrad_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "esr_zopt_tanh_pack": (C.c_int, [_vp, C.c_float, _i32, _i32, _i32, _vp, _vp]),
+    "esr_zopt_loss_workspace_floats": (_i32, [_i32, _i32]),
+    "esr_zopt_loss": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "esr_zopt_loss_grad": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "esr_zopt_adam": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, _i32, _i32, _i32, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "esr_grad_combine": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32,
                                    _i32, _i32, _f, _f, _vp, _i32, _i32, _i32, _vp]),
     "esr_g_input_prep": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

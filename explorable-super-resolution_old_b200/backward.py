@@ -13,6 +13,7 @@ Gradient buffers (DESIGN.md "backward"):
         64+32(k-1).. = d(pre-activation of x_k) = LeakyReLU'(x_k) * d(x_k).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -115,15 +116,17 @@ class DgradSpecs:
 class BackwardPlan:
     """Buffers and recorded dgrad sequences for one GPlan (built with keep_activations=True)."""
 
-    def __init__(self, plan, specs, use_simt=False):
+    def __init__(self, plan, specs, use_simt=False, keep_gb=False):
         self.plan, self.specs = plan, specs
+        self.keep_gb = keep_gb          # training: every RDB keeps its own gradient buffer (the weight gradients read them
+                                        # after the data-gradient pass); Z optimisation: two buffers take turns
         eng = plan.eng
         B, hp, wp, sf, dev = plan.B, plan.hp, plan.wp, plan.sf, plan.device
         f32 = dict(dtype=torch.float32, device=dev)
         bf = dict(dtype=torch.bfloat16, device=dev)
         self.GF32 = torch.zeros(B * 4 * FRAME * hp * wp, **f32)
-        self.GBs = [torch.zeros(B, hp, wp, 192, **bf) for _ in range(2)]   # RDB g works in GBs[g % 2]; its d(x_0) launch reads
-                                                                         # all of it and writes the next g_5 into the other one
+        self.GBs = [torch.zeros(B, hp, wp, 192, **bf) for _ in range(3 * eng.nb if keep_gb else 2)]   # RDB g works in gb(g); its
+                                                                         # d(x_0) launch reads all of it and writes the next g_5 into gb(g-1)
         self.GS = torch.zeros(B, hp, wp, 128, **bf)
         self.Gsc = torch.zeros(B * 64 * hp * wp, **f32)
         self.GFea = torch.zeros(B, hp, wp, 128, **bf)
@@ -155,6 +158,9 @@ class BackwardPlan:
                 capi.lib().esr_seq_destroy(s)
         except Exception:
             pass
+
+    def gb(self, g):
+        return self.GBs[g] if self.keep_gb else self.GBs[g % 2]
 
     # ------------------------------------------------------------------ recording helpers
     def _conv(self, name, H, W, src, out_f32, out_stride, out_choff=0, accum=False, no_accum=0, lat_tile_to=None,
@@ -193,11 +199,15 @@ class BackwardPlan:
             d.flags |= capi.EPI_RES2
             d.res2, d.res2_stride, d.res2_choff, d.beta = res2.data_ptr(), out_stride, res2_choff, 1.0
         d.no_res_tiles = no_res
+        self._descs.append(d)
+        if os.environ.get("ESR_BWD_EAGER") == "1":         # debug: one launch + sync per conv, names the failing one
+            tag = (name or pc.name, H, W)
+            self.steps.append(("conv", (d, tag)))
+            return
         if self._cur is None:
             self._cur = capi.lib().esr_seq_create()
             self._seqs.append(self._cur)
             self.steps.append(("seq", self._cur))
-        self._descs.append(d)
         capi.check(capi.lib().esr_seq_add_conv(self._cur, C.byref(d), 1 if self.use_simt else 0))
 
     def _call(self, fn):
@@ -243,7 +253,7 @@ class BackwardPlan:
         q0 = n_rdb % 4
         touched.add(q0)
         self._conv(names[0], hp, wp, self.GS, self.GF32, 4 * FRAME, out_choff=FRAME * q0, lat_tile_to=LAT_OFF if nz else None,
-                   out_bf16=self.GBs[(n_rdb - 1) % 2], bf16_stride=192, scale=0.04, only_bf16_tiles=(0, 1))
+                   out_bf16=self.gb(n_rdb - 1), bf16_stride=192, scale=0.04, only_bf16_tiles=(0, 1))
         # ---- the trunk, last RDB first
         for g in reversed(range(n_rdb)):
             r, dd = divmod(g, 3)            # dd = 0,1,2 -> RDB1,2,3
@@ -251,7 +261,7 @@ class BackwardPlan:
             first_touch = q not in touched
             touched.add(q)
             buf = plan.bufs[g]
-            GB = self.GBs[g % 2]
+            GB = self.gb(g)
             pre = "model.1.sub.%d.RDB%d.convs." % (r, dd + 1)
             for k in (5, 4, 3, 2):
                 # d(x_{k-1}) complete in one launch (K over g_5, g_4 .. g_k); emit g_{k-1} = LeakyReLU'(x_{k-1}) * d(x_{k-1})
@@ -269,7 +279,7 @@ class BackwardPlan:
             if dd == 0:
                 kw.update(res2=self.GF32, res2_choff=FRAME * ((3 * r + 3) % 4))
             if g > 0:
-                kw.update(out_bf16=self.GBs[(g - 1) % 2], bf16_stride=192, only_bf16_tiles=(0, 1), scale=0.04 if dd == 0 else 0.2)
+                kw.update(out_bf16=self.gb(g - 1), bf16_stride=192, only_bf16_tiles=(0, 1), scale=0.04 if dd == 0 else 0.2)
             self._conv(None, hp, wp, GB, self.GF32, 4 * FRAME, pc=pc, **kw)
         # ---- d(fea) = d(RRDB0 input) + shortcut gradient -> first conv's latent rows
         if eng.nz_in:
@@ -288,6 +298,12 @@ class BackwardPlan:
         for kind, obj in self.steps:
             if kind == "seq":
                 capi.check(l.esr_seq_run(obj, capi.stream_ptr()))
+            elif kind == "conv":
+                try:
+                    capi.check(l.esr_conv3x3_tc(C.byref(obj[0]), capi.stream_ptr()))
+                    torch.cuda.synchronize()
+                except Exception as e:
+                    raise capi.EsrError("dgrad launch %s failed: %s" % (obj[1], e))
             else:
                 obj()
         g_in = torch.empty(B, eng.nz_in * sf * sf + 3, plan.h, plan.w, dtype=torch.float32, device=plan.device)

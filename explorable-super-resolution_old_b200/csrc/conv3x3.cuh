@@ -252,7 +252,10 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, i
     else if ((flags & ESR_EPI_RES1) && (flags & ESR_EPI_RES1_HILO)) load16_hilo(d, pix, co0, P.r1);
     else if (flags & ESR_EPI_RES1) load16f_at(d, d.res1, d.res1_stride, d.res1_choff, n, y, x, co0, P.r1);
     if (flags & ESR_EPI_RES2) load16f_at(d, d.res2, d.res2_stride, d.res2_choff, n, y, x, co0, P.r2);
-    if (flags & ESR_EPI_MASK) {
+    // the mask only scales the 16-bit output: a cout tile without one (the routed latent rows of a dgrad, whose channel
+    // index lies beyond the mask tensor's channels) must not touch it - for the tensor's last pixel that read ran past
+    // the end of the allocation (found in round 2 when a different allocation order put it at the end of a segment)
+    if ((flags & ESR_EPI_MASK) && d.out_bf16 != nullptr && !((d.no_bf16_tiles >> ct) & 1)) {
         const uint4* m = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.mask) +
                                                         pix * d.mask_stride + d.mask_choff + co0);
         P.m[0] = __ldg(m);

@@ -1,0 +1,204 @@
+// Weight gradients of the generator's 3x3 convolutions (the GAN training step's generator half,
+// codes/models/SRRaGAN_model.py:463-547: l_g_total.backward() with trainable G parameters).
+//   dW[co, ci, ky, kx] = sum_{n,y,x} g[n, y, x, co] * X[n, y+ky-1, x+kx-1, ci]      (zero outside the image)
+//   db[co]             = sum_{n,y,x} g[n, y, x, co]
+// where X is the conv's input as the forward left it in HBM (16-bit NHWC slices of the dense-block / outer buffers,
+// plus the small fp32 NCHW latent / LR planes) and g the gradient w.r.t. its pre-activation output as the data-gradient
+// backward left it (bf16 NHWC).  Two kernels:
+//   wgrad16_kernel    one CTA per (conv, block of 16 input channels): K = pixels, warp-level bf16 MMAs (m16n16k16,
+//                     fp32 accumulate) on shared-memory tiles; every CTA owns its slice of dW for all pixels (no atomics,
+//                     deterministic) unless the item is a spatial chunk of a high-resolution conv (atomicAdd then).
+//   wgrad_small_kernel  the <= 8 fp32 NCHW input channels (latent, LR image) and the bias: lanes = output channels.
+// First version: legacy mma.sync tensor path (HMMA), not tcgen05 - DESIGN.md lists the tcgen05 form (MN-major
+// operands straight from the NHWC tiles) as the next step.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <mma.h>
+
+#include "esr_common.cuh"
+
+namespace esr {
+
+using namespace nvcuda;
+
+constexpr int kWgTH = 8, kWgTW = 16;               // spatial tile: 8 rows x 16 pixels (one k-step per row)
+constexpr int kWgThreads = 256;
+constexpr int kWgXPitch = 16;                      // input channels per item
+constexpr int kWgMaxCout = 64;
+
+__global__ void __launch_bounds__(kWgThreads) wgrad16_kernel(const esr_wgrad_item* __restrict__ items) {
+    const esr_wgrad_item it = items[blockIdx.x];
+    __shared__ __align__(32) __nv_bfloat16 Xs[(kWgTH + 2) * (kWgTW + 2) * kWgXPitch];
+    __shared__ __align__(32) __nv_bfloat16 Gs[kWgTH * kWgTW * (kWgMaxCout + 16)];
+    __shared__ __align__(32) float Os[8][16 * 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncb = it.cout >> 4;                  // 16-channel blocks of the output
+    const int nfrag = 9 * ncb;                     // (tap, co block) accumulators, round-robin over the 8 warps
+    const int gp = it.cout + 16;                   // pixel pitch of the g tile (elements): keeps 32-byte fragment alignment
+    constexpr int kMaxFr = (9 * (kWgMaxCout / 16) + 7) / 8;
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[kMaxFr];
+#pragma unroll
+    for (int f = 0; f < kMaxFr; ++f) wmma::fill_fragment(acc[f], 0.f);
+    const int tiles_x = (it.W + kWgTW - 1) / kWgTW, tiles_y = (it.H + kWgTH - 1) / kWgTH;
+    const int tiles_img = tiles_x * tiles_y;
+    const int t_end = it.tile_end > 0 ? it.tile_end : it.B * tiles_img;
+    const uint16_t* xg = static_cast<const uint16_t*>(it.x);
+    const uint16_t* gg = static_cast<const uint16_t*>(it.g);
+    for (int t = it.tile_begin; t < t_end; ++t) {
+        const int n = t / tiles_img, r = t - n * tiles_img;
+        const int y0 = (r / tiles_x) * kWgTH, x0 = (r % tiles_x) * kWgTW;
+        // ---- stage the input halo tile (zero outside the image = the conv's zero padding) and the gradient tile
+        for (int idx = threadIdx.x; idx < (kWgTH + 2) * (kWgTW + 2) * 2; idx += kWgThreads) {
+            const int half = idx & 1, p = idx >> 1;
+            const int yy = y0 - 1 + p / (kWgTW + 2), xx = x0 - 1 + p % (kWgTW + 2);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (yy >= 0 && yy < it.H && xx >= 0 && xx < it.W) {
+                const uint16_t* src = xg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.x_stride + static_cast<size_t>(xx) * it.x_stride +
+                                      it.x_c0 + half * 8;
+                v = *reinterpret_cast<const uint4*>(src);
+                if (it.x_f16) {                    // fp16 activations of the outer convs -> bf16 operands
+                    const __half2* h = reinterpret_cast<const __half2*>(&v);
+                    __nv_bfloat162 o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = __float22bfloat162_rn(__half22float2(h[k]));
+                    v = *reinterpret_cast<const uint4*>(o);
+                }
+                if (it.n_ci < 16) {                // channels beyond the conv's input belong to someone else: contribute nothing
+                    uint16_t* e = reinterpret_cast<uint16_t*>(&v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (half * 8 + k >= it.n_ci) e[k] = 0;
+                }
+            }
+            *reinterpret_cast<uint4*>(Xs + p * kWgXPitch + half * 8) = v;
+        }
+        const int g_vec = it.cout >> 3;            // uint4 per pixel
+        for (int idx = threadIdx.x; idx < kWgTH * kWgTW * g_vec; idx += kWgThreads) {
+            const int p = idx / g_vec, q = idx - p * g_vec;
+            const int yy = y0 + p / kWgTW, xx = x0 + p % kWgTW;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (yy < it.H && xx < it.W)
+                v = *reinterpret_cast<const uint4*>(gg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.g_stride +
+                                                    static_cast<size_t>(xx) * it.g_stride + it.g_c0 + q * 8);
+            *reinterpret_cast<uint4*>(Gs + p * gp + q * 8) = v;
+        }
+        __syncthreads();
+        // ---- K = the tile's 128 pixels, 16 per step (one tile row)
+#pragma unroll
+        for (int f = 0; f < kMaxFr; ++f) {
+            const int fr = warp + f * 8;
+            if (fr < nfrag) {
+                const int tap = fr / ncb, cb = fr - tap * ncb;
+                const int ky = tap / 3, kx = tap - ky * 3;
+#pragma unroll
+                for (int y = 0; y < kWgTH; ++y) {
+                    wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> a;     // (m = co, k = pixel)
+                    wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> b;     // (k = pixel, n = ci)
+                    wmma::load_matrix_sync(a, Gs + (y * kWgTW) * gp + cb * 16, gp);
+                    wmma::load_matrix_sync(b, Xs + ((y + ky) * (kWgTW + 2) + kx) * kWgXPitch, kWgXPitch);
+                    wmma::mma_sync(acc[f], a, b, acc[f]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- dW[co, ci0 + ci, ky, kx]
+#pragma unroll
+    for (int f = 0; f < kMaxFr; ++f) {
+        const int fr = warp + f * 8;
+        if (fr < nfrag) {
+            const int tap = fr / ncb, cb = fr - tap * ncb;
+            wmma::store_matrix_sync(Os[warp], acc[f], 16, wmma::mem_row_major);                       // [co][ci]
+            __syncwarp();
+            for (int e = lane; e < 256; e += 32) {
+                const int co = cb * 16 + (e >> 4), ci = e & 15;
+                if (co < it.n_co && ci < it.n_ci) {
+                    float* dst = it.dw + (static_cast<size_t>(co) * it.cin_total + it.ci0 + ci) * 9 + tap;
+                    if (it.tile_end > 0) atomicAdd(dst, Os[warp][e]);
+                    else *dst = Os[warp][e];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// lanes = output channels (one 64-byte run of g per pixel and warp), narrow fp32 NCHW input planes broadcast
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const esr_wgrad_small_item* __restrict__ items) {
+    const esr_wgrad_small_item it = items[blockIdx.x];
+    constexpr int kMaxC = 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co_blocks = (it.cout + 31) >> 5;
+    __shared__ float red[8][32];
+    const uint16_t* gg = static_cast<const uint16_t*>(it.g);
+    const size_t plane = static_cast<size_t>(it.H) * it.W;
+    for (int cb = 0; cb < co_blocks; ++cb) {
+        const int co = cb * 32 + lane;
+        const bool live = co < it.cout;
+        float acc[kMaxC * 9 + 1];
+#pragma unroll
+        for (int k = 0; k < kMaxC * 9 + 1; ++k) acc[k] = 0.f;
+        const int rows = it.B * it.H;
+        for (int rw = warp; rw < rows; rw += 8) {                  // a warp per image row
+            const int n = rw / it.H, y = rw - n * it.H;
+            for (int x = 0; x < it.W; ++x) {
+                float gv = 0.f;
+                if (live) {
+                    const uint16_t bits = gg[(static_cast<size_t>(rw) * it.W + x) * it.g_stride + it.g_c0 + co];
+                    gv = __uint_as_float(static_cast<uint32_t>(bits) << 16);
+                }
+                acc[kMaxC * 9] += gv;                              // bias gradient
+                if (it.n_c > 0) {
+#pragma unroll
+                    for (int c = 0; c < kMaxC; ++c) {
+                        if (c >= it.n_c) break;
+                        const float* sp = it.s + (static_cast<size_t>(n) * it.s_channels + it.s_c0 + c) * plane;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int yy = y + ky - 1;
+                            if (yy < 0 || yy >= it.H) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int xx = x + kx - 1;
+                                if (xx < 0 || xx >= it.W) continue;
+                                acc[c * 9 + ky * 3 + kx] = fmaf(gv, __ldg(sp + static_cast<size_t>(yy) * it.W + xx), acc[c * 9 + ky * 3 + kx]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxC * 9 + 1; ++k) {                  // cross-warp sums, one accumulator at a time (unrolled: acc stays in registers)
+            if (k < kMaxC * 9 && k / 9 >= it.n_c) continue;        // block-uniform
+            red[warp][lane] = acc[k];
+            __syncthreads();
+            if (warp == 0) {
+                float v = 0.f;
+#pragma unroll
+                for (int w2 = 0; w2 < 8; ++w2) v += red[w2][lane];
+                if (live && co < it.n_co) {
+                    if (k == kMaxC * 9) { if (it.db != nullptr) it.db[co] = v; }
+                    else it.dw[(static_cast<size_t>(co) * it.cin_total + it.ci0 + k / 9) * 9 + k % 9] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace esr
+
+using namespace esr;
+
+extern "C" int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* stream) {
+    ESR_CHECK_ARG(items_device != nullptr && n_items > 0, "esr_wgrad16: bad arguments");
+    wgrad16_kernel<<<n_items, kWgThreads, 0, static_cast<cudaStream_t>(stream)>>>(items_device);
+    return check_launch("wgrad16_kernel");
+}
+
+extern "C" int esr_wgrad_small(const esr_wgrad_small_item* items_device, int32_t n_items, void* stream) {
+    ESR_CHECK_ARG(items_device != nullptr && n_items > 0, "esr_wgrad_small: bad arguments");
+    wgrad_small_kernel<<<n_items, 256, 0, static_cast<cudaStream_t>(stream)>>>(items_device);
+    return check_launch("wgrad_small_kernel");
+}

@@ -73,8 +73,9 @@ class PackedConv:
 
     def pack(self, weight, bias, off, s_row, s_slot, s_ky, s_kx):
         dev = weight.device
-        self.wpack = torch.empty(self.total_bytes, dtype=torch.uint8, device=dev)
-        self.bias = torch.empty(self.cout_tiles * self.cout_tile, dtype=torch.float32, device=dev)
+        if self.wpack is None or self.wpack.device != dev:     # re-packing after a weight update reuses the buffers: the recorded
+            self.wpack = torch.empty(self.total_bytes, dtype=torch.uint8, device=dev)      # launch sequences point at them
+            self.bias = torch.empty(self.cout_tiles * self.cout_tile, dtype=torch.float32, device=dev)
         rows_d = _struct_array_to_device(self.rows, WRow, dev)
         slots_d = _struct_array_to_device(self.slots, WSlot, dev)
         capi.check(capi.lib().esr_pack_conv_weights(

@@ -82,18 +82,29 @@ class RRDBNet(nn.Module):
 
     def engine(self):
         params = dict(self.named_parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params.values()) + (self.precise_outer, self.outer_mode)
-        if self._engine is None or key != self._engine_key:
-            eng = GEngine(precise_outer=self.precise_outer, outer_mode=self.outer_mode, **self._cfg)
-            packed = {}
-            for name in eng.convs:
-                w, b = params[name + ".weight"], params[name + ".bias"]
-                if not w.is_cuda:
-                    raise capi.EsrError("RRDBNet parameters live on %s; move the module to a B200 (no CPU path)" % w.device)
-                packed[name] = (w.detach().contiguous().float(), b.detach().contiguous().float())
-            eng.pack(packed)
-            self._engine, self._engine_key, self._plans = eng, key, {}
+        ptr_key = tuple(p.data_ptr() for p in params.values()) + (self.precise_outer, self.outer_mode)
+        key = ptr_key + tuple(p._version for p in params.values())
+        if self._engine is not None and key == self._engine_key:
+            return self._engine
+        same_storage = self._engine is not None and getattr(self, "_engine_ptr_key", None) == ptr_key
+        eng = self._engine if same_storage else GEngine(precise_outer=self.precise_outer, outer_mode=self.outer_mode, **self._cfg)
+        packed = {}
+        for name in eng.convs:
+            w, b = params[name + ".weight"], params[name + ".bias"]
+            if not w.is_cuda:
+                raise capi.EsrError("RRDBNet parameters live on %s; move the module to a B200 (no CPU path)" % w.device)
+            packed[name] = (w.detach().contiguous().float(), b.detach().contiguous().float())
+        eng.pack(packed)
+        if same_storage:
+            # a weight update in place (optimizer step, load_state_dict): the packed images are refreshed inside their
+            # existing buffers, so plans, recorded launch sequences and captured graphs stay valid
+            self._packed_params = packed
+            if self._dgrad is not None:
+                self._dgrad.pack(packed)
+        else:
+            self._engine, self._plans = eng, {}
             self._packed_params, self._dgrad, self._bplans = packed, None, {}
+        self._engine_key, self._engine_ptr_key = key, ptr_key
         return self._engine
 
     def backward_plan(self, plan):

@@ -1,0 +1,219 @@
+"""Generator half of the GAN training step, data parallel (BASELINE config 5).
+
+The reference's ``SRRaGANModel.optimize_parameters`` (codes/models/SRRaGAN_model.py:463-547) runs
+``fake_H = netG(model_input)``, builds ``l_g_total`` from ``fake_H`` (pixel / feature / GAN / range terms) and calls
+``l_g_total.backward(); optimizer_G.step()`` with every generator parameter trainable, under ``nn.DataParallel``
+(models/networks.py:99-101).  Here the generator's part of that is explicit:
+
+    trainer = GeneratorTrainer(netG)                  # netG: this package's CEM_PyTorch(RRDBNet), parameters on the GPU
+    fake_H = trainer.forward(model_input)             # leaf tensor: build any torch loss on it (the reference's own
+    loss(fake_H).backward()                           #   criteria, a discriminator, ...) and back-propagate to fake_H
+    trainer.backward(fake_H.grad)                     # dL/dW, dL/db of all 351 convs into p.grad, averaged over the ranks
+    optimizer_G.step()
+
+``backward`` = the data-gradient pass of Z optimisation (backward.py: the same tcgen05 dgrad launches, with one gradient
+buffer kept per dense block) followed by the weight-gradient kernels of csrc/wgrad.cu over the activations / gradients
+both passes left in HBM.  One process per GPU: all gradients live in ONE flat fp32 buffer ordered last layer first; it is
+cut into buckets, and as soon as a bucket's weight-gradient launches are queued its ``all_reduce`` (NCCL, average) is
+issued on a communication stream, so the exchange of the late layers runs under the weight-gradient kernels of the
+early ones (68.2 MB for the production generator).  ``p.grad`` of every parameter is a view into that buffer.
+
+Not built here: the discriminator, VGG feature extractor, WGAN-GP double backward and range loss of the full step
+(they consume ``fake_H`` in torch through the boundary above), and a tcgen05 form of the weight-gradient GEMM
+(csrc/wgrad.cu uses warp-level bf16 MMAs).
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _capi as capi
+from ._capi import WgradItem, WgradSmallItem
+from .backward import BackwardPlan, DgradSpecs, generator_backward_eager
+from .cem import CEM_PyTorch
+from .engine import NF, GC, _struct_array_to_device
+from .rrdbnet import RRDBNet, _forward_eager
+
+TILE_H, TILE_W = 8, 16
+
+
+class GeneratorTrainer:
+    def __init__(self, netG, bucket_bytes=8 << 20, process_group=None):
+        wrapper = getattr(netG, 'module', netG)
+        G = getattr(wrapper, 'generated_image_model', wrapper)
+        if not isinstance(G, RRDBNet):
+            raise capi.EsrError("GeneratorTrainer needs this package's RRDBNet (optionally wrapped by CEM_PyTorch)")
+        if G._cfg['nz_in'] == 0:
+            raise NotImplementedError("training a generator without a latent input is not built (the production configuration has one)")
+        self.wrapper = wrapper if isinstance(wrapper, CEM_PyTorch) else None
+        self.G, self.group, self.bucket_bytes = G, process_group, bucket_bytes
+        self.dev = next(G.parameters()).device
+        if self.dev.type != 'cuda':
+            raise capi.EsrError("GeneratorTrainer: move the generator to a B200 first (no CPU path)")
+        self.comm = torch.cuda.Stream(device=self.dev)
+        # parameters in backward order (last conv first): the flat gradient buffer and its buckets follow it
+        named = dict(G.named_parameters())
+        eng = G.engine()
+        order = list(reversed(eng.outer_names[1:])) + [eng.outer_names[0]]
+        for r in reversed(range(eng.nb)):
+            for d in (3, 2, 1):
+                order += ["model.1.sub.%d.RDB%d.convs.%d.0" % (r, d, i) for i in (4, 3, 2, 1, 0)]
+        order.append("model.0")
+        assert sorted(order) == sorted(eng.convs.keys())
+        self.order = order
+        total, self.slices = 0, {}
+        for name in order:
+            for suffix in (".weight", ".bias"):
+                p = named[name + suffix]
+                self.slices[name + suffix] = (total, p.numel(), p)
+                total += (p.numel() + 3) & ~3
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        for key, (off, n, p) in self.slices.items():
+            p.grad = self.flat[off:off + n].view_as(p)
+        # buckets: contiguous ranges of `order`
+        self.buckets, cur, cur_bytes, start = [], [], 0, 0
+        for name in order:
+            cur.append(name)
+            cur_bytes += 4 * (self.slices[name + ".weight"][1] + self.slices[name + ".bias"][1])
+            if cur_bytes >= bucket_bytes:
+                end = self.slices[name + ".bias"][0] + ((self.slices[name + ".bias"][1] + 3) & ~3)
+                self.buckets.append((cur, start, end))
+                cur, cur_bytes, start = [], 0, end
+        if cur:
+            self.buckets.append((cur, start, total))
+        self._state = None
+        self._tables = {}
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, model_input):
+        """fake_H = netG(model_input) with the activations kept; returns a leaf tensor that requires grad."""
+        G, w = self.G, self.wrapper
+        x = model_input.contiguous().float()
+        capi.require_device(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+        B, _, h, wd = x.shape
+        margin = (w._margin_LR if w.pre_pad else 0) if w is not None else 0
+        filters = w._filters if w is not None else None
+        with torch.cuda.device(self.dev):
+            plan = G.plan(B, h, wd, margin, keep=True, slot='train')
+            sf = G.upscale
+            crop = sf * margin
+            onc = plan.y.size(1)
+            out = torch.empty(B, onc, sf * plan.hp - 2 * crop, sf * plan.wp - 2 * crop, device=self.dev, dtype=torch.float32)
+            ws = torch.empty(max(1, 2 * B * onc * plan.hp * plan.wp), device=self.dev, dtype=torch.float32) if filters is not None else None
+            _forward_eager(plan, x, filters, crop, out, ws)
+        self._state = (plan, filters, margin)
+        return out.requires_grad_(True)
+
+    # ------------------------------------------------------------------ weight-gradient work items
+    def _backward_plan(self, plan):
+        G = self.G
+        key = id(plan)
+        ent = getattr(self, '_bp', None)
+        if ent is None or ent[0] != key or ent[2] != G._engine_ptr_key:
+            if G._dgrad is None:
+                G._dgrad = DgradSpecs(G._engine)
+                G._dgrad.pack(G._packed_params)
+            self._bp = (key, BackwardPlan(plan, G._dgrad, keep_gb=True), G._engine_ptr_key)
+            self._tables = {}
+        return self._bp[1]
+
+    def _items(self, plan, bp):
+        """Device tables of esr_wgrad_item / esr_wgrad_small_item per bucket (built once per plan)."""
+        key = (id(plan), id(bp))
+        if key in self._tables:
+            return self._tables[key]
+        eng = plan.eng
+        B, hp, wp, sf = plan.B, plan.hp, plan.wp, plan.sf
+        nz, nzi = eng.nz, eng.nz_in
+        f16 = 1 if eng.outer_mode == "f16" else 0
+        n_rdb = 3 * eng.nb
+        names = eng.outer_names
+        H4, W4 = sf * hp, sf * wp
+        # conv -> (x16 tensor, channels, is fp16, small planes tensor, planes used, g tensor, g first channel, cout staged, n_co, H, W)
+        spec = {}
+        spec[names[-1]] = (plan.V2, NF, f16, plan.z_hr, nz, bp.E6, 0, 16, eng.out_nc, H4, W4)
+        spec[names[-2]] = (plan.V1, NF, f16, plan.z_hr, nz, bp.GV, 0, NF, NF, H4, W4)
+        for u in range(eng.n_up):
+            res = 2 ** (u + 1)
+            spec[names[1 + u]] = (plan.U[u], NF, f16, None, 0, bp.GVu[u], 0, NF, NF, res * hp, res * wp)
+        spec[names[0]] = (plan.buf(n_rdb), NF, f16, plan.z_lr, nz, bp.GS, 0, NF, NF, hp, wp)
+        for g in range(n_rdb):
+            r, dd = divmod(g, 3)
+            for i in range(5):
+                cout = GC if i < 4 else NF
+                gc0 = 0 if i == 4 else NF + GC * i
+                spec["model.1.sub.%d.RDB%d.convs.%d.0" % (r, dd + 1, i)] = (plan.bufs[g], NF + GC * i, 0, plan.z_lr, nz, bp.gb(g), gc0,
+                                                                             cout, cout, hp, wp)
+        spec["model.0"] = (None, 0, 0, plan.fea_in, nzi + 3, bp.GFea, 0, NF, NF, hp, wp)
+        tables = []
+        for names_b, _, _ in self.buckets:
+            big, small = [], []
+            for name in names_b:
+                x16, c16, xf16, sm, n_c, g, gc0, cout, n_co, H, W = spec[name]
+                w_off, _, wp_ = self.slices[name + ".weight"]
+                b_off = self.slices[name + ".bias"][0]
+                cin_total = wp_.shape[1]
+                dw = self.flat.data_ptr() + 4 * w_off
+                assert cin_total == c16 + n_c, (name, cin_total, c16, n_c)
+                tiles = B * ((H + TILE_H - 1) // TILE_H) * ((W + TILE_W - 1) // TILE_W)
+                chunks = max(1, (H * W) // (hp * wp))          # higher-resolution convs are cut into chunks of LR-conv size
+                for c0 in range(0, c16, 16):
+                    for ch in range(chunks):
+                        it = WgradItem()
+                        it.x, it.g, it.dw = x16.data_ptr(), g.data_ptr(), dw
+                        it.x_stride, it.x_c0, it.x_f16 = x16.shape[-1], c0, xf16
+                        it.g_stride, it.g_c0, it.cout = g.shape[-1], gc0, cout
+                        it.n_co, it.n_ci, it.cin_total, it.ci0 = n_co, min(16, c16 - c0), cin_total, n_c + c0
+                        it.B, it.H, it.W = B, H, W
+                        if chunks > 1:
+                            it.tile_begin, it.tile_end = tiles * ch // chunks, tiles * (ch + 1) // chunks
+                        big.append(it)
+                sit = WgradSmallItem()
+                sit.g, sit.dw, sit.db = g.data_ptr(), dw, self.flat.data_ptr() + 4 * b_off
+                sit.s = sm.data_ptr() if (sm is not None and n_c > 0) else 0
+                sit.g_stride, sit.g_c0, sit.cout, sit.n_co = g.shape[-1], gc0, cout, n_co
+                sit.s_channels, sit.s_c0, sit.n_c = (sm.shape[1] if sm is not None else 0), 0, n_c
+                sit.cin_total, sit.ci0, sit.B, sit.H, sit.W = cin_total, 0, B, H, W
+                small.append(sit)
+            big_arr = (WgradItem * max(1, len(big)))(*big)
+            small_arr = (WgradSmallItem * len(small))(*small)
+            tables.append((_struct_array_to_device(big_arr, WgradItem, self.dev) if big else None, len(big),
+                           _struct_array_to_device(small_arr, WgradSmallItem, self.dev), len(small)))
+        self._tables = {key: tables}
+        return tables
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, grad_fake_H, all_reduce=True):
+        """dL/dW and dL/db of every generator conv for the gradient w.r.t. the last forward's output; with an initialised
+        process group the result is averaged over the ranks.  Returns the gradient w.r.t. model_input."""
+        if self._state is None:
+            raise capi.EsrError("GeneratorTrainer.backward before forward")
+        plan, filters, margin = self._state
+        self._state = None
+        l = capi.lib()
+        world = dist.get_world_size(self.group) if (all_reduce and dist.is_available() and dist.is_initialized()) else 1
+        with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream()
+            bp = self._backward_plan(plan)
+            g_in = generator_backward_eager(plan, bp, filters, margin, grad_fake_H.contiguous().float())
+            tables = self._items(plan, bp)
+            self.flat.zero_()                                  # chunked high-resolution items accumulate
+            handles = []
+            for (names_b, lo, hi), (big, nbig, small, nsmall) in zip(self.buckets, tables):
+                if nbig:
+                    capi.check(l.esr_wgrad16(C.c_void_p(big.data_ptr()), nbig, capi.stream_ptr()))
+                capi.check(l.esr_wgrad_small(C.c_void_p(small.data_ptr()), nsmall, capi.stream_ptr()))
+                if world > 1:                                  # this bucket's exchange runs under the next buckets' kernels
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    with torch.cuda.stream(self.comm):
+                        self.comm.wait_event(ev)
+                        handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            for hnd in handles:
+                hnd.wait()
+            if world > 1:
+                cur.wait_stream(self.comm)
+        return g_in
+
+    def grad_bytes(self):
+        return self.flat.numel() * 4

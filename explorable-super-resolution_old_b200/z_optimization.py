@@ -70,6 +70,89 @@ class Optimizable_Z(torch.nn.Module):
 
 
 _BUILT = ('l1', 'TV', 'max_STD', 'min_STD', 'STD_increase', 'STD_decrease')
+_FUSED = ('TV', 'max_STD', 'min_STD', 'STD_increase', 'STD_decrease')
+HIST_LEN = 4096
+
+
+class _FusedZLoop:
+    """The whole iteration of Z_optimizer.optimize (Z_optimization.py:572-635) as ONE CUDA graph of this package's
+    kernels: tanh + packing -> G forward -> CEM -> objective -> its gradient -> CEM adjoint -> G data-gradient ->
+    tanh' + Adam.  No ATen kernel and no host read inside the loop; losses are collected on the device and read once."""
+
+    def __init__(self, zopt, wrapper, G, lr_img, key):
+        import ctypes as C
+        from . import _capi as capi
+        from .rrdbnet import _forward_eager, _capture
+        from .backward import generator_backward_eager
+        self.key = key
+        Zp = zopt.Z_model.Z
+        dev = Zp.device
+        # the graph works on its own copy of Z: Optimizable_Z.forward re-assigns Z.data (its clamp), so the parameter's
+        # storage is not a stable address across optimize() calls; run() copies Z in before and out after the replays
+        self.zbuf = Zp.data.clone()
+        B, nz = Zp.shape[0], Zp.shape[1]
+        h, w = lr_img.shape[2:]
+        sf = G.upscale
+        margin = wrapper._margin_LR if wrapper.pre_pad else 0
+        filters = wrapper._filters
+        self.B, self.n_lat, self.n_img = B, nz * sf * sf * h * w, (nz * sf * sf + 3) * h * w
+        self.x = torch.empty(B, nz * sf * sf + 3, h, w, device=dev, dtype=torch.float32)
+        self.x[:, nz * sf * sf:] = lr_img.to(dev).float().expand(B, -1, -1, -1)
+        plan = G.plan(B, h, w, margin, keep=True)
+        bp = G.backward_plan(plan)
+        crop = sf * margin
+        H, W = sf * plan.hp - 2 * crop, sf * plan.wp - 2 * crop
+        onc = plan.y.size(1)
+        self.out = torch.empty(B, onc, H, W, device=dev, dtype=torch.float32)
+        self.ws = torch.empty(max(1, 2 * B * onc * plan.hp * plan.wp), device=dev, dtype=torch.float32)
+        self.g = torch.zeros_like(self.out)
+        l = capi.lib()
+        self.red = torch.empty(int(l.esr_zopt_loss_workspace_floats(B, H)), device=dev, dtype=torch.float32)
+        self.stats = torch.zeros(B, 8, device=dev, dtype=torch.float32)
+        self.hist = torch.zeros(HIST_LEN, device=dev, dtype=torch.float32)
+        self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        opt = zopt.optimizer
+        grp = opt.param_groups[0]
+        st = opt.state[Zp]                           # created by Z_optimizer._fused_loop when torch had not yet
+        self.state = st
+        mode, sign, w_std, target = zopt._fused_objective()
+        self.target = target.to(dev).float().reshape(-1).expand(B).contiguous() if target is not None else None
+        self.plan, self.bp, self.keep = plan, bp, (wrapper, G, filters)
+        z_range = float(zopt.Z_model.Z_range)
+        lr, (b1, b2), eps = float(grp['lr']), grp['betas'], float(grp['eps'])
+
+        def iteration():
+            sp = capi.stream_ptr()
+            capi.check(l.esr_zopt_tanh_pack(capi.ptr(self.zbuf), z_range, B, self.n_lat, self.n_img, capi.ptr(self.x), sp))
+            _forward_eager(plan, self.x, filters, crop, self.out, self.ws)
+            capi.check(l.esr_zopt_loss(capi.ptr(self.out), B, onc, H, W, mode, sign, w_std, capi.ptr(self.target), capi.ptr(self.red),
+                                       capi.ptr(self.stats), capi.ptr(self.hist), HIST_LEN, capi.ptr(self.step), sp))
+            capi.check(l.esr_zopt_loss_grad(capi.ptr(self.out), B, onc, H, W, capi.ptr(self.stats), capi.ptr(self.g), sp))
+            g_in = generator_backward_eager(plan, bp, filters, margin, self.g)
+            capi.check(l.esr_zopt_adam(capi.ptr(self.zbuf), capi.ptr(st['exp_avg']), capi.ptr(st['exp_avg_sq']), capi.ptr(g_in), z_range, B,
+                                       self.n_lat, self.n_img, lr, float(b1), float(b2), eps, capi.ptr(self.step), sp))
+            return g_in
+        # the warm-up pass that precedes the capture is a real iteration: put the state back afterwards
+        keep = [t.clone() for t in (st['exp_avg'], st['exp_avg_sq'])]
+        with torch.cuda.device(dev):
+            self.graph, self.g_in = _capture(iteration, dev)
+        for t, k in zip((st['exp_avg'], st['exp_avg_sq']), keep):
+            t.copy_(k)
+        self.launches = None
+
+    def run(self, iters, Zp):
+        """Replays `iters` iterations on the parameter Zp; returns (loss per iteration, per-image losses of the last one)."""
+        k0 = int(float(self.state['step']))
+        self.step.fill_(k0)
+        self.zbuf.copy_(Zp.data)
+        for _ in range(iters):
+            self.graph.replay()
+        Zp.data.copy_(self.zbuf)
+        idx = (torch.arange(k0, k0 + iters, device=self.hist.device) % HIST_LEN)
+        losses = self.hist[idx].cpu().tolist()                     # the one host read of the loop
+        latest = self.stats[:, 4].cpu().tolist()
+        self.state['step'] = torch.tensor(float(k0 + iters))
+        return losses, latest
 
 
 class Z_optimizer():
@@ -138,6 +221,68 @@ class Z_optimizer():
             else 'allButFirst' if (initial_pre_tanh_Z is not None and initial_pre_tanh_Z.size(0) < batch_size) else False
         self.HR_unpadder = HR_unpadder
 
+    def _fused_objective(self):
+        """(mode, sign, std weight, per-image target STD) of esr_zopt_loss for this objective."""
+        o = self.objective
+        if o == 'TV':
+            return 0, 1.0, float(self.STD_PRESERVING_WEIGHT), self.initial_STD
+        if o in ('max_STD', 'min_STD'):
+            return 1, (-1.0 if 'max' in o else 1.0), 0.0, None
+        return 2, 1.0, 0.0, self.desired_STD
+
+    def _fused_loop(self):
+        """The single-graph loop when everything in the iteration is this package's: a built objective without masks, a
+        fixed iteration count, no loggers, GUI (eval) mode, torch's plain Adam on Z alone, and a netG that is this
+        package's CEM-wrapped RRDBNet with a latent input.  None otherwise (the generic loop below runs instead)."""
+        from .cem import CEM_PyTorch
+        from .rrdbnet import RRDBNet
+        if os.environ.get('ESR_ZOPT_FUSED', '1') == '0' or self.objective not in _FUSED:
+            return None
+        if not (0 < self.max_iters <= HIST_LEN) or self.loggers is not None or self.model_training or self.scheduler is not None:
+            return None
+        if self.Z_model.mask is not None or self.Z_mask is not None or self.Z_model.Z_range is None:
+            return None
+        if self.objective in ('STD_increase', 'STD_decrease', 'TV') and not hasattr(self, 'desired_STD' if 'STD' in self.objective else 'STD_PRESERVING_WEIGHT'):
+            return None
+        wrapper = getattr(self.model.netG, 'module', self.model.netG)
+        G = getattr(wrapper, 'generated_image_model', None)
+        if not isinstance(wrapper, CEM_PyTorch) or not isinstance(G, RRDBNet) or G._cfg['nz_in'] == 0:
+            return None
+        opt = self.optimizer
+        if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
+            return None
+        grp = opt.param_groups[0]
+        if len(grp['params']) != 1 or grp['params'][0] is not self.Z_model.Z or grp.get('amsgrad') or grp.get('weight_decay') \
+                or grp.get('maximize') or grp.get('capturable') or grp.get('differentiable'):
+            return None
+        Zp, lr_img = self.Z_model.Z, self.data['LR']
+        sf = G.upscale
+        if not Zp.is_cuda or Zp.dtype != torch.float32 or not Zp.is_contiguous() or lr_img.dim() != 4 or \
+                lr_img.size(0) not in (1, Zp.size(0)) or tuple(Zp.shape[2:]) != (sf * lr_img.size(2), sf * lr_img.size(3)) or \
+                Zp.size(1) != G._cfg['nz_in'] or (lr_img.size(2) * lr_img.size(3)) % 4 != 0:
+            return None
+        if self.objective in ('TV', 'STD_increase', 'STD_decrease'):
+            tgt = self.initial_STD if self.objective == 'TV' else self.desired_STD
+            if tgt.numel() not in (1, Zp.size(0)):
+                return None
+        st = opt.state[Zp]
+        if 'exp_avg' not in st:                     # torch.optim.Adam creates these lazily at its first step()
+            st['step'] = torch.tensor(0.0)
+            st['exp_avg'] = torch.zeros_like(Zp, memory_format=torch.preserve_format)
+            st['exp_avg_sq'] = torch.zeros_like(Zp, memory_format=torch.preserve_format)
+        key = (tuple(Zp.shape), tuple(lr_img.shape), wrapper.pre_pad, id(wrapper._filters), float(grp['lr']), tuple(grp['betas']),
+               float(grp['eps']), self.objective, tuple((p.data_ptr(), p._version) for p in G.parameters()),
+               float(self.Z_model.Z_range), lr_img.data_ptr(), lr_img._version,
+               st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr())
+        cur = getattr(self, '_fused', None)
+        if cur is None or cur.key != key:
+            if cur is not None and os.environ.get('ESR_ZOPT_DEBUG'):
+                import sys
+                print('fused Z loop re-captured; key fields that changed:', [(i, a, b) for i, (a, b) in enumerate(zip(cur.key, key)) if a != b and i != 8], file=sys.stderr)
+            self._fused = None                      # free the old graph's buffers first
+            self._fused = _FusedZLoop(self, wrapper, G, lr_img, key)
+        return self._fused
+
     def Masked_STD(self, first_image_only=False):
         return torch.std(self.model.fake_H * self.image_mask, dim=(1, 2, 3)).view(1, -1)
 
@@ -173,7 +318,16 @@ class Z_optimizer():
         if self.random_Z_inits and self.cur_iter == 0:
             self.Z_model.Randomize_Z(what_2_shuffle=self.random_Z_inits)
         z_iter = self.cur_iter
-        while True:
+        fused = self._fused_loop()
+        while fused is not None:                    # one pass: every iteration is a replay of one CUDA graph
+            self.loss_values, self.latest_Z_loss_values = fused.run(self.max_iters, self.Z_model.Z)
+            z_iter += self.max_iters
+            self.data['Z'] = fused.x[:, :-3].reshape(self.Z_model.Z.shape).clone()     # the Z of the last forward, as in the reference
+            self.model.feed_data(self.data, need_HR=False)
+            self.model.fake_H = fused.out.clone()
+            defer, pending_latest = False, None
+            break
+        while fused is None:
             if self.max_iters > 0:
                 if z_iter == (self.cur_iter + self.max_iters):
                     break

@@ -323,6 +323,58 @@ int esr_cem2d_project(const esr_cem_filters2d* f, const float* y, const float* x
 int esr_cem2d_project_bwd(const esr_cem_filters2d* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
                           int32_t crop, float* g_y, float* workspace, void* stream);
 
+/* ------------------------------------------------- Z optimisation plumbing (csrc/zopt.cu)
+ * One iteration of the editing loop (codes/Z_optimization.py:572-635) without ATen kernels: Optimizable_Z.forward
+ * (:300-305), the 'TV' / global-STD objectives on fake_H (:322-324, :426-435, :474-475, :525-535, :603-607, :618-619)
+ * with their gradient, and tanh' chained with torch.optim.Adam's update (:512).  All tensors fp32, contiguous.
+ *   Z           [B, n_lat] pre-tanh control signal (n_lat = nz * sf^2 * h * w), clamped to finite in place
+ *   model_input [B, n_img] packed [Z.view, LR] generator input (n_img = n_lat + 3*h*w): only the latent part is written
+ *   mode        0: w_std * (std - target[b])^2 + TV,  1: sign * std,  2: (std - target[b])^2   (std = torch.std, unbiased)
+ *   stats       [B, 8] out: mean, std, gradient coefficients, loss_b (index 4), 1/nx, 1/ny, tv_b
+ *   hist        [hist_len] or NULL: mean loss of iteration *step is stored at hist[*step]; *step is then incremented
+ *   step        device int: completed iterations before the call; esr_zopt_adam reads the incremented value */
+int esr_zopt_tanh_pack(float* Z, float z_range, int32_t B, int32_t n_lat, int32_t n_img, float* model_input, void* stream);
+int32_t esr_zopt_loss_workspace_floats(int32_t B, int32_t H);
+int esr_zopt_loss(const float* fake_H, int32_t B, int32_t C, int32_t H, int32_t W, int32_t mode, float sign, float w_std,
+                  const float* target, float* workspace, float* stats, float* hist, int32_t hist_len, int32_t* step,
+                  void* stream);
+int esr_zopt_loss_grad(const float* fake_H, int32_t B, int32_t C, int32_t H, int32_t W, const float* stats, float* g,
+                       void* stream);
+/* g_in: [B, n_img] gradient w.r.t. model_input; Z, exp_avg, exp_avg_sq: [B, n_lat], updated in place */
+int esr_zopt_adam(float* Z, float* exp_avg, float* exp_avg_sq, const float* g_in, float z_range, int32_t B, int32_t n_lat,
+                  int32_t n_img, float lr, float beta1, float beta2, float eps, const int32_t* step, void* stream);
+
+/* ------------------------------------------------- generator weight gradients (csrc/wgrad.cu)
+ * What autograd computes for the generator's conv parameters in the reference's training step
+ * (codes/models/SRRaGAN_model.py:463-547 with the block definitions of modules/block.py:129-155):
+ *   dW[co, ci, ky, kx] = sum g[n,y,x,co] * X[n, y+ky-1, x+kx-1, ci],   db[co] = sum g[n,y,x,co]
+ * from the tensors the forward and the data-gradient backward leave in HBM.  Item tables live in DEVICE memory. */
+typedef struct esr_wgrad_item {       /* one conv x one block of 16 input channels (x one spatial chunk) */
+    const void* x;                    /* conv input, NHWC 16-bit (bf16, or fp16 when x_f16), 16-byte aligned at x_c0 */
+    const void* g;                    /* gradient w.r.t. the conv's pre-activation output, NHWC bf16 */
+    float* dw;                        /* [n_co, cin_total, 3, 3] fp32 */
+    int32_t x_stride, x_c0, x_f16;    /* channels per pixel of x, first channel of this block */
+    int32_t g_stride, g_c0, cout;     /* channels per pixel of g, first channel, channels staged (16, 32, 48 or 64) */
+    int32_t n_co, n_ci;               /* valid output channels (<= cout) / valid input channels of the block (<= 16) */
+    int32_t cin_total, ci0;           /* dW's input-channel extent and this block's first input channel in it */
+    int32_t B, H, W;
+    int32_t tile_begin, tile_end;     /* tile_end > 0: only tiles [tile_begin, tile_end) of the B*ceil(H/8)*ceil(W/16), dW accumulated
+                                         with atomicAdd (must be zeroed by the caller); 0: all tiles, dW slice overwritten */
+} esr_wgrad_item;
+int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* stream);
+
+typedef struct esr_wgrad_small_item { /* one conv: its <= 8 fp32 NCHW input channels (latent, LR image) and its bias */
+    const void* g;                    /* NHWC bf16 */
+    const float* s;                   /* [B, s_channels, H, W] fp32 */
+    float* dw;                        /* [n_co, cin_total, 3, 3] */
+    float* db;                        /* [n_co] or NULL */
+    int32_t g_stride, g_c0, cout, n_co;
+    int32_t s_channels, s_c0, n_c;    /* planes per image, first plane, planes used (0: bias only) */
+    int32_t cin_total, ci0;
+    int32_t B, H, W;
+} esr_wgrad_small_item;
+int esr_wgrad_small(const esr_wgrad_small_item* items_device, int32_t n_items, void* stream);
+
 /* Debug aid: the x4 CEM streaming kernels record a ring wait that never completed instead of trapping;
  * out4 = {code (0 = none, 1 = Down, 2 = K+Up), block, thread, group}; reading clears it. */
 int esr_debug_cem_timeout(uint32_t* out4);

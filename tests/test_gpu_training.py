@@ -1,0 +1,78 @@
+"""Generator weight gradients (csrc/wgrad.cu, training.GeneratorTrainer) against autograd through the CPU oracle: the
+generator half of the reference's training step (codes/models/SRRaGAN_model.py:463-547 with trainable G parameters).
+Tolerance: bf16 gradient and activation operands (8 significant bits, random rounding errors averaged over the pixels):
+relative error of every weight gradient < 6 % (bias gradient < 8 %), cosine > 0.998 (0.997).  The error is the data-gradient chain's (the bound of
+tests/test_gpu_backward.py): measured 2.6-4.8 %, equal for the latent (exact fp32 input) and the 16-bit input channels of
+a conv, largest for the earliest blocks whose gradient went through the most bf16 dgrads."""
+import pytest
+import torch
+
+from esr_b200 import synth
+from esr_b200.training import GeneratorTrainer
+from oracle.cem_ops import concat_latent
+from oracle.rrdbnet import GCEMOracle
+from tests.test_gpu_net import build_product_G
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_grads(wts, nb, mi, gout, train):
+    w = {k: v.clone().requires_grad_(True) for k, v in wts.items()}
+    out = GCEMOracle(w, pre_pad=not train, nb=nb).forward(mi)
+    (out * gout).sum().backward()
+    return out.detach(), {k: v.grad for k, v in w.items()}
+
+
+@pytest.mark.parametrize("nb,B,h,w,train,kind", [(1, 2, 24, 32, True, "default"), (2, 1, 28, 24, False, "kaiming")])
+def test_weight_gradients_match_oracle_autograd(cuda_device, nb, B, h, w, train, kind):
+    wts = synth.make_weights(kind, seed=3, nb=nb)
+    lr, z = synth.make_inputs(B, h, w, seed=3)
+    mi = concat_latent(lr, z)
+    netG = build_product_G(cuda_device, nb, "all_layers_HR_downscaled", wts, train=train)
+    trainer = GeneratorTrainer(netG)
+    fake = trainer.forward(mi.to(cuda_device))
+    gout = torch.randn(fake.shape, generator=torch.Generator().manual_seed(4))
+    ref_out, ref = _oracle_grads(wts, nb, mi, gout, train)
+    assert (fake.detach().cpu() - ref_out).abs().max().item() <= 1e-2
+    trainer.backward(gout.to(cuda_device))
+    G = netG.generated_image_model
+    worst = (0.0, None)
+    for name, p in G.named_parameters():
+        got, want = p.grad.cpu(), ref[name]
+        assert got.shape == want.shape and torch.isfinite(got).all(), name
+        rel = float((got - want).norm() / want.norm().clamp_min(1e-20))
+        cos = float((got * want).sum() / (got.norm() * want.norm()).clamp_min(1e-30))
+        worst = max(worst, (rel, name))
+        if want.dim() == 4 and want.shape[1] > 3:
+            print("%-40s rel %.4f cos %.5f | latent part rel %.4f, main part rel %.4f" % (
+                name, rel, cos, float((got[:, :3] - want[:, :3]).norm() / want[:, :3].norm()), float((got[:, 3:] - want[:, 3:]).norm() / want[:, 3:].norm())))
+        # a bias gradient is the plain sum of the bf16 gradient over the pixels (signs cancel): a little above the weights'
+        lim, cmin = (8e-2, 0.997) if name.endswith(".bias") else (6e-2, 0.998)
+        assert rel < lim and cos > cmin, "%s: relative error %g, cosine %g" % (name, rel, cos)
+    print("worst relative error", worst)
+
+
+def test_training_steps_reduce_the_loss_and_update_in_place(cuda_device):
+    """Three Adam steps of an L1 pixel loss through GeneratorTrainer: the loss falls, and the weight updates reach the
+    kernels without rebuilding plans (the packed weight images are refreshed inside their buffers)."""
+    wts = synth.make_weights("kaiming", seed=6, nb=1)
+    lr, z = synth.make_inputs(2, 16, 16, seed=6)
+    netG = build_product_G(cuda_device, 1, "all_layers_HR_downscaled", wts, train=True)
+    G = netG.generated_image_model
+    for p in G.parameters():
+        p.requires_grad_(True)
+    trainer = GeneratorTrainer(netG)
+    opt = torch.optim.Adam(G.parameters(), lr=1e-3)
+    target = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(7)).to(cuda_device)
+    mi = concat_latent(lr, z).to(cuda_device)
+    losses, plans = [], []
+    for _ in range(3):
+        fake = trainer.forward(mi)
+        loss = (fake - target).abs().mean()
+        loss.backward()
+        trainer.backward(fake.grad)
+        opt.step()
+        losses.append(float(loss))
+        plans.append(id(trainer._bp[1]))
+    assert losses[2] < losses[0], losses
+    assert len(set(plans)) == 1, "the backward plan was rebuilt after a weight update"
