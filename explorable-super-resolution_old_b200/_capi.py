@@ -130,7 +130,7 @@ SIGNATURES = {
     "esr_debug_set_profile_buffer": (None, [_vp]),
     "esr_debug_cem_timeout": (C.c_int, [C.POINTER(C.c_uint32)]),
     "esr_wgrad16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
-    "esr_wgrad_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "esr_wgrad_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "esr_zopt_tanh_pack": (C.c_int, [_vp, C.c_float, _i32, _i32, _i32, _vp, _vp]),
     "esr_zopt_loss_workspace_floats": (_i32, [_i32, _i32]),
     "esr_zopt_loss": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -99,18 +99,21 @@ class DgradSpecs:
             # logical dgrad weight [row = ci, slot = co, ky, kx] = W[co, ci, 2-ky, 2-kx]
             pc.pack(w, None, 8, 9, cin * 9, -3, -1)
         eng = self.eng
-        for r in range(eng.nb):
+        if not hasattr(self, "_U"):
+            self._U = {}                       # gathered [co_slot, ci, ky, kx] weights per RDB, kept: re-packing after a
+        for r in range(eng.nb):                # weight update is copies + pack launches, no allocation and no host sync
             for d in (1, 2, 3):
                 pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
                 ws = [params[pre + "%d.0" % i][0] for i in range(5)]
                 ci = ws[4].shape[1]
-                U = torch.zeros(NF + 4 * GC, ci, 3, 3, dtype=torch.float32, device=ws[0].device)   # [co_slot, ci, ky, kx]
+                U = self._U.get(pre)
+                if U is None or U.device != ws[0].device:
+                    U = self._U[pre] = torch.zeros(NF + 4 * GC, ci, 3, 3, dtype=torch.float32, device=ws[0].device)
                 U[:NF] = ws[4]
                 for m in range(1, 5):
                     U[NF + GC * (m - 1):NF + GC * m, :ws[m - 1].shape[1]] = ws[m - 1]
                 for k in (5, 4, 3, 2, 1):
                     self.trunk[pre + "%d" % k].pack(U, None, 8, 9, ci * 9, -3, -1)
-                torch.cuda.current_stream().synchronize()      # U is reused RDB by RDB
 
 
 class BackwardPlan:

@@ -76,13 +76,16 @@ class PackedConv:
         if self.wpack is None or self.wpack.device != dev:     # re-packing after a weight update reuses the buffers: the recorded
             self.wpack = torch.empty(self.total_bytes, dtype=torch.uint8, device=dev)      # launch sequences point at them
             self.bias = torch.empty(self.cout_tiles * self.cout_tile, dtype=torch.float32, device=dev)
-        rows_d = _struct_array_to_device(self.rows, WRow, dev)
-        slots_d = _struct_array_to_device(self.slots, WSlot, dev)
+        keep = getattr(self, "_keep", None)
+        if keep is None or keep[0].device != dev:              # the row / slot tables never change: uploaded once (a training
+            keep = (_struct_array_to_device(self.rows, WRow, dev),           # step re-packs all 351 convs after every update)
+                    _struct_array_to_device(self.slots, WSlot, dev))
+        rows_d, slots_d = keep
         capi.check(capi.lib().esr_pack_conv_weights(
             capi.ptr(weight), off, s_row, s_slot, s_ky, s_kx, capi.ptr(bias), self.cout_tile, self.cout_tiles,
             self.pair, self.nkb, self.kblocks, self.w_tile_bytes, capi.ptr(rows_d), capi.ptr(slots_d), capi.ptr(self.wpack),
             capi.ptr(self.bias), capi.stream_ptr()))
-        self._keep = (rows_d, slots_d)  # until the stream has consumed them
+        self._keep = keep
 
 
 def expand_slots(nvals_channels, precise, second="lo"):

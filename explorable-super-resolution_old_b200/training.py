@@ -178,7 +178,7 @@ class GeneratorTrainer:
             big_arr = (WgradItem * max(1, len(big)))(*big)
             small_arr = (WgradSmallItem * len(small))(*small)
             tables.append((_struct_array_to_device(big_arr, WgradItem, self.dev) if big else None, len(big),
-                           _struct_array_to_device(small_arr, WgradSmallItem, self.dev), len(small)))
+                           _struct_array_to_device(small_arr, WgradSmallItem, self.dev), len(small), max(s_.B * s_.H for s_ in small)))
         self._tables = {key: tables}
         return tables
 
@@ -199,10 +199,10 @@ class GeneratorTrainer:
             tables = self._items(plan, bp)
             self.flat.zero_()                                  # chunked high-resolution items accumulate
             handles = []
-            for (names_b, lo, hi), (big, nbig, small, nsmall) in zip(self.buckets, tables):
+            for (names_b, lo, hi), (big, nbig, small, nsmall, max_rows) in zip(self.buckets, tables):
                 if nbig:
                     capi.check(l.esr_wgrad16(C.c_void_p(big.data_ptr()), nbig, capi.stream_ptr()))
-                capi.check(l.esr_wgrad_small(C.c_void_p(small.data_ptr()), nsmall, capi.stream_ptr()))
+                capi.check(l.esr_wgrad_small(C.c_void_p(small.data_ptr()), nsmall, max_rows, capi.stream_ptr()))
                 if world > 1:                                  # this bucket's exchange runs under the next buckets' kernels
                     ev = torch.cuda.Event()
                     ev.record(cur)

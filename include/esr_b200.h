@@ -366,14 +366,15 @@ int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* strea
 typedef struct esr_wgrad_small_item { /* one conv: its <= 8 fp32 NCHW input channels (latent, LR image) and its bias */
     const void* g;                    /* NHWC bf16 */
     const float* s;                   /* [B, s_channels, H, W] fp32 */
-    float* dw;                        /* [n_co, cin_total, 3, 3] */
-    float* db;                        /* [n_co] or NULL */
+    float* dw;                        /* [n_co, cin_total, 3, 3], ACCUMULATED (atomicAdd over row chunks): zero it first */
+    float* db;                        /* [n_co] or NULL, accumulated likewise */
     int32_t g_stride, g_c0, cout, n_co;
     int32_t s_channels, s_c0, n_c;    /* planes per image, first plane, planes used (0: bias only) */
     int32_t cin_total, ci0;
     int32_t B, H, W;
 } esr_wgrad_small_item;
-int esr_wgrad_small(const esr_wgrad_small_item* items_device, int32_t n_items, void* stream);
+/* max_rows: the largest B*H among the items (row chunks of the grid) */
+int esr_wgrad_small(const esr_wgrad_small_item* items_device, int32_t n_items, int32_t max_rows, void* stream);
 
 /* Debug aid: the x4 CEM streaming kernels record a ring wait that never completed instead of trapping;
  * out4 = {code (0 = none, 1 = Down, 2 = K+Up), block, thread, group}; reading clears it. */
