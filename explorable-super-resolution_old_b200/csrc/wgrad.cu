@@ -5,45 +5,61 @@
 // where X is the conv's input as the forward left it in HBM (16-bit NHWC slices of the dense-block / outer buffers,
 // plus the small fp32 NCHW latent / LR planes) and g the gradient w.r.t. its pre-activation output as the data-gradient
 // backward left it (bf16 NHWC).  Two kernels:
-//   wgrad16_kernel    one CTA per (conv, block of 16 input channels): K = pixels, warp-level bf16 MMAs (m16n16k16,
-//                     fp32 accumulate) on shared-memory tiles; every CTA owns its slice of dW for all pixels (no atomics,
+//   wgrad16_kernel    one CTA per (conv, block of 16 input channels): K = pixels, warp-level bf16 MMAs (mma.sync m16n8k16
+//                     fed by ldmatrix.trans, fp32 accumulate) on shared-memory tiles; every CTA owns its slice of dW for all pixels (no atomics,
 //                     deterministic) unless the item is a spatial chunk of a high-resolution conv (atomicAdd then).
 //   wgrad_small_kernel  the <= 8 fp32 NCHW input channels (latent, LR image) and the bias: lanes = output channels.
 // First version: legacy mma.sync tensor path (HMMA), not tcgen05 - DESIGN.md lists the tcgen05 form (MN-major
 // operands straight from the NHWC tiles) as the next step.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
-#include <mma.h>
 
 #include "esr_common.cuh"
 
 namespace esr {
-
-using namespace nvcuda;
 
 constexpr int kWgTH = 8, kWgTW = 16;               // spatial tile: 8 rows x 16 pixels (one k-step per row)
 constexpr int kWgThreads = 256;
 constexpr int kWgXPitch = 16;                      // input channels per item
 constexpr int kWgMaxCout = 64;
 
-__global__ void __launch_bounds__(kWgThreads) wgrad16_kernel(const esr_wgrad_item* __restrict__ items) {
+// ldmatrix.trans: both operands are stored pixel-major ([k = pixel][m or n = channel]) and the MMA wants K innermost, so
+// every 8x8 block is transposed on the way into the fragment.  (The first version went through wmma::load_matrix_sync:
+// generic LD.E loads + MOVM register transposes, 49 instructions per MMA; this form is 2 LDSM + 2 HMMA.)
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_row))));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kWgThreads, 3) wgrad16_kernel(const esr_wgrad_item* __restrict__ items) {
     const esr_wgrad_item it = items[blockIdx.x];
     __shared__ __align__(32) __nv_bfloat16 Xs[(kWgTH + 2) * (kWgTW + 2) * kWgXPitch];
     __shared__ __align__(32) __nv_bfloat16 Gs[kWgTH * kWgTW * (kWgMaxCout + 16)];
-    __shared__ __align__(32) float Os[8][16 * 16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncb = it.cout >> 4;                  // 16-channel blocks of the output
     const int nfrag = 9 * ncb;                     // (tap, co block) accumulators, round-robin over the 8 warps
-    const int gp = it.cout + 16;                   // pixel pitch of the g tile (elements): keeps 32-byte fragment alignment
+    const int gp = it.cout + 16;                   // pixel pitch of the g tile (elements): rows stay 32-byte aligned
     constexpr int kMaxFr = (9 * (kWgMaxCout / 16) + 7) / 8;
-    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[kMaxFr];
+    float acc[kMaxFr][2][4];                       // [fragment][ci half (n8)][mma accumulator]
 #pragma unroll
-    for (int f = 0; f < kMaxFr; ++f) wmma::fill_fragment(acc[f], 0.f);
+    for (int f = 0; f < kMaxFr; ++f)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[f][q >> 2][q & 3] = 0.f;
     const int tiles_x = (it.W + kWgTW - 1) / kWgTW, tiles_y = (it.H + kWgTH - 1) / kWgTH;
     const int tiles_img = tiles_x * tiles_y;
     const int t_end = it.tile_end > 0 ? it.tile_end : it.B * tiles_img;
     const uint16_t* xg = static_cast<const uint16_t*>(it.x);
     const uint16_t* gg = static_cast<const uint16_t*>(it.g);
+    // ldmatrix row of this lane inside a 16 (k) x 16 (m or n) operand block: matrices 0..3 = lanes 0-7, 8-15, 16-23, 24-31
+    const int lj = lane >> 3, lr = lane & 7;
+    const int a_k = (lj >> 1) * 8 + lr, a_m = (lj & 1) * 8;        // A: (k0,m0) = (0,0), (0,8), (8,0), (8,8)  -> a0..a3
+    const int b_k = (lj & 1) * 8 + lr, b_n = (lj >> 1) * 8;        // B: (k0,n0) = (0,0), (8,0), (0,8), (8,8)  -> b0,b1 | b0,b1
     for (int t = it.tile_begin; t < t_end; ++t) {
         const int n = t / tiles_img, r = t - n * tiles_img;
         const int y0 = (r / tiles_x) * kWgTH, x0 = (r % tiles_x) * kWgTW;
@@ -63,11 +79,11 @@ __global__ void __launch_bounds__(kWgThreads) wgrad16_kernel(const esr_wgrad_ite
                     for (int k = 0; k < 4; ++k) o[k] = __float22bfloat162_rn(__half22float2(h[k]));
                     v = *reinterpret_cast<const uint4*>(o);
                 }
-                if (it.n_ci < 16) {                // channels beyond the conv's input belong to someone else: contribute nothing
+                if (it.n_ci < 16 || it.ci_lo > 0) { // channels outside [ci_lo, n_ci) belong to someone else: contribute nothing
                     uint16_t* e = reinterpret_cast<uint16_t*>(&v);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        if (half * 8 + k >= it.n_ci) e[k] = 0;
+                        if (half * 8 + k >= it.n_ci || half * 8 + k < it.ci_lo) e[k] = 0;
                 }
             }
             *reinterpret_cast<uint4*>(Xs + p * kWgXPitch + half * 8) = v;
@@ -83,7 +99,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad16_kernel(const esr_wgrad_ite
             *reinterpret_cast<uint4*>(Gs + p * gp + q * 8) = v;
         }
         __syncthreads();
-        // ---- K = the tile's 128 pixels, 16 per step (one tile row)
+        // ---- K = the tile's 128 pixels, 16 per step (one tile row): D[co, ci] += sum_px g[px, co] * X[px + tap, ci]
 #pragma unroll
         for (int f = 0; f < kMaxFr; ++f) {
             const int fr = warp + f * 8;
@@ -92,38 +108,38 @@ __global__ void __launch_bounds__(kWgThreads) wgrad16_kernel(const esr_wgrad_ite
                 const int ky = tap / 3, kx = tap - ky * 3;
 #pragma unroll
                 for (int y = 0; y < kWgTH; ++y) {
-                    wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> a;     // (m = co, k = pixel)
-                    wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> b;     // (k = pixel, n = ci)
-                    wmma::load_matrix_sync(a, Gs + (y * kWgTW) * gp + cb * 16, gp);
-                    wmma::load_matrix_sync(b, Xs + ((y + ky) * (kWgTW + 2) + kx) * kWgXPitch, kWgXPitch);
-                    wmma::mma_sync(acc[f], a, b, acc[f]);
+                    uint32_t a[4], b[4];
+                    ldsm_x4_trans(a, Gs + (y * kWgTW + a_k) * gp + cb * 16 + a_m);
+                    ldsm_x4_trans(b, Xs + ((y + ky) * (kWgTW + 2) + kx + b_k) * kWgXPitch + b_n);
+                    mma_bf16_16816(acc[f][0], a, b[0], b[1]);          // ci 0..7
+                    mma_bf16_16816(acc[f][1], a, b[2], b[3]);          // ci 8..15
                 }
             }
         }
         __syncthreads();
     }
-    // ---- dW[co, ci0 + ci, ky, kx]
+    // ---- dW[co, ci0 + ci, ky, kx]: accumulator (row g / g+8, cols 2t, 2t+1) of each n8 half
+    const int gq = lane >> 2, tq = lane & 3;
 #pragma unroll
     for (int f = 0; f < kMaxFr; ++f) {
         const int fr = warp + f * 8;
         if (fr < nfrag) {
             const int tap = fr / ncb, cb = fr - tap * ncb;
-            wmma::store_matrix_sync(Os[warp], acc[f], 16, wmma::mem_row_major);                       // [co][ci]
-            __syncwarp();
-            for (int e = lane; e < 256; e += 32) {
-                const int co = cb * 16 + (e >> 4), ci = e & 15;
-                if (co < it.n_co && ci < it.n_ci) {
-                    float* dst = it.dw + (static_cast<size_t>(co) * it.cin_total + it.ci0 + ci) * 9 + tap;
-                    if (it.tile_end > 0) atomicAdd(dst, Os[warp][e]);
-                    else *dst = Os[warp][e];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int co = cb * 16 + gq + (e >> 1) * 8, ci = hlf * 8 + 2 * tq + (e & 1);
+                    if (co < it.n_co && ci < it.n_ci && ci >= it.ci_lo) {
+                        float* dst = it.dw + (static_cast<size_t>(co) * it.cin_total + it.ci0 + ci - it.ci_lo) * 9 + tap;
+                        if (it.tile_end > 0) atomicAdd(dst, acc[f][hlf][e]);
+                        else *dst = acc[f][hlf][e];
+                    }
                 }
-            }
-            __syncwarp();
         }
     }
 }
 
-// lanes = output channels (one 64-byte run of g per pixel and warp), narrow fp32 NCHW input planes broadcast
 // grid = (items, row chunks): a CTA sums over `rows_per_cta` image rows and adds its partial sums with atomicAdd (dW / db
 // zeroed by the caller); one CTA per conv over all pixels took 71 ms on the 128x128 convs of config 5
 __global__ void __launch_bounds__(256) wgrad_small_kernel(const esr_wgrad_small_item* __restrict__ items, int rows_per_cta) {
@@ -150,7 +166,10 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const esr_wgrad_small_
                     const uint16_t bits = gg[(static_cast<size_t>(rw) * it.W + x) * it.g_stride + it.g_c0 + co];
                     gv = __uint_as_float(static_cast<uint32_t>(bits) << 16);
                 }
-                acc[kMaxC * 9] += gv;                              // bias gradient
+                // bias gradient; the last conv's comes from the fp32 gradient planes (its true value is ~0 after the CEM
+                // adjoint removed the DC component: a sum of bf16-rounded terms would be pure rounding noise)
+                acc[kMaxC * 9] += (it.g32 != nullptr && live && co < it.n_co)
+                                      ? it.g32[(static_cast<size_t>(n) * it.n_co + co) * plane + static_cast<size_t>(y) * it.W + x] : gv;
                 if (it.n_c > 0) {
 #pragma unroll
                     for (int c = 0; c < kMaxC; ++c) {

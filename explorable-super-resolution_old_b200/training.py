@@ -129,50 +129,62 @@ class GeneratorTrainer:
         n_rdb = 3 * eng.nb
         names = eng.outer_names
         H4, W4 = sf * hp, sf * wp
-        # conv -> (x16 tensor, channels, is fp16, small planes tensor, planes used, g tensor, g first channel, cout staged, n_co, H, W)
+        # conv -> (x16 tensor, channels, is fp16, row-expanded small-channel tensor, its fp16 flag, small channels,
+        #          g tensor, g first channel, cout staged, n_co, H, W)
+        # The <= 6 small input channels (latent, LR image) are taken from the forward's row-expanded 16-bit tensors
+        # (E_lat / E_lath / E_fea: slot dy * n + c holds channel c of row y + dy - 1, so the centre row dy = 1 is the
+        # plain channel): one more 16-channel block on the tensor path instead of a scalar kernel over fp32 planes.
         spec = {}
-        spec[names[-1]] = (plan.V2, NF, f16, plan.z_hr, nz, bp.E6, 0, 16, eng.out_nc, H4, W4)
-        spec[names[-2]] = (plan.V1, NF, f16, plan.z_hr, nz, bp.GV, 0, NF, NF, H4, W4)
+        lat, lath = (plan.E_lat, 0, nz), (plan.E_lath, 0, nz)
+        spec[names[-1]] = (plan.V2, NF, f16, lath, bp.E6, 0, 16, eng.out_nc, H4, W4)
+        spec[names[-2]] = (plan.V1, NF, f16, lath, bp.GV, 0, NF, NF, H4, W4)
         for u in range(eng.n_up):
             res = 2 ** (u + 1)
-            spec[names[1 + u]] = (plan.U[u], NF, f16, None, 0, bp.GVu[u], 0, NF, NF, res * hp, res * wp)
-        spec[names[0]] = (plan.buf(n_rdb), NF, f16, plan.z_lr, nz, bp.GS, 0, NF, NF, hp, wp)
+            spec[names[1 + u]] = (plan.U[u], NF, f16, (None, 0, 0), bp.GVu[u], 0, NF, NF, res * hp, res * wp)
+        spec[names[0]] = (plan.buf(n_rdb), NF, f16, lat, bp.GS, 0, NF, NF, hp, wp)
         for g in range(n_rdb):
             r, dd = divmod(g, 3)
             for i in range(5):
                 cout = GC if i < 4 else NF
                 gc0 = 0 if i == 4 else NF + GC * i
-                spec["model.1.sub.%d.RDB%d.convs.%d.0" % (r, dd + 1, i)] = (plan.bufs[g], NF + GC * i, 0, plan.z_lr, nz, bp.gb(g), gc0,
+                spec["model.1.sub.%d.RDB%d.convs.%d.0" % (r, dd + 1, i)] = (plan.bufs[g], NF + GC * i, 0, lat, bp.gb(g), gc0,
                                                                              cout, cout, hp, wp)
-        spec["model.0"] = (None, 0, 0, plan.fea_in, nzi + 3, bp.GFea, 0, NF, NF, hp, wp)
+        spec["model.0"] = (None, 0, 0, (plan.E_fea, f16, nzi + 3), bp.GFea, 0, NF, NF, hp, wp)
         tables = []
         for names_b, _, _ in self.buckets:
             big, small = [], []
             for name in names_b:
-                x16, c16, xf16, sm, n_c, g, gc0, cout, n_co, H, W = spec[name]
+                x16, c16, xf16, (xs, xsf16, n_c), g, gc0, cout, n_co, H, W = spec[name]
                 w_off, _, wp_ = self.slices[name + ".weight"]
                 b_off = self.slices[name + ".bias"][0]
                 cin_total = wp_.shape[1]
                 dw = self.flat.data_ptr() + 4 * w_off
+                if xs is None:
+                    n_c = 0
                 assert cin_total == c16 + n_c, (name, cin_total, c16, n_c)
                 tiles = B * ((H + TILE_H - 1) // TILE_H) * ((W + TILE_W - 1) // TILE_W)
                 chunks = max(1, (H * W) // (hp * wp))          # higher-resolution convs are cut into chunks of LR-conv size
-                for c0 in range(0, c16, 16):
+                blocks = [(x16, c0, xf16, 0, min(16, c16 - c0), n_c + c0) for c0 in range(0, c16, 16)]
+                if n_c:                                        # the centre-row slots [n_c, 2 n_c) of the row-expanded tensor
+                    assert 2 * n_c <= 16
+                    blocks.append((xs, 0, xsf16, n_c, 2 * n_c, 0))
+                for (src, c0, sf16, ci_lo, ci_hi, ci0) in blocks:
                     for ch in range(chunks):
                         it = WgradItem()
-                        it.x, it.g, it.dw = x16.data_ptr(), g.data_ptr(), dw
-                        it.x_stride, it.x_c0, it.x_f16 = x16.shape[-1], c0, xf16
+                        it.x, it.g, it.dw = src.data_ptr(), g.data_ptr(), dw
+                        it.x_stride, it.x_c0, it.x_f16 = src.shape[-1], c0, sf16
                         it.g_stride, it.g_c0, it.cout = g.shape[-1], gc0, cout
-                        it.n_co, it.n_ci, it.cin_total, it.ci0 = n_co, min(16, c16 - c0), cin_total, n_c + c0
+                        it.n_co, it.n_ci, it.ci_lo, it.cin_total, it.ci0 = n_co, ci_hi, ci_lo, cin_total, ci0
                         it.B, it.H, it.W = B, H, W
                         if chunks > 1:
                             it.tile_begin, it.tile_end = tiles * ch // chunks, tiles * (ch + 1) // chunks
                         big.append(it)
-                sit = WgradSmallItem()
+                sit = WgradSmallItem()                         # the bias: sum of g over the pixels
                 sit.g, sit.dw, sit.db = g.data_ptr(), dw, self.flat.data_ptr() + 4 * b_off
-                sit.s = sm.data_ptr() if (sm is not None and n_c > 0) else 0
+                sit.g32 = bp.g_y.data_ptr() if name == names[-1] else 0
+                sit.s = 0
                 sit.g_stride, sit.g_c0, sit.cout, sit.n_co = g.shape[-1], gc0, cout, n_co
-                sit.s_channels, sit.s_c0, sit.n_c = (sm.shape[1] if sm is not None else 0), 0, n_c
+                sit.s_channels, sit.s_c0, sit.n_c = 0, 0, 0
                 sit.cin_total, sit.ci0, sit.B, sit.H, sit.W = cin_total, 0, B, H, W
                 small.append(sit)
             big_arr = (WgradItem * max(1, len(big)))(*big)
@@ -195,7 +207,10 @@ class GeneratorTrainer:
         with torch.cuda.device(self.dev):
             cur = torch.cuda.current_stream()
             bp = self._backward_plan(plan)
-            g_in = generator_backward_eager(plan, bp, filters, margin, grad_fake_H.contiguous().float())
+            gout = grad_fake_H.contiguous().float()
+            if filters is None:
+                bp.g_y.copy_(gout)                             # the last conv's bias gradient reads the fp32 planes from bp.g_y
+            g_in = generator_backward_eager(plan, bp, filters, margin, gout)
             tables = self._items(plan, bp)
             self.flat.zero_()                                  # chunked high-resolution items accumulate
             handles = []

@@ -355,7 +355,8 @@ typedef struct esr_wgrad_item {       /* one conv x one block of 16 input channe
     float* dw;                        /* [n_co, cin_total, 3, 3] fp32 */
     int32_t x_stride, x_c0, x_f16;    /* channels per pixel of x, first channel of this block */
     int32_t g_stride, g_c0, cout;     /* channels per pixel of g, first channel, channels staged (16, 32, 48 or 64) */
-    int32_t n_co, n_ci;               /* valid output channels (<= cout) / valid input channels of the block (<= 16) */
+    int32_t n_co, n_ci;               /* valid output channels (<= cout) / end of the valid input channels of the block (<= 16) */
+    int32_t ci_lo;                    /* first valid input channel of the block: channels [ci_lo, n_ci) map to dW[:, ci0 ...] */
     int32_t cin_total, ci0;           /* dW's input-channel extent and this block's first input channel in it */
     int32_t B, H, W;
     int32_t tile_begin, tile_end;     /* tile_end > 0: only tiles [tile_begin, tile_end) of the B*ceil(H/8)*ceil(W/16), dW accumulated
@@ -365,6 +366,7 @@ int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* strea
 
 typedef struct esr_wgrad_small_item { /* one conv: its <= 8 fp32 NCHW input channels (latent, LR image) and its bias */
     const void* g;                    /* NHWC bf16 */
+    const float* g32;                 /* optional [B, n_co, H, W] fp32 gradient: used for the bias sum instead of g */
     const float* s;                   /* [B, s_channels, H, W] fp32 */
     float* dw;                        /* [n_co, cin_total, 3, 3], ACCUMULATED (atomicAdd over row chunks): zero it first */
     float* db;                        /* [n_co] or NULL, accumulated likewise */

@@ -48,6 +48,11 @@ def test_weight_gradients_match_oracle_autograd(cuda_device, nb, B, h, w, train,
         if want.dim() == 4 and want.shape[1] > 3:
             print("%-40s rel %.4f cos %.5f | latent part rel %.4f, main part rel %.4f" % (
                 name, rel, cos, float((got[:, :3] - want[:, :3]).norm() / want[:, :3].norm()), float((got[:, 3:] - want[:, 3:]).norm() / want[:, 3:].norm())))
+        if name == "model.6.bias":
+            # the CEM projection does not depend on a constant added to the generator's output, so this gradient is zero up
+            # to border effects: compare absolutely (a sum of bf16-rounded terms would miss by ~0.5 here, fp32 sums by 1e-4)
+            assert float((got - want).abs().max()) <= 1e-6 * float(gout.abs().sum()), name
+            continue
         # a bias gradient is the plain sum of the bf16 gradient over the pixels (signs cancel): a little above the weights'
         lim, cmin = (10e-2, 0.995) if name.endswith(".bias") else (8e-2, 0.996)
         assert rel < lim and cos > cmin, "%s: relative error %g, cosine %g" % (name, rel, cos)
