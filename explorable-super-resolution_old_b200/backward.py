@@ -148,6 +148,11 @@ class BackwardPlan:
         self.g_z_hr = torch.zeros(B, max(eng.nz, 1), H4, W4, **f32)
         self.gy_x = _xslot_array(specs.gy_xslots)
         self.lat_x = _xslot_array([(c, dy - 1, 0) for dy in range(3) for c in range(max(eng.nz_in, 1))])
+        # backward twin of the fused growth launch (engine.GPlan.fuse_rdb): the four Mask dgrads of an RDB as one persistent
+        # launch with tile-level dependencies (mode 1 of esr_rdb_growth_tc); its own dependency counters
+        self.fuse_rdb = bool(getattr(plan, "fuse_rdb", False)) and not use_simt and os.environ.get("ESR_FUSE_RDB_BWD", "1") != "0"
+        self.rdb_flags = torch.zeros(int(capi.lib().esr_rdb_growth_flag_words(B, hp, wp)), dtype=torch.int32, device=dev) \
+            if self.fuse_rdb else None
         self.steps = []          # ("seq", handle) | ("call", fn)
         self._seqs = []
         self._cur = None
@@ -266,11 +271,23 @@ class BackwardPlan:
             buf = plan.bufs[g]
             GB = self.gb(g)
             pre = "model.1.sub.%d.RDB%d.convs." % (r, dd + 1)
-            for k in (5, 4, 3, 2):
-                # d(x_{k-1}) complete in one launch (K over g_5, g_4 .. g_k); emit g_{k-1} = LeakyReLU'(x_{k-1}) * d(x_{k-1})
-                ch = NF + GC * (k - 2)
-                self._conv(None, hp, wp, GB, None, 0, pc=self.specs.trunk[pre + "%d" % k], out_bf16=GB, bf16_stride=192,
-                           bf16_choff=ch, mask=buf, mask_stride=192, mask_choff=ch)
+            if self.fuse_rdb and os.environ.get("ESR_BWD_EAGER") != "1":
+                # the four launches below as ONE persistent launch: layer k may read what layers > k wrote once the 3x3 tile
+                # neighbourhood is stored (same kernel as the forward's fused growth convs, Mask epilogue)
+                layers = [(self.specs.trunk[pre + "%d" % k], NF + GC * (k - 2)) for k in (5, 4, 3, 2)]
+                d = plan._growth_desc(layers, GB, None, n_rdb - 1 - g, n_rdb, mode=1, mask=buf, flags=self.rdb_flags)
+                if self._cur is None:
+                    self._cur = capi.lib().esr_seq_create()
+                    self._seqs.append(self._cur)
+                    self.steps.append(("seq", self._cur))
+                self._descs.append(d)
+                capi.check(capi.lib().esr_seq_add_rdb_growth(self._cur, C.byref(d)))
+            else:
+                for k in (5, 4, 3, 2):
+                    # d(x_{k-1}) complete in one launch (K over g_5, g_4 .. g_k); emit g_{k-1} = LeakyReLU'(x_{k-1}) * d(x_{k-1})
+                    ch = NF + GC * (k - 2)
+                    self._conv(None, hp, wp, GB, None, 0, pc=self.specs.trunk[pre + "%d" % k], out_bf16=GB, bf16_stride=192,
+                               bf16_choff=ch, mask=buf, mask_stride=192, mask_choff=ch)
             # d(x_0): all five convs read it; add the residual paths, emit 0.2x (0.04x across an RRDB boundary) as the
             # g_5 of the RDB below; the last cout tile holds the block's 9 latent rows (accumulated per frame)
             pc = self.specs.trunk[pre + "1"]

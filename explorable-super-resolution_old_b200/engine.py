@@ -292,13 +292,18 @@ class GPlan:
         self.seq = capi.lib().esr_seq_create()
         self.descs = []
         # Fused growth convs (conv 0..3 of every RDB in one persistent launch with tile-level dependencies, csrc/
-        # conv3x3_tc2.cu).  Opt-in (ESR_FUSE_RDB=1): bit-identical, 78 % less DRAM traffic for those convs at 4-8 images
-        # per chunk, but with all four weight images resident only 4 A-ring stages fit and it measures 3 % slower
-        # than the separate launches at config 2.
+        # conv3x3_tc2.cu): bit-identical to the separate launches, 78 % less DRAM traffic for those convs at 4-8 images per
+        # chunk, 207 launches fewer.  With all four weight images resident only 4 A-ring stages fit, which costs 3 % at
+        # config 2 - but small plans are bound by the per-launch fixed cost and tile-round quantisation, not
+        # by the ring: there the fused launch wins (config 3: forward + backward 10.6 vs 10.9 ms in round 1).  Default:
+        # fused when the plan has at most ESR_FUSE_RDB_MAX_PIXELS padded LR pixels (120 k: config 3 = 76 k, two images of
+        # config 2 = 44 k, config 2 itself = 350 k); ESR_FUSE_RDB=1 / 0 forces it on / off.
         # (Round 1 kept plans below 32 x 32 padded pixels on separate launches because a 12 x 14 plan faulted: the item
         # decode divided by 1 through a magic number that had wrapped to 0 - fixed in csrc/conv3x3_tc2.cu: fast_div -
         # so every plan size takes the fused launch now; tests/test_gpu_net.py covers 12x14, 22x24, 33x35.)
-        self.fuse_rdb = eng.pair and not use_simt and os.environ.get("ESR_FUSE_RDB", "0") == "1"
+        force = os.environ.get("ESR_FUSE_RDB")
+        small = B * hp * wp <= int(os.environ.get("ESR_FUSE_RDB_MAX_PIXELS", 120000))
+        self.fuse_rdb = eng.pair and not use_simt and (force == "1" or (force is None and small))
         self.rdb_flags = torch.zeros(int(capi.lib().esr_rdb_growth_flag_words(B, hp, wp)), dtype=torch.int32, device=device) \
             if self.fuse_rdb else None
         self._record_forward(use_simt)
@@ -350,7 +355,7 @@ class GPlan:
             d.out_nchw, d.cout_real = out_nchw.data_ptr(), pc.cout
         return d
 
-    def _growth_desc(self, names, buf, lat, k, n, mode=0, mask=None):
+    def _growth_desc(self, names, buf, lat, k, n, mode=0, mask=None, flags=None):
         """esr_rdb_growth_desc of launch k of n: the convs `names` read / write the dense-block buffer `buf`."""
         d = RdbGrowthDesc()
         d.B, d.H, d.W = self.B, self.hp, self.wp
@@ -369,7 +374,7 @@ class GPlan:
         if mask is not None:
             d.mask, d.mask_stride = mask.data_ptr(), mask.shape[-1]
         d.imgs_per_chunk = int(os.environ.get("ESR_RDB_CHUNK", 0))
-        d.flags = self.rdb_flags.data_ptr()
+        d.flags = (flags if flags is not None else self.rdb_flags).data_ptr()
         assert n >= 2
         use = lambda i: 2 if (i == n - 1 and n % 2 == 1) else i % 2       # consecutive launches never share a third,
         d.flags_use, d.flags_zero = use(k), use((k + 1) % n)               # including last -> first of the next replay
