@@ -1111,18 +1111,22 @@ struct Adj1dArgs {
     const float* base;   // optional: out = base - result  (same shape as out)
 };
 
-__global__ void cem_adj1d_kernel(const __grid_constant__ Adj1dArgs a) {
-    const size_t total = static_cast<size_t>(a.planes) * a.other * a.nout;
-    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        int j, o;
-        size_t p;
-        if (a.axis == 0) { j = static_cast<int>(idx % a.nout); o = static_cast<int>((idx / a.nout) % a.other); }
-        else { o = static_cast<int>(idx % a.other); j = static_cast<int>((idx / a.other) % a.nout); }
-        p = idx / (static_cast<size_t>(a.nout) * a.other);
-        const float* gl = a.axis == 0 ? a.g + (p * a.other + o) * a.na : a.g + p * a.na * a.other + o;
-        const size_t gstride = a.axis == 0 ? 1 : a.other;
-        const int m = a.so * j + a.po;
+// Round 2: taps in shared memory (the tap index differs from lane to lane: as kernel-parameter / constant-bank reads
+// those were serialised up to 32x) and 32-bit index arithmetic (the 64-bit div / mod per output was most of the
+// instruction count).  The six passes of esr_cem_project_bwd took 1.3 ms of a 10.7 ms Z-optimisation iteration.
+__global__ void __launch_bounds__(256) cem_adj1d_kernel(const __grid_constant__ Adj1dArgs a) {
+    __shared__ float taps[ESR_CEM_MAX_TAPS];
+    for (int t = threadIdx.x; t < a.nt; t += blockDim.x) taps[t] = a.taps[t];
+    __syncthreads();
+    const uint32_t total = static_cast<uint32_t>(a.planes) * a.other * a.nout;      // host checks that it fits 32 bits
+    const uint32_t nout = a.nout, other = a.other;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        uint32_t j, o, p;
+        if (a.axis == 0) { const uint32_t q = idx / nout; j = idx - q * nout; p = q / other; o = q - p * other; }
+        else { const uint32_t q = idx / other; o = idx - q * other; p = q / nout; j = q - p * nout; }
+        const float* gl = a.axis == 0 ? a.g + (static_cast<size_t>(p) * other + o) * a.na : a.g + static_cast<size_t>(p) * a.na * other + o;
+        const int gstride = a.axis == 0 ? 1 : static_cast<int>(other);
+        const int m = a.so * static_cast<int>(j) + a.po;
         float acc = 0.f;
         // t = m + pad - off - sa*i (interior); borders collect every (i,t) that clamps onto them
         const int c0 = m + a.pad - a.off;
@@ -1131,7 +1135,7 @@ __global__ void cem_adj1d_kernel(const __grid_constant__ Adj1dArgs a) {
             i_lo = i_lo <= 0 ? 0 : i_lo / a.sa;
             int i_hi = c0 < 0 ? -1 : c0 / a.sa;
             if (i_hi > a.na - 1) i_hi = a.na - 1;
-            for (int i = i_lo; i <= i_hi; ++i) acc = fmaf(a.taps[c0 - a.sa * i], gl[i * gstride], acc);
+            for (int i = i_lo; i <= i_hi; ++i) acc = fmaf(taps[c0 - a.sa * i], gl[static_cast<size_t>(i) * gstride], acc);
         } else {
             // only the samples whose window reaches past the border can clamp onto it (conservative bounds; the
             // exact test is inside): pos <= 0 needs sa*i <= pad - off, pos >= Ls-1 needs sa*i >= Ls-1-off+pad-(nt-1)
@@ -1146,9 +1150,9 @@ __global__ void cem_adj1d_kernel(const __grid_constant__ Adj1dArgs a) {
                 for (int t = 0; t < a.nt; ++t) {
                     const int pos = base_pos + t;
                     const int cl = pos < 0 ? 0 : (pos > a.Ls - 1 ? a.Ls - 1 : pos);
-                    if (cl == m) wsum += a.taps[t];
+                    if (cl == m) wsum += taps[t];
                 }
-                if (wsum != 0.f) acc = fmaf(wsum, gl[i * gstride], acc);
+                if (wsum != 0.f) acc = fmaf(wsum, gl[static_cast<size_t>(i) * gstride], acc);
             }
         }
         acc *= a.scale;
@@ -1180,6 +1184,7 @@ int cem_pad_zero(const float* g, float* out, int planes, int H, int W, int crop,
 
 static int launch_adj1d(Adj1dArgs& a, cudaStream_t s) {
     const size_t total = static_cast<size_t>(a.planes) * a.other * a.nout;
+    ESR_CHECK_ARG(total < (1ull << 31), "CEM adjoint: %zu elements per pass exceed the 32-bit index range", total);
     const size_t want = (total + 255) / 256;
     const int grid = static_cast<int>(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
     cem_adj1d_kernel<<<grid, 256, 0, s>>>(a);
