@@ -94,26 +94,24 @@ __device__ __forceinline__ float gz_total(const PrepBwdArgs& a, int b, int c, in
     return v;
 }
 
-// One thread per element of the PADDED HR gradient: the replicate-pad adjoint folds every margin sample onto the
-// border pixel it was copied from (atomicAdd: a corner collects (M+1)^2 samples), interior samples have a single
-// writer.  g_in is zero-filled by the caller.
+// One thread per element of the UNPADDED HR gradient (gather form of the replicate-pad adjoint): an interior pixel has one
+// source, a border pixel sums the margin samples that were copied from it (a corner: (M+1)^2 of them) in a fixed order -
+// run-to-run reproducible, unlike the round-1 scatter with atomicAdd.  Every element of the latent part of g_in is written.
 __global__ void prep_bwd_kernel(const __grid_constant__ PrepBwdArgs a) {
     const int Hh = a.sf * a.h, Wh = a.sf * a.w, M = a.sf * a.m, cin = a.nz * a.sf * a.sf + 3;
-    const int Hp = Hh + 2 * M, Wp = Wh + 2 * M;
-    const size_t total = static_cast<size_t>(a.B) * a.nz * Hp * Wp;
+    const size_t total = static_cast<size_t>(a.B) * a.nz * Hh * Wh;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int X = static_cast<int>(idx % Wp);
-        const int Y = static_cast<int>((idx / Wp) % Hp);
-        const int c = static_cast<int>((idx / (static_cast<size_t>(Wp) * Hp)) % a.nz);
-        const int b = static_cast<int>(idx / (static_cast<size_t>(Wp) * Hp * a.nz));
-        const float v = gz_total(a, b, c, Y, X);
-        int y = Y - M, x = X - M;
-        y = y < 0 ? 0 : (y > Hh - 1 ? Hh - 1 : y);
-        x = x < 0 ? 0 : (x > Wh - 1 ? Wh - 1 : x);
-        float* dst = a.g_in + static_cast<size_t>(b) * cin * a.h * a.w + (static_cast<size_t>(c) * Hh + y) * Wh + x;
-        if (M > 0 && (y == 0 || y == Hh - 1 || x == 0 || x == Wh - 1)) atomicAdd(dst, v);
-        else *dst = v;
+        const int x = static_cast<int>(idx % Wh);
+        const int y = static_cast<int>((idx / Wh) % Hh);
+        const int c = static_cast<int>((idx / (static_cast<size_t>(Wh) * Hh)) % a.nz);
+        const int b = static_cast<int>(idx / (static_cast<size_t>(Wh) * Hh * a.nz));
+        const int Y0 = y == 0 ? 0 : y + M, Y1 = y == Hh - 1 ? Hh - 1 + 2 * M : y + M;       // padded rows that clamp onto y
+        const int X0 = x == 0 ? 0 : x + M, X1 = x == Wh - 1 ? Wh - 1 + 2 * M : x + M;
+        float v = 0.f;
+        for (int Y = Y0; Y <= Y1; ++Y)
+            for (int X = X0; X <= X1; ++X) v += gz_total(a, b, c, Y, X);
+        a.g_in[static_cast<size_t>(b) * cin * a.h * a.w + (static_cast<size_t>(c) * Hh + y) * Wh + x] = v;
     }
 }
 
@@ -222,7 +220,7 @@ extern "C" int esr_g_input_prep_bwd(const float* g_z_hr, const float* g_z_lr, in
     zero_kernel<<<grid_for(n_in), 256, 0, s>>>(g_model_input, n_in);
     if (int rc = check_launch("zero_kernel")) return rc;
     PrepBwdArgs a{g_z_hr, g_z_lr, B, nz, h, w, m, sf, g_model_input};
-    prep_bwd_kernel<<<grid_for(static_cast<size_t>(B) * nz * (h + 2 * m) * (w + 2 * m) * sf * sf), 256, 0, s>>>(a);
+    prep_bwd_kernel<<<grid_for(static_cast<size_t>(B) * nz * h * w * sf * sf), 256, 0, s>>>(a);
     return check_launch("prep_bwd_kernel");
 }
 

@@ -8,12 +8,17 @@ The module tree below only holds parameters under the reference's names
 ``process_loaded_state_dict`` (codes/models/base_model.py:113-144) keep working.
 """
 import math
+import threading
 
 import torch
 import torch.nn as nn
 
 from . import _capi as capi
 from .engine import GEngine, GPlan
+
+
+_CACHE_LOCK = threading.RLock()      # engine / plan caches of every RRDBNet are built under it (module level: an nn.Module
+                                     # must stay deep-copyable, a lock attribute is not); plans are keyed per host thread
 
 
 def _conv(cin, cout):
@@ -81,6 +86,10 @@ class RRDBNet(nn.Module):
         return {n[:-len(".weight")]: None for n, _ in self.named_parameters() if n.endswith(".weight")}
 
     def engine(self):
+        with _CACHE_LOCK:
+            return self._engine_locked()
+
+    def _engine_locked(self):
         params = dict(self.named_parameters())
         ptr_key = tuple(p.data_ptr() for p in params.values()) + (self.precise_outer, self.outer_mode)
         key = ptr_key + tuple(p._version for p in params.values())
@@ -108,6 +117,10 @@ class RRDBNet(nn.Module):
         return self._engine
 
     def backward_plan(self, plan):
+        with _CACHE_LOCK:
+            return self._backward_plan_locked(plan)
+
+    def _backward_plan_locked(self, plan):
         from .backward import DgradSpecs, BackwardPlan
         if self._dgrad is None:
             self._dgrad = DgradSpecs(self._engine)
@@ -122,14 +135,21 @@ class RRDBNet(nn.Module):
     def plan(self, B, h, w, m, keep, slot=0):
         """Buffers + recorded launches for one geometry.  `slot` selects an independent buffer set, for callers
         that keep several sub-batches in flight on different streams."""
-        eng = self.engine()
-        key = (B, h, w, m, keep, self.debug_simt, slot)
-        if key not in self._plans:
-            if len(self._plans) >= 4:
-                self._plans.pop(next(iter(self._plans)))
-            dev = next(self.parameters()).device
-            self._plans[key] = GPlan(eng, B, h, w, m, dev, keep_activations=keep, use_simt=self.debug_simt)
-        return self._plans[key]
+        # A plan's buffers hold one forward's activations: two host threads driving the same module (SURVEY.md 8b: the
+        # module must be replica-safe) get their own plans; an evicted plan stays alive as long as a captured graph or an
+        # autograd context still references it (they hold the object, the cache only holds the most recent four per thread).
+        tid = threading.get_ident()
+        thread_key = 0 if tid == threading.main_thread().ident else tid
+        with _CACHE_LOCK:
+            eng = self._engine_locked()
+            key = (B, h, w, m, keep, self.debug_simt, slot, thread_key)
+            if key not in self._plans:
+                mine = [k for k in self._plans if k[-1] == thread_key]
+                if len(mine) >= 4:
+                    self._plans.pop(mine[0])
+                dev = next(self.parameters()).device
+                self._plans[key] = GPlan(eng, B, h, w, m, dev, keep_activations=keep, use_simt=self.debug_simt)
+            return self._plans[key]
 
     def forward(self, x):
         return run_generator(self, x, margin=0, cem_filters=None)
