@@ -205,7 +205,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm + 1, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(1, BATCH), sample_images_per_step=n_img),
+            "config": workload_config(world, BATCH),              # the same dict as this repo's arm at the same N
             "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
