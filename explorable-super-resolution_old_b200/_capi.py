@@ -98,6 +98,11 @@ class CemFilters2d(C.Structure):
 
 CEM2D_MAX_SIDE = 63
 
+class CopySeg(C.Structure):              # esr_copy_seg
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("row_elems", C.c_int32),
+                ("src_pitch", C.c_int32), ("dst_pitch", C.c_int32)]
+
+
 class WgradItem(C.Structure):            # esr_wgrad_item
     _fields_ = [("x", C.c_void_p), ("g", C.c_void_p), ("dw", C.c_void_p),
                 ("x_stride", C.c_int32), ("x_c0", C.c_int32), ("x_f16", C.c_int32),
@@ -124,6 +129,11 @@ SIGNATURES = {
     "esr_pack_layout": (_i64, [_i32, _i32, _i32, _i32, C.POINTER(KBlock), C.POINTER(C.c_uint32)]),
     "esr_pack_conv_weights": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, C.POINTER(KBlock),
                                         C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "esr_pack_entry_bytes": (_i32, []),
+    "esr_pack_entry_fill": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, C.POINTER(KBlock),
+                                      C.c_uint32, _vp, _vp, _vp, _vp]),
+    "esr_pack_table_run": (C.c_int, [_vp, _i32, _vp]),
+    "esr_copy_segments": (C.c_int, [_vp, _i32, _vp]),
     "esr_expand_rows": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32, _vp, _vp]),
     "esr_expand_rows_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(XSlot), _i32,
                                       _vp, _vp]),

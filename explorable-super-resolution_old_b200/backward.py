@@ -91,29 +91,45 @@ class DgradSpecs:
         self.convs["model.0"] = PackedConv("model.0.dgrad", 32, kb, sl, _lat_rows(eng.nz_in), 32, pair=eng.pair) if eng.nz_in else None
 
     def pack(self, params):
-        for name, pc in self.convs.items():
-            if pc is None:
-                continue
-            w, _ = params[name]
-            cin = w.shape[1]
-            # logical dgrad weight [row = ci, slot = co, ky, kx] = W[co, ci, 2-ky, 2-kx]
-            pc.pack(w, None, 8, 9, cin * 9, -3, -1)
+        """Packs every dgrad weight image: one segment-copy launch gathers each dense block's five weight tensors into its
+        [co_slot, ci, 3, 3] array U, one table launch packs all ~420 images (built once per set of source pointers)."""
+        from .engine import PackTable
+        from ._capi import CopySeg
         eng = self.eng
-        if not hasattr(self, "_U"):
-            self._U = {}                       # gathered [co_slot, ci, ky, kx] weights per RDB, kept: re-packing after a
-        for r in range(eng.nb):                # weight update is copies + pack launches, no allocation and no host sync
-            for d in (1, 2, 3):
-                pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
-                ws = [params[pre + "%d.0" % i][0] for i in range(5)]
-                ci = ws[4].shape[1]
-                U = self._U.get(pre)
-                if U is None or U.device != ws[0].device:
-                    U = self._U[pre] = torch.zeros(NF + 4 * GC, ci, 3, 3, dtype=torch.float32, device=ws[0].device)
-                U[:NF] = ws[4]
-                for m in range(1, 5):
-                    U[NF + GC * (m - 1):NF + GC * m, :ws[m - 1].shape[1]] = ws[m - 1]
-                for k in (5, 4, 3, 2, 1):
-                    self.trunk[pre + "%d" % k].pack(U, None, 8, 9, ci * 9, -3, -1)
+        key = tuple(params[name][0].data_ptr() for name in sorted(params))
+        tab = getattr(self, "_pack_table", None)
+        if tab is None or tab.key != key:
+            dev = next(iter(params.values()))[0].device
+            entries, segs = [], []
+            self._U = {}
+            for name, pc in self.convs.items():
+                if pc is None:
+                    continue
+                w, _ = params[name]
+                cin = w.shape[1]
+                # logical dgrad weight [row = ci, slot = co, ky, kx] = W[co, ci, 2-ky, 2-kx]
+                pc.pack(w, None, 8, 9, cin * 9, -3, -1, table=entries)
+            for r in range(eng.nb):
+                for d in (1, 2, 3):
+                    pre = "model.1.sub.%d.RDB%d.convs." % (r, d)
+                    ws = [params[pre + "%d.0" % i][0] for i in range(5)]
+                    ci = ws[4].shape[1]
+                    U = self._U[pre] = torch.zeros(NF + 4 * GC, ci, 3, 3, dtype=torch.float32, device=dev)   # [co_slot, ci, ky, kx]
+                    for m in range(5):          # U[:64] = W5, U[64 + 32(m-1) ..][:, :cin_m] = W_m
+                        w = ws[4] if m == 0 else ws[m - 1]
+                        row0 = 0 if m == 0 else NF + GC * (m - 1)
+                        sg = CopySeg()
+                        sg.src, sg.dst = w.data_ptr(), U.data_ptr() + 4 * row0 * ci * 9
+                        sg.rows, sg.row_elems, sg.src_pitch, sg.dst_pitch = w.shape[0], w.shape[1] * 9, w.shape[1] * 9, ci * 9
+                        segs.append(sg)
+                    for k in (5, 4, 3, 2, 1):
+                        self.trunk[pre + "%d" % k].pack(U, None, 8, 9, ci * 9, -3, -1, table=entries)
+            arr = (CopySeg * len(segs))(*segs)
+            self._segs = (torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(dev), len(segs))
+            tab = self._pack_table = PackTable()
+            tab.build(key, entries, dev)
+        capi.check(capi.lib().esr_copy_segments(capi.ptr(self._segs[0]), self._segs[1], capi.stream_ptr()))
+        tab.run()
 
 
 class BackwardPlan:

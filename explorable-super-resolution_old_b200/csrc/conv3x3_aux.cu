@@ -2,6 +2,8 @@
 // same descriptor / packed weights as the tcgen05 kernel, and the small-channel row expansion.
 #include <cuda_bf16.h>
 
+#include <cstring>
+
 #include "conv3x3.cuh"
 
 namespace esr {
@@ -82,13 +84,13 @@ struct PackArgs {
     float* bias_out;
 };
 
-__global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
+__device__ __forceinline__ void pack_one(const PackArgs& a, const unsigned bx, const unsigned nbx) {
     const int CT = a.cout_tile, N = 3 * CT;
     // element index space: [ct][kb][wi(3)][n][k]
     const size_t per_kb = static_cast<size_t>(3) * N * kKB;
     const size_t total = static_cast<size_t>(a.cout_tiles) * a.num_kblocks * per_kb;
-    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    for (size_t idx = bx * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(nbx) * blockDim.x) {
         size_t r = idx;
         const int k = static_cast<int>(r % kKB); r /= kKB;
         const int n = static_cast<int>(r % N); r /= N;
@@ -126,9 +128,26 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) {
         *reinterpret_cast<uint16_t*>(dst) = val;
     }
     const int nb = a.cout_tiles * CT;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
+    for (int i = bx * blockDim.x + threadIdx.x; i < nb; i += nbx * blockDim.x) {
         const esr_wrow row = a.rows[i];
         a.bias_out[i] = (a.bias_src != nullptr && row.idx >= 0 && row.ky < 0) ? a.bias_src[row.idx] : 0.f;
+    }
+}
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackArgs a) { pack_one(a, blockIdx.x, gridDim.x); }
+
+// Every conv of a network in ONE launch (grid.y = table entry): a training step re-packs 351 forward and ~420 dgrad weight
+// images after each update; as separate launches that was 12.5 ms of 16 us launches, host bound.
+__global__ void pack_table_kernel(const PackArgs* __restrict__ table) { pack_one(table[blockIdx.y], blockIdx.x, gridDim.x); }
+
+// Strided row copies (gathering the five weight tensors of a dense block into the [co_slot, ci, 3, 3] array its dgrad
+// images are packed from), one launch for all segments.
+__global__ void copy_segments_kernel(const esr_copy_seg* __restrict__ segs) {
+    const esr_copy_seg sg = segs[blockIdx.y];
+    const int total = sg.rows * sg.row_elems;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / sg.row_elems, c = i - r * sg.row_elems;
+        sg.dst[static_cast<size_t>(r) * sg.dst_pitch + c] = sg.src[static_cast<size_t>(r) * sg.src_pitch + c];
     }
 }
 
@@ -234,6 +253,48 @@ extern "C" int esr_pack_conv_weights(const float* wsrc, int64_t off, int64_t s_r
     const int grid = static_cast<int>((total + block - 1) / block);
     esr::pack_weights_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return esr::check_launch("pack_weights_kernel");
+}
+
+static int fill_pack_args(esr::PackArgs& a, const float* wsrc, int64_t off, int64_t s_row, int64_t s_slot, int64_t s_ky, int64_t s_kx,
+                          const float* bias_src, int32_t cout_tile, int32_t cout_tiles, int32_t pair, int32_t num_kblocks,
+                          const esr_kblock* kblocks, uint32_t w_tile_bytes, const esr_wrow* rows_dev, const esr_wslot* slots_dev,
+                          void* wpack_out, float* bias_out) {
+    ESR_CHECK_ARG(wsrc && kblocks && rows_dev && slots_dev && wpack_out && bias_out, "pack: null argument");
+    ESR_CHECK_ARG(cout_tile_ok(cout_tile, pair) && cout_tiles > 0 && num_kblocks > 0 && num_kblocks <= ESR_MAX_KBLOCKS, "pack: bad sizes");
+    a.wsrc = wsrc; a.off = off; a.s_row = s_row; a.s_slot = s_slot; a.s_ky = s_ky; a.s_kx = s_kx;
+    a.bias_src = bias_src; a.cout_tile = cout_tile; a.cout_tiles = cout_tiles; a.pair = pair ? 1 : 0; a.num_kblocks = num_kblocks;
+    a.w_tile_bytes = w_tile_bytes;
+    for (int i = 0; i < num_kblocks; ++i) a.kblocks[i] = kblocks[i];
+    a.rows = rows_dev; a.slots = slots_dev; a.out = static_cast<uint8_t*>(wpack_out); a.bias_out = bias_out;
+    return ESR_OK;
+}
+
+extern "C" int32_t esr_pack_entry_bytes() { return static_cast<int32_t>(sizeof(esr::PackArgs)); }
+
+extern "C" int esr_pack_entry_fill(void* entry_host, const float* wsrc, int64_t off, int64_t s_row, int64_t s_slot, int64_t s_ky,
+                                   int64_t s_kx, const float* bias_src, int32_t cout_tile, int32_t cout_tiles, int32_t pair,
+                                   int32_t num_kblocks, const esr_kblock* kblocks, uint32_t w_tile_bytes, const esr_wrow* rows_dev,
+                                   const esr_wslot* slots_dev, void* wpack_out, float* bias_out) {
+    ESR_CHECK_ARG(entry_host != nullptr, "esr_pack_entry_fill: null entry");
+    esr::PackArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = fill_pack_args(a, wsrc, off, s_row, s_slot, s_ky, s_kx, bias_src, cout_tile, cout_tiles, pair, num_kblocks, kblocks,
+                            w_tile_bytes, rows_dev, slots_dev, wpack_out, bias_out);
+    if (rc != ESR_OK) return rc;
+    memcpy(entry_host, &a, sizeof(a));
+    return ESR_OK;
+}
+
+extern "C" int esr_pack_table_run(const void* table_device, int32_t n, void* stream) {
+    ESR_CHECK_ARG(table_device != nullptr && n > 0, "esr_pack_table_run: bad arguments");
+    esr::pack_table_kernel<<<dim3(24, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const esr::PackArgs*>(table_device));
+    return esr::check_launch("pack_table_kernel");
+}
+
+extern "C" int esr_copy_segments(const esr_copy_seg* segs_device, int32_t n, void* stream) {
+    ESR_CHECK_ARG(segs_device != nullptr && n > 0, "esr_copy_segments: bad arguments");
+    esr::copy_segments_kernel<<<dim3(8, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(segs_device);
+    return esr::check_launch("copy_segments_kernel");
 }
 
 extern "C" int esr_expand_rows(const float* src_nchw, int32_t B, int32_t C, int32_t H, int32_t W,

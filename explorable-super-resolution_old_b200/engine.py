@@ -71,7 +71,9 @@ class PackedConv:
             self.rows[i].idx, self.rows[i].ky = idx, ky
         self.wpack = self.bias = None
 
-    def pack(self, weight, bias, off, s_row, s_slot, s_ky, s_kx):
+    def pack(self, weight, bias, off, s_row, s_slot, s_ky, s_kx, table=None):
+        """Packs this conv's weight image.  With `table` (a list) nothing is launched: the entry of the batched pack
+        table (esr_pack_entry_fill) is appended instead and PackTable.run() packs every conv of the table in one launch."""
         dev = weight.device
         if self.wpack is None or self.wpack.device != dev:     # re-packing after a weight update reuses the buffers: the recorded
             self.wpack = torch.empty(self.total_bytes, dtype=torch.uint8, device=dev)      # launch sequences point at them
@@ -81,11 +83,32 @@ class PackedConv:
             keep = (_struct_array_to_device(self.rows, WRow, dev),           # step re-packs all 351 convs after every update)
                     _struct_array_to_device(self.slots, WSlot, dev))
         rows_d, slots_d = keep
-        capi.check(capi.lib().esr_pack_conv_weights(
-            capi.ptr(weight), off, s_row, s_slot, s_ky, s_kx, capi.ptr(bias), self.cout_tile, self.cout_tiles,
-            self.pair, self.nkb, self.kblocks, self.w_tile_bytes, capi.ptr(rows_d), capi.ptr(slots_d), capi.ptr(self.wpack),
-            capi.ptr(self.bias), capi.stream_ptr()))
         self._keep = keep
+        args = (capi.ptr(weight), off, s_row, s_slot, s_ky, s_kx, capi.ptr(bias), self.cout_tile, self.cout_tiles,
+                self.pair, self.nkb, self.kblocks, self.w_tile_bytes, capi.ptr(rows_d), capi.ptr(slots_d), capi.ptr(self.wpack),
+                capi.ptr(self.bias))
+        if table is not None:
+            entry = (C.c_uint8 * capi.lib().esr_pack_entry_bytes())()
+            capi.check(capi.lib().esr_pack_entry_fill(entry, *args))
+            table.append(bytes(entry))
+            return
+        capi.check(capi.lib().esr_pack_conv_weights(*args, capi.stream_ptr()))
+
+
+class PackTable:
+    """Every conv of a network packed by ONE launch (esr_pack_table_run): entries are built once per set of source
+    pointers, re-run after every weight update (training: 351 + ~420 images per step)."""
+
+    def __init__(self):
+        self.key, self.dev, self.n = None, None, 0
+
+    def build(self, key, entries, device):
+        raw = b"".join(entries)
+        self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.key, self.n = key, len(entries)
+
+    def run(self):
+        capi.check(capi.lib().esr_pack_table_run(capi.ptr(self.dev), self.n, capi.stream_ptr()))
 
 
 def expand_slots(nvals_channels, precise, second="lo"):
@@ -234,11 +257,18 @@ class GEngine:
     # ---------------------------------------------------------------- packing
     def pack(self, params):
         """params: dict name -> (weight OIHW f32 CUDA contiguous, bias f32 CUDA)."""
-        for name, pc in self.convs.items():
-            w, b = params[name]
-            cin = w.shape[1]
-            pc.pack(w, b, 0, cin * 9, 9, 3, 1)
-            pc.cin = cin
+        key = tuple((params[name][0].data_ptr(), params[name][1].data_ptr()) for name in self.convs)
+        tab = getattr(self, "_pack_table", None)
+        if tab is None or tab.key != key:
+            entries = []
+            for name, pc in self.convs.items():
+                w, b = params[name]
+                cin = w.shape[1]
+                pc.pack(w, b, 0, cin * 9, 9, 3, 1, table=entries)
+                pc.cin = cin
+            tab = self._pack_table = PackTable()
+            tab.build(key, entries, next(iter(params.values()))[0].device)
+        tab.run()
 
     def flops_per_lr_pixel(self):
         """Algorithmic MACs*2 of the reference network per (padded) LR pixel."""

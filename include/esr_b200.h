@@ -217,6 +217,22 @@ int esr_pack_conv_weights(const float* wsrc, int64_t off, int64_t s_row, int64_t
                           const esr_kblock* kblocks, uint32_t w_tile_bytes, const esr_wrow* rows_dev,
                           const esr_wslot* slots_dev, void* wpack_out, float* bias_out, void* stream);
 
+/* The same for a whole network in one launch: fill one table entry per conv on the host (esr_pack_entry_bytes() bytes each,
+ * same arguments as esr_pack_conv_weights), copy the table to the device, run it after every weight update. */
+int32_t esr_pack_entry_bytes(void);
+int esr_pack_entry_fill(void* entry_host, const float* wsrc, int64_t off, int64_t s_row, int64_t s_slot, int64_t s_ky,
+                        int64_t s_kx, const float* bias_src, int32_t cout_tile, int32_t cout_tiles, int32_t pair,
+                        int32_t num_kblocks, const esr_kblock* kblocks, uint32_t w_tile_bytes, const esr_wrow* rows_dev,
+                        const esr_wslot* slots_dev, void* wpack_out, float* bias_out);
+int esr_pack_table_run(const void* table_device, int32_t n, void* stream);
+/* n strided row copies in one launch: dst[r*dst_pitch + c] = src[r*src_pitch + c], r < rows, c < row_elems (fp32) */
+typedef struct esr_copy_seg {
+    const float* src;
+    float* dst;
+    int32_t rows, row_elems, src_pitch, dst_pitch;
+} esr_copy_seg;
+int esr_copy_segments(const esr_copy_seg* segs_device, int32_t n, void* stream);
+
 /* ------------------------------------------------------- small-channel sources */
 
 typedef struct esr_xslot {
