@@ -152,6 +152,8 @@ constexpr int kEpiRes = 2;       // conv 4 of an RDB: alpha*(acc+bias) + gamma*r
 constexpr int kEpiAct = 3;       // bias [+ LeakyReLU] -> 16-bit NHWC (bf16 or fp16), optionally replicated 2x2 (upconv / HR conv)
 constexpr int kEpiNchw = 4;      // bias -> f32 NCHW, first cout_real channels (last conv of the generator)
 constexpr int kEpiMask = 5;      // dgrad of a trunk conv: (acc + bias) * LeakyReLU'(stored activation) -> bf16 slice
+constexpr int kEpiDx0Mask = 7;   // kEpiDx0 whose 16-bit output is also scaled by LeakyReLU'(mask): the dgrads of the HR convs (f32 rows
+                                 // for the latent + masked bf16 gradient of the conv below); round 1 ran them on the generic epilogue
 constexpr int kEpiDx0 = 6;       // dgrad of a block input: per cout tile either v + out_f32 (accumulate, routed latent rows) or
                                  // alpha*v + gamma*res1 [, beta*. + res2] -> blocked f32 [+ scale*v as bf16]
 // The generic epilogue costs ~5000 clk per 128-pixel x 64-channel tile (issue bound: two epilogue warps per
@@ -210,8 +212,16 @@ template <int MODE>
 __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, int ct, int n, int y, int x, int co0,
                                                        EpiOperands& P) {
     if constexpr (MODE == kEpiTrunk || MODE == kEpiAct || MODE == kEpiNchw) return;
-    if constexpr (MODE == kEpiDx0) {
+    if constexpr (MODE == kEpiDx0 || MODE == kEpiDx0Mask) {
         const uint32_t flags = tile_flags(d, ct);
+        if constexpr (MODE == kEpiDx0Mask) {
+            if (d.out_bf16 != nullptr && !((d.no_bf16_tiles >> ct) & 1)) {
+                const uint4* m = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.mask) +
+                                                                ((static_cast<size_t>(n) * d.H + y) * d.W + x) * d.mask_stride + d.mask_choff + co0);
+                P.m[0] = __ldg(m);
+                P.m[1] = __ldg(m + 1);
+            }
+        }
         if (flags & ESR_EPI_ACCUM) {
             ld_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), P.r1);
             ld_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), P.r1 + 8);
@@ -331,7 +341,7 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
         }
         return;
     }
-    if constexpr (MODE == kEpiDx0) {
+    if constexpr (MODE == kEpiDx0 || MODE == kEpiDx0Mask) {
         const uint32_t flags = tile_flags(d, ct);
         if (flags & ESR_EPI_ACCUM) {
 #pragma unroll
@@ -348,8 +358,18 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
         st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
         if (d.out_bf16 != nullptr && !((d.no_bf16_tiles >> ct) & 1)) {
             uint32_t pk[8];
+            if constexpr (MODE == kEpiDx0Mask) {
+                const uint16_t* mv = reinterpret_cast<const uint16_t*>(P.m);   // raw bits: bf16 or fp16 activations
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(d.out_bf16_scale * v[2 * i], d.out_bf16_scale * v[2 * i + 1]);
+                for (int i = 0; i < 8; ++i) {
+                    const float s0 = ((mv[2 * i] & 0x8000u) == 0 && (mv[2 * i] & 0x7fffu) != 0) ? 1.f : d.slope;
+                    const float s1 = ((mv[2 * i + 1] & 0x8000u) == 0 && (mv[2 * i + 1] & 0x7fffu) != 0) ? 1.f : d.slope;
+                    pk[i] = pack_bf16x2(d.out_bf16_scale * v[2 * i] * s0, d.out_bf16_scale * v[2 * i + 1] * s1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(d.out_bf16_scale * v[2 * i], d.out_bf16_scale * v[2 * i + 1]);
+            }
             st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
         }
         return;
@@ -459,8 +479,14 @@ inline int classify_epilogue(const esr_conv_desc& d) {
     const auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
     bool routed = d.no_accum_tiles || d.no_bf16_tiles || d.no_res_tiles;
     for (int t = 0; t < d.cout_tiles; ++t) routed = routed || d.tile_choff[t] >= 0;
-    if ((f & ESR_EPI_F32_BLOCKED) && (f & ~static_cast<uint32_t>(ESR_EPI_RES1 | ESR_EPI_RES2 | ESR_EPI_ACCUM | ESR_EPI_F32_BLOCKED)) == 0 &&
-        (routed || (f & ESR_EPI_ACCUM)) && d.out_f32 != nullptr && d.out_nchw == nullptr && d.up == 1 && d.cout_tile == 32 &&
+    // (a plain f32-only output - the dgrads of the upconvs - qualifies too: no other specialisation writes out_f32 alone)
+    const bool f32_only = d.out_bf16 == nullptr && (f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == 0;
+    const bool with_mask = (f & ESR_EPI_MASK) != 0 && d.mask != nullptr && d.out_bf16 != nullptr && d.mask_stride % 8 == 0 &&
+                           d.mask_choff % 8 == 0;
+    if ((f & ESR_EPI_F32_BLOCKED) &&
+        (f & ~static_cast<uint32_t>(ESR_EPI_RES1 | ESR_EPI_RES2 | ESR_EPI_ACCUM | ESR_EPI_F32_BLOCKED | (with_mask ? ESR_EPI_MASK : 0))) == 0 &&
+        (routed || (f & ESR_EPI_ACCUM) || f32_only) && d.out_f32 != nullptr && d.out_nchw == nullptr && d.up == 1 && d.cout_tile == 32 &&
+        d.out_lo == nullptr &&
         (d.out_bf16 == nullptr || (d.out_bf16_lo_choff < 0 && d.out_bf16_stride % 16 == 0 && d.out_bf16_choff % 16 == 0 &&
                                    al32(d.out_bf16)))) {
         bool ok = true;                    // a tile either accumulates or takes residuals, and routed tiles stay 16-aligned
@@ -469,7 +495,7 @@ inline int classify_epilogue(const esr_conv_desc& d) {
             const bool res = (f & (ESR_EPI_RES1 | ESR_EPI_RES2)) && !((d.no_res_tiles >> t) & 1);
             ok = ok && !(acc && res) && (d.tile_choff[t] < 0 || d.tile_choff[t] % 8 == 0);
         }
-        if (ok) return kEpiDx0;
+        if (ok) return with_mask ? kEpiDx0Mask : kEpiDx0;
     }
     if (routed) return kEpiGeneric;
     const bool bf_ok = d.out_bf16 != nullptr && d.out_bf16_lo_choff < 0 && d.out_bf16_scale == 1.0f && d.out_bf16_stride % 16 == 0 &&

@@ -435,16 +435,16 @@ int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLa
 int launch_conv_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream) {
     if (L.pair_nb) return launch_conv_tc2(tm0, tm1, L, stream, g_use_pdl);
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ConvLaunch);
-    static const KernelFn kernels[2][7] = {
+    static const KernelFn kernels[2][8] = {
         {conv3x3_tc_kernel<16, kEpiGeneric>, conv3x3_tc_kernel<16, kEpiGeneric>, conv3x3_tc_kernel<16, kEpiGeneric>,
          conv3x3_tc_kernel<16, kEpiGeneric>, conv3x3_tc_kernel<16, kEpiNchw>, conv3x3_tc_kernel<16, kEpiGeneric>,
-         conv3x3_tc_kernel<16, kEpiGeneric>},
+         conv3x3_tc_kernel<16, kEpiGeneric>, conv3x3_tc_kernel<16, kEpiGeneric>},
         {conv3x3_tc_kernel<32, kEpiGeneric>, conv3x3_tc_kernel<32, kEpiTrunk>, conv3x3_tc_kernel<32, kEpiRes>,
          conv3x3_tc_kernel<32, kEpiAct>, conv3x3_tc_kernel<32, kEpiGeneric>, conv3x3_tc_kernel<32, kEpiMask>,
-         conv3x3_tc_kernel<32, kEpiDx0>}};
+         conv3x3_tc_kernel<32, kEpiDx0>, conv3x3_tc_kernel<32, kEpiGeneric>}};
     ESR_ONCE_PER_DEVICE(
         for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 7; ++b)
+            for (int b = 0; b < 8; ++b)
                 ESR_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     );
     ESR_CHECK_ARG(L.nstages >= 2, "conv weights (%u B per cout tile) leave no room for the A-tile ring", L.d.w_tile_bytes);
