@@ -9,6 +9,7 @@ The module tree below only holds parameters under the reference's names
 """
 import math
 import threading
+import weakref
 
 import torch
 import torch.nn as nn
@@ -302,6 +303,42 @@ def capture_inference(net, x_static, margin, cem_filters, slot=0):
     return graph, out
 
 
+_TRAINERS = weakref.WeakKeyDictionary()      # RRDBNet -> its GeneratorTrainer (kept off the module: deepcopy / state_dict stay plain)
+
+
+class _TrainFn(torch.autograd.Function):
+    """G (+ CEM) with trainable parameters as one autograd node.  forward keeps the activations
+    (training.GeneratorTrainer.forward); backward runs the dgrad chain and the weight-gradient kernels of csrc/wgrad.cu
+    and returns dL/dW, dL/db of the 351 convs to autograd, which accumulates them into ``p.grad`` as for any torch
+    module (gradient accumulation over several backward calls, ``optimizer.zero_grad()``, DDP hooks all behave as
+    usual).  With an initialised process group and ``net.esr_all_reduce`` (default True) the gradients are averaged over
+    the ranks inside backward, bucketed under the weight-gradient kernels (training.py).  One forward per backward:
+    the activations live in the plan's buffers (same rule as _GeneratorFn)."""
+
+    @staticmethod
+    def forward(ctx, x, net, margin, cem_filters, *params):
+        from .training import GeneratorTrainer
+        with _CACHE_LOCK:
+            tr = _TRAINERS.get(net)
+            if tr is None or tr.dev != x.device:
+                tr = _TRAINERS[net] = GeneratorTrainer(net, attach_grads=False)
+        out = tr.forward(x, margin=margin, filters=cem_filters, leaf=False)
+        ctx.trainer, ctx.stamp, ctx.net = tr, tr.stamp, net
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        tr = ctx.trainer
+        if tr._state is None or tr.stamp != ctx.stamp:
+            raise capi.EsrError("backward through a training forward of the generator whose activations were overwritten "
+                                "by a later forward (or a second backward): one forward per backward")
+        params = list(ctx.net.parameters())
+        g_in = tr.backward(g, all_reduce=getattr(ctx.net, "esr_all_reduce", True))
+        grads = tr.grads_like(params)
+        grads = [gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[4:])]
+        return (g_in if ctx.needs_input_grad[0] else None, None, None, None) + tuple(grads)
+
+
 def run_generator(net, x, margin, cem_filters):
     if not x.is_cuda:
         raise capi.EsrError("RRDBNet.forward: expected a CUDA tensor; this package has no CPU or PyTorch fallback")
@@ -313,16 +350,9 @@ def run_generator(net, x, margin, cem_filters):
         raise ValueError("expected %d input channels (Z.view(B,%d,h,w) ++ LR), got %d" % (nz_in * sf * sf + 3, nz_in * sf * sf, x.size(1)))
     need_grad = torch.is_grad_enabled() and x.requires_grad
     if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
-        if need_grad:
-            raise NotImplementedError("weight gradients through this autograd node are not built; freeze the generator "
-                                      "(Z_optimizer does, Z_optimization.py:545-553), run under torch.no_grad(), or use "
-                                      "training.generator_step for the explicit weight-gradient path")
-        # a plain netG(x) right after define_G (parameters still require grad, input does not): forward only, like the
-        # reference's output values; no graph is recorded, so a later .backward() on it raises in autograd itself
-        if not getattr(net, "_warned_fwd_only", False):
-            net._warned_fwd_only = True
-            import warnings
-            warnings.warn("RRDBNet: parameters require grad but no weight-gradient graph is recorded by forward(); "
-                          "running forward-only")
+        # the reference's training step (SRRaGAN_model.py:349,533: fake_H = netG(model_input) ... l_g_total.backward()):
+        # data-gradient pass + weight-gradient kernels behind one autograd node
+        params = [p for p in net.parameters()]
+        return _TrainFn.apply(x.contiguous().float(), net, margin, cem_filters, *params)
     xc = x.contiguous().float()
     return _GeneratorFn.apply(xc, net, margin, cem_filters, need_grad)

@@ -38,7 +38,7 @@ TILE_H, TILE_W = 8, 16
 
 
 class GeneratorTrainer:
-    def __init__(self, netG, bucket_bytes=8 << 20, process_group=None):
+    def __init__(self, netG, bucket_bytes=8 << 20, process_group=None, attach_grads=True):
         wrapper = getattr(netG, 'module', netG)
         G = getattr(wrapper, 'generated_image_model', wrapper)
         if not isinstance(G, RRDBNet):
@@ -68,8 +68,9 @@ class GeneratorTrainer:
                 self.slices[name + suffix] = (total, p.numel(), p)
                 total += (p.numel() + 3) & ~3
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        for key, (off, n, p) in self.slices.items():
-            p.grad = self.flat[off:off + n].view_as(p)
+        if attach_grads:                 # explicit API: p.grad IS the flat buffer.  The autograd node (rrdbnet._TrainFn)
+            for key, (off, n, p) in self.slices.items():   # hands copies to autograd's own accumulation instead
+                p.grad = self.flat[off:off + n].view_as(p)
         # buckets: contiguous ranges of `order`
         self.buckets, cur, cur_bytes, start = [], [], 0, 0
         for name in order:
@@ -85,14 +86,16 @@ class GeneratorTrainer:
         self._tables = {}
 
     # ------------------------------------------------------------------ forward
-    def forward(self, model_input):
-        """fake_H = netG(model_input) with the activations kept; returns a leaf tensor that requires grad."""
+    def forward(self, model_input, margin=None, filters=None, leaf=True):
+        """fake_H = netG(model_input) with the activations kept; returns a leaf tensor that requires grad.
+        margin / filters: given by the autograd node, which is called below the CEM wrapper (leaf=False there)."""
         G, w = self.G, self.wrapper
         x = model_input.contiguous().float()
         capi.require_device(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
         B, _, h, wd = x.shape
-        margin = (w._margin_LR if w.pre_pad else 0) if w is not None else 0
-        filters = w._filters if w is not None else None
+        if margin is None:
+            margin = (w._margin_LR if w.pre_pad else 0) if w is not None else 0
+            filters = w._filters if w is not None else None
         with torch.cuda.device(self.dev):
             plan = G.plan(B, h, wd, margin, keep=True, slot='train')
             sf = G.upscale
@@ -102,7 +105,8 @@ class GeneratorTrainer:
             ws = torch.empty(max(1, 2 * B * onc * plan.hp * plan.wp), device=self.dev, dtype=torch.float32) if filters is not None else None
             _forward_eager(plan, x, filters, crop, out, ws)
         self._state = (plan, filters, margin)
-        return out.requires_grad_(True)
+        self.stamp = getattr(self, 'stamp', 0) + 1
+        return out.requires_grad_(True) if leaf else out
 
     # ------------------------------------------------------------------ weight-gradient work items
     def _backward_plan(self, plan):
@@ -229,6 +233,12 @@ class GeneratorTrainer:
             if world > 1:
                 cur.wait_stream(self.comm)
         return g_in
+
+    def grads_like(self, params):
+        """Copies of the flat gradient buffer's slices for `params` (for autograd, which may keep what it is handed)."""
+        by_id = {id(p): (off, n) for (off, n, p) in self.slices.values()}
+        flat = self.flat.clone()
+        return [flat[by_id[id(p)][0]:by_id[id(p)][0] + by_id[id(p)][1]].view_as(p) if id(p) in by_id else None for p in params]
 
     def grad_bytes(self):
         return self.flat.numel() * 4

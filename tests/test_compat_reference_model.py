@@ -132,3 +132,53 @@ def test_reference_model_runs_on_b200(cuda_device):
     # the GUI's other objectives run as the reference's loss code on top of this package's G+CEM
     assert res["periodicity_class"] == "Z_optimization__reference"
     assert len(res["periodicity_losses"]) == 4 and res["periodicity_losses"][-1] < res["periodicity_losses"][0]
+
+
+def _train_arm(impl, extra):
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "train_ref_model.py"), "--impl", impl, "--device", "cuda", "--steps", "3",
+           "--nb", "2", "--patch", "128", "--batch", "2"] + extra
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + "\n" + p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[len("RESULT "):])
+
+
+@pytest.mark.gpu
+def test_reference_training_step_runs_on_b200_generator(cuda_device, tmp_path):
+    """SURVEY.md §8f rank 1 through the reference's own loop: ``SRRaGANModel.optimize_parameters``
+    (codes/models/SRRaGAN_model.py:307-547; pixel + range loss, Adam, its step logic) with ``netG`` = this package's
+    generator, against the same loop on the reference's torch generator from the same initial weights and data.
+    (The GAN terms cannot be part of it: the reference's ``define_D`` passes ``nb=`` to a ``Discriminator_VGG_128`` that
+    does not take it, models/networks.py:119 vs architecture.py:184, so its shipped code cannot construct a
+    discriminator.)  Gradient tolerance as in tests/test_gpu_training.py (bf16 operands)."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("reference tree not available (neither /root/reference nor oracle/_ref)")
+    wfile = str(tmp_path / "init.pth")
+    ref = _train_arm("reference", ["--save-weights", wfile])
+    got = _train_arm("compat", ["--weights", wfile, "--save-weights", str(tmp_path / "compat.pth")])
+    assert ref["G_class"] == "models.modules.architecture" and got["G_class"].endswith("rrdbnet")
+    assert os.path.realpath(got["model_file"]).startswith(os.path.realpath(ref_shims.REF_ROOT))
+    assert [s["generator_step"] for s in got["steps"]] == [s["generator_step"] for s in ref["steps"]] == [False, True, True]
+    for a, b in zip(got["steps"], ref["steps"]):
+        assert a["fake_H"] == b["fake_H"] and abs(a["fake_mean"] - b["fake_mean"]) < 2e-3 and abs(a["fake_std"] - b["fake_std"]) < 2e-3
+    for k in ("l_g_pix", "l_g_range"):
+        assert len(got["log"][k]) == len(ref["log"][k]) == 2
+        for a, b in zip(got["log"][k], ref["log"][k]):
+            assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (k, got["log"][k], ref["log"][k])
+    g_ref = torch.load(wfile + ".grads")
+    g_got = torch.load(str(tmp_path / "compat.pth") + ".grads")
+    assert sorted(g_ref) == sorted(g_got)
+    worst = 0.0
+    for k, want in g_ref.items():
+        have = g_got[k]
+        rel = float((have - want).norm() / want.norm().clamp_min(1e-30))
+        cos = float((have * want).sum() / (have.norm() * want.norm()).clamp_min(1e-30))
+        worst = max(worst, rel)
+        if k == "model.6.bias":          # zero up to border effects (tests/test_gpu_training.py)
+            continue
+        assert rel < 0.10 and cos > 0.995, "%s: relative error %g, cosine %g" % (k, rel, cos)
+    print("worst relative gradient error", worst)
+    assert got["G_change"] > 0 and abs(got["G_change"] - ref["G_change"]) < 0.05 * ref["G_change"]

@@ -83,3 +83,43 @@ def test_training_steps_reduce_the_loss_and_update_in_place(cuda_device):
         plans.append(id(trainer._bp[1]))
     assert losses[2] < losses[0], losses
     assert len(set(plans)) == 1, "the backward plan was rebuilt after a weight update"
+
+
+def test_autograd_node_returns_weight_gradients(cuda_device):
+    """``netG(model_input)`` with trainable parameters (the reference's own training call, SRRaGAN_model.py:349,533):
+    ``loss.backward()`` fills ``p.grad`` through autograd with the same values as the explicit GeneratorTrainer, a
+    second forward + backward accumulates, and the latent gradient comes back too."""
+    nb, B, h, w = 1, 2, 16, 24
+    wts = synth.make_weights("kaiming", seed=8, nb=nb)
+    lr, z = synth.make_inputs(B, h, w, seed=8)
+    mi = concat_latent(lr, z).to(cuda_device)
+    ref_net = build_product_G(cuda_device, nb, "all_layers_HR_downscaled", wts, train=True)
+    trainer = GeneratorTrainer(ref_net)
+    fake = trainer.forward(mi)
+    gout = torch.randn(fake.shape, generator=torch.Generator().manual_seed(9)).to(cuda_device)
+    g_in_ref = trainer.backward(gout).clone()
+    want = {k: p.grad.clone() for k, p in ref_net.generated_image_model.named_parameters()}
+
+    netG = build_product_G(cuda_device, nb, "all_layers_HR_downscaled", wts, train=True)
+    for p in netG.parameters():
+        p.requires_grad_(True)
+    x = mi.clone().requires_grad_(True)
+    out = netG(x)
+    assert out.requires_grad and torch.equal(out.detach(), fake.detach())
+    (out * gout).sum().backward()
+    assert torch.allclose(x.grad, g_in_ref, rtol=1e-4, atol=1e-6 * float(g_in_ref.abs().max()))
+    for k, p in netG.generated_image_model.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        # chunked high-resolution items add with atomics: equal up to fp32 summation order
+        assert float((p.grad - want[k]).norm()) <= 1e-4 * float(want[k].norm()) + 1e-7 * float(gout.abs().sum()), k
+    (netG(mi) * gout).sum().backward()                       # accumulation, like any torch module
+    for k, p in netG.generated_image_model.named_parameters():
+        assert float((p.grad - 2 * want[k]).norm()) <= 2e-4 * float(want[k].norm()) + 2e-7 * float(gout.abs().sum()), k
+    out2 = netG(mi)
+    netG(mi)
+    with pytest.raises(Exception, match="one forward per backward"):
+        (out2 * gout).sum().backward()
+    # frozen generator, grad enabled (the reference's D-only steps): plain forward, nothing recorded
+    for p in netG.parameters():
+        p.requires_grad_(False)
+    assert not netG(mi).requires_grad
