@@ -416,6 +416,77 @@ def run_train_g(args):
         torch.distributed.destroy_process_group()
 
 
+def run_train_gan(args):
+    """BASELINE config 5, the whole step: batch 16 x 128x128 HR patches (3x32x32 LR) per rank, train mode, through
+    training.GanTrainer — G forward, critic update on real / fake / WGAN-GP interpolates (double backward), generator update
+    with the adversarial + range terms back-propagated through the critic into this package's dgrad and weight-gradient
+    kernels, NCCL all-reduce of the 13.6 MB critic gradient (one call) and the 68.2 MB generator gradient (buckets under the
+    weight-gradient kernels), fused Adam on both.  The critic (Discriminator_VGG_128_, n_layers 6, nf 64) is torch code on
+    cuDNN (library); it sees the whole 128x128 patch (the CEM-cropped 48x48 one is below its 8x8 head's minimum)."""
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    from esr_b200 import _capi as capi, cem as pcem, networks, synth
+    from esr_b200.discriminator import Discriminator_VGG_128_
+    from esr_b200.training import GanTrainer
+    capi.lib()
+    opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 128}},
+           "network_G": dict(which_model_G="RRDB_net", CEM_arch=1, latent_input="all_layers", latent_input_domain="HR_downscaled",
+                             latent_channels=3, norm_type=None, mode="CNA", nf=64, nb=23, in_nc=3, out_nc=3, gc=32, scale=SF)}
+    netG = networks.define_G(opt, CEM=pcem.CEMnet(pcem.Get_CEM_Config(SF)), num_latent_channels=3)
+    sd = netG.state_dict()
+    sd.update({"generated_image_model." + k: v for k, v in synth.make_weights("kaiming", seed=0).items()})
+    netG.load_state_dict(sd)
+    netG.to(dev).train()
+    torch.manual_seed(0)
+    netD = Discriminator_VGG_128_(3, 64, nb=6, input_patch_size=128)
+    networks.init_weights(netD, init_type="kaiming", scale=1)
+    netD.to(dev).train()
+    gan = GanTrainer(netG, netD, lr_G=1e-5, lr_D=1e-5, pixel_weight=1e-2, gan_weight=1.0, gp_weight=10.0, range_weight=5000.0, crop=0)
+    Bp, hl = 16, 32
+    lr, z = synth.make_inputs(Bp, hl, hl, seed=rank)
+    mi = torch.cat([z.contiguous().view(Bp, 48, hl, hl), lr], 1).contiguous().to(dev)
+    target = torch.rand(Bp, 3, SF * hl, SF * hl, generator=torch.Generator().manual_seed(rank)).to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        l0 = dict(gan.step(mi, target))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        l1 = gan.step(mi, target)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.cpu())
+    if rank == 0:
+        gb, db = gan.grad_bytes()
+        flops = 3 * netG.generated_image_model.engine().flops_per_lr_pixel() * Bp * hl * hl
+        print(json.dumps({"metric": "GAN training step (RRDBNet+CEM generator, VGG-128 critic, WGAN-GP), 128x128 HR patches/s", "value": world * Bp / (ms * 1e-3),
+                          "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "generator: bf16 MMA operands, fp32 master weights; critic: torch fp32 (cuDNN, TF32 as torch defaults)",
+                          "data": "synthetic", "config": {"workload": "BASELINE config 5: 16 x 128x128 HR patches (3x32x32 LR + Z) per rank, train mode, "
+                                                                      "critic update + generator update every step (D_update_ratio 1)",
+                                                          "global_batch": Bp * world,
+                                                          "parallelism": "data parallel x%d, NCCL all-reduce (AVG): generator %.1f MB in buckets under the "
+                                                                         "weight-gradient kernels, critic %.1f MB in one call" % (world, gb / 1e6, db / 1e6)},
+                          "generator_algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+                          "losses_first": {k: float(v) for k, v in l0.items()}, "losses_last": {k: float(v) for k, v in l1.items()}}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,7 +495,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 16 images per rank (default); strong: BASELINE config 2's one batch of 16 split over the ranks")
-    ap.add_argument("--workload", default="infer", choices=["infer", "train_g"],
+    ap.add_argument("--workload", default="infer", choices=["infer", "train_g", "train_gan"],
                     help="infer: BASELINE config 2 (default, the headline metric); train_g: the generator half of config 5's "
                          "training step (forward, data + weight gradients, NCCL gradient all-reduce, Adam), 16 x 32x32 LR patches per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -435,6 +506,8 @@ def main():
         return run_reference(args)
     if args.workload == "train_g":
         return run_train_g(args)
+    if args.workload == "train_gan":
+        return run_train_gan(args)
 
     rank, local_rank, world = dist_env()
     if world > 1:

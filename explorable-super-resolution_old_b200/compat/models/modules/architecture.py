@@ -4,3 +4,4 @@ from .._shadow_loader import reexport as _reexport
 
 _reference = _reexport(__name__, globals())
 from esr_b200.rrdbnet import RRDBNet  # noqa: E402,F401
+from esr_b200.discriminator import Discriminator_VGG_128_  # noqa: E402,F401

@@ -117,6 +117,13 @@ class RRDBNet(nn.Module):
         self._engine_key, self._engine_ptr_key = key, ptr_key
         return self._engine
 
+    def weights_changed(self):
+        """Forces the next forward to re-pack the weights.  In-place updates are normally seen through the parameters'
+        version counters, but torch's fused optimizers (``Adam(fused=True)``: ``_fused_adam_``) write the parameters
+        without bumping them, so the training paths (training.GeneratorTrainer.forward, _TrainFn) call this every step."""
+        with _CACHE_LOCK:
+            self._engine_key = None
+
     def backward_plan(self, plan):
         with _CACHE_LOCK:
             return self._backward_plan_locked(plan)

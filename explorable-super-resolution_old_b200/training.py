@@ -97,6 +97,7 @@ class GeneratorTrainer:
             margin = (w._margin_LR if w.pre_pad else 0) if w is not None else 0
             filters = w._filters if w is not None else None
         with torch.cuda.device(self.dev):
+            G.weights_changed()                              # training: the optimiser wrote the weights since the last forward
             plan = G.plan(B, h, wd, margin, keep=True, slot='train')
             sf = G.upscale
             crop = sf * margin
@@ -242,3 +243,93 @@ class GeneratorTrainer:
 
     def grad_bytes(self):
         return self.flat.numel() * 4
+
+
+class GanTrainer:
+    """One iteration of the reference's GAN training step (codes/models/SRRaGAN_model.py:307-547) in the shipped
+    configuration (options/train/train_esrgan_CEM.json: ``gan_type`` wgan-gp, non-relativistic critic, l1 pixel
+    criterion, range loss), data parallel, one process per GPU:
+
+      fake_H = netG(model_input)                                   :349    this package's kernels, activations kept
+      critic:  l_d = (2*(-D(real).mean()) + 2*D(fake.detach()).mean())/2   :378-388
+               + gp_weight * mean((|d D(interp) / d interp|_2 - 1)^2), interp = u*fake + (1-u)*real   :390-399, loss.py:244-263
+               l_d.backward(); optimizer_D.step()                  :433,444
+      generator: l_g = pixel_weight*L1(fake_H, HR) + range_weight*RangeLoss(fake_H) + gan_weight*(-D(fake_H).mean())
+               l_g.backward(); optimizer_G.step()                  :478-533,565     dgrad + weight-gradient kernels
+
+    The critic (esr_b200.discriminator, 1.6 % of the step's FLOPs, needs a double backward) is torch code on torch autograd;
+    its gradient is flattened into one buffer and averaged with ONE all_reduce (13.6 MB), the generator's 68.2 MB gradient
+    goes out in buckets under the weight-gradient kernels (GeneratorTrainer.backward).  ``crop``: the CEM margin the
+    reference removes from fake_H / HR before the losses (``HR_unpadder``, :343-355); 0 keeps the whole patch (BASELINE
+    config 5's 128x128 patches: the critic's 8x8 head needs >= 64 pixels)."""
+
+    def __init__(self, netG, netD, lr_G=1e-5, lr_D=1e-5, betas_G=(0.9, 0.999), betas_D=(0.9, 0.999), pixel_weight=0.0, gan_weight=1.0,
+                 gp_weight=10.0, range_weight=5000.0, crop=0, process_group=None):
+        self.gen = GeneratorTrainer(netG, process_group=process_group)
+        self.netD = netD
+        self.group = process_group
+        self.w = dict(pix=float(pixel_weight), gan=float(gan_weight), gp=float(gp_weight), range=float(range_weight))
+        self.crop = int(crop)
+        d_params = [p for p in netD.parameters()]
+        self.d_flat = torch.zeros(sum(p.numel() for p in d_params), dtype=torch.float32, device=self.gen.dev)
+        off = 0
+        for p in d_params:                                   # p.grad of every critic parameter is a view of one buffer
+            p.grad = self.d_flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.d_params = d_params
+        self.optimizer_G = torch.optim.Adam(self.gen.G.parameters(), lr=lr_G, betas=betas_G, fused=True)
+        self.optimizer_D = torch.optim.Adam(d_params, lr=lr_D, betas=betas_D, fused=True)
+        self.log = {}
+
+    def _cropped(self, t):
+        c = self.crop
+        return t[..., c:t.size(-2) - c, c:t.size(-1) - c] if c else t
+
+    def step(self, model_input, var_H, generator_step=True, interpolation=None):
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        w, D = self.w, self.netD
+        real = self._cropped(var_H)
+        fake_full = self.gen.forward(model_input)            # leaf; the graph below it is this package's backward
+        fake = self._cropped(fake_full)
+        fake_d = fake.detach()
+        # ---- critic
+        for p in self.d_params:
+            p.requires_grad_(True)
+        self.d_flat.zero_()
+        pred_real, pred_fake = D(real), D(fake_d)
+        l_d_real, l_d_fake = -2.0 * pred_real.mean(), 2.0 * pred_fake.mean()
+        u = torch.rand(real.size(0), 1, 1, 1, device=real.device) if interpolation is None else interpolation
+        interp = (u * fake_d + (1 - u) * real).requires_grad_(True)
+        crit = D(interp)
+        g_interp, = torch.autograd.grad(crit, interp, torch.ones_like(crit), create_graph=True)
+        l_d_gp = w['gp'] * ((g_interp.reshape(g_interp.size(0), -1).norm(2, dim=1) - 1) ** 2).mean()
+        ((l_d_real + l_d_fake) / 2 + l_d_gp).backward()
+        if world > 1:
+            dist.all_reduce(self.d_flat, op=dist.ReduceOp.AVG, group=self.group)
+        self.optimizer_D.step()
+        self.log = {'l_d_real': l_d_real.detach(), 'l_d_fake': l_d_fake.detach(), 'l_d_gp': l_d_gp.detach(),
+                    'D_real': pred_real.detach().mean(), 'D_fake': pred_fake.detach().mean()}
+        if not generator_step:
+            self.gen._state = None
+            return self.log
+        # ---- generator (the critic is a fixed function here: its parameters take no gradient, :465-467)
+        for p in self.d_params:
+            p.requires_grad_(False)
+        l_g = 0
+        if w['pix']:
+            l_pix = (fake - real).abs().mean()
+            l_g = l_g + w['pix'] * l_pix
+            self.log['l_g_pix'] = l_pix.detach()
+        if w['range']:                                       # mean excursion out of [0, 1] (loss.py:236-242)
+            l_range = torch.maximum(fake - 1, -fake).clamp_min(0).mean()
+            l_g = l_g + w['range'] * l_range
+            self.log['l_g_range'] = l_range.detach()
+        l_gan = -w['gan'] * D(fake).mean()
+        self.log['l_g_gan'] = l_gan.detach()
+        (l_g + l_gan).backward()
+        self.gen.backward(fake_full.grad)                    # dgrad chain, weight gradients, bucketed all-reduce
+        self.optimizer_G.step()
+        return self.log
+
+    def grad_bytes(self):
+        return self.gen.grad_bytes(), self.d_flat.numel() * 4

@@ -134,9 +134,9 @@ def test_reference_model_runs_on_b200(cuda_device):
     assert len(res["periodicity_losses"]) == 4 and res["periodicity_losses"][-1] < res["periodicity_losses"][0]
 
 
-def _train_arm(impl, extra):
+def _train_arm(impl, extra, patch=128):
     cmd = [sys.executable, os.path.join(ROOT, "tools", "train_ref_model.py"), "--impl", impl, "--device", "cuda", "--steps", "3",
-           "--nb", "2", "--patch", "128", "--batch", "2"] + extra
+           "--nb", "2", "--patch", str(patch), "--batch", "2"] + extra
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + "\n" + p.stderr[-3000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
@@ -182,3 +182,42 @@ def test_reference_training_step_runs_on_b200_generator(cuda_device, tmp_path):
         assert rel < 0.10 and cos > 0.995, "%s: relative error %g, cosine %g" % (k, rel, cos)
     print("worst relative gradient error", worst)
     assert got["G_change"] > 0 and abs(got["G_change"] - ref["G_change"]) < 0.05 * ref["G_change"]
+
+
+@pytest.mark.gpu
+def test_reference_gan_training_step_runs_on_b200_generator(cuda_device, tmp_path):
+    """BASELINE config 5 through the reference's own loop: ``optimize_parameters`` with ``gan_weight > 0`` — critic
+    updates on real / fake / WGAN-GP interpolates (SRRaGAN_model.py:357-433, loss.py:244-263), then the generator step
+    with the adversarial term back-propagated through the critic into this package's data- and weight-gradient kernels
+    (:463-547).  Arm "compat": ``define_D`` = esr_b200.discriminator (the shipped one cannot construct a critic),
+    ``netG`` = this package's generator.  Arm "reference": the reference's torch generator and its
+    ``Discriminator_VGG_128_``; same initial weights, data and interpolation points."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("reference tree not available (neither /root/reference nor oracle/_ref)")
+    wfile = str(tmp_path / "init.pth")
+    extra = ["--gan", "5e-3", "--nf-d", "16"]
+    ref = _train_arm("reference", extra + ["--save-weights", wfile], patch=208)
+    got = _train_arm("compat", extra + ["--weights", wfile, "--save-weights", str(tmp_path / "compat.pth")], patch=208)
+    assert ref["D_class"] == "models.modules.architecture" and got["D_class"].endswith("discriminator")
+    assert got["G_class"].endswith("rrdbnet")
+    assert [s["generator_step"] for s in got["steps"]] == [s["generator_step"] for s in ref["steps"]]
+    assert any(s["generator_step"] for s in got["steps"])
+    for k in ("l_d_real", "l_d_fake", "l_d_gp", "D_real", "D_fake", "l_g_gan", "l_g_pix"):
+        assert len(got["log"][k]) == len(ref["log"][k]) >= 1, k
+        for a, b in zip(got["log"][k], ref["log"][k]):
+            # the critic sees fake_H from two engines (bf16 operands here): its BatchNorm statistics amplify that
+            assert abs(a - b) <= 3e-2 * max(abs(b), 1e-2), (k, got["log"][k], ref["log"][k])
+    g_ref = torch.load(wfile + ".grads")
+    g_got = torch.load(str(tmp_path / "compat.pth") + ".grads")
+    for k, want in g_ref.items():
+        if k == "model.6.bias":
+            continue
+        have = g_got[k]
+        rel = float((have - want).norm() / want.norm().clamp_min(1e-30))
+        cos = float((have * want).sum() / (have.norm() * want.norm()).clamp_min(1e-30))
+        assert rel < 0.12 and cos > 0.99, "%s: relative error %g, cosine %g" % (k, rel, cos)
+    assert abs(got["D_change"] - ref["D_change"]) < 0.05 * ref["D_change"]
+    assert abs(got["G_change"] - ref["G_change"]) < 0.05 * ref["G_change"]

@@ -123,3 +123,79 @@ def test_autograd_node_returns_weight_gradients(cuda_device):
     for p in netG.parameters():
         p.requires_grad_(False)
     assert not netG(mi).requires_grad
+
+
+def test_gan_step_matches_torch_autograd_on_the_oracle(cuda_device):
+    """training.GanTrainer.step (BASELINE config 5; SRRaGAN_model.py:349-547 in the shipped wgan-gp configuration)
+    against the same iteration written with torch autograd on the CPU oracle generator and a CPU copy of the critic:
+    critic losses incl. the gradient penalty, the critic's Adam update, the generator's loss terms, its weight gradients
+    (tolerance as above plus the critic's BatchNorm in the chain) and its Adam update."""
+    import copy
+    from esr_b200.discriminator import Discriminator_VGG_128_
+    from esr_b200.training import GanTrainer
+    nb, B, h = 1, 2, 24
+    wts = synth.make_weights("kaiming", seed=11, nb=nb)
+    lr, z = synth.make_inputs(B, h, h, seed=11)
+    mi = concat_latent(lr, z)
+    hr = torch.rand(B, 3, 4 * h, 4 * h, generator=torch.Generator().manual_seed(12))
+    u = torch.rand(B, 1, 1, 1, generator=torch.Generator().manual_seed(13))
+    torch.manual_seed(14)
+    d_cpu = Discriminator_VGG_128_(3, 8, nb=4, input_patch_size=4 * h)
+    for m in d_cpu.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            torch.nn.init.kaiming_normal_(m.weight, a=0, mode='fan_in')
+    d_gpu = copy.deepcopy(d_cpu).to(cuda_device)
+    weights = dict(pixel_weight=1e-2, gan_weight=5e-3, gp_weight=10.0, range_weight=50.0)
+    netG = build_product_G(cuda_device, nb, "all_layers_HR_downscaled", wts, train=True)
+    gan = GanTrainer(netG, d_gpu, lr_G=1e-4, lr_D=1e-4, **weights)
+    log = {k: float(v) for k, v in gan.step(mi.to(cuda_device), hr.to(cuda_device), interpolation=u.to(cuda_device)).items()}
+    # ---- the same iteration on the CPU oracle
+    w = {k: v.clone().requires_grad_(True) for k, v in wts.items()}
+    fake = GCEMOracle(w, pre_pad=False, nb=nb).forward(mi)
+    opt_d = torch.optim.Adam(d_cpu.parameters(), lr=1e-4)
+    pr, pf = d_cpu(hr), d_cpu(fake.detach())
+    interp = (u * fake.detach() + (1 - u) * hr).requires_grad_(True)
+    crit = d_cpu(interp)
+    gi, = torch.autograd.grad(crit, interp, torch.ones_like(crit), create_graph=True)
+    gp = 10.0 * ((gi.reshape(B, -1).norm(2, dim=1) - 1) ** 2).mean()
+    want = {"l_d_real": float(-2 * pr.mean()), "l_d_fake": float(2 * pf.mean()), "l_d_gp": float(gp), "D_real": float(pr.mean()), "D_fake": float(pf.mean())}
+    ((-2 * pr.mean() + 2 * pf.mean()) / 2 + gp).backward()
+    opt_d.step()
+    for p in d_cpu.parameters():
+        p.requires_grad_(False)
+    l_pix, l_range = (fake - hr).abs().mean(), torch.maximum(fake - 1, -fake).clamp_min(0).mean()
+    l_gan = -5e-3 * d_cpu(fake).mean()
+    want.update(l_g_pix=float(l_pix), l_g_range=float(l_range), l_g_gan=float(l_gan))
+    (1e-2 * l_pix + 50.0 * l_range + l_gan).backward()
+    for k, v in want.items():
+        assert abs(log[k] - v) <= 2e-2 * max(abs(v), 1e-3), (k, log[k], v)
+    for (k, p), q in zip(d_gpu.named_parameters(), d_cpu.parameters()):           # the critic after its Adam step
+        assert float((p.detach().cpu() - q).abs().max()) <= 2.5e-4, k             # lr 1e-4: one step moves every weight by <= 1e-4
+    G = netG.generated_image_model
+    for name, p in G.named_parameters():
+        if name == "model.6.bias":
+            continue
+        got, ref = p.grad.cpu(), w[name].grad
+        rel = float((got - ref).norm() / ref.norm().clamp_min(1e-20))
+        cos = float((got * ref).sum() / (got.norm() * ref.norm()).clamp_min(1e-30))
+        assert rel < 0.12 and cos > 0.992, "%s: relative error %g, cosine %g" % (name, rel, cos)
+        assert float((p.detach().cpu() - wts[name]).abs().max()) > 0, name          # optimizer_G.step() reached the parameter
+
+
+def test_fused_adam_updates_reach_the_kernels(cuda_device):
+    """``torch.optim.Adam(fused=True)`` writes the parameters without bumping their version counters (the key of the
+    packed-weight cache): the training forward re-packs every step regardless, so the next fake_H differs."""
+    wts = synth.make_weights("kaiming", seed=6, nb=1)
+    lr, z = synth.make_inputs(1, 16, 16, seed=6)
+    netG = build_product_G(cuda_device, 1, "all_layers_HR_downscaled", wts, train=True)
+    trainer = GeneratorTrainer(netG)
+    opt = torch.optim.Adam(netG.generated_image_model.parameters(), lr=1e-3, fused=True)
+    mi = concat_latent(lr, z).to(cuda_device)
+    outs = []
+    for _ in range(2):
+        fake = trainer.forward(mi)
+        outs.append(fake.detach().clone())
+        fake.abs().mean().backward()
+        trainer.backward(fake.grad)
+        opt.step()
+    assert float((outs[1] - outs[0]).abs().max()) > 1e-4

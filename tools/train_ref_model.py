@@ -25,6 +25,11 @@ def build(args):
         ref_shims.load_reference()
     import options.options as option
     from models import create_model
+    if args.impl == "reference" and args.gan > 0:
+        # the shipped define_D names Discriminator_VGG_128 but passes the nb= that only Discriminator_VGG_128_ takes
+        # (networks.py:119 vs architecture.py:182,222): the reference arm gets the class its options mean
+        import models.modules.architecture as ref_arch
+        ref_arch.Discriminator_VGG_128 = ref_arch.Discriminator_VGG_128_
     opt = option.parse(os.path.join(ref_shims.REF_ROOT, "options", "train", "train_esrgan_CEM.json"), is_train=True)
     tmp = tempfile.mkdtemp()
     for k in ("root", "experiments_root", "models", "log", "val_images"):
@@ -33,6 +38,7 @@ def build(args):
     opt["gpu_ids"] = [0] if args.device == "cuda" else None
     opt["network_G"]["nb"] = args.nb
     opt["network_G"]["latent_channels"] = 3
+    opt["network_D"]["nf"] = args.nf_d
     opt["datasets"]["train"].update(batch_size=args.batch, batch_size_4_grads_G=args.batch * args.accum, batch_size_4_grads_D=args.batch * args.accum,
                                     patch_size=args.patch)
     opt["train"].update(grad_accumulation_steps_G=args.accum, grad_accumulation_steps_D=args.accum, D_update_ratio=1, D_verification=None,
@@ -53,6 +59,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--accum", type=int, default=1)
     ap.add_argument("--gan", type=float, default=0.0, help="gan_weight; > 0 needs the reference's discriminator")
+    ap.add_argument("--nf-d", type=int, default=64, help="network_D.nf")
     ap.add_argument("--weights", default="")
     ap.add_argument("--save-weights", default="")
     args = ap.parse_args()
