@@ -139,6 +139,7 @@ SIGNATURES = {
                                       _vp, _vp]),
     "esr_debug_set_profile_buffer": (None, [_vp]),
     "esr_debug_cem_timeout": (C.c_int, [C.POINTER(C.c_uint32)]),
+    "esr_debug_cem_fused_prof": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "esr_wgrad16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "esr_wgrad_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "esr_zopt_tanh_pack": (C.c_int, [_vp, C.c_float, _i32, _i32, _i32, _vp, _vp]),
@@ -155,6 +156,7 @@ SIGNATURES = {
     "esr_cem_inv_hth": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "esr_cem_upscale": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "esr_cem_project": (C.c_int, [C.POINTER(CemFilters), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "esr_cem_project_fused": (C.c_int, [C.POINTER(CemFilters), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esr_cem_project_bwd": (C.c_int, [C.POINTER(CemFilters), _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "esr_cem2d_downscale": (C.c_int, [C.POINTER(CemFilters2d), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "esr_cem2d_inv_hth": (C.c_int, [C.POINTER(CemFilters2d), _vp, _i32, _i32, _i32, _i32, _vp, _vp]),

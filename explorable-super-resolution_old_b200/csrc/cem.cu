@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "cem_tabs.cuh"
 #include "esr_common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -172,17 +173,6 @@ __global__ void __launch_bounds__(256) cem_up_kernel(const __grid_constant__ esr
 // every HR float4 is loaded / stored exactly once per strip, fully coalesced (448 B per warp row).
 constexpr int kStripCells = 28;
 constexpr int kSegRows = 8;          // LR rows per warp (host-chosen launch parameter of the kernels below)
-
-struct CemTab {            // polyphase tap tables, [phase][cell offset -2..2]
-    float down_h[4][5];    // down: weight of element e of cell j+c for output column j
-    float down_v[4][5];    // down: weight of HR row 4I+q for output row I-m, index [q][m+2]
-    float up[4][5];        // up: weight of cell j+c for HR phase phi (same table for rows)
-    // packed-fp32 (FFMA2) operand forms of the same numbers
-    float2 down_v2[4][5];  // (down_v, down_v)
-    float2 up_v2[4][5];    // (up, up)
-    float2 up_h01[5];      // (up[0][c], up[1][c])
-    float2 up_h23[5];      // (up[2][c], up[3][c])
-};
 
 // Vertical taps first: every HR row costs 20 FMAs into five float4 accumulators (LR rows I-2..I+2) and no
 // shuffles; the horizontal taps run once per LR row on the finished accumulator (20 FMAs for the cell's five
@@ -581,7 +571,7 @@ static bool fast4_ok(const esr_cem_filters& f, int H, int W, int crop, const voi
     return f.sf == 4 && f.n_ds == 17 && H % 4 == 0 && W % 4 == 0 && crop % 4 == 0 && al(a) && al(b) && al(c);
 }
 
-static CemTab make_tab(const esr_cem_filters& f) {
+CemTab make_tab(const esr_cem_filters& f) {
     CemTab T;
     const int nt = f.n_ds, pad = nt / 2, pre = f.pre;
     for (int p = 0; p < 4; ++p)
@@ -972,7 +962,7 @@ cem_invup4s_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
     if (!waited) pdl_wait();
 }
 
-static int make_plane_map(CUtensorMap* tm, const float* base, int planes, int rows, int cols, int box_cols, int box_rows) {
+int make_plane_map(CUtensorMap* tm, const float* base, int planes, int rows, int cols, int box_cols, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ESR_ERR_CUDA; }
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
@@ -1345,6 +1335,7 @@ extern "C" int esr_cem_project(const esr_cem_filters* f, const float* y, const f
     const int h = H / f->sf, w = W / f->sf, planes = B * C;
     float* d = workspace;
     float* e = workspace + static_cast<size_t>(planes) * h * w;
+    if (cem_fused_enabled() && (rc = cem_project4f(*f, y, x, planes, H, W, crop, out, workspace, s)) <= 0) return rc;   // opt-in: one launch, y read once
     if (stream4_ok(*f, H, W, crop, y, x, out, d)) {                         // round-2 TMA streaming kernels
         static const int dbg = []() { const char* v = getenv("ESR_CEM_DEBUG"); return v ? atoi(v) : 0; }();   // 1: new Down only, 2: new K+Up only
         if ((rc = dbg == 2 ? cem_down(*f, y, x, planes, H, W, d, s) : cem_down4s(*f, y, x, planes, H, W, d, s))) return rc;

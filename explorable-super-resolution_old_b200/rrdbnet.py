@@ -56,9 +56,16 @@ class RRDBNet(nn.Module):
             raise NotImplementedError("nf=%d: the kernels are specialised for nf=64, gc=32" % nf)
         if norm_type is not None or act_type != 'leakyrelu' or mode != 'CNA' or upsample_mode != 'upconv':
             raise NotImplementedError("only norm_type=None, leakyrelu, mode='CNA', upconv are built (the production config)")
-        if latent_input is not None and 'HR_downscaled' not in latent_input:
-            raise NotImplementedError("latent_input_domain other than HR_downscaled is not built (SURVEY.md §8f rank 4)")
+        if latent_input is not None and 'HR_rearranged' in latent_input:
+            # the reference's own forward raises 'Unsupported yet' for all_layers_HR_rearranged (architecture.py:167-169);
+            # first_layer_HR_rearranged (48 extra input channels on the first conv) is not built here
+            raise NotImplementedError("latent_input_domain HR_rearranged is not built (SURVEY.md §8f rank 4)")
+        if latent_input is not None and 'HR_downscaled' not in latent_input and 'LR' not in latent_input:
+            raise NotImplementedError("latent_input %r: expected <all_layers|first_layer>_<HR_downscaled|LR>" % (latent_input,))
         self.latent_input = latent_input
+        # 'LR' domain (architecture.py:159,165-166): Z has the LR image's size and is assigned to ``self.Z`` by the caller
+        # (SRRaGAN_model.py:260-261); forward(x) takes the 3 image channels only.  See _lr_domain_input.
+        self.latent_domain = None if latent_input is None else ('HR_downscaled' if 'HR_downscaled' in latent_input else 'LR')
         nz_in = num_latent_channels if (latent_input is not None and num_latent_channels) else 0
         self.num_latent_channels = 1 * num_latent_channels if num_latent_channels is not None else None
         self.upscale = upscale
@@ -72,6 +79,8 @@ class RRDBNet(nn.Module):
                                       _conv(nf, nf), nn.LeakyReLU(0.2, True)))
         mods += [_conv(nf + nz, nf), nn.LeakyReLU(0.2, True), _conv(nf + nz, out_nc)]
         self.model = nn.ModuleList(mods)
+        if self.latent_domain == 'LR' and nz:
+            self.latent_upsampler = nn.Upsample(scale_factor=upscale if upscale == 3 else 2)   # attribute parity (:137-139)
         self._cfg = dict(nb=nb, nz_in=nz_in, all_layers=all_layers, out_nc=out_nc, in_nc=in_nc, upscale=upscale)
         self._engine, self._engine_key, self._plans = None, None, {}
         self._packed_params, self._dgrad, self._bplans = None, None, {}
@@ -346,9 +355,39 @@ class _TrainFn(torch.autograd.Function):
         return (g_in if ctx.needs_input_grad[0] else None, None, None, None) + tuple(grads)
 
 
+def _lr_domain_input(net, x, margin):
+    """LR-domain latent (architecture.py:159-166): ``x`` is the bare LR image, ``net.Z`` [B, Cz, H, W] has the size of the
+    image the generator sees (in eval mode the CEM wrapper replicate-pads x by its margin first, CEMnet.py:180-181, so Z
+    must already have the padded size — as in the reference, where a mismatch fails in torch.cat).  The reference
+    concatenates Z to the LR-resolution convs as it is and its nearest-neighbour upsampling (``latent_upsampler`` once
+    per upconv stage) to the HR convs.  That is exactly the HR_downscaled path fed with Z_HR = nearest_upsample(Z, sf):
+    the centre-2x2 mean that path takes of every sf x sf block returns Z bit-exactly.  Plumbing in torch (pad, repeat,
+    view, cat; differentiable w.r.t. Z and indexing-only), arithmetic in the kernels."""
+    Z = getattr(net, 'Z', None)
+    nz_in, sf = net._cfg["nz_in"], net.upscale
+    if Z is None:
+        raise AttributeError("RRDBNet with an LR-domain latent input: assign the latent to .Z before forward (SRRaGAN_model.py:260-261)")
+    if margin > 0:
+        x = torch.nn.functional.pad(x.float(), (margin,) * 4, mode='replicate')
+    if x.size(1) != 3 or Z.dim() != 4 or Z.size(1) != nz_in or Z.shape[0] != x.shape[0] or Z.shape[2:] != x.shape[2:]:
+        raise RuntimeError("LR-domain latent: Z %s does not match the (padded) LR input %s with %d latent channels"
+                           % (tuple(Z.shape), tuple(x.shape), nz_in))
+    B, _, H, W = x.shape
+    z_hr = Z.to(x.device).float().repeat_interleave(sf, 2).repeat_interleave(sf, 3)
+    return torch.cat([z_hr.contiguous().view(B, nz_in * sf * sf, H, W), x.float()], 1)
+
+
 def run_generator(net, x, margin, cem_filters):
     if not x.is_cuda:
         raise capi.EsrError("RRDBNet.forward: expected a CUDA tensor; this package has no CPU or PyTorch fallback")
+    if net.latent_domain == 'LR':
+        crop = net.upscale * margin
+        out = _run_generator(net, _lr_domain_input(net, x, margin), 0, cem_filters)
+        return out[..., crop:out.size(-2) - crop, crop:out.size(-1) - crop] if crop else out
+    return _run_generator(net, x, margin, cem_filters)
+
+
+def _run_generator(net, x, margin, cem_filters):
     dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
     capi.require_device(dev)
     nz_in = net._cfg["nz_in"]

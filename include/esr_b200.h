@@ -307,6 +307,12 @@ int esr_cem_upscale(const esr_cem_filters* f, const float* x, int32_t B, int32_t
  * workspace: 2*B*C*(H/sf)*(W/sf) floats. */
 int esr_cem_project(const esr_cem_filters* f, const float* y, const float* x, int32_t B, int32_t C, int32_t H,
                     int32_t W, int32_t crop, float* out, float* workspace, void* stream);
+/* The same projection as ONE cooperative launch that keeps y on chip between Down and Up (csrc/cem_fused.cu): y is read
+ * from HBM once.  x4 bicubic only, H % 16 == 0, W % 32 == 0, 1024 <= W <= 2048, H / 16 <= SM count; other shapes return
+ * ESR_ERR_UNSUPPORTED.  Slower than the two-launch path at BASELINE config 4 (lock-step rounds), hence not the default of
+ * esr_cem_project (ESR_CEM_FUSED=1 routes it here).  Same workspace. */
+int esr_cem_project_fused(const esr_cem_filters* f, const float* y, const float* x, int32_t B, int32_t C, int32_t H,
+                          int32_t W, int32_t crop, float* out, float* workspace, void* stream);
 /* g_y[B,C,H,W] = pad(g_out) - Down^T(K^T(Up^T(pad(g_out)))), exact adjoint including the
  * replicate-padding folds.  workspace: B*C*(H*W + H*(W/sf) + 2*(H/sf)*(W/sf)) floats. */
 int esr_cem_project_bwd(const esr_cem_filters* f, const float* g_out, int32_t B, int32_t C, int32_t H, int32_t W,
@@ -397,6 +403,8 @@ int esr_wgrad_small(const esr_wgrad_small_item* items_device, int32_t n_items, i
 /* Debug aid: the x4 CEM streaming kernels record a ring wait that never completed instead of trapping;
  * out4 = {code (0 = none, 1 = Down, 2 = K+Up), block, thread, group}; reading clears it. */
 int esr_debug_cem_timeout(uint32_t* out4);
+/* ESR_CEM_PROF=1: phase time stamps of the last single-launch x4 projection, [cta < 160][round < 4][8] globaltimer ns. */
+int esr_debug_cem_fused_prof(unsigned long long* out, int n);
 
 /* Debug aid (tools/prof.py): per-CTA role cycle counters of later tcgen05 conv launches, when the
  * library was built with -DESR_PROFILE_ROLES.  buf: [148][16] uint64 device memory or NULL. */

@@ -118,6 +118,46 @@ def gen_x2(CEMnet, networks):
     np.savez_compressed(os.path.join(OUT, "g_cem_x2.npz"), **out)
 
 
+def gen_lr_domain(CEMnet, networks):
+    """latent_input_domain 'LR' (architecture.py:137-139,159,165-166): Z at the LR image's size assigned to ``.Z``, the
+    3-channel image as forward's argument.  Outputs in train and eval mode (eval: the CEM wrapper pads x by its margin, so
+    Z is given at the padded size) and the Z gradient of the reference's autograd; all_layers and first_layer."""
+    from oracle.ref_shims import make_opt
+    import CEM.imresize_CEM as im
+    out = {}
+    for name, latent, nb, kind, seed, B, h, w, train in (("lr_all_nb2_train", "all_layers", 2, "default", 21, 2, 12, 10, True),
+                                                        ("lr_all_nb1_eval", "all_layers", 1, "kaiming", 22, 1, 9, 14, False),
+                                                        ("lr_first_nb1_train", "first_layer", 1, "default", 23, 1, 10, 12, True)):
+        im.imresize.kernels = {}
+        cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(4))
+        opt = make_opt(nb, latent)
+        opt["network_G"]["latent_input_domain"] = "LR"
+        netG = networks.define_G(opt, CEM=cem, num_latent_channels=3)
+        wts = synth.make_weights(kind, seed=seed, nb=nb, latent_input=latent + "_HR_downscaled")     # same conv shapes
+        sd = netG.state_dict()
+        assert [k for k in sd if "Filter" not in k] == ["generated_image_model." + k for k in wts]
+        sd.update({"generated_image_model." + k: v for k, v in wts.items()})
+        netG.load_state_dict(sd)
+        netG.train(train)
+        for p in netG.parameters():
+            p.requires_grad = False
+        m = 0 if train else int(cem.invalidity_margins_LR)
+        rng = np.random.default_rng(seed)
+        lr = torch.from_numpy(rng.random((B, 3, h, w), dtype=np.float32))
+        z = torch.from_numpy((2 * rng.random((B, 3, h + 2 * m, w + 2 * m), dtype=np.float32) - 1))
+        zg = z.clone().requires_grad_(True)
+        netG.generated_image_model.Z = zg
+        res = netG(lr)
+        g = torch.from_numpy(rng.standard_normal(tuple(res.shape)).astype(np.float32))
+        (res * g).sum().backward()
+        out[name + "_lr"], out[name + "_z"] = lr.numpy(), z.numpy()
+        out[name + "_out"], out[name + "_gout"], out[name + "_gz"] = res.detach().numpy(), g.numpy(), zg.grad.numpy()
+        out[name + "_cfg"] = np.array([nb, seed, int(train)])
+        out[name + "_kind"], out[name + "_latent"] = np.array(kind), np.array(latent)
+        print(name, tuple(res.shape), float(res.abs().max()), float(zg.grad.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "g_cem_lr_domain.npz"), **out)
+
+
 class RefModel:
     """Minimal stand-in for SRRaGANModel (codes/models/SRRaGAN_model.py:249-302 restated): only what Z_optimizer touches."""
 
@@ -230,6 +270,8 @@ def main():
         return gen_nondefault(CEMnet)
     if "x2" in sys.argv[1:]:              # only the x2 fixture
         return gen_x2(CEMnet, networks)
+    if "lr_domain" in sys.argv[1:]:       # only the LR-domain latent fixture
+        return gen_lr_domain(CEMnet, networks)
     if "zopt2" in sys.argv[1:]:           # only the extra Z_optimizer trajectories
         return gen_zopt2(CEMnet, networks, zopt)
     if "cfg3" in sys.argv[1:]:            # only the config-3-size output / gradient windows (about a minute, ~20 GB)
@@ -340,6 +382,9 @@ def main():
     # 7. more Z_optimizer paths, config-3-size gradient ----------------------------------------
     gen_zopt2(CEMnet, networks, zopt)
     gen_cfg3(CEMnet, networks)
+
+    # 8. LR-domain latent input ------------------------------------------------------------------
+    gen_lr_domain(CEMnet, networks)
 
 
 if __name__ == "__main__":

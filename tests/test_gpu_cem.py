@@ -85,6 +85,45 @@ def test_ops_match_oracle_and_consistency(cuda_device, sf, shape):
         assert (out12 - out - out2).abs().max().item() <= 2e-5
 
 
+@pytest.mark.parametrize("shape,crop", [((1, 3, 2048, 2048), 0),      # BASELINE config 4: 3 rounds of one plane
+                                        ((2, 3, 1024, 1088), 0),       # two planes per round; W not a multiple of 256
+                                        ((1, 3, 112, 1344), 40),       # eval-mode crop, 7 slabs per plane, all planes in one round
+                                        ((1, 3, 16, 1024), 0),         # a single slab: top and bottom replicate rows in the same CTA
+                                        ((2, 3, 2368, 1024), 8)])      # 148 slabs per plane: every SM of the part
+def test_single_launch_projection(cuda_device, shape, crop):
+    """esr_cem_project_fused (csrc/cem_fused.cu: one cooperative launch, y read once, u = K_h(x - Down y) accumulated
+    through L2) against the CPU oracle (1e-5) and the default two-launch path; run-to-run identical."""
+    from esr_b200 import _capi as capi
+    B, Cc, H, W = shape
+    gen = torch.Generator().manual_seed(5)
+    y = torch.rand(shape, generator=gen)
+    x = torch.rand(B, Cc, H // 4, W // 4, generator=gen)
+    net = pcem.CEMnet(pcem.Get_CEM_Config(4))
+    f = net._filters
+    yd, xd = y.to(cuda_device), x.to(cuda_device)
+    out = torch.full((B, Cc, H - 2 * crop, W - 2 * crop), float("nan"), device=cuda_device)
+    ws = torch.full((2 * B * Cc * (H // 4) * (W // 4),), float("nan"), device=cuda_device)       # the launch must not rely on a clean workspace
+    with torch.cuda.device(cuda_device):
+        for _ in range(2):                                                                            # and must leave it reusable
+            capi.cem_call("project_fused", f, capi.ptr(yd), capi.ptr(xd), B, Cc, H, W, crop, capi.ptr(out), capi.ptr(ws), capi.stream_ptr())
+    torch.cuda.synchronize()
+    ref = CEMOracle(4).project(y, x)
+    if crop:
+        ref = ref[..., crop:H - crop, crop:W - crop]
+    got = out.cpu()
+    assert torch.isfinite(got).all()
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-5)
+    # run-to-run identical (two order-independent contributions per cell, no other atomics)
+    out2, out3 = torch.empty_like(out), torch.empty_like(out)
+    with torch.cuda.device(cuda_device):
+        capi.cem_call("project_fused", f, capi.ptr(yd), capi.ptr(xd), B, Cc, H, W, crop, capi.ptr(out2), capi.ptr(ws), capi.stream_ptr())
+        capi.cem_call("project", f, capi.ptr(yd), capi.ptr(xd), B, Cc, H, W, crop, capi.ptr(out3), capi.ptr(ws), capi.stream_ptr())
+    assert torch.equal(out, out2)
+    assert float((out - out3).abs().max()) <= 1e-5
+    with pytest.raises(capi.EsrError, match="single-launch"):      # a shape outside its domain is refused, not mangled
+        capi.cem_call("project_fused", f, capi.ptr(yd), capi.ptr(xd), B, Cc, H // 2 + 4, W, 0, capi.ptr(out2), capi.ptr(ws), capi.stream_ptr())
+
+
 # ------------------------------------------------------------------ non-default kernels (csrc/cem2d.cu)
 NONDEFAULT_OP_CASES = ["blur1_x4", "blur2_x4", "aniso13_x4", "aniso15_x2", "aniso15_x3"]
 

@@ -16,11 +16,11 @@ from tests.test_oracle_golden import CASES, oracle_for_case
 pytestmark = pytest.mark.gpu
 
 
-def build_product_G(dev, nb, latent, weights, train=False, sf=4):
+def build_product_G(dev, nb, latent, weights, train=False, sf=4, domain="HR_downscaled"):
     opt = {"gpu_ids": None, "is_train": False, "datasets": {"train": {"patch_size": 256}},
            "network_G": dict(which_model_G="RRDB_net", CEM_arch=1,
                              latent_input="None" if latent is None else latent.split("_HR_")[0],
-                             latent_input_domain="HR_downscaled", latent_channels=3, norm_type=None, mode="CNA",
+                             latent_input_domain=domain, latent_channels=3, norm_type=None, mode="CNA",
                              nf=64, nb=nb, in_nc=3, out_nc=3, gc=32, scale=sf)}
     cemnet = pcem.CEMnet(pcem.Get_CEM_Config(sf))
     netG = networks.define_G(opt, CEM=cemnet, num_latent_channels=3 if latent else 0)
@@ -261,6 +261,38 @@ def test_x2_generator_matches_reference_golden(golden, cuda_device, name):
     (out * torch.from_numpy(g[name + "_gout"]).to(cuda_device)).sum().backward()
     got, gz = zp.grad.cpu(), torch.from_numpy(g[name + "_gz"])
     assert float((got - gz).norm() / gz.norm()) < 4e-2 and float((got * gz).sum() / (got.norm() * gz.norm())) > 0.999
+
+
+@pytest.mark.parametrize("name", ["lr_all_nb2_train", "lr_all_nb1_eval", "lr_first_nb1_train"])
+def test_lr_domain_latent_matches_reference_golden(golden, cuda_device, name):
+    """``latent_input_domain: "LR"`` (architecture.py:137-139,159,165-166): Z of the LR image's size
+    assigned to ``.Z`` (SRRaGAN_model.py:260-261), forward on the bare image; all_layers (nearest-upsampled Z at the HR
+    convs) and first_layer; train and eval mode (eval: Z at the CEM-padded size).  Against the unmodified reference:
+    output max error <= 1e-2 / PSNR >= 50 dB, Z gradient of its autograd within the dgrad tolerance."""
+    g = golden("g_cem_lr_domain")
+    nb, seed, train = [int(v) for v in g[name + "_cfg"]]
+    latent = str(g[name + "_latent"])
+    wts = synth.make_weights(str(g[name + "_kind"]), seed=seed, nb=nb, latent_input=latent + "_HR_downscaled")
+    netG = build_product_G(cuda_device, nb, latent + "_HR_downscaled", wts, train=bool(train), domain="LR")
+    G = netG.generated_image_model
+    assert G.latent_input == latent + "_LR" and G.num_latent_channels == 3
+    assert hasattr(G, "latent_upsampler") == (latent == "all_layers")
+    lr = torch.from_numpy(g[name + "_lr"]).to(cuda_device)
+    with pytest.raises(AttributeError):
+        netG(lr)                                                    # no Z assigned yet
+    zp = torch.from_numpy(g[name + "_z"]).to(cuda_device).requires_grad_(True)
+    G.Z = zp
+    out = netG(lr)
+    ref = torch.from_numpy(g[name + "_out"])
+    assert out.shape == ref.shape
+    assert (out.detach().cpu() - ref).abs().max().item() <= 1e-2
+    assert psnr(out.detach().cpu(), ref) >= 50.0
+    (out * torch.from_numpy(g[name + "_gout"]).to(cuda_device)).sum().backward()
+    got, gz = zp.grad.cpu(), torch.from_numpy(g[name + "_gz"])
+    assert float((got - gz).norm() / gz.norm()) < 5e-2 and float((got * gz).sum() / (got.norm() * gz.norm())) > 0.999
+    G.Z = zp.detach()[..., 1:, :]
+    with pytest.raises(RuntimeError, match="does not match"):
+        netG(lr)
 
 
 def test_pretrained_checkpoint_without_latent_is_reproduced(cuda_device):

@@ -103,3 +103,35 @@ def test_x2_generator_matches_reference(golden, name):
     np.testing.assert_allclose(out.detach().numpy(), g[name + "_out"], atol=2e-5)
     (out * torch.from_numpy(g[name + "_gout"])).sum().backward()
     np.testing.assert_allclose(zg.grad.numpy(), g[name + "_gz"], atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["lr_all_nb2_train", "lr_all_nb1_eval", "lr_first_nb1_train"])
+def test_lr_domain_plumbing_maps_onto_the_hr_downscaled_path(golden, name):
+    """The product serves ``latent_input_domain: "LR"`` by feeding its HR_downscaled path with
+    Z_HR = nearest_upsample(Z, 4) (rrdbnet._lr_domain_input).  Here that host-side packing (no kernels involved) goes
+    through the CPU oracle of the HR_downscaled path and must reproduce the reference's LR-domain output and Z gradient."""
+    from esr_b200.rrdbnet import RRDBNet, _lr_domain_input
+    g = golden("g_cem_lr_domain")
+    nb, seed, train = [int(v) for v in g[name + "_cfg"]]
+    latent = str(g[name + "_latent"])
+    wts = synth.make_weights(str(g[name + "_kind"]), seed=seed, nb=nb, latent_input=latent + "_HR_downscaled")
+    net = RRDBNet(3, 3, 64, nb, latent_input=latent + "_LR", num_latent_channels=3)
+    assert [k for k, _ in net.named_parameters()] == list(wts)
+    z = torch.from_numpy(g[name + "_z"]).requires_grad_(True)
+    net.Z = z
+    margin = 0 if train else 10
+    packed = _lr_domain_input(net, torch.from_numpy(g[name + "_lr"]), margin)
+    assert packed.shape[1] == 51 and packed.shape[2:] == z.shape[2:]
+    ora = GCEMOracle(wts, pre_pad=False, nb=nb, latent_input=latent + "_HR_downscaled", num_latent_channels=3)
+    out = ora.forward(packed)
+    c = 4 * margin
+    out = out[..., c:out.size(-2) - c, c:out.size(-1) - c]
+    np.testing.assert_allclose(out.detach().numpy(), g[name + "_out"], atol=2e-5)
+    (out * torch.from_numpy(g[name + "_gout"])).sum().backward()
+    np.testing.assert_allclose(z.grad.numpy(), g[name + "_gz"], atol=1e-5 * float(np.abs(g[name + "_gz"]).max()) + 1e-7)
+
+
+def test_hr_rearranged_domain_is_refused():
+    from esr_b200.rrdbnet import RRDBNet
+    with pytest.raises(NotImplementedError, match="HR_rearranged"):
+        RRDBNet(3, 3, 64, 1, latent_input="all_layers_HR_rearranged", num_latent_channels=3)
