@@ -94,9 +94,11 @@ __device__ __forceinline__ float gz_total(const PrepBwdArgs& a, int b, int c, in
     return v;
 }
 
-// One thread per element of the UNPADDED HR gradient (gather form of the replicate-pad adjoint): an interior pixel has one
-// source, a border pixel sums the margin samples that were copied from it (a corner: (M+1)^2 of them) in a fixed order -
-// run-to-run reproducible, unlike the round-1 scatter with atomicAdd.  Every element of the latent part of g_in is written.
+// Gather form of the replicate-pad adjoint over the UNPADDED HR gradient: an interior pixel has one source (one thread
+// each); a border pixel sums the margin samples that were copied from it - M+1 along an edge, (M+1)^2 in a corner - and
+// is summed by a whole WARP (lanes stride over the samples in a fixed order, then a butterfly reduction), so the result is
+// run-to-run reproducible (unlike the round-1 scatter with atomicAdd) without four corner threads walking 1681 samples each
+// (that tail was 0.41 ms of a 10 ms Z-optimisation iteration).  Every element of the latent part of g_in is written.
 __global__ void prep_bwd_kernel(const __grid_constant__ PrepBwdArgs a) {
     const int Hh = a.sf * a.h, Wh = a.sf * a.w, M = a.sf * a.m, cin = a.nz * a.sf * a.sf + 3;
     const size_t total = static_cast<size_t>(a.B) * a.nz * Hh * Wh;
@@ -104,14 +106,34 @@ __global__ void prep_bwd_kernel(const __grid_constant__ PrepBwdArgs a) {
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int x = static_cast<int>(idx % Wh);
         const int y = static_cast<int>((idx / Wh) % Hh);
+        if (x == 0 || y == 0 || x == Wh - 1 || y == Hh - 1) continue;          // border: the warp pass below
         const int c = static_cast<int>((idx / (static_cast<size_t>(Wh) * Hh)) % a.nz);
         const int b = static_cast<int>(idx / (static_cast<size_t>(Wh) * Hh * a.nz));
+        a.g_in[static_cast<size_t>(b) * cin * a.h * a.w + (static_cast<size_t>(c) * Hh + y) * Wh + x] = gz_total(a, b, c, y + M, x + M);
+    }
+    const int per_plane = (Hh > 1 ? 2 * Wh : Wh) + (Wh > 1 ? 2 : 1) * (Hh > 2 ? Hh - 2 : 0);
+    const size_t nborder = static_cast<size_t>(a.B) * a.nz * per_plane;
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5, nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    for (size_t e = warp0; e < nborder; e += nwarps) {
+        const int k = static_cast<int>(e % per_plane);
+        const int c = static_cast<int>((e / per_plane) % a.nz);
+        const int b = static_cast<int>(e / (static_cast<size_t>(per_plane) * a.nz));
+        int y, x;
+        if (k < Wh) { y = 0; x = k; }
+        else if (Hh > 1 && k < 2 * Wh) { y = Hh - 1; x = k - Wh; }
+        else {
+            const int r = k - (Hh > 1 ? 2 * Wh : Wh);
+            if (Wh > 1) { y = 1 + (r >> 1); x = (r & 1) ? Wh - 1 : 0; } else { y = 1 + r; x = 0; }
+        }
         const int Y0 = y == 0 ? 0 : y + M, Y1 = y == Hh - 1 ? Hh - 1 + 2 * M : y + M;       // padded rows that clamp onto y
         const int X0 = x == 0 ? 0 : x + M, X1 = x == Wh - 1 ? Wh - 1 + 2 * M : x + M;
+        const int nx = X1 - X0 + 1, n = (Y1 - Y0 + 1) * nx;
         float v = 0.f;
-        for (int Y = Y0; Y <= Y1; ++Y)
-            for (int X = X0; X <= X1; ++X) v += gz_total(a, b, c, Y, X);
-        a.g_in[static_cast<size_t>(b) * cin * a.h * a.w + (static_cast<size_t>(c) * Hh + y) * Wh + x] = v;
+        for (int i = lane; i < n; i += 32) v += gz_total(a, b, c, Y0 + i / nx, X0 + i % nx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) a.g_in[static_cast<size_t>(b) * cin * a.h * a.w + (static_cast<size_t>(c) * Hh + y) * Wh + x] = v;
     }
 }
 
@@ -256,9 +278,12 @@ __global__ void grad_combine_kernel(const __grid_constant__ CombineArgs a) {
     const size_t total = static_cast<size_t>(a.B) * a.H * a.W * 8;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(idx % a.W);
-        const int y = static_cast<int>((idx / a.W) % a.H);
-        const int blk = static_cast<int>((idx / (static_cast<size_t>(a.W) * a.H)) % 8);
+        // channel block fastest: a warp covers 4 pixels x 64 channels = 512 contiguous bytes of the 16-bit NHWC mask / output
+        // (with x fastest every lane touched 16 bytes of a different 128-byte pixel: half-used sectors both ways) and
+        // 256-byte runs of each of the eight blocked fp32 planes
+        const int blk = static_cast<int>(idx & 7);
+        const int x = static_cast<int>((idx >> 3) % a.W);
+        const int y = static_cast<int>((idx / (static_cast<size_t>(a.W) * 8)) % a.H);
         const int b = static_cast<int>(idx / (static_cast<size_t>(a.W) * a.H * 8));
         const int c0 = blk * 8;
         float v[8];
