@@ -445,6 +445,7 @@ def run_train_gan(args):
     netD = Discriminator_VGG_128_(3, 64, nb=6, input_patch_size=128)
     networks.init_weights(netD, init_type="kaiming", scale=1)
     netD.to(dev).train()
+    torch.backends.cudnn.benchmark = os.environ.get("ESR_D_CUDNN_BENCHMARK", "1") == "1"   # the torch critic: 55.8 -> 50.8 ms per step
     gan = GanTrainer(netG, netD, lr_G=1e-5, lr_D=1e-5, pixel_weight=1e-2, gan_weight=1.0, gp_weight=10.0, range_weight=5000.0, crop=0)
     Bp, hl = 16, 32
     lr, z = synth.make_inputs(Bp, hl, hl, seed=rank)

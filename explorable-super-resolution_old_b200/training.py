@@ -1,4 +1,6 @@
-"""Generator half of the GAN training step, data parallel (BASELINE config 5).
+"""The GAN training step, data parallel (BASELINE config 5): ``GeneratorTrainer`` (the generator's
+half: forward with kept activations, data + weight gradients, bucketed NCCL all-reduce) and ``GanTrainer`` (the whole
+iteration with the critic of esr_b200.discriminator and the WGAN-GP penalty).
 
 The reference's ``SRRaGANModel.optimize_parameters`` (codes/models/SRRaGAN_model.py:463-547) runs
 ``fake_H = netG(model_input)``, builds ``l_g_total`` from ``fake_H`` (pixel / feature / GAN / range terms) and calls
@@ -18,9 +20,9 @@ cut into buckets, and as soon as a bucket's weight-gradient launches are queued 
 issued on a communication stream, so the exchange of the late layers runs under the weight-gradient kernels of the
 early ones (68.2 MB for the production generator).  ``p.grad`` of every parameter is a view into that buffer.
 
-Not built here: the discriminator, VGG feature extractor, WGAN-GP double backward and range loss of the full step
-(they consume ``fake_H`` in torch through the boundary above), and a tcgen05 form of the weight-gradient GEMM
-(csrc/wgrad.cu uses warp-level bf16 MMAs).
+The critic, the WGAN-GP double backward and the range / pixel criteria of the full step are torch code on ``fake_H``
+(``GanTrainer`` below, or the reference's own ``optimize_parameters`` through the autograd node rrdbnet._TrainFn).
+Not built: the VGG feature loss, and a tcgen05 form of the weight-gradient GEMM (csrc/wgrad.cu uses warp-level bf16 MMAs).
 """
 import ctypes as C
 

@@ -25,7 +25,8 @@ def _oracle_grads(wts, nb, mi, gout, train):
     return out.detach(), {k: v.grad for k, v in w.items()}
 
 
-@pytest.mark.parametrize("nb,B,h,w,train,kind", [(1, 2, 24, 32, True, "default"), (2, 1, 28, 24, False, "kaiming")])
+@pytest.mark.parametrize("nb,B,h,w,train,kind", [(1, 2, 24, 32, True, "default"), (2, 1, 28, 24, False, "kaiming"),
+                                                 (23, 1, 32, 32, True, "kaiming")])     # BASELINE config 5's generator and patch size
 def test_weight_gradients_match_oracle_autograd(cuda_device, nb, B, h, w, train, kind):
     wts = synth.make_weights(kind, seed=3, nb=nb)
     lr, z = synth.make_inputs(B, h, w, seed=3)
