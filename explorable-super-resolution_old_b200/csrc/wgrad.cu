@@ -37,10 +37,24 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;                            // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc), "r"(n)
+                 : "memory");
+}
+
+constexpr int kWgXsElems = (kWgTH + 2) * (kWgTW + 2) * kWgXPitch;   // input halo tile (bf16 elements)
+constexpr int kWgGsElems = kWgTH * kWgTW * (kWgMaxCout + 16);       // gradient tile
+constexpr int kWgStageElems = kWgXsElems + kWgGsElems;
+constexpr int kWgSmemBytes = 2 * kWgStageElems * 2;                 // two stages: the next tile lands while this one is multiplied
+
+// Round-2b: the tiles come in through a two-stage cp.async pipeline.  The first version staged every tile with blocking
+// loads between two __syncthreads(): ~100 MMA-side instructions per warp behind ~1 us of exposed load latency per tile,
+// 13.5 ms of a 27 ms generator step.
 __global__ void __launch_bounds__(kWgThreads, 3) wgrad16_kernel(const esr_wgrad_item* __restrict__ items) {
     const esr_wgrad_item it = items[blockIdx.x];
-    __shared__ __align__(32) __nv_bfloat16 Xs[(kWgTH + 2) * (kWgTW + 2) * kWgXPitch];
-    __shared__ __align__(32) __nv_bfloat16 Gs[kWgTH * kWgTW * (kWgMaxCout + 16)];
+    extern __shared__ __align__(128) unsigned char wg_smem[];
+    __nv_bfloat16* const stage0 = reinterpret_cast<__nv_bfloat16*>(wg_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncb = it.cout >> 4;                  // 16-channel blocks of the output
     const int nfrag = 9 * ncb;                     // (tap, co block) accumulators, round-robin over the 8 warps
@@ -51,27 +65,64 @@ __global__ void __launch_bounds__(kWgThreads, 3) wgrad16_kernel(const esr_wgrad_
     for (int f = 0; f < kMaxFr; ++f)
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[f][q >> 2][q & 3] = 0.f;
+    float bsum = 0.f;                              // bias gradient: thread (co = tid % 64, quarter = tid / 64) sums every 4th pixel
+    const int b_co = threadIdx.x & 63, b_part = threadIdx.x >> 6;
+    const bool do_bias = it.db != nullptr && b_co < it.cout;
     const int tiles_x = (it.W + kWgTW - 1) / kWgTW, tiles_y = (it.H + kWgTH - 1) / kWgTH;
     const int tiles_img = tiles_x * tiles_y;
     const int t_end = it.tile_end > 0 ? it.tile_end : it.B * tiles_img;
     const uint16_t* xg = static_cast<const uint16_t*>(it.x);
     const uint16_t* gg = static_cast<const uint16_t*>(it.g);
+    const bool fix_x = it.x_f16 || it.n_ci < 16 || it.ci_lo > 0;    // the input chunks need a pass after they landed (CTA-uniform)
+    const int g_vec = it.cout >> 3;                // uint4 per pixel of the gradient tile
     // ldmatrix row of this lane inside a 16 (k) x 16 (m or n) operand block: matrices 0..3 = lanes 0-7, 8-15, 16-23, 24-31
     const int lj = lane >> 3, lr = lane & 7;
     const int a_k = (lj >> 1) * 8 + lr, a_m = (lj & 1) * 8;        // A: (k0,m0) = (0,0), (0,8), (8,0), (8,8)  -> a0..a3
     const int b_k = (lj & 1) * 8 + lr, b_n = (lj >> 1) * 8;        // B: (k0,n0) = (0,0), (8,0), (0,8), (8,8)  -> b0,b1 | b0,b1
-    for (int t = it.tile_begin; t < t_end; ++t) {
+
+    // issues the copies of tile t into stage `buf` (zero outside the image = the conv's zero padding); one commit group
+    auto prefetch = [&](int t, int buf) {
+        __nv_bfloat16* Xs = stage0 + buf * kWgStageElems;
+        __nv_bfloat16* Gs = Xs + kWgXsElems;
         const int n = t / tiles_img, r = t - n * tiles_img;
         const int y0 = (r / tiles_x) * kWgTH, x0 = (r % tiles_x) * kWgTW;
-        // ---- stage the input halo tile (zero outside the image = the conv's zero padding) and the gradient tile
         for (int idx = threadIdx.x; idx < (kWgTH + 2) * (kWgTW + 2) * 2; idx += kWgThreads) {
             const int half = idx & 1, p = idx >> 1;
             const int yy = y0 - 1 + p / (kWgTW + 2), xx = x0 - 1 + p % (kWgTW + 2);
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (yy >= 0 && yy < it.H && xx >= 0 && xx < it.W) {
-                const uint16_t* src = xg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.x_stride + static_cast<size_t>(xx) * it.x_stride +
-                                      it.x_c0 + half * 8;
-                v = *reinterpret_cast<const uint4*>(src);
+            const bool ok = yy >= 0 && yy < it.H && xx >= 0 && xx < it.W;
+            const uint16_t* src = ok ? xg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.x_stride + static_cast<size_t>(xx) * it.x_stride +
+                                            it.x_c0 + half * 8
+                                     : xg;
+            cp_async16_zfill(Xs + p * kWgXPitch + half * 8, src, ok);
+        }
+        for (int idx = threadIdx.x; idx < kWgTH * kWgTW * g_vec; idx += kWgThreads) {
+            const int p = idx / g_vec, q = idx - p * g_vec;
+            const int yy = y0 + p / kWgTW, xx = x0 + p % kWgTW;
+            const bool ok = yy < it.H && xx < it.W;
+            const uint16_t* src = ok ? gg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.g_stride + static_cast<size_t>(xx) * it.g_stride +
+                                            it.g_c0 + q * 8
+                                     : gg;
+            cp_async16_zfill(Gs + p * gp + q * 8, src, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (it.tile_begin < t_end) prefetch(it.tile_begin, 0);
+    for (int t = it.tile_begin; t < t_end; ++t) {
+        const int buf = (t - it.tile_begin) & 1;
+        __nv_bfloat16* Xs = stage0 + buf * kWgStageElems;
+        __nv_bfloat16* Gs = Xs + kWgXsElems;
+        if (t + 1 < t_end) {
+            prefetch(t + 1, buf ^ 1);              // the other stage was released by the barrier that ended tile t-1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        if (fix_x) {
+            // every thread post-processes the input chunks IT copied (its own cp.async results are visible to it after the wait)
+            for (int idx = threadIdx.x; idx < (kWgTH + 2) * (kWgTW + 2) * 2; idx += kWgThreads) {
+                const int half = idx & 1, p = idx >> 1;
+                uint4 v = *reinterpret_cast<const uint4*>(Xs + p * kWgXPitch + half * 8);
                 if (it.x_f16) {                    // fp16 activations of the outer convs -> bf16 operands
                     const __half2* h = reinterpret_cast<const __half2*>(&v);
                     __nv_bfloat162 o[4];
@@ -85,18 +136,8 @@ __global__ void __launch_bounds__(kWgThreads, 3) wgrad16_kernel(const esr_wgrad_
                     for (int k = 0; k < 8; ++k)
                         if (half * 8 + k >= it.n_ci || half * 8 + k < it.ci_lo) e[k] = 0;
                 }
+                *reinterpret_cast<uint4*>(Xs + p * kWgXPitch + half * 8) = v;
             }
-            *reinterpret_cast<uint4*>(Xs + p * kWgXPitch + half * 8) = v;
-        }
-        const int g_vec = it.cout >> 3;            // uint4 per pixel
-        for (int idx = threadIdx.x; idx < kWgTH * kWgTW * g_vec; idx += kWgThreads) {
-            const int p = idx / g_vec, q = idx - p * g_vec;
-            const int yy = y0 + p / kWgTW, xx = x0 + p % kWgTW;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (yy < it.H && xx < it.W)
-                v = *reinterpret_cast<const uint4*>(gg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.g_stride +
-                                                    static_cast<size_t>(xx) * it.g_stride + it.g_c0 + q * 8);
-            *reinterpret_cast<uint4*>(Gs + p * gp + q * 8) = v;
         }
         __syncthreads();
         // ---- K = the tile's 128 pixels, 16 per step (one tile row): D[co, ci] += sum_px g[px, co] * X[px + tap, ci]
@@ -116,7 +157,22 @@ __global__ void __launch_bounds__(kWgThreads, 3) wgrad16_kernel(const esr_wgrad_
                 }
             }
         }
+        if (do_bias) {                             // pixels outside the image were zero-filled
+            const uint16_t* gs16 = reinterpret_cast<const uint16_t*>(Gs) + b_co;
+#pragma unroll 8
+            for (int p = b_part; p < kWgTH * kWgTW; p += 4) bsum += __uint_as_float(static_cast<uint32_t>(gs16[p * gp]) << 16);
+        }
         __syncthreads();
+    }
+    if (it.db != nullptr) {                        // CTA-uniform; the stages are free after the last barrier
+        float* red = reinterpret_cast<float*>(wg_smem);
+        red[threadIdx.x] = do_bias ? bsum : 0.f;
+        __syncthreads();
+        if (threadIdx.x < it.n_co) {
+            const float v = (red[threadIdx.x] + red[64 + threadIdx.x]) + (red[128 + threadIdx.x] + red[192 + threadIdx.x]);
+            if (it.tile_end > 0) atomicAdd(it.db + threadIdx.x, v);
+            else it.db[threadIdx.x] = v;
+        }
     }
     // ---- dW[co, ci0 + ci, ky, kx]: accumulator (row g / g+8, cols 2t, 2t+1) of each n8 half
     const int gq = lane >> 2, tq = lane & 3;
@@ -215,7 +271,8 @@ using namespace esr;
 
 extern "C" int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* stream) {
     ESR_CHECK_ARG(items_device != nullptr && n_items > 0, "esr_wgrad16: bad arguments");
-    wgrad16_kernel<<<n_items, kWgThreads, 0, static_cast<cudaStream_t>(stream)>>>(items_device);
+    ESR_ONCE_PER_DEVICE(ESR_CUDA(cudaFuncSetAttribute(wgrad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes)););
+    wgrad16_kernel<<<n_items, kWgThreads, kWgSmemBytes, static_cast<cudaStream_t>(stream)>>>(items_device);
     return check_launch("wgrad16_kernel");
 }
 

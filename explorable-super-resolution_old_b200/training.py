@@ -175,7 +175,8 @@ class GeneratorTrainer:
                 if n_c:                                        # the centre-row slots [n_c, 2 n_c) of the row-expanded tensor
                     assert 2 * n_c <= 16
                     blocks.append((xs, 0, xsf16, n_c, 2 * n_c, 0))
-                for (src, c0, sf16, ci_lo, ci_hi, ci0) in blocks:
+                last = name == names[-1]                       # its bias gradient is summed from the fp32 planes (below)
+                for bi, (src, c0, sf16, ci_lo, ci_hi, ci0) in enumerate(blocks):
                     for ch in range(chunks):
                         it = WgradItem()
                         it.x, it.g, it.dw = src.data_ptr(), g.data_ptr(), dw
@@ -185,8 +186,13 @@ class GeneratorTrainer:
                         it.B, it.H, it.W = B, H, W
                         if chunks > 1:
                             it.tile_begin, it.tile_end = tiles * ch // chunks, tiles * (ch + 1) // chunks
+                        # the bias gradient (sum of g over the pixels) rides with the conv's first block: the CTA has the
+                        # gradient tile in shared memory anyway (a separate bias kernel took 3.7 of the step's 26 ms)
+                        it.db = self.flat.data_ptr() + 4 * b_off if (bi == 0 and not last) else 0
                         big.append(it)
-                sit = WgradSmallItem()                         # the bias: sum of g over the pixels
+                if not last:
+                    continue
+                sit = WgradSmallItem()                         # last conv: the bias sum of the fp32 gradient planes
                 sit.g, sit.dw, sit.db = g.data_ptr(), dw, self.flat.data_ptr() + 4 * b_off
                 sit.g32 = bp.g_y.data_ptr() if name == names[-1] else 0
                 sit.s = 0
@@ -195,9 +201,10 @@ class GeneratorTrainer:
                 sit.cin_total, sit.ci0, sit.B, sit.H, sit.W = cin_total, 0, B, H, W
                 small.append(sit)
             big_arr = (WgradItem * max(1, len(big)))(*big)
-            small_arr = (WgradSmallItem * len(small))(*small)
+            small_arr = (WgradSmallItem * max(1, len(small)))(*small)
             tables.append((_struct_array_to_device(big_arr, WgradItem, self.dev) if big else None, len(big),
-                           _struct_array_to_device(small_arr, WgradSmallItem, self.dev), len(small), max(s_.B * s_.H for s_ in small)))
+                           _struct_array_to_device(small_arr, WgradSmallItem, self.dev) if small else None, len(small),
+                           max([s_.B * s_.H for s_ in small] + [1])))
         self._tables = {key: tables}
         return tables
 
@@ -224,7 +231,8 @@ class GeneratorTrainer:
             for (names_b, lo, hi), (big, nbig, small, nsmall, max_rows) in zip(self.buckets, tables):
                 if nbig:
                     capi.check(l.esr_wgrad16(C.c_void_p(big.data_ptr()), nbig, capi.stream_ptr()))
-                capi.check(l.esr_wgrad_small(C.c_void_p(small.data_ptr()), nsmall, max_rows, capi.stream_ptr()))
+                if nsmall:
+                    capi.check(l.esr_wgrad_small(C.c_void_p(small.data_ptr()), nsmall, max_rows, capi.stream_ptr()))
                 if world > 1:                                  # this bucket's exchange runs under the next buckets' kernels
                     ev = torch.cuda.Event()
                     ev.record(cur)

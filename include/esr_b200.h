@@ -383,6 +383,8 @@ typedef struct esr_wgrad_item {       /* one conv x one block of 16 input channe
     int32_t B, H, W;
     int32_t tile_begin, tile_end;     /* tile_end > 0: only tiles [tile_begin, tile_end) of the B*ceil(H/8)*ceil(W/16), dW accumulated
                                          with atomicAdd (must be zeroed by the caller); 0: all tiles, dW slice overwritten */
+    float* db;                        /* optional [n_co]: this item also sums g over its tiles (the bias gradient; give it to ONE
+                                         block of the conv).  Overwritten / accumulated like dW */
 } esr_wgrad_item;
 int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* stream);
 
