@@ -142,6 +142,7 @@ SIGNATURES = {
     "esr_debug_cem_timeout": (C.c_int, [C.POINTER(C.c_uint32)]),
     "esr_debug_cem_fused_prof": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "esr_wgrad16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "esr_wgrad16r": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "esr_wgrad_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "esr_zopt_tanh_pack": (C.c_int, [_vp, C.c_float, _i32, _i32, _i32, _vp, _vp]),
     "esr_zopt_loss_workspace_floats": (_i32, [_i32, _i32]),

@@ -196,6 +196,165 @@ __global__ void __launch_bounds__(kWgThreads, 3) wgrad16_kernel(const esr_wgrad_
     }
 }
 
+// Round-2c: K split over the warps.  Warp w owns tile row y = w (one 16-pixel k-step) for ALL nine taps and both 16-channel
+// output blocks: per tile it loads 2 gradient fragments and 9 input fragments (11 ldmatrix.x4) for 36 MMAs, where the
+// fragment-per-warp mapping above loads 2 per 2 MMAs (the shared-memory pipe, not the tensor pipe, bounded it).  Items
+// stage at most 32 output channels (the host cuts the 64-channel convs in two), so the 9 x 2 x 2 accumulator fragments are
+// 144 registers; the eight warps' partial sums meet in shared memory once per item.  Four cp.async stages: a tile is now
+// ~50 instructions per warp, less than the L2 latency.
+constexpr int kWgRStages = 4;
+constexpr int kWgRGsElems = kWgTH * kWgTW * (32 + 16);
+constexpr int kWgRStageElems = kWgXsElems + kWgRGsElems;
+constexpr int kWgRSmemBytes = kWgRStages * kWgRStageElems * 2;
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad16r_kernel(const esr_wgrad_item* __restrict__ items) {
+    const esr_wgrad_item it = items[blockIdx.x];
+    extern __shared__ __align__(128) unsigned char wg_smem[];
+    __nv_bfloat16* const stage0 = reinterpret_cast<__nv_bfloat16*>(wg_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncb = it.cout >> 4;                  // 1 or 2
+    const int gp = it.cout + 16;
+    float acc[9][2][2][4];                         // [tap][co block][ci half][mma accumulator]
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[t9][q >> 3][(q >> 2) & 1][q & 3] = 0.f;
+    float bsum = 0.f;
+    const int b_co = threadIdx.x & 63, b_part = threadIdx.x >> 6;
+    const bool do_bias = it.db != nullptr && b_co < it.cout;
+    const int tiles_x = (it.W + kWgTW - 1) / kWgTW, tiles_y = (it.H + kWgTH - 1) / kWgTH;
+    const int tiles_img = tiles_x * tiles_y;
+    const int t_end = it.tile_end > 0 ? it.tile_end : it.B * tiles_img;
+    const uint16_t* xg = static_cast<const uint16_t*>(it.x);
+    const uint16_t* gg = static_cast<const uint16_t*>(it.g);
+    const bool fix_x = it.x_f16 || it.n_ci < 16 || it.ci_lo > 0;
+    const int g_vec = it.cout >> 3;
+    const int lj = lane >> 3, lr = lane & 7;
+    const int a_k = (lj >> 1) * 8 + lr, a_m = (lj & 1) * 8;
+    const int b_k = (lj & 1) * 8 + lr, b_n = (lj >> 1) * 8;
+
+    auto prefetch = [&](int t, int buf) {
+        __nv_bfloat16* Xs = stage0 + buf * kWgRStageElems;
+        __nv_bfloat16* Gs = Xs + kWgXsElems;
+        const int n = t / tiles_img, r = t - n * tiles_img;
+        const int y0 = (r / tiles_x) * kWgTH, x0 = (r % tiles_x) * kWgTW;
+        for (int idx = threadIdx.x; idx < (kWgTH + 2) * (kWgTW + 2) * 2; idx += kWgThreads) {
+            const int half = idx & 1, p = idx >> 1;
+            const int yy = y0 - 1 + p / (kWgTW + 2), xx = x0 - 1 + p % (kWgTW + 2);
+            const bool ok = yy >= 0 && yy < it.H && xx >= 0 && xx < it.W;
+            const uint16_t* src = ok ? xg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.x_stride + static_cast<size_t>(xx) * it.x_stride +
+                                            it.x_c0 + half * 8
+                                     : xg;
+            cp_async16_zfill(Xs + p * kWgXPitch + half * 8, src, ok);
+        }
+        for (int idx = threadIdx.x; idx < kWgTH * kWgTW * g_vec; idx += kWgThreads) {
+            const int p = idx / g_vec, q = idx - p * g_vec;
+            const int yy = y0 + p / kWgTW, xx = x0 + p % kWgTW;
+            const bool ok = yy < it.H && xx < it.W;
+            const uint16_t* src = ok ? gg + (static_cast<size_t>(n) * it.H + yy) * it.W * it.g_stride + static_cast<size_t>(xx) * it.g_stride +
+                                            it.g_c0 + q * 8
+                                     : gg;
+            cp_async16_zfill(Gs + p * gp + q * 8, src, ok);
+        }
+    };
+    // prologue: kWgRStages - 1 tiles in flight; one commit group per tile slot (empty groups keep the count uniform)
+#pragma unroll
+    for (int k = 0; k < kWgRStages - 1; ++k) {
+        if (it.tile_begin + k < t_end) prefetch(it.tile_begin + k, k);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int t = it.tile_begin; t < t_end; ++t) {
+        const int buf = (t - it.tile_begin) % kWgRStages;
+        __nv_bfloat16* Xs = stage0 + buf * kWgRStageElems;
+        __nv_bfloat16* Gs = Xs + kWgXsElems;
+        // the stage of tile t + S - 1 was read during tile t - 1: released by the barrier that ended it
+        if (t + kWgRStages - 1 < t_end) prefetch(t + kWgRStages - 1, (buf + kWgRStages - 1) % kWgRStages);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(kWgRStages - 1) : "memory");
+        if (fix_x) {
+            for (int idx = threadIdx.x; idx < (kWgTH + 2) * (kWgTW + 2) * 2; idx += kWgThreads) {
+                const int half = idx & 1, p = idx >> 1;
+                uint4 v = *reinterpret_cast<const uint4*>(Xs + p * kWgXPitch + half * 8);
+                if (it.x_f16) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&v);
+                    __nv_bfloat162 o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = __float22bfloat162_rn(__half22float2(h[k]));
+                    v = *reinterpret_cast<const uint4*>(o);
+                }
+                if (it.n_ci < 16 || it.ci_lo > 0) {
+                    uint16_t* e = reinterpret_cast<uint16_t*>(&v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (half * 8 + k >= it.n_ci || half * 8 + k < it.ci_lo) e[k] = 0;
+                }
+                *reinterpret_cast<uint4*>(Xs + p * kWgXPitch + half * 8) = v;
+            }
+        }
+        __syncthreads();
+        {
+            const int y = warp;                    // this warp's k-step: the 16 pixels of tile row y
+            uint32_t a[2][4];
+            ldsm_x4_trans(a[0], Gs + (y * kWgTW + a_k) * gp + a_m);
+            if (ncb > 1) ldsm_x4_trans(a[1], Gs + (y * kWgTW + a_k) * gp + 16 + a_m);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    uint32_t b[4];
+                    ldsm_x4_trans(b, Xs + ((y + ky) * (kWgTW + 2) + kx + b_k) * kWgXPitch + b_n);
+                    mma_bf16_16816(acc[ky * 3 + kx][0][0], a[0], b[0], b[1]);
+                    mma_bf16_16816(acc[ky * 3 + kx][0][1], a[0], b[2], b[3]);
+                    if (ncb > 1) {
+                        mma_bf16_16816(acc[ky * 3 + kx][1][0], a[1], b[0], b[1]);
+                        mma_bf16_16816(acc[ky * 3 + kx][1][1], a[1], b[2], b[3]);
+                    }
+                }
+        }
+        if (do_bias) {
+            const uint16_t* gs16 = reinterpret_cast<const uint16_t*>(Gs) + b_co;
+#pragma unroll 8
+            for (int p = b_part; p < kWgTH * kWgTW; p += 4) bsum += __uint_as_float(static_cast<uint32_t>(gs16[p * gp]) << 16);
+        }
+        __syncthreads();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(wg_smem);                    // [8 warps][32 lanes][16]: 16 KiB, one tap at a time
+    if (it.db != nullptr) {
+        red[threadIdx.x] = do_bias ? bsum : 0.f;
+        __syncthreads();
+        if (threadIdx.x < it.n_co) {
+            const float v = (red[threadIdx.x] + red[64 + threadIdx.x]) + (red[128 + threadIdx.x] + red[192 + threadIdx.x]);
+            if (it.tile_end > 0) atomicAdd(it.db + threadIdx.x, v);
+            else it.db[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) red[(warp * 16 + q) * 32 + lane] = acc[tap][q >> 3][(q >> 2) & 1][q & 3];
+        __syncthreads();
+        // 512 outputs (q, lane) per tap, two per thread, summed over the warps in a fixed order
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int o = threadIdx.x + k * kWgThreads, q = o >> 5, ln = o & 31;
+            float v = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) v += red[(w8 * 16 + q) * 32 + ln];
+            const int cb = q >> 3, hlf = (q >> 2) & 1, e = q & 3;
+            const int co = cb * 16 + (ln >> 2) + (e >> 1) * 8, ci = hlf * 8 + 2 * (ln & 3) + (e & 1);
+            if (cb < ncb && co < it.n_co && ci < it.n_ci && ci >= it.ci_lo) {
+                float* dst = it.dw + (static_cast<size_t>(co) * it.cin_total + it.ci0 + ci - it.ci_lo) * 9 + tap;
+                if (it.tile_end > 0) atomicAdd(dst, v);
+                else *dst = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // grid = (items, row chunks): a CTA sums over `rows_per_cta` image rows and adds its partial sums with atomicAdd (dW / db
 // zeroed by the caller); one CTA per conv over all pixels took 71 ms on the 128x128 convs of config 5
 __global__ void __launch_bounds__(256) wgrad_small_kernel(const esr_wgrad_small_item* __restrict__ items, int rows_per_cta) {
@@ -268,6 +427,14 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const esr_wgrad_small_
 }  // namespace esr
 
 using namespace esr;
+
+// Items with at most 32 staged output channels, K split over the warps (wgrad16r_kernel).
+extern "C" int esr_wgrad16r(const esr_wgrad_item* items_device, int32_t n_items, void* stream) {
+    ESR_CHECK_ARG(items_device != nullptr && n_items > 0, "esr_wgrad16r: bad arguments");
+    ESR_ONCE_PER_DEVICE(ESR_CUDA(cudaFuncSetAttribute(wgrad16r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgRSmemBytes)););
+    wgrad16r_kernel<<<n_items, kWgThreads, kWgRSmemBytes, static_cast<cudaStream_t>(stream)>>>(items_device);
+    return check_launch("wgrad16r_kernel");
+}
 
 extern "C" int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* stream) {
     ESR_CHECK_ARG(items_device != nullptr && n_items > 0, "esr_wgrad16: bad arguments");

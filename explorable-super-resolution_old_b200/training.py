@@ -25,6 +25,7 @@ The critic, the WGAN-GP double backward and the range / pixel criteria of the fu
 Not built: the VGG feature loss, and a tcgen05 form of the weight-gradient GEMM (csrc/wgrad.cu uses warp-level bf16 MMAs).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -86,6 +87,7 @@ class GeneratorTrainer:
             self.buckets.append((cur, start, total))
         self._state = None
         self._tables = {}
+        self.split_k = os.environ.get("ESR_WGRAD_SPLITK", "1") != "0"      # esr_wgrad16r (0: the fragment-per-warp kernel, A/B timing)
 
     # ------------------------------------------------------------------ forward
     def forward(self, model_input, margin=None, filters=None, leaf=True):
@@ -176,20 +178,24 @@ class GeneratorTrainer:
                     assert 2 * n_c <= 16
                     blocks.append((xs, 0, xsf16, n_c, 2 * n_c, 0))
                 last = name == names[-1]                       # its bias gradient is summed from the fp32 planes (below)
+                # esr_wgrad16r keeps all nine taps' accumulators per warp: at most 32 staged output channels per item, so
+                # the 64-channel convs are cut into two halves of the output channels
+                halves = [(0, cout, n_co)] if (cout <= 32 or not self.split_k) else [(0, 32, 32), (32, 32, n_co - 32)]
                 for bi, (src, c0, sf16, ci_lo, ci_hi, ci0) in enumerate(blocks):
                     for ch in range(chunks):
-                        it = WgradItem()
-                        it.x, it.g, it.dw = src.data_ptr(), g.data_ptr(), dw
-                        it.x_stride, it.x_c0, it.x_f16 = src.shape[-1], c0, sf16
-                        it.g_stride, it.g_c0, it.cout = g.shape[-1], gc0, cout
-                        it.n_co, it.n_ci, it.ci_lo, it.cin_total, it.ci0 = n_co, ci_hi, ci_lo, cin_total, ci0
-                        it.B, it.H, it.W = B, H, W
-                        if chunks > 1:
-                            it.tile_begin, it.tile_end = tiles * ch // chunks, tiles * (ch + 1) // chunks
-                        # the bias gradient (sum of g over the pixels) rides with the conv's first block: the CTA has the
-                        # gradient tile in shared memory anyway (a separate bias kernel took 3.7 of the step's 26 ms)
-                        it.db = self.flat.data_ptr() + 4 * b_off if (bi == 0 and not last) else 0
-                        big.append(it)
+                        for (co0, co_staged, co_valid) in halves:
+                            it = WgradItem()
+                            it.x, it.g, it.dw = src.data_ptr(), g.data_ptr(), dw + 4 * co0 * cin_total * 9
+                            it.x_stride, it.x_c0, it.x_f16 = src.shape[-1], c0, sf16
+                            it.g_stride, it.g_c0, it.cout = g.shape[-1], gc0 + co0, co_staged
+                            it.n_co, it.n_ci, it.ci_lo, it.cin_total, it.ci0 = co_valid, ci_hi, ci_lo, cin_total, ci0
+                            it.B, it.H, it.W = B, H, W
+                            if chunks > 1:
+                                it.tile_begin, it.tile_end = tiles * ch // chunks, tiles * (ch + 1) // chunks
+                            # the bias gradient (sum of g over the pixels) rides with the conv's first block: the CTA has the
+                            # gradient tile in shared memory anyway (a separate bias kernel took 3.7 of the step's 26 ms)
+                            it.db = self.flat.data_ptr() + 4 * (b_off + co0) if (bi == 0 and not last) else 0
+                            big.append(it)
                 if not last:
                     continue
                 sit = WgradSmallItem()                         # last conv: the bias sum of the fp32 gradient planes
@@ -230,7 +236,7 @@ class GeneratorTrainer:
             handles = []
             for (names_b, lo, hi), (big, nbig, small, nsmall, max_rows) in zip(self.buckets, tables):
                 if nbig:
-                    capi.check(l.esr_wgrad16(C.c_void_p(big.data_ptr()), nbig, capi.stream_ptr()))
+                    capi.check((l.esr_wgrad16r if self.split_k else l.esr_wgrad16)(C.c_void_p(big.data_ptr()), nbig, capi.stream_ptr()))
                 if nsmall:
                     capi.check(l.esr_wgrad_small(C.c_void_p(small.data_ptr()), nsmall, max_rows, capi.stream_ptr()))
                 if world > 1:                                  # this bucket's exchange runs under the next buckets' kernels

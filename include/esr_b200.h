@@ -387,6 +387,9 @@ typedef struct esr_wgrad_item {       /* one conv x one block of 16 input channe
                                          block of the conv).  Overwritten / accumulated like dW */
 } esr_wgrad_item;
 int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* stream);
+/* Same items, cout <= 32 each (cut 64-channel convs in two): the tile's eight pixel rows are split over the warps, every
+ * warp keeping all nine taps' accumulators (11 ldmatrix per 36 MMAs instead of 2 per 2). */
+int esr_wgrad16r(const esr_wgrad_item* items_device, int32_t n_items, void* stream);
 
 typedef struct esr_wgrad_small_item { /* one conv: its <= 8 fp32 NCHW input channels (latent, LR image) and its bias */
     const void* g;                    /* NHWC bf16 */
