@@ -171,6 +171,11 @@ class RRDBNet(nn.Module):
     def forward(self, x):
         return run_generator(self, x, margin=0, cem_filters=None)
 
+    def train(self, mode=True):
+        # switching between training and evaluation re-packs the weights on the next forward (see weights_changed)
+        self._engine_key = None
+        return super().train(mode)
+
 
 def _capture(run, device):
     """Runs `run` once on a side stream (lazy initialisation inside the library happens outside the capture), then
@@ -395,7 +400,12 @@ def _run_generator(net, x, margin, cem_filters):
     if x.size(1) != nz_in * sf * sf + 3:
         raise ValueError("expected %d input channels (Z.view(B,%d,h,w) ++ LR), got %d" % (nz_in * sf * sf + 3, nz_in * sf * sf, x.size(1)))
     need_grad = torch.is_grad_enabled() and x.requires_grad
-    if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+    trainable = any(p.requires_grad for p in net.parameters())
+    if trainable and not torch.is_grad_enabled():
+        # a validation forward between training steps: a fused optimiser may have written the weights since the last
+        # training forward without bumping their versions (weights_changed), so re-pack rather than trust the cache key
+        net.weights_changed()
+    if torch.is_grad_enabled() and trainable:
         # the reference's training step (SRRaGAN_model.py:349,533: fake_H = netG(model_input) ... l_g_total.backward()):
         # data-gradient pass + weight-gradient kernels behind one autograd node
         params = [p for p in net.parameters()]

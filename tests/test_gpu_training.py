@@ -200,3 +200,32 @@ def test_fused_adam_updates_reach_the_kernels(cuda_device):
         trainer.backward(fake.grad)
         opt.step()
     assert float((outs[1] - outs[0]).abs().max()) > 1e-4
+
+
+def test_eval_forward_after_a_fused_step_sees_the_new_weights(cuda_device):
+    """After ``optimizer.step()`` of a fused optimiser (no version bump) a validation forward must use the updated
+    weights: under no_grad with trainable parameters, and after ``.eval()`` with frozen ones."""
+    wts = synth.make_weights("kaiming", seed=6, nb=1)
+    lr, z = synth.make_inputs(1, 16, 16, seed=6)
+    netG = build_product_G(cuda_device, 1, "all_layers_HR_downscaled", wts, train=True)
+    G = netG.generated_image_model
+    for p in G.parameters():
+        p.requires_grad_(True)
+    opt = torch.optim.Adam(G.parameters(), lr=1e-3, fused=True)
+    mi = concat_latent(lr, z).to(cuda_device)
+    out = netG(mi)
+    out.abs().mean().backward()
+    before = out.detach().clone()
+    opt.step()
+    with torch.no_grad():
+        after = netG(mi)
+    assert float((after - before).abs().max()) > 1e-4
+    netG.eval()
+    for p in G.parameters():
+        p.requires_grad_(False)
+    with torch.no_grad():
+        ev1 = netG(mi)
+    netG.train()
+    with torch.no_grad():
+        tr1 = netG(mi)
+    assert torch.equal(tr1, after) and ev1.shape == after.shape
