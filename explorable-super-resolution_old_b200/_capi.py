@@ -112,6 +112,12 @@ class WgradItem(C.Structure):            # esr_wgrad_item
                 ("db", C.c_void_p)]
 
 
+class WgradTcItem(C.Structure):          # esr_wgrad_tc_item
+    _fields_ = [("x_map", C.c_uint32), ("g_map", C.c_uint32), ("x_c0", C.c_int32), ("g_c0", C.c_int32), ("dw", C.c_void_p),
+                ("n_ci", C.c_int32), ("n_co", C.c_int32), ("cin_total", C.c_int32), ("ci0", C.c_int32),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("tile_begin", C.c_int32), ("tile_end", C.c_int32)]
+
+
 class WgradSmallItem(C.Structure):       # esr_wgrad_small_item
     _fields_ = [("g", C.c_void_p), ("g32", C.c_void_p), ("s", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p),
                 ("g_stride", C.c_int32), ("g_c0", C.c_int32), ("cout", C.c_int32), ("n_co", C.c_int32),
@@ -143,6 +149,9 @@ SIGNATURES = {
     "esr_debug_cem_fused_prof": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "esr_wgrad16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "esr_wgrad16r": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "esr_wgrad_tc_map_bytes": (C.c_int32, []),
+    "esr_wgrad_tc_make_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "esr_wgrad_tc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "esr_wgrad_small": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "esr_zopt_tanh_pack": (C.c_int, [_vp, C.c_float, _i32, _i32, _i32, _vp, _vp]),
     "esr_zopt_loss_workspace_floats": (_i32, [_i32, _i32]),

@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16r_kernel(const esr_wgrad
         __syncthreads();
         {
             const int y = warp;                    // this warp's k-step: the 16 pixels of tile row y
+            const bool wide = it.n_ci > 8;         // the latent blocks use channels [3, 6) only: half the MMAs (CTA-uniform)
             uint32_t a[2][4];
             ldsm_x4_trans(a[0], Gs + (y * kWgTW + a_k) * gp + a_m);
             if (ncb > 1) ldsm_x4_trans(a[1], Gs + (y * kWgTW + a_k) * gp + 16 + a_m);
@@ -304,10 +305,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16r_kernel(const esr_wgrad
                     uint32_t b[4];
                     ldsm_x4_trans(b, Xs + ((y + ky) * (kWgTW + 2) + kx + b_k) * kWgXPitch + b_n);
                     mma_bf16_16816(acc[ky * 3 + kx][0][0], a[0], b[0], b[1]);
-                    mma_bf16_16816(acc[ky * 3 + kx][0][1], a[0], b[2], b[3]);
+                    if (wide) mma_bf16_16816(acc[ky * 3 + kx][0][1], a[0], b[2], b[3]);     // input channels 8..15
                     if (ncb > 1) {
                         mma_bf16_16816(acc[ky * 3 + kx][1][0], a[1], b[0], b[1]);
-                        mma_bf16_16816(acc[ky * 3 + kx][1][1], a[1], b[2], b[3]);
+                        if (wide) mma_bf16_16816(acc[ky * 3 + kx][1][1], a[1], b[2], b[3]);
                     }
                 }
         }

@@ -31,7 +31,7 @@ import torch
 import torch.distributed as dist
 
 from . import _capi as capi
-from ._capi import WgradItem, WgradSmallItem
+from ._capi import WgradItem, WgradSmallItem, WgradTcItem
 from .backward import BackwardPlan, DgradSpecs, generator_backward_eager
 from .cem import CEM_PyTorch
 from .engine import NF, GC, _struct_array_to_device
@@ -88,6 +88,13 @@ class GeneratorTrainer:
         self._state = None
         self._tables = {}
         self.split_k = os.environ.get("ESR_WGRAD_SPLITK", "1") != "0"      # esr_wgrad16r (0: the fragment-per-warp kernel, A/B timing)
+        # esr_wgrad_tc: the dense-block convs' 16-bit input channels on the tcgen05 path (0: everything on the mma.sync kernels)
+        self.use_tc = os.environ.get("ESR_WGRAD_TC", "1") != "0"
+        self.tc_chunks = int(os.environ.get("ESR_WGRAD_TC_CHUNKS", "2"))
+        # one launch per kernel for the whole network (default) instead of one per gradient bucket: a bucket's 50-80 CTAs
+        # leave half of the 148 SMs idle, which costs more than the all-reduce overlap gains (the buckets' all-reduces are
+        # then issued back to back after the last launch)
+        self.per_bucket = os.environ.get("ESR_WGRAD_PER_BUCKET", "0") == "1"
 
     # ------------------------------------------------------------------ forward
     def forward(self, model_input, margin=None, filters=None, leaf=True):
@@ -159,9 +166,24 @@ class GeneratorTrainer:
                 spec["model.1.sub.%d.RDB%d.convs.%d.0" % (r, dd + 1, i)] = (plan.bufs[g], NF + GC * i, 0, lat, bp.gb(g), gc0,
                                                                              cout, cout, hp, wp)
         spec["model.0"] = (None, 0, 0, (plan.E_fea, f16, nzi + 3), bp.GFea, 0, NF, NF, hp, wp)
+        # tensor-map table of the tcgen05 path: one map per dense-block buffer (kind 0) and per gradient buffer (kind 1)
+        l = capi.lib()
+        map_bytes = int(l.esr_wgrad_tc_map_bytes())
+        maps_raw, map_index = [], {}
+
+        def map_of(t, kind):
+            k = (t.data_ptr(), kind)
+            if k not in map_index:
+                buf = (C.c_uint8 * map_bytes)()
+                capi.check(l.esr_wgrad_tc_make_map(buf, C.c_void_p(t.data_ptr()), t.shape[-1], t.shape[0], t.shape[1], t.shape[2], kind))
+                map_index[k] = len(maps_raw)
+                maps_raw.append(bytes(buf))
+            return map_index[k]
+        tc_ok = self.use_tc and nz > 0
         tables = []
-        for names_b, _, _ in self.buckets:
-            big, small = [], []
+        groups = [b[0] for b in self.buckets] if self.per_bucket else [[n for b in self.buckets for n in b[0]]]
+        for names_b in groups:
+            big, small, tcs = [], [], []
             for name in names_b:
                 x16, c16, xf16, (xs, xsf16, n_c), g, gc0, cout, n_co, H, W = spec[name]
                 w_off, _, wp_ = self.slices[name + ".weight"]
@@ -174,6 +196,23 @@ class GeneratorTrainer:
                 tiles = B * ((H + TILE_H - 1) // TILE_H) * ((W + TILE_W - 1) // TILE_W)
                 chunks = max(1, (H * W) // (hp * wp))          # higher-resolution convs are cut into chunks of LR-conv size
                 blocks = [(x16, c0, xf16, 0, min(16, c16 - c0), n_c + c0) for c0 in range(0, c16, 16)]
+                if tc_ok and ".RDB" in name and n_c and not xf16:
+                    # dense-block convs: the bf16 input channels go to esr_wgrad_tc in blocks of 128 x 32 output channels;
+                    # the latent block below (which also carries the bias sum) stays on the mma.sync kernel
+                    blocks = []
+                    for c0 in range(0, c16, 128):
+                        for co0 in range(0, cout, 32):
+                            for ch in range(self.tc_chunks):       # tile ranges: more, shorter CTAs fill the last wave better
+                                ti = WgradTcItem()
+                                ti.x_map, ti.g_map = map_of(x16, 0), map_of(g, 1)
+                                ti.x_c0, ti.g_c0 = c0, gc0 + co0
+                                ti.dw = dw + 4 * co0 * cin_total * 9
+                                ti.n_ci, ti.n_co = min(128, c16 - c0), min(32, n_co - co0)
+                                ti.cin_total, ti.ci0 = cin_total, n_c + c0
+                                ti.B, ti.H, ti.W = B, H, W
+                                if self.tc_chunks > 1:             # two order-independent atomic contributions onto a zeroed dW
+                                    ti.tile_begin, ti.tile_end = tiles * ch // self.tc_chunks, tiles * (ch + 1) // self.tc_chunks
+                                tcs.append(ti)
                 if n_c:                                        # the centre-row slots [n_c, 2 n_c) of the row-expanded tensor
                     assert 2 * n_c <= 16
                     blocks.append((xs, 0, xsf16, n_c, 2 * n_c, 0))
@@ -208,9 +247,12 @@ class GeneratorTrainer:
                 small.append(sit)
             big_arr = (WgradItem * max(1, len(big)))(*big)
             small_arr = (WgradSmallItem * max(1, len(small)))(*small)
+            tc_arr = (WgradTcItem * max(1, len(tcs)))(*tcs)
             tables.append((_struct_array_to_device(big_arr, WgradItem, self.dev) if big else None, len(big),
                            _struct_array_to_device(small_arr, WgradSmallItem, self.dev) if small else None, len(small),
-                           max([s_.B * s_.H for s_ in small] + [1])))
+                           max([s_.B * s_.H for s_ in small] + [1]),
+                           _struct_array_to_device(tc_arr, WgradTcItem, self.dev) if tcs else None, len(tcs)))
+        self._tc_maps = torch.frombuffer(bytearray(b"".join(maps_raw)), dtype=torch.uint8).to(self.dev) if maps_raw else None
         self._tables = {key: tables}
         return tables
 
@@ -234,17 +276,31 @@ class GeneratorTrainer:
             tables = self._items(plan, bp)
             self.flat.zero_()                                  # chunked high-resolution items accumulate
             handles = []
-            for (names_b, lo, hi), (big, nbig, small, nsmall, max_rows) in zip(self.buckets, tables):
+            def launch(tab):
+                big, nbig, small, nsmall, max_rows, tcs, ntc = tab
+                if ntc:
+                    capi.check(l.esr_wgrad_tc(C.c_void_p(tcs.data_ptr()), ntc, C.c_void_p(self._tc_maps.data_ptr()), capi.stream_ptr()))
                 if nbig:
                     capi.check((l.esr_wgrad16r if self.split_k else l.esr_wgrad16)(C.c_void_p(big.data_ptr()), nbig, capi.stream_ptr()))
                 if nsmall:
                     capi.check(l.esr_wgrad_small(C.c_void_p(small.data_ptr()), nsmall, max_rows, capi.stream_ptr()))
-                if world > 1:                                  # this bucket's exchange runs under the next buckets' kernels
-                    ev = torch.cuda.Event()
-                    ev.record(cur)
-                    with torch.cuda.stream(self.comm):
-                        self.comm.wait_event(ev)
-                        handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+
+            def exchange(lo, hi):
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ev)
+                    return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            handles = []
+            if self.per_bucket:
+                for (names_b, lo, hi), tab in zip(self.buckets, tables):
+                    launch(tab)
+                    if world > 1:                              # this bucket's exchange runs under the next buckets' kernels
+                        handles.append(exchange(lo, hi))
+            else:
+                launch(tables[0])
+                if world > 1:                                  # the buckets' exchanges pipeline among themselves on the comm stream
+                    handles = [exchange(lo, hi) for (_, lo, hi) in self.buckets]
             for hnd in handles:
                 hnd.wait()
             if world > 1:

@@ -391,6 +391,23 @@ int esr_wgrad16(const esr_wgrad_item* items_device, int32_t n_items, void* strea
  * warp keeping all nine taps' accumulators (11 ldmatrix per 36 MMAs instead of 2 per 2). */
 int esr_wgrad16r(const esr_wgrad_item* items_device, int32_t n_items, void* stream);
 
+/* The same sums for one (conv, block of 128 input channels, block of 32 output channels) on the tcgen05 tensor cores
+ * (csrc/wgrad_tc.cu): both operands are read as TMA boxes of the NHWC bf16 tensors (MN-major MMA operands, no transposition),
+ * nine accumulators [128 x 32] live in tensor memory over the item's pixel loop.  x_map / g_map index a DEVICE table of
+ * tensor maps built with esr_wgrad_tc_make_map (kind 0 for conv inputs, 1 for gradients). */
+typedef struct esr_wgrad_tc_item {
+    uint32_t x_map, g_map;
+    int32_t x_c0, g_c0;               /* first input channel of the block (boxes at x_c0 and x_c0 + 64) / first output channel */
+    float* dw;                        /* [n_co, cin_total, 3, 3] fp32, at the block's first output channel */
+    int32_t n_ci, n_co;               /* valid input channels (<= 128) / output channels (<= 32) of the block */
+    int32_t cin_total, ci0;           /* dW's input-channel extent, index of channel x_c0 in it */
+    int32_t B, H, W;
+    int32_t tile_begin, tile_end;     /* as in esr_wgrad_item (tiles of 8 x 16 pixels) */
+} esr_wgrad_tc_item;
+int32_t esr_wgrad_tc_map_bytes(void);
+int esr_wgrad_tc_make_map(void* map_host, const void* base, int32_t channels, int32_t B, int32_t H, int32_t W, int32_t kind);
+int esr_wgrad_tc(const esr_wgrad_tc_item* items_device, int32_t n_items, const void* maps_device, void* stream);
+
 typedef struct esr_wgrad_small_item { /* one conv: its <= 8 fp32 NCHW input channels (latent, LR image) and its bias */
     const void* g;                    /* NHWC bf16 */
     const float* g32;                 /* optional [B, n_co, H, W] fp32 gradient: used for the bias sum instead of g */
