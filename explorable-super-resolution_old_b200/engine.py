@@ -331,13 +331,14 @@ class GPlan:
         # (Round 1 kept plans below 32 x 32 padded pixels on separate launches because a 12 x 14 plan faulted: the item
         # decode divided by 1 through a magic number that had wrapped to 0 - fixed in csrc/conv3x3_tc2.cu: fast_div -
         # so every plan size takes the fused launch now; tests/test_gpu_net.py covers 12x14, 22x24, 33x35.)
-        # ... and only for plans of a few LARGE images: with many small images (training patches: 16 x 32x32) the per-image
-        # tile lists are short, the layer-to-layer dependencies serialise and the fused launch is twice as slow as the
-        # separate ones (tools/fuse_shapes.py on B200, forward graph, separate vs fused: 1x64x64 1.78 / 1.89 ms, 1x128x128
-        # 2.22 / 2.21, 4x128x128 4.23 / 4.17, 1x256x256 4.03 / 3.87, 16x32x32 2.96 / 6.05, 16x12x12 2.35 / 5.52).
+        # ... and only when a layer has at least two rounds of tile pairs (2 x 74 clusters): below that the clusters run
+        # into the next layer's items and stall on their neighbours (tools/fuse_shapes.py on B200, forward graph, separate vs
+        # fused launches: 1x64x64 = 33 pairs 1.78 / 1.89 ms).  Many small images need all of them in one chunk for the same
+        # reason (csrc/conv3x3_tc2.cu: images per chunk; with chunks of 4 the fused launches were twice as slow on 16 x 32x32).
         force = os.environ.get("ESR_FUSE_RDB")
+        pairs = B * ((((hp + 7) // 8) * ((wp + 29) // 30) + 1) // 2)
         small = B * hp * wp <= int(os.environ.get("ESR_FUSE_RDB_MAX_PIXELS", 120000)) and \
-            hp * wp >= int(os.environ.get("ESR_FUSE_RDB_MIN_IMAGE_PIXELS", 20000))
+            pairs >= int(os.environ.get("ESR_FUSE_RDB_MIN_PAIRS", 90))
         self.fuse_rdb = eng.pair and not use_simt and (force == "1" or (force is None and small))
         self.rdb_flags = torch.zeros(int(capi.lib().esr_rdb_growth_flag_words(B, hp, wp)), dtype=torch.int32, device=device) \
             if self.fuse_rdb else None
