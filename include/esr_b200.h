@@ -402,7 +402,7 @@ typedef struct esr_wgrad_tc_item {
     int32_t n_ci, n_co;               /* valid input channels (<= 128) / output channels (<= 32) of the block */
     int32_t cin_total, ci0;           /* dW's input-channel extent, index of channel x_c0 in it */
     int32_t B, H, W;
-    int32_t tile_begin, tile_end;     /* as in esr_wgrad_item (tiles of 8 x 16 pixels) */
+    int32_t tile_begin, tile_end;     /* tile range as in the esr_wgrad_item struct; tiles of 8 x 16 pixels */
 } esr_wgrad_tc_item;
 int32_t esr_wgrad_tc_map_bytes(void);
 int esr_wgrad_tc_make_map(void* map_host, const void* base, int32_t channels, int32_t B, int32_t H, int32_t W, int32_t kind);
