@@ -372,7 +372,7 @@ def run_train_g(args):
     netG.to(dev).train()
     trainer = GeneratorTrainer(netG)
     G = netG.generated_image_model
-    optim = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.9, 0.999), fused=True)    # torch's multi-tensor Adam: one launch for 702 tensors
+    optim = torch.optim.Adam([trainer.flat_parameter()], lr=1e-4, betas=(0.9, 0.999), fused=True)   # every weight as views of one flat parameter: one launch
     Bp, hl = 16, 32
     lr, z = synth.make_inputs(Bp, hl, hl, seed=rank)
     mi = torch.cat([z.contiguous().view(Bp, 48, hl, hl), lr], 1).contiguous().to(dev)

@@ -307,6 +307,21 @@ class GeneratorTrainer:
                 cur.wait_stream(self.comm)
         return g_in
 
+    def flat_parameter(self):
+        """ONE fp32 parameter holding every generator weight in the layout of the flat gradient buffer (its ``.grad``):
+        each ``p.data`` becomes a view into it, so module, state_dict and checkpoints are unchanged, while an optimiser
+        built on ``[trainer.flat_parameter()]`` updates the whole network with one fused launch (torch's fused Adam over the
+        702 separate tensors is 20 launches of ~40 CTAs: 0.78 ms of a 9 ms step)."""
+        if getattr(self, "_flat_param", None) is None:
+            w = torch.zeros_like(self.flat)
+            for key, (off, n, p) in self.slices.items():
+                w[off:off + n].copy_(p.data.reshape(-1))
+                p.data = w[off:off + n].view_as(p)
+            self._flat_param = torch.nn.Parameter(w)
+            self._flat_param.grad = self.flat
+            self.G.weights_changed()
+        return self._flat_param
+
     def grads_like(self, params):
         """Copies of the flat gradient buffer's slices for `params` (for autograd, which may keep what it is handed)."""
         by_id = {id(p): (off, n) for (off, n, p) in self.slices.values()}
@@ -349,7 +364,7 @@ class GanTrainer:
             p.grad = self.d_flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.d_params = d_params
-        self.optimizer_G = torch.optim.Adam(self.gen.G.parameters(), lr=lr_G, betas=betas_G, fused=True)
+        self.optimizer_G = torch.optim.Adam([self.gen.flat_parameter()], lr=lr_G, betas=betas_G, fused=True)   # one launch
         self.optimizer_D = torch.optim.Adam(d_params, lr=lr_D, betas=betas_D, fused=True)
         self.log = {}
 

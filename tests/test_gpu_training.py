@@ -229,3 +229,37 @@ def test_eval_forward_after_a_fused_step_sees_the_new_weights(cuda_device):
     with torch.no_grad():
         tr1 = netG(mi)
     assert torch.equal(tr1, after) and ev1.shape == after.shape
+
+
+def test_flat_parameter_optimiser_updates_the_module(cuda_device):
+    """GeneratorTrainer.flat_parameter(): every weight becomes a view of one flat fp32 parameter whose .grad is the flat
+    gradient buffer; optimiser steps on it equal steps on the separate parameters, and state_dict / forward follow.
+    (SGD: linear in the gradient.  Adam's first steps are +-lr * sign(g), so the fp32 summation-order noise of the chunked
+    high-resolution items flips elements whose gradient is ~0.)"""
+    wts = synth.make_weights("kaiming", seed=6, nb=1)
+    lr, z = synth.make_inputs(1, 16, 16, seed=6)
+    mi = concat_latent(lr, z).to(cuda_device)
+    outs = []
+    for flat in (False, True):
+        netG = build_product_G(cuda_device, 1, "all_layers_HR_downscaled", wts, train=True)
+        G = netG.generated_image_model
+        for p in G.parameters():
+            p.requires_grad_(True)
+        trainer = GeneratorTrainer(netG)
+        opt = torch.optim.SGD([trainer.flat_parameter()] if flat else list(G.parameters()), lr=0.05)
+        for _ in range(2):
+            fake = trainer.forward(mi)
+            fake.abs().mean().backward()
+            trainer.backward(fake.grad)
+            opt.step()
+        outs.append(({k: v.detach().clone() for k, v in G.state_dict().items()}, trainer.forward(mi).detach().clone()))
+        trainer._state = None
+    moved = 0.0
+    for k in outs[0][0]:
+        if "Filter" in k:
+            continue
+        a, b = outs[0][0][k], outs[1][0][k]
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-7, k
+        moved = max(moved, float((a.cpu() - wts[k.replace("generated_image_model.", "")]).abs().max()) if k.replace("generated_image_model.", "") in wts else 0.0)
+    assert moved > 1e-5, "the optimiser steps did not reach the module's parameters"
+    assert torch.allclose(outs[0][1], outs[1][1], atol=1e-4)
