@@ -367,54 +367,111 @@ class GanTrainer:
         self.optimizer_G = torch.optim.Adam([self.gen.flat_parameter()], lr=lr_G, betas=betas_G, fused=True)   # one launch
         self.optimizer_D = torch.optim.Adam(d_params, lr=lr_D, betas=betas_D, fused=True)
         self.log = {}
+        # the torch halves of the step (critic update; generator loss terms through the critic) replay as CUDA graphs
+        self.use_graphs = os.environ.get("ESR_GAN_GRAPHS", "1") != "0"
+        self._graphs = {}
 
     def _cropped(self, t):
         c = self.crop
         return t[..., c:t.size(-2) - c, c:t.size(-1) - c] if c else t
 
-    def step(self, model_input, var_H, generator_step=True, interpolation=None):
-        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+    # ---- the two torch halves of the step, written once and run either eagerly or as captured CUDA graphs
+    def _critic_losses(self, real, fake_d, u):
+        """Critic forward on real / fake / interpolates and the backward of its loss into d_flat (no optimiser step)."""
         w, D = self.w, self.netD
-        real = self._cropped(var_H)
-        fake_full = self.gen.forward(model_input)            # leaf; the graph below it is this package's backward
-        fake = self._cropped(fake_full)
-        fake_d = fake.detach()
-        # ---- critic
-        for p in self.d_params:
-            p.requires_grad_(True)
         self.d_flat.zero_()
         pred_real, pred_fake = D(real), D(fake_d)
         l_d_real, l_d_fake = -2.0 * pred_real.mean(), 2.0 * pred_fake.mean()
-        u = torch.rand(real.size(0), 1, 1, 1, device=real.device) if interpolation is None else interpolation
         interp = (u * fake_d + (1 - u) * real).requires_grad_(True)
         crit = D(interp)
         g_interp, = torch.autograd.grad(crit, interp, torch.ones_like(crit), create_graph=True)
         l_d_gp = w['gp'] * ((g_interp.reshape(g_interp.size(0), -1).norm(2, dim=1) - 1) ** 2).mean()
         ((l_d_real + l_d_fake) / 2 + l_d_gp).backward()
+        return {'l_d_real': l_d_real.detach(), 'l_d_fake': l_d_fake.detach(), 'l_d_gp': l_d_gp.detach(),
+                'D_real': pred_real.detach().mean(), 'D_fake': pred_fake.detach().mean()}
+
+    def _generator_losses(self, fake_full, real):
+        """Generator loss terms on fake_H and their gradient w.r.t. it (through the fixed critic)."""
+        w, D = self.w, self.netD
+        fake = self._cropped(fake_full)
+        log, l_g = {}, 0
+        if w['pix']:
+            l_pix = (fake - real).abs().mean()
+            l_g = l_g + w['pix'] * l_pix
+            log['l_g_pix'] = l_pix.detach()
+        if w['range']:                                       # mean excursion out of [0, 1] (loss.py:236-242)
+            l_range = torch.maximum(fake - 1, -fake).clamp_min(0).mean()
+            l_g = l_g + w['range'] * l_range
+            log['l_g_range'] = l_range.detach()
+        l_gan = -w['gan'] * D(fake).mean()
+        log['l_g_gan'] = l_gan.detach()
+        grad, = torch.autograd.grad(l_g + l_gan, fake_full)
+        return grad, log
+
+    def _captured(self, key, fn, static_inputs):
+        """CUDA graph of fn(*static_inputs) (torch autograd included: the critic is ~600 small kernels whose launches, not
+        their run time, bound the eager step).  Warm-up runs on a side stream with the critic's BatchNorm statistics restored
+        afterwards; returns (graph, static inputs, static outputs)."""
+        ent = self._graphs.get(key)
+        if ent is None:
+            bufs = [(b, b.detach().clone()) for b in self.netD.buffers()]
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn(*static_inputs)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            for b, saved in bufs:
+                b.copy_(saved)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = fn(*static_inputs)
+            ent = self._graphs[key] = (g, static_inputs, out)
+        return ent
+
+    def step(self, model_input, var_H, generator_step=True, interpolation=None):
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        real = self._cropped(var_H).contiguous()
+        fake_full = self.gen.forward(model_input)            # leaf; the graph below it is this package's backward
+        fake_d = self._cropped(fake_full).detach()
+        u = torch.rand(real.size(0), 1, 1, 1, device=real.device) if interpolation is None else interpolation
+        # ---- critic
+        for p in self.d_params:
+            p.requires_grad_(True)
+        if self.use_graphs:
+            key = ('critic', tuple(real.shape))
+            if key not in self._graphs:
+                self._captured(key, self._critic_losses, (real.clone(), fake_d.clone(), u.clone()))
+            g, (s_real, s_fake, s_u), out = self._graphs[key]
+            s_real.copy_(real), s_fake.copy_(fake_d), s_u.copy_(u)
+            g.replay()
+            self.log = {k: v.clone() for k, v in out.items()}
+        else:
+            self.log = self._critic_losses(real, fake_d, u)
         if world > 1:
             dist.all_reduce(self.d_flat, op=dist.ReduceOp.AVG, group=self.group)
         self.optimizer_D.step()
-        self.log = {'l_d_real': l_d_real.detach(), 'l_d_fake': l_d_fake.detach(), 'l_d_gp': l_d_gp.detach(),
-                    'D_real': pred_real.detach().mean(), 'D_fake': pred_fake.detach().mean()}
         if not generator_step:
             self.gen._state = None
             return self.log
         # ---- generator (the critic is a fixed function here: its parameters take no gradient, :465-467)
         for p in self.d_params:
             p.requires_grad_(False)
-        l_g = 0
-        if w['pix']:
-            l_pix = (fake - real).abs().mean()
-            l_g = l_g + w['pix'] * l_pix
-            self.log['l_g_pix'] = l_pix.detach()
-        if w['range']:                                       # mean excursion out of [0, 1] (loss.py:236-242)
-            l_range = torch.maximum(fake - 1, -fake).clamp_min(0).mean()
-            l_g = l_g + w['range'] * l_range
-            self.log['l_g_range'] = l_range.detach()
-        l_gan = -w['gan'] * D(fake).mean()
-        self.log['l_g_gan'] = l_gan.detach()
-        (l_g + l_gan).backward()
-        self.gen.backward(fake_full.grad)                    # dgrad chain, weight gradients, bucketed all-reduce
+        if self.use_graphs:
+            key = ('generator', tuple(fake_full.shape))
+            if key not in self._graphs:
+                self._captured(key, self._generator_losses, (fake_full.detach().clone().requires_grad_(True), real.clone()))
+            g, (s_fake, s_real), (grad, out) = self._graphs[key]
+            with torch.no_grad():
+                s_fake.copy_(fake_full), s_real.copy_(real)
+            g.replay()
+            self.log.update({k: v.clone() for k, v in out.items()})
+        else:
+            grad, out = self._generator_losses(fake_full, real)
+            self.log.update(out)
+        self.gen.backward(grad)                              # dgrad chain, weight gradients, bucketed all-reduce
         self.optimizer_G.step()
         return self.log
 
