@@ -115,7 +115,8 @@ class WgradItem(C.Structure):            # esr_wgrad_item
 class WgradTcItem(C.Structure):          # esr_wgrad_tc_item
     _fields_ = [("x_map", C.c_uint32), ("g_map", C.c_uint32), ("x_c0", C.c_int32), ("g_c0", C.c_int32), ("dw", C.c_void_p),
                 ("n_ci", C.c_int32), ("n_co", C.c_int32), ("cin_total", C.c_int32), ("ci0", C.c_int32),
-                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("tile_begin", C.c_int32), ("tile_end", C.c_int32)]
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("tile_begin", C.c_int32), ("tile_end", C.c_int32),
+                ("x_f16", C.c_int32)]
 
 
 class WgradSmallItem(C.Structure):       # esr_wgrad_small_item

@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(128, 1) wgrad_tc_kernel(const esr_wgrad_tc_ite
             // of the gradient tile are three 32-channel swizzle atoms along N (LBO = one copy apart), so ONE instruction does
             // the three kx taps of a filter row.  (Nine N = 32 instructions per k-step re-read the 4 KiB X operand nine times:
             // 5 KiB of shared memory per 16-clock MMA, 1.94 us per tile; this form reads 7 KiB per 48-clock MMA.)
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (((3 * kTcN) >> 3) << 17) | ((kTcM >> 4) << 24);
+            // a_format [7,10): 1 = bf16, 0 = fp16; b_format [10,13) = bf16.  NOTE: the hardware rejects the mixed pair (fp16 x
+            // bf16: illegal instruction), so the host only sends bf16 inputs (x_f16 = 0); the field is kept for an fp16 x fp16 use
+            const uint32_t idesc = (1u << 4) | (it.x_f16 ? 0u : (1u << 7)) | (1u << 10) | (1u << 15) | (1u << 16) | (((3 * kTcN) >> 3) << 17) |
+                                   ((kTcM >> 4) << 24);
             uint32_t stage = 0, phase = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 mbar_wait(&full_bar[stage], phase);
@@ -198,6 +201,7 @@ extern "C" int esr_wgrad_tc_make_map(void* map_host, const void* base, int32_t c
 extern "C" int esr_wgrad_tc(const esr_wgrad_tc_item* items_device, int32_t n_items, const void* maps_device, void* stream) {
     ESR_CHECK_ARG(items_device != nullptr && n_items > 0 && maps_device != nullptr, "esr_wgrad_tc: bad arguments");
     ESR_CHECK_ARG((reinterpret_cast<uintptr_t>(maps_device) & 63) == 0, "esr_wgrad_tc: the tensor-map table must be 64-byte aligned");
+    // (items live in device memory: x_f16 != 0 cannot be refused here; the host mirror never sets it)
     ESR_ONCE_PER_DEVICE(ESR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes)););
     wgrad_tc_kernel<<<n_items, 128, kTcSmemBytes, static_cast<cudaStream_t>(stream)>>>(items_device, static_cast<const CUtensorMap*>(maps_device));
     return check_launch("wgrad_tc_kernel");

@@ -196,22 +196,28 @@ class GeneratorTrainer:
                 tiles = B * ((H + TILE_H - 1) // TILE_H) * ((W + TILE_W - 1) // TILE_W)
                 chunks = max(1, (H * W) // (hp * wp))          # higher-resolution convs are cut into chunks of LR-conv size
                 blocks = [(x16, c0, xf16, 0, min(16, c16 - c0), n_c + c0) for c0 in range(0, c16, 16)]
-                if tc_ok and ".RDB" in name and n_c and not xf16:
-                    # dense-block convs: the bf16 input channels go to esr_wgrad_tc in blocks of 128 x 32 output channels;
-                    # the latent block below (which also carries the bias sum) stays on the mma.sync kernel
-                    blocks = []
-                    for c0 in range(0, c16, 128):
+                if tc_ok and x16 is not None and c16 >= 64 and cout >= 32 and not xf16:
+                    # the bf16 input channels go to esr_wgrad_tc in blocks of 128 x 32 output channels; what stays on the
+                    # mma.sync kernel is the block that carries the bias sum: the latent block below (or the first 16
+                    # channels of a conv without one).  The outer convs stay there entirely: their activations are fp16 and
+                    # tcgen05 kind::f16 rejects an fp16 x bf16 operand pair (illegal instruction, tried), while their
+                    # gradients (~1e-6) do not fit fp16
+                    tc_c0 = 0 if n_c else 16
+                    blocks = blocks[:tc_c0 // 16]
+                    per_item = 64                              # tiles per CTA (the dense-block convs: two halves of 128)
+                    nchunk = max(self.tc_chunks, tiles // per_item) if tiles > 128 else self.tc_chunks
+                    for c0 in range(tc_c0, c16, 128):
                         for co0 in range(0, cout, 32):
-                            for ch in range(self.tc_chunks):       # tile ranges: more, shorter CTAs fill the last wave better
+                            for ch in range(nchunk):           # tile ranges: more, shorter CTAs fill the last wave better
                                 ti = WgradTcItem()
                                 ti.x_map, ti.g_map = map_of(x16, 0), map_of(g, 1)
-                                ti.x_c0, ti.g_c0 = c0, gc0 + co0
+                                ti.x_c0, ti.g_c0, ti.x_f16 = c0, gc0 + co0, xf16
                                 ti.dw = dw + 4 * co0 * cin_total * 9
                                 ti.n_ci, ti.n_co = min(128, c16 - c0), min(32, n_co - co0)
                                 ti.cin_total, ti.ci0 = cin_total, n_c + c0
                                 ti.B, ti.H, ti.W = B, H, W
-                                if self.tc_chunks > 1:             # two order-independent atomic contributions onto a zeroed dW
-                                    ti.tile_begin, ti.tile_end = tiles * ch // self.tc_chunks, tiles * (ch + 1) // self.tc_chunks
+                                if nchunk > 1:                 # order-independent only for two contributions; more: fp32 sum order
+                                    ti.tile_begin, ti.tile_end = tiles * ch // nchunk, tiles * (ch + 1) // nchunk
                                 tcs.append(ti)
                 if n_c:                                        # the centre-row slots [n_c, 2 n_c) of the row-expanded tensor
                     assert 2 * n_c <= 16

@@ -403,6 +403,7 @@ typedef struct esr_wgrad_tc_item {
     int32_t cin_total, ci0;           /* dW's input-channel extent, index of channel x_c0 in it */
     int32_t B, H, W;
     int32_t tile_begin, tile_end;     /* tile range as in the esr_wgrad_item struct; tiles of 8 x 16 pixels */
+    int32_t x_f16;                    /* must be 0: tcgen05 kind::f16 rejects an fp16 input with the bf16 gradient (illegal instruction) */
 } esr_wgrad_tc_item;
 int32_t esr_wgrad_tc_map_bytes(void);
 int esr_wgrad_tc_make_map(void* map_host, const void* base, int32_t channels, int32_t B, int32_t H, int32_t W, int32_t kind);
