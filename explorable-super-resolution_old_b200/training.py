@@ -181,7 +181,13 @@ class GeneratorTrainer:
             return map_index[k]
         tc_ok = self.use_tc and nz > 0
         tables = []
-        groups = [b[0] for b in self.buckets] if self.per_bucket else [[n for b in self.buckets for n in b[0]]]
+        # launch groups: one per bucket (per_bucket), or the whole network at once on a single GPU, or two halves when the
+        # gradients are exchanged: the first half's all-reduce then runs under the second half's kernels
+        nb_ = len(self.buckets)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        cuts = list(range(nb_ + 1)) if self.per_bucket else ([0, (nb_ + 1) // 2, nb_] if (multi and nb_ > 1) else [0, nb_])
+        self._group_cuts = cuts
+        groups = [[n for b in self.buckets[a:b_] for n in b[0]] for a, b_ in zip(cuts[:-1], cuts[1:])]
         for names_b in groups:
             big, small, tcs = [], [], []
             for name in names_b:
@@ -298,15 +304,10 @@ class GeneratorTrainer:
                     self.comm.wait_event(ev)
                     return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             handles = []
-            if self.per_bucket:
-                for (names_b, lo, hi), tab in zip(self.buckets, tables):
-                    launch(tab)
-                    if world > 1:                              # this bucket's exchange runs under the next buckets' kernels
-                        handles.append(exchange(lo, hi))
-            else:
-                launch(tables[0])
-                if world > 1:                                  # the buckets' exchanges pipeline among themselves on the comm stream
-                    handles = [exchange(lo, hi) for (_, lo, hi) in self.buckets]
+            for (a, b_), tab in zip(zip(self._group_cuts[:-1], self._group_cuts[1:]), tables):
+                launch(tab)
+                if world > 1:                                  # this group's exchanges run under the next group's kernels
+                    handles += [exchange(lo, hi) for (_, lo, hi) in self.buckets[a:b_]]
             for hnd in handles:
                 hnd.wait()
             if world > 1:
