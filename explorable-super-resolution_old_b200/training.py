@@ -180,6 +180,7 @@ class GeneratorTrainer:
                 maps_raw.append(bytes(buf))
             return map_index[k]
         tc_ok = self.use_tc and nz > 0
+        self._bf16_copies = []                             # (fp16 view of an outer conv's input, its bf16 copy for esr_wgrad_tc)
         tables = []
         # launch groups: one per bucket (per_bucket), or the whole network at once on a single GPU, or two halves when the
         # gradients are exchanged: the first half's all-reduce then runs under the second half's kernels
@@ -202,22 +203,27 @@ class GeneratorTrainer:
                 tiles = B * ((H + TILE_H - 1) // TILE_H) * ((W + TILE_W - 1) // TILE_W)
                 chunks = max(1, (H * W) // (hp * wp))          # higher-resolution convs are cut into chunks of LR-conv size
                 blocks = [(x16, c0, xf16, 0, min(16, c16 - c0), n_c + c0) for c0 in range(0, c16, 16)]
-                if tc_ok and x16 is not None and c16 >= 64 and cout >= 32 and not xf16:
-                    # the bf16 input channels go to esr_wgrad_tc in blocks of 128 x 32 output channels; what stays on the
-                    # mma.sync kernel is the block that carries the bias sum: the latent block below (or the first 16
-                    # channels of a conv without one).  The outer convs stay there entirely: their activations are fp16 and
-                    # tcgen05 kind::f16 rejects an fp16 x bf16 operand pair (illegal instruction, tried), while their
-                    # gradients (~1e-6) do not fit fp16
+                if tc_ok and x16 is not None and c16 >= 64 and cout >= 32:
+                    # the 16-bit input channels go to esr_wgrad_tc in blocks of 128 x 32 output channels; what stays on the
+                    # mma.sync kernel is the block that carries the bias sum: the latent block below, or - for the upconvs,
+                    # which take no latent - the first 16 channels.  The outer convs' activations are fp16 and tcgen05
+                    # kind::f16 rejects an fp16 x bf16 operand pair (illegal instruction, tried), while their gradients
+                    # (~1e-6) do not fit fp16: they are read from a bf16 copy made at the start of backward - the rounding
+                    # the mma.sync kernel applies to them while staging
+                    x_tc = x16
+                    if xf16:
+                        x_tc = torch.empty_like(x16)                                   # bf16 storage
+                        self._bf16_copies.append((x16.view(torch.float16), x_tc))
                     tc_c0 = 0 if n_c else 16
                     blocks = blocks[:tc_c0 // 16]
-                    per_item = 64                              # tiles per CTA (the dense-block convs: two halves of 128)
+                    per_item = int(os.environ.get("ESR_WGRAD_TC_TILES", 128))       # tiles per CTA of a high-resolution conv
                     nchunk = max(self.tc_chunks, tiles // per_item) if tiles > 128 else self.tc_chunks
                     for c0 in range(tc_c0, c16, 128):
                         for co0 in range(0, cout, 32):
                             for ch in range(nchunk):           # tile ranges: more, shorter CTAs fill the last wave better
                                 ti = WgradTcItem()
-                                ti.x_map, ti.g_map = map_of(x16, 0), map_of(g, 1)
-                                ti.x_c0, ti.g_c0, ti.x_f16 = c0, gc0 + co0, xf16
+                                ti.x_map, ti.g_map = map_of(x_tc, 0), map_of(g, 1)
+                                ti.x_c0, ti.g_c0, ti.x_f16 = c0, gc0 + co0, 0
                                 ti.dw = dw + 4 * co0 * cin_total * 9
                                 ti.n_ci, ti.n_co = min(128, c16 - c0), min(32, n_co - co0)
                                 ti.cin_total, ti.ci0 = cin_total, n_c + c0
@@ -259,6 +265,7 @@ class GeneratorTrainer:
                 small.append(sit)
             big_arr = (WgradItem * max(1, len(big)))(*big)
             small_arr = (WgradSmallItem * max(1, len(small)))(*small)
+            tcs.sort(key=lambda t_: -((t_.tile_end - t_.tile_begin) if t_.tile_end > 0 else t_.B * ((t_.H + 7) // 8) * ((t_.W + 15) // 16)))   # longest first
             tc_arr = (WgradTcItem * max(1, len(tcs)))(*tcs)
             tables.append((_struct_array_to_device(big_arr, WgradItem, self.dev) if big else None, len(big),
                            _struct_array_to_device(small_arr, WgradSmallItem, self.dev) if small else None, len(small),
@@ -286,6 +293,8 @@ class GeneratorTrainer:
                 bp.g_y.copy_(gout)                             # the last conv's bias gradient reads the fp32 planes from bp.g_y
             g_in = generator_backward_eager(plan, bp, filters, margin, gout)
             tables = self._items(plan, bp)
+            for src16, dst in self._bf16_copies:
+                dst.copy_(src16)
             self.flat.zero_()                                  # chunked high-resolution items accumulate
             handles = []
             def launch(tab):
