@@ -385,6 +385,7 @@ class GanTrainer:
         self.log = {}
         # the torch halves of the step (critic update; generator loss terms through the critic) replay as CUDA graphs
         self.use_graphs = os.environ.get("ESR_GAN_GRAPHS", "1") != "0"
+        self.channels_last = os.environ.get("ESR_GAN_CHANNELS_LAST", "1") != "0"
         self._graphs = {}
 
     def _cropped(self, t):
@@ -396,6 +397,9 @@ class GanTrainer:
         """Critic forward on real / fake / interpolates and the backward of its loss into d_flat (no optimiser step)."""
         w, D = self.w, self.netD
         self.d_flat.zero_()
+        if self.channels_last:                               # the critic's activations in NHWC: cuDNN's tensor-core kernels take
+            real = real.contiguous(memory_format=torch.channels_last)      # them as they are (its NCHW <-> NHWC conversion kernels
+            fake_d = fake_d.contiguous(memory_format=torch.channels_last)  # were ~200 launches of the eager step)
         pred_real, pred_fake = D(real), D(fake_d)
         l_d_real, l_d_fake = -2.0 * pred_real.mean(), 2.0 * pred_fake.mean()
         interp = (u * fake_d + (1 - u) * real).requires_grad_(True)
@@ -419,7 +423,7 @@ class GanTrainer:
             l_range = torch.maximum(fake - 1, -fake).clamp_min(0).mean()
             l_g = l_g + w['range'] * l_range
             log['l_g_range'] = l_range.detach()
-        l_gan = -w['gan'] * D(fake).mean()
+        l_gan = -w['gan'] * D(fake.contiguous(memory_format=torch.channels_last) if self.channels_last else fake).mean()
         log['l_g_gan'] = l_gan.detach()
         grad, = torch.autograd.grad(l_g + l_gan, fake_full)
         return grad, log
