@@ -136,3 +136,22 @@ def test_library_exports_every_declared_symbol():
     assert (wtb.value, total, kb[1].w_off) == (2 * 24576, 2 * 24576, 18432)
     assert lib.esr_pack_layout(64, 1, 0, 2, kb, ctypes.byref(wtb)) < 0          # 64-channel tiles need pair mode
     assert lib.esr_pack_layout(7, 1, 0, 1, kb, ctypes.byref(wtb)) < 0 and b"esr_pack_layout" in lib.esr_last_error()
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument validation of the round-2 entry points happens before any CUDA call: bad arguments return ESR_ERR_INVALID
+    with a message, struct mirrors match the header's layout (sizes the kernels index by)."""
+    lib = capi.lib()
+    assert ctypes.sizeof(capi.WgradTcItem) == 64 and ctypes.sizeof(capi.WgradItem) % 8 == 0
+    assert lib.esr_wgrad_tc_map_bytes() == 128
+    assert lib.esr_wgrad_tc(None, 0, None, None) == -1 and b"esr_wgrad_tc" in lib.esr_last_error()
+    assert lib.esr_wgrad16r(None, 1, None) == -1
+    buf = (ctypes.c_uint8 * 128)()
+    assert lib.esr_wgrad_tc_make_map(buf, None, 64, 1, 8, 16, 0) == -1            # null base
+    assert lib.esr_wgrad_tc_make_map(buf, ctypes.c_void_p(4096), 60, 1, 8, 16, 0) == -1    # channels % 8
+    assert lib.esr_wgrad_tc_make_map(buf, ctypes.c_void_p(4096), 64, 1, 8, 16, 2) == -1    # kind
+    f = capi.cem_filters_struct(4, 1, [0.0] * 17, [0.0] * 27)
+    assert lib.esr_cem_project_fused(f, None, None, 1, 3, 64, 1024, 0, None, None, None) == -1
+    assert b"esr_cem_project_fused" in lib.esr_last_error()
+    assert lib.esr_cem_project_fused(f, ctypes.c_void_p(4096), ctypes.c_void_p(4096), 1, 3, 64, 1024, 40, ctypes.c_void_p(4096),
+                                     ctypes.c_void_p(4096), None) == -1       # crop too large for H = 64
