@@ -163,7 +163,7 @@ class GEngine:
     """Packed weights of one RRDBNet; geometry-independent."""
 
     def __init__(self, nb, nz_in, all_layers, out_nc=3, in_nc=3, upscale=4, precise_outer=True, pair=True,
-                 outer_mode=None):
+                 outer_mode=None, z_rearranged=0):
         if upscale not in (2, 4):
             # x3: the reference's own RRDBNet cannot be constructed for upscale=3 (architecture.py:144 concatenates a
             # list with the nn.Sequential its x3 upsampler is: TypeError), so there is nothing to be a drop-in for
@@ -171,6 +171,12 @@ class GEngine:
         if in_nc != 3 or out_nc > 16:
             raise NotImplementedError("in_nc must be 3 and out_nc <= 16")
         self.nb, self.nz_in, self.all_layers = nb, nz_in, all_layers
+        # first_layer_HR_rearranged (architecture.py:109-110,159): `z_rearranged` = Cz * sf^2 extra input channels of the
+        # first conv, given at LR resolution; that conv then has the shape of the outer convs (a 64-channel 16-bit tensor
+        # holding Z, zero padded, + the 3 image channels as the row-expanded small block)
+        self.z_rearranged = int(z_rearranged)
+        if self.z_rearranged and (nz_in or self.z_rearranged > NF):
+            raise NotImplementedError("HR_rearranged latent: first_layer only, at most %d rearranged channels" % NF)
         self.nz = nz_in if all_layers else 0          # latent channels concatenated to every later conv
         self.out_nc, self.upscale = out_nc, upscale
         self.n_up = int(math.log2(upscale))
@@ -222,8 +228,20 @@ class GEngine:
         self.lat_second = "f16" if p == "f16" else "lo"
         # first conv: every input is row-expanded (E_fea), centre tap only
         self.fea_xslots, fea_ws = expand_slots(self.nz_in + 3, precise="f16" if p == "f16" else True)
-        kb = [(0, c0, DY_CENTRE, 0b11) for c0 in range(0, len(fea_ws), 32)]
-        self._add("model.0", NF, kb, fea_ws, 32)
+        if self.z_rearranged:
+            if p == "split":
+                raise NotImplementedError("HR_rearranged latent with outer_mode 'split'")
+            zr = self.z_rearranged
+            kb, sl = self._main_blocks(NF, p)                  # weight input channel c < zr: Z channel c of the 16-bit tensor
+            sl = [(i if 0 <= i < zr else -1, ky, t) for (i, ky, t) in sl]
+            _, ws = expand_slots(3, precise=False, second=self.lat_second)     # the image: weight input channels zr .. zr + 2
+            ws = [(zr + i if i >= 0 else i, ky, t) for (i, ky, t) in ws]
+            kb.append((1, 0, DY_CENTRE, 0b10 if p == "f16" else 0b01))
+            self._add("model.0", NF, kb, sl + ws, 32)
+            self.lr_xslots, _ = expand_slots(3, precise=False, second=self.lat_second)
+        else:
+            kb = [(0, c0, DY_CENTRE, 0b11) for c0 in range(0, len(fea_ws), 32)]
+            self._add("model.0", NF, kb, fea_ws, 32)
         self.lat_xslots, _ = expand_slots(max(self.nz, 1), precise=False, second=self.lat_second)
         for r in range(self.nb):
             for d in (1, 2, 3):
@@ -300,6 +318,9 @@ class GPlan:
         self.z_hr = torch.empty(B, nz, sf * hp, sf * wp, **f32) if nz else None
         self.z_lr = torch.empty(B, nz, hp, wp, **f32) if nz else None
         self.E_fea = torch.empty(B, hp, wp, len(eng.fea_xslots), **bf)
+        if eng.z_rearranged:                                   # Z as a 64-channel 16-bit tensor (zero padded) + the image rows
+            self.Zbuf = torch.zeros(B, hp, wp, NF, **bf)
+            self.E_lr = torch.empty(B, hp, wp, 32, **bf)
         self.E_lat = torch.empty(B, hp, wp, 32, **bf) if nz else None
         self.E_lath = torch.empty(B, sf * hp, sf * wp, 32, **bf) if nz else None
         n_rdb = 3 * eng.nb
@@ -424,7 +445,10 @@ class GPlan:
         n_rdb = 3 * eng.nb
         lo = 64 if eng.outer_mode == "split" else -1
         F16 = capi.EPI_OUT_F16 if eng.outer_mode == "f16" else 0      # outputs consumed by an fp16 conv
-        add(self._desc("model.0", hp, wp, self.E_fea, out_f32=self.T_fea, out_bf16=self.buf(0)))
+        if eng.z_rearranged:
+            add(self._desc("model.0", hp, wp, self.Zbuf, self.E_lr, out_f32=self.T_fea, out_bf16=self.buf(0)))
+        else:
+            add(self._desc("model.0", hp, wp, self.E_fea, out_f32=self.T_fea, out_bf16=self.buf(0)))
         g = 0
         for r in range(eng.nb):
             rin = self.T_fea if r == 0 else self.R[r % 2]
@@ -473,6 +497,7 @@ class GPlan:
                 capi.check(capi.lib().esr_seq_add_conv(self.seq, C.byref(d), 1 if use_simt else 0))
         self.fea_x = _xslot_array(eng.fea_xslots)
         self.lat_x = _xslot_array(eng.lat_xslots)
+        self.lr_x = _xslot_array(eng.lr_xslots) if eng.z_rearranged else None
 
     # ------------------------------------------------------------------ run
     def run_prep(self, model_input):
@@ -488,6 +513,14 @@ class GPlan:
             capi.check(l.esr_expand_rows(capi.ptr(self.z_lr), B, eng.nz, hp, wp, self.lat_x, 32, capi.ptr(self.E_lat), st))
             capi.check(l.esr_expand_rows(capi.ptr(self.z_hr), B, eng.nz, sf * hp, sf * wp, self.lat_x, 32,
                                          capi.ptr(self.E_lath), st))
+
+    def run_prep_rearranged(self, lr_pad, z):
+        """first_layer_HR_rearranged: `lr_pad` [B,3,hp,wp] (already padded) and Z [B,Cz*sf^2,hp,wp] given at LR resolution."""
+        eng, l, st = self.eng, capi.lib(), capi.stream_ptr()
+        self.lr_pad.copy_(lr_pad)
+        zb = self.Zbuf.view(torch.float16) if eng.outer_mode == "f16" else self.Zbuf       # the conv's operand format
+        zb[..., :eng.z_rearranged].copy_(z.permute(0, 2, 3, 1))
+        capi.check(l.esr_expand_rows(capi.ptr(self.lr_pad), self.B, 3, self.hp, self.wp, self.lr_x, 32, capi.ptr(self.E_lr), st))
 
     def run_convs(self):
         capi.check(capi.lib().esr_seq_run(self.seq, capi.stream_ptr()))

@@ -56,24 +56,31 @@ class RRDBNet(nn.Module):
             raise NotImplementedError("nf=%d: the kernels are specialised for nf=64, gc=32" % nf)
         if norm_type is not None or act_type != 'leakyrelu' or mode != 'CNA' or upsample_mode != 'upconv':
             raise NotImplementedError("only norm_type=None, leakyrelu, mode='CNA', upconv are built (the production config)")
-        if latent_input is not None and 'HR_rearranged' in latent_input:
-            # the reference's own forward raises 'Unsupported yet' for all_layers_HR_rearranged (architecture.py:167-169);
-            # first_layer_HR_rearranged (48 extra input channels on the first conv) is not built here
-            raise NotImplementedError("latent_input_domain HR_rearranged is not built (SURVEY.md §8f rank 4)")
-        if latent_input is not None and 'HR_downscaled' not in latent_input and 'LR' not in latent_input:
-            raise NotImplementedError("latent_input %r: expected <all_layers|first_layer>_<HR_downscaled|LR>" % (latent_input,))
+        if latent_input is not None and 'HR_rearranged' in latent_input and 'all_layers' in latent_input:
+            # the reference's own forward raises 'Unsupported yet' for all_layers_HR_rearranged (architecture.py:167-169)
+            raise NotImplementedError("latent_input all_layers_HR_rearranged is unsupported (in the reference too)")
+        if latent_input is not None and not any(d in latent_input for d in ('HR_downscaled', 'HR_rearranged', 'LR')):
+            raise NotImplementedError("latent_input %r: expected <all_layers|first_layer>_<HR_downscaled|HR_rearranged|LR>" % (latent_input,))
         self.latent_input = latent_input
         # 'LR' domain (architecture.py:159,165-166): Z has the LR image's size and is assigned to ``self.Z`` by the caller
         # (SRRaGAN_model.py:260-261); forward(x) takes the 3 image channels only.  See _lr_domain_input.
-        self.latent_domain = None if latent_input is None else ('HR_downscaled' if 'HR_downscaled' in latent_input else 'LR')
+        self.latent_domain = None if latent_input is None else next(d for d in ('HR_downscaled', 'HR_rearranged', 'LR') if d in latent_input)
+        # 'HR_rearranged' (first_layer only): Z [B, Cz*sf^2, H, W] = the HR latent rearranged into channels, assigned to
+        # ``.Z`` like an LR-domain latent; it enters the first conv only (architecture.py:109-110: num_latent_channels *= sf^2)
+        z_rearranged = 0
+        if self.latent_domain == 'HR_rearranged' and num_latent_channels:
+            num_latent_channels = num_latent_channels * upscale ** 2
+            z_rearranged = num_latent_channels
         nz_in = num_latent_channels if (latent_input is not None and num_latent_channels) else 0
+        if z_rearranged:
+            nz_in = 0                                  # the engine's head kernels un-view an HR-domain latent: not this one
         self.num_latent_channels = 1 * num_latent_channels if num_latent_channels is not None else None
         self.upscale = upscale
         all_layers = latent_input is not None and 'all_layers' in latent_input
         nz = nz_in if all_layers else 0
         gc = 32                                        # hard-coded in the reference (architecture.py:123)
         n_up = 1 if upscale == 3 else int(math.log(upscale, 2))
-        mods = [_conv(in_nc + nz_in, nf), _Trunk(nf, gc, nb, nz)]
+        mods = [_conv(in_nc + nz_in + z_rearranged, nf), _Trunk(nf, gc, nb, nz)]
         for _ in range(n_up):
             mods.append(nn.Sequential(nn.Upsample(scale_factor=3 if upscale == 3 else 2, mode='nearest'),
                                       _conv(nf, nf), nn.LeakyReLU(0.2, True)))
@@ -81,7 +88,7 @@ class RRDBNet(nn.Module):
         self.model = nn.ModuleList(mods)
         if self.latent_domain == 'LR' and nz:
             self.latent_upsampler = nn.Upsample(scale_factor=upscale if upscale == 3 else 2)   # attribute parity (:137-139)
-        self._cfg = dict(nb=nb, nz_in=nz_in, all_layers=all_layers, out_nc=out_nc, in_nc=in_nc, upscale=upscale)
+        self._cfg = dict(nb=nb, nz_in=nz_in, all_layers=all_layers, out_nc=out_nc, in_nc=in_nc, upscale=upscale, z_rearranged=z_rearranged)
         self._engine, self._engine_key, self._plans = None, None, {}
         self._packed_params, self._dgrad, self._bplans = None, None, {}
         self.precise_outer = True
@@ -385,11 +392,46 @@ def _lr_domain_input(net, x, margin):
 def run_generator(net, x, margin, cem_filters):
     if not x.is_cuda:
         raise capi.EsrError("RRDBNet.forward: expected a CUDA tensor; this package has no CPU or PyTorch fallback")
+    if net.latent_domain == 'HR_rearranged':
+        return _run_rearranged(net, x, margin, cem_filters)
     if net.latent_domain == 'LR':
         crop = net.upscale * margin
         out = _run_generator(net, _lr_domain_input(net, x, margin), 0, cem_filters)
         return out[..., crop:out.size(-2) - crop, crop:out.size(-1) - crop] if crop else out
     return _run_generator(net, x, margin, cem_filters)
+
+
+def _run_rearranged(net, x, margin, cem_filters):
+    """first_layer_HR_rearranged (architecture.py:109-110,159): ``net.Z`` [B, Cz*sf^2, H, W] is concatenated in front of the
+    (padded) image for the first conv only.  Forward only: no gradient w.r.t. Z or the weights is built for this variant."""
+    Z = getattr(net, 'Z', None)
+    zr, sf = net._cfg["z_rearranged"], net.upscale
+    if Z is None:
+        raise AttributeError("RRDBNet with an HR_rearranged latent input: assign the latent to .Z before forward (SRRaGAN_model.py:260-261)")
+    if torch.is_grad_enabled() and (Z.requires_grad or x.requires_grad or any(p.requires_grad for p in net.parameters())):
+        raise NotImplementedError("gradients through the first_layer_HR_rearranged variant are not built (forward only)")
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    capi.require_device(dev)
+    xp = torch.nn.functional.pad(x.float(), (margin,) * 4, mode='replicate') if margin > 0 else x.float()
+    if xp.size(1) != 3 or Z.dim() != 4 or Z.size(1) != zr or Z.shape[0] != xp.shape[0] or Z.shape[2:] != xp.shape[2:]:
+        raise RuntimeError("HR_rearranged latent: Z %s does not match the (padded) LR input %s with %d rearranged channels"
+                           % (tuple(Z.shape), tuple(xp.shape), zr))
+    B, _, H, W = xp.shape
+    plan = net.plan(B, H, W, 0, keep=False)
+    crop = sf * margin
+    onc = plan.y.size(1)
+    with torch.cuda.device(x.device):
+        plan.run_prep_rearranged(xp.contiguous(), Z.to(x.device).float())
+        plan.run_convs()
+        y = plan.y
+        out = torch.empty(B, onc, sf * H - 2 * crop, sf * W - 2 * crop, device=x.device, dtype=torch.float32)
+        if cem_filters is None:
+            out.copy_(y[..., crop:sf * H - crop, crop:sf * W - crop])
+        else:
+            ws = torch.empty(2 * B * onc * H * W, device=x.device, dtype=torch.float32)
+            capi.cem_call("project", cem_filters, capi.ptr(y), capi.ptr(plan.lr_pad), B, onc, y.size(2), y.size(3), crop,
+                          capi.ptr(out), capi.ptr(ws), capi.stream_ptr())
+    return out
 
 
 def _run_generator(net, x, margin, cem_filters):

@@ -158,6 +158,41 @@ def gen_lr_domain(CEMnet, networks):
     np.savez_compressed(os.path.join(OUT, "g_cem_lr_domain.npz"), **out)
 
 
+def gen_rearranged(CEMnet, networks):
+    """latent_input "first_layer" with latent_input_domain "HR_rearranged" (architecture.py:109-110,159): the HR latent
+    rearranged into Cz * sf^2 = 48 channels at the LR image's size, assigned to ``.Z`` and concatenated to the first conv
+    only.  (all_layers_HR_rearranged raises 'Unsupported yet' in the reference's own forward.)  Train and eval outputs."""
+    from oracle.ref_shims import make_opt
+    import CEM.imresize_CEM as im
+    out = {}
+    for name, nb, kind, seed, B, h, w, train in (("rearr_nb2_train", 2, "default", 31, 2, 12, 10, True),
+                                                 ("rearr_nb1_eval", 1, "kaiming", 32, 1, 9, 14, False)):
+        im.imresize.kernels = {}
+        cem = CEMnet.CEMnet(CEMnet.Get_CEM_Config(4))
+        opt = make_opt(nb, "first_layer")
+        opt["network_G"]["latent_input_domain"] = "HR_rearranged"
+        netG = networks.define_G(opt, CEM=cem, num_latent_channels=3)
+        wts = synth.make_weights(kind, seed=seed, nb=nb, latent_input="first_layer_HR_rearranged", num_latent_channels=48)
+        sd = netG.state_dict()
+        assert [k for k in sd if "Filter" not in k] == ["generated_image_model." + k for k in wts]
+        assert netG.generated_image_model.num_latent_channels == 48
+        sd.update({"generated_image_model." + k: v for k, v in wts.items()})
+        netG.load_state_dict(sd)
+        netG.train(train)
+        m = 0 if train else int(cem.invalidity_margins_LR)
+        rng = np.random.default_rng(seed)
+        lr = torch.from_numpy(rng.random((B, 3, h, w), dtype=np.float32))
+        z = torch.from_numpy((2 * rng.random((B, 48, h + 2 * m, w + 2 * m), dtype=np.float32) - 1))
+        netG.generated_image_model.Z = z
+        with torch.no_grad():
+            res = netG(lr)
+        out[name + "_lr"], out[name + "_z"], out[name + "_out"] = lr.numpy(), z.numpy(), res.numpy()
+        out[name + "_cfg"] = np.array([nb, seed, int(train)])
+        out[name + "_kind"] = np.array(kind)
+        print(name, tuple(res.shape), float(res.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "g_cem_rearranged.npz"), **out)
+
+
 class RefModel:
     """Minimal stand-in for SRRaGANModel (codes/models/SRRaGAN_model.py:249-302 restated): only what Z_optimizer touches."""
 
@@ -270,6 +305,8 @@ def main():
         return gen_nondefault(CEMnet)
     if "x2" in sys.argv[1:]:              # only the x2 fixture
         return gen_x2(CEMnet, networks)
+    if "rearranged" in sys.argv[1:]:      # only the first_layer_HR_rearranged fixture
+        return gen_rearranged(CEMnet, networks)
     if "lr_domain" in sys.argv[1:]:       # only the LR-domain latent fixture
         return gen_lr_domain(CEMnet, networks)
     if "zopt2" in sys.argv[1:]:           # only the extra Z_optimizer trajectories
@@ -385,6 +422,7 @@ def main():
 
     # 8. LR-domain latent input ------------------------------------------------------------------
     gen_lr_domain(CEMnet, networks)
+    gen_rearranged(CEMnet, networks)
 
 
 if __name__ == "__main__":

@@ -295,6 +295,30 @@ def test_lr_domain_latent_matches_reference_golden(golden, cuda_device, name):
         netG(lr)
 
 
+@pytest.mark.parametrize("name", ["rearr_nb2_train", "rearr_nb1_eval"])
+def test_hr_rearranged_first_layer_matches_reference_golden(golden, cuda_device, name):
+    """``latent_input: "first_layer"`` with ``latent_input_domain: "HR_rearranged"`` (architecture.py:109-110,159): 48
+    rearranged latent channels at LR size in ``.Z``, concatenated to the first conv only (the first conv then runs like the
+    outer convs: Z as a 64-channel 16-bit tensor + the image as the row-expanded block).  Forward only."""
+    g = golden("g_cem_rearranged")
+    nb, seed, train = [int(v) for v in g[name + "_cfg"]]
+    wts = synth.make_weights(str(g[name + "_kind"]), seed=seed, nb=nb, latent_input="first_layer_HR_rearranged", num_latent_channels=48)
+    netG = build_product_G(cuda_device, nb, "first_layer_HR_downscaled", wts, train=bool(train), domain="HR_rearranged")
+    G = netG.generated_image_model
+    assert G.latent_input == "first_layer_HR_rearranged" and G.num_latent_channels == 48
+    lr = torch.from_numpy(g[name + "_lr"]).to(cuda_device)
+    G.Z = torch.from_numpy(g[name + "_z"]).to(cuda_device)
+    with torch.no_grad():
+        out = netG(lr)
+    ref = torch.from_numpy(g[name + "_out"])
+    assert out.shape == ref.shape
+    assert (out.cpu() - ref).abs().max().item() <= 1e-2
+    assert psnr(out.cpu(), ref) >= 50.0
+    G.Z = G.Z.clone().requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="forward only"):
+        netG(lr)
+
+
 def test_pretrained_checkpoint_without_latent_is_reproduced(cuda_device):
     """base_model.py:126-136: a generator without Z loaded into the Z-conditioned one (zero weights for the new input
     channels) must output what the original does, whatever Z is - until the Z weights are trained."""
