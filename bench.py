@@ -416,19 +416,14 @@ def run_train_g(args):
         torch.distributed.destroy_process_group()
 
 
-def run_train_gan(args):
+def gan_step_measure(dev, rank, world, steps, warmup):
     """BASELINE config 5, the whole step: batch 16 x 128x128 HR patches (3x32x32 LR) per rank, train mode, through
     training.GanTrainer — G forward, critic update on real / fake / WGAN-GP interpolates (double backward), generator update
     with the adversarial + range terms back-propagated through the critic into this package's dgrad and weight-gradient
-    kernels, NCCL all-reduce of the 13.6 MB critic gradient (one call) and the 68.2 MB generator gradient (buckets under the
-    weight-gradient kernels), fused Adam on both.  The critic (Discriminator_VGG_128_, n_layers 6, nf 64) is torch code on
-    cuDNN (library); it sees the whole 128x128 patch (the CEM-cropped 48x48 one is below its 8x8 head's minimum)."""
-    rank, local_rank, world = dist_env()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
+    kernels, NCCL all-reduce of the 13.6 MB critic gradient (one call) and the 68.2 MB generator gradient (buckets, half of
+    them under the weight-gradient kernels), fused Adam on both.  The critic (Discriminator_VGG_128_, n_layers 6, nf 64) is
+    torch code on cuDNN (library); it sees the whole 128x128 patch (the CEM-cropped 48x48 one is below its 8x8 head's
+    minimum).  Needs an initialised process group when world > 1.  Returns the JSON-able result (max over ranks)."""
     from esr_b200 import _capi as capi, cem as pcem, networks, synth
     from esr_b200.discriminator import Discriminator_VGG_128_
     from esr_b200.training import GanTrainer
@@ -457,33 +452,48 @@ def run_train_gan(args):
         if world > 1:
             torch.distributed.barrier()
             torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         l0 = dict(gan.step(mi, target))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         l1 = gan.step(mi, target)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t.cpu())
+    gb, db = gan.grad_bytes()
+    flops = 3 * netG.generated_image_model.engine().flops_per_lr_pixel() * Bp * hl * hl
+    res = {"metric": "GAN training step (RRDBNet+CEM generator, VGG-128 critic, WGAN-GP), 128x128 HR patches/s", "value": world * Bp / (ms * 1e-3),
+           "unit": "patches/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "generator: bf16 MMA operands, fp32 master weights; critic: torch fp32 (cuDNN, TF32 as torch defaults)",
+           "data": "synthetic", "config": {"workload": "BASELINE config 5: 16 x 128x128 HR patches (3x32x32 LR + Z) per rank, train mode, "
+                                                       "critic update + generator update every step (D_update_ratio 1)",
+                                           "global_batch": Bp * world,
+                                           "parallelism": "data parallel x%d, NCCL all-reduce (AVG): generator %.1f MB in buckets (half of them under the "
+                                                          "weight-gradient kernels), critic %.1f MB in one call" % (world, gb / 1e6, db / 1e6)},
+           "generator_algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+           "losses_first": {k: float(v) for k, v in l0.items()}, "losses_last": {k: float(v) for k, v in l1.items()}}
+    del gan, netG, netD
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_train_gan(args):
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    with contextlib.redirect_stdout(sys.stderr):
+        res = gan_step_measure(dev, rank, world, args.steps, args.warmup)
     if rank == 0:
-        gb, db = gan.grad_bytes()
-        flops = 3 * netG.generated_image_model.engine().flops_per_lr_pixel() * Bp * hl * hl
-        print(json.dumps({"metric": "GAN training step (RRDBNet+CEM generator, VGG-128 critic, WGAN-GP), 128x128 HR patches/s", "value": world * Bp / (ms * 1e-3),
-                          "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "generator: bf16 MMA operands, fp32 master weights; critic: torch fp32 (cuDNN, TF32 as torch defaults)",
-                          "data": "synthetic", "config": {"workload": "BASELINE config 5: 16 x 128x128 HR patches (3x32x32 LR + Z) per rank, train mode, "
-                                                                      "critic update + generator update every step (D_update_ratio 1)",
-                                                          "global_batch": Bp * world,
-                                                          "parallelism": "data parallel x%d, NCCL all-reduce (AVG): generator %.1f MB in buckets under the "
-                                                                         "weight-gradient kernels, critic %.1f MB in one call" % (world, gb / 1e6, db / 1e6)},
-                          "generator_algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
-                          "losses_first": {k: float(v) for k, v in l0.items()}, "losses_last": {k: float(v) for k, v in l1.items()}}))
+        print(json.dumps(res))
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -502,6 +512,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-zopt", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the BASELINE config 5 (GAN training step) block of the default run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -699,6 +710,16 @@ def main():
     if rank == 0 and not args.no_zopt:
         line["cem_roofline"] = cem_standalone(dev, pk)
         line["config1"] = config1_latency(netG, dev)
+    if not args.no_train:
+        # BASELINE config 5 beside the headline (every rank takes part: the step all-reduces its gradients over NCCL)
+        try:
+            G._plans.clear()
+            torch.cuda.empty_cache()
+            with contextlib.redirect_stdout(sys.stderr):         # init_weights prints like the reference's: keep stdout to ONE line
+                tr = gan_step_measure(dev, rank, world, 10, 4)
+            line["train_gan"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "n_gpus", "dtype", "config", "losses_last")}
+        except Exception as e:                                 # never at the expense of the headline line
+            line["train_gan"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
