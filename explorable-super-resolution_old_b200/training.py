@@ -47,7 +47,8 @@ class GeneratorTrainer:
         if not isinstance(G, RRDBNet):
             raise capi.EsrError("GeneratorTrainer needs this package's RRDBNet (optionally wrapped by CEM_PyTorch)")
         if G._cfg['nz_in'] == 0:
-            raise NotImplementedError("training a generator without a latent input is not built (the production configuration has one)")
+            raise NotImplementedError("training a generator without an HR_downscaled / LR latent input is not built (the "
+                                      "production configuration has one)")
         self.wrapper = wrapper if isinstance(wrapper, CEM_PyTorch) else None
         self.G, self.group, self.bucket_bytes = G, process_group, bucket_bytes
         self.dev = next(G.parameters()).device
@@ -91,9 +92,9 @@ class GeneratorTrainer:
         # esr_wgrad_tc: the dense-block convs' 16-bit input channels on the tcgen05 path (0: everything on the mma.sync kernels)
         self.use_tc = os.environ.get("ESR_WGRAD_TC", "1") != "0"
         self.tc_chunks = int(os.environ.get("ESR_WGRAD_TC_CHUNKS", "2"))
-        # one launch per kernel for the whole network (default) instead of one per gradient bucket: a bucket's 50-80 CTAs
-        # leave half of the 148 SMs idle, which costs more than the all-reduce overlap gains (the buckets' all-reduces are
-        # then issued back to back after the last launch)
+        # one launch per kernel for the whole network (two halves when gradients are exchanged, so that the first half's
+        # all-reduce runs under the second half's kernels) instead of one per gradient bucket: a bucket's 50-80 CTAs leave half
+        # of the 148 SMs idle, which costs more than the finer overlap gains
         self.per_bucket = os.environ.get("ESR_WGRAD_PER_BUCKET", "0") == "1"
 
     # ------------------------------------------------------------------ forward
