@@ -126,7 +126,8 @@ def test_autograd_node_returns_weight_gradients(cuda_device):
     assert not netG(mi).requires_grad
 
 
-def test_gan_step_matches_torch_autograd_on_the_oracle(cuda_device):
+@pytest.mark.parametrize("crop", [0, 8])
+def test_gan_step_matches_torch_autograd_on_the_oracle(cuda_device, crop):
     """training.GanTrainer.step (BASELINE config 5; SRRaGAN_model.py:349-547 in the shipped wgan-gp configuration)
     against the same iteration written with torch autograd on the CPU oracle generator and a CPU copy of the critic:
     critic losses incl. the gradient penalty, the critic's Adam update, the generator's loss terms, its weight gradients
@@ -141,18 +142,20 @@ def test_gan_step_matches_torch_autograd_on_the_oracle(cuda_device):
     hr = torch.rand(B, 3, 4 * h, 4 * h, generator=torch.Generator().manual_seed(12))
     u = torch.rand(B, 1, 1, 1, generator=torch.Generator().manual_seed(13))
     torch.manual_seed(14)
-    d_cpu = Discriminator_VGG_128_(3, 8, nb=4, input_patch_size=4 * h)
+    d_cpu = Discriminator_VGG_128_(3, 8, nb=4, input_patch_size=4 * h - 2 * crop)
     for m in d_cpu.modules():
         if isinstance(m, torch.nn.Conv2d):
             torch.nn.init.kaiming_normal_(m.weight, a=0, mode='fan_in')
     d_gpu = copy.deepcopy(d_cpu).to(cuda_device)
     weights = dict(pixel_weight=1e-2, gan_weight=5e-3, gp_weight=10.0, range_weight=50.0)
     netG = build_product_G(cuda_device, nb, "all_layers_HR_downscaled", wts, train=True)
-    gan = GanTrainer(netG, d_gpu, lr_G=1e-4, lr_D=1e-4, **weights)
+    gan = GanTrainer(netG, d_gpu, lr_G=1e-4, lr_D=1e-4, crop=crop, **weights)       # crop: the reference's HR_unpadder on fake_H / HR
     log = {k: float(v) for k, v in gan.step(mi.to(cuda_device), hr.to(cuda_device), interpolation=u.to(cuda_device)).items()}
     # ---- the same iteration on the CPU oracle
     w = {k: v.clone().requires_grad_(True) for k, v in wts.items()}
     fake = GCEMOracle(w, pre_pad=False, nb=nb).forward(mi)
+    if crop:
+        fake, hr = fake[..., crop:-crop, crop:-crop], hr[..., crop:-crop, crop:-crop]
     opt_d = torch.optim.Adam(d_cpu.parameters(), lr=1e-4)
     pr, pf = d_cpu(hr), d_cpu(fake.detach())
     interp = (u * fake.detach() + (1 - u) * hr).requires_grad_(True)
