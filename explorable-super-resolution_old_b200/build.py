@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libesr_b200.so")
-SOURCES = ["capi.cu", "conv3x3_tc.cu", "conv3x3_tc2.cu", "conv3x3_aux.cu", "cem.cu", "cem_fused.cu", "cem2d.cu", "prep.cu", "zopt.cu", "wgrad.cu", "wgrad_tc.cu"]
+SOURCES = ["capi.cu", "conv3x3_tc.cu", "conv3x3_tc2.cu", "conv3x3_aux.cu", "cem.cu", "cem_fused.cu", "cem2d.cu", "prep.cu", "zopt.cu", "zobj.cu", "wgrad.cu", "wgrad_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=177"]
 

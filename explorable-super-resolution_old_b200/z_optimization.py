@@ -4,9 +4,11 @@ of the reference's ``Z_optimization.py``: ``Z_optimizer`` (:326-682, loop :555-6
 
 The generator forward and its data-gradient backward run in libesr_b200.so; the scalar objectives are
 plain torch ops on ``fake_H`` (they only consume the hot path's output and hand back dL/d fake_H).
-Objectives built here: 'l1' (training mode, HR_unpadder given), 'TV', 'max_STD' / 'min_STD' /
-'STD_increase' / 'STD_decrease' (global).  The histogram / dictionary / scribble / periodicity / VGG /
-adversarial objectives of the GUI are out of this path's scope.
+Objectives: 'l1' (training mode, HR_unpadder given), 'TV', 'max_STD' / 'min_STD' / 'STD_increase' /
+'STD_decrease' (global; these run as one CUDA graph per iteration when nothing else is in the loop), and -
+through ``z_objectives`` - the GUI's 'local_' STD / Mag variants, histogram and
+dictionary imitation (the density sums are kernels of libesr_b200.so), periodicity, scribbles and the
+diverse-solutions 'random_l1' objectives.  Not built: VGG, adversarial, desired_SVD, automatic temperature.
 """
 import os
 import time
@@ -162,8 +164,11 @@ class Z_optimizer():
     def __init__(self, objective, Z_size, model, Z_range, max_iters, data=None, loggers=None, image_mask=None, Z_mask=None,
                  initial_Z=None, initial_LR=None, existing_optimizer=None, batch_size=1, HR_unpadder=None,
                  auto_set_hist_temperature=False, random_Z_inits=False):
+        from . import z_objectives
         if objective not in _BUILT:
-            raise NotImplementedError("Z objective %r is outside the built hot path (built: %s)" % (objective, ', '.join(_BUILT)))
+            why = z_objectives.unsupported_reason(objective, auto_set_hist_temperature)
+            if why is not None:
+                raise NotImplementedError("Z objective %r %s (built into the single-graph loop: %s)" % (objective, why, ', '.join(_BUILT)))
         self.device = next(model.netG.parameters()).device
         if initial_Z is not None or 'cur_Z' in model.__dict__.keys():
             if initial_Z is None:
@@ -174,8 +179,9 @@ class Z_optimizer():
         else:
             initial_pre_tanh_Z = None
         self.Z_model = Optimizable_Z(Z_shape=[batch_size, model.num_latent_channels] + list(Z_size), Z_range=Z_range,
-                                     initial_pre_tanh_Z=initial_pre_tanh_Z, Z_mask=Z_mask, random_perturbations=random_Z_inits,
-                                     device=self.device)
+                                     initial_pre_tanh_Z=initial_pre_tanh_Z, Z_mask=Z_mask, device=self.device,
+                                     random_perturbations=(random_Z_inits and 'random' not in objective) or
+                                     ('random' in objective and 'limited' in objective))
         assert (initial_LR is not None) or (existing_optimizer is not None), \
             'Should either supply optimizer from previous iterations or initial LR for new optimizer'
         self.objective, self.data, self.model = objective, data, model
@@ -189,16 +195,25 @@ class Z_optimizer():
             self.image_mask = torch.from_numpy(image_mask).to(model.fake_H.dtype).to(self.device)
             self.Z_mask = torch.from_numpy(Z_mask).to(model.fake_H.dtype).to(self.device)
             self.initial_Z = 1. * model.GetLatent()
+        # Masked_STD: global, or per 7x7 patch for the 'local' objectives (Z_optimization.py:356-361, :525-535)
+        self._std = z_objectives.LocalStd(self, 'local' in objective, image_mask, self.PATCH_SIZE_4_STD)
+        self._rich = None
         if not self.model_training:
             self.initial_STD = self.Masked_STD(first_image_only=True)
             print('Initial STD: %.3e' % (self.initial_STD.mean().item()))
         if existing_optimizer is None:
-            if objective == 'l1':
+            if any(p in objective for p in ('l1', 'scribble')) and 'random' not in objective:
                 if data is not None and 'HR' in data.keys():
                     self.GT_HR = data['HR']
-                if self.image_mask is not None:
-                    raise NotImplementedError("'l1' with an image mask is the scribble objective (not built)")
-                self.loss = torch.nn.L1Loss().to(self.device)
+                if self.image_mask is None:
+                    self.loss = torch.nn.L1Loss().to(self.device)
+                elif 'scribble' in objective:
+                    self._rich = self.loss = z_objectives.ScribbleObjective(self, data)
+                else:
+                    raise NotImplementedError("'l1' with an image mask only exists as the scribble objective (the reference's "
+                                              "masked l1 reads masks that only the scribble set-up defines, Z_optimization.py:390-398)")
+            elif objective not in _BUILT:
+                self._rich = z_objectives.resolve(self, data, auto_set_hist_temperature)
             elif 'STD' in objective:
                 if any(p in objective for p in ['increase', 'decrease']):
                     inc = data['STD_increment']
@@ -284,13 +299,15 @@ class Z_optimizer():
         return self._fused
 
     def Masked_STD(self, first_image_only=False):
-        return torch.std(self.model.fake_H * self.image_mask, dim=(1, 2, 3)).view(1, -1)
+        return self._std(first_image_only)
 
     def feed_data(self, data):
         self.data = data
         self.cur_iter = 0
         if 'l1' in self.objective:
             self.GT_HR = data['HR'].to(self.device)
+        elif 'hist' in self.objective:
+            self.loss.Feed_Desired_Hist_Im(data['HR'].to(self.device))
 
     def Manage_Model_Grad_Requirements(self, disable):
         if disable:
@@ -343,7 +360,9 @@ class Z_optimizer():
             if self.model_training:
                 self.model.fake_H = self.HR_unpadder(self.model.fake_H)
             fake_H = self.model.fake_H
-            if self.objective == 'l1':
+            if self._rich is not None:
+                Z_loss = self._rich(fake_H)
+            elif 'l1' in self.objective:
                 Z_loss = self.loss(fake_H, self.GT_HR.to(self.device))
             elif 'STD' in self.objective:
                 Z_loss = self.Masked_STD(first_image_only=False)
@@ -355,6 +374,8 @@ class Z_optimizer():
                     TV_Loss(fake_H * self.image_mask)
             if 'max' in self.objective:
                 Z_loss = -1 * Z_loss
+            if Z_loss.dim() == 0:            # plain 'hist': one KL divergence for the batch (the reference's loop cannot
+                Z_loss = Z_loss.reshape(1)   # iterate over it, Z_optimization.py:622)
             cur_LR = self.optimizer.param_groups[0]['lr']
             if self.loggers is not None:
                 for logger_num, logger in enumerate(self.loggers):
@@ -376,6 +397,8 @@ class Z_optimizer():
                 self.loss_values = torch.stack(self.loss_values).cpu().tolist()
             if pending_latest is not None:
                 self.latest_Z_loss_values = pending_latest.cpu().tolist()
+        if 'random' in self.objective and 'limited' in self.objective and len(self.loss_values) > 1:
+            self.loss_values[0] = self.loss_values[1]          # the first value is ~0 there (Z_optimization.py:638-639)
         if not self.model_training:
             print('Final STDs: ', ['%.3e' % (val.item()) for val in self.Masked_STD(first_image_only=False).mean(0)])
         self.cur_iter = z_iter + 1

@@ -366,6 +366,27 @@ int esr_zopt_loss_grad(const float* fake_H, int32_t B, int32_t C, int32_t H, int
 int esr_zopt_adam(float* Z, float* exp_avg, float* exp_avg_sq, const float* g_in, float z_range, int32_t B, int32_t n_lat,
                   int32_t n_img, float lr, float beta1, float beta2, float eps, const int32_t* step, void* stream);
 
+/* ------------------------------------------------- rich Z objectives (csrc/zobj.cu)
+ * The pairwise kernel-density sums of SoftHistogramLoss.ComputeSoftHistogram (codes/Z_optimization.py:168-200) without
+ * the reference's [D, N, M] fp64 intermediates:
+ *   E[i,j] = exp(-(1 / (temperature * D)) * sum_d (min(|x|, |x - period|, |x + period|) + eps)^2),  x = p[d,i] - b[d,j]
+ * samples p: fp32 [D, N] (d-major);  bins b: fp64 [D, M].  All arithmetic fp64, fixed summation order.
+ * esr_kde_sums: sums[i] = sum over the OTHER set of E for every OWN vector: own = samples (own_is_f64 0, other_is_f64 1)
+ *   gives the per-sample sums of the dictionary objective (:193-194), own = bins (1, 0) the per-bin sums of the histogram
+ *   (:195).  workspace: esr_kde_workspace_bytes(n_own, n_other) bytes (may be 0 -> NULL allowed).
+ * esr_kde_grad: grad[d,i] = sum_j (w_sample[i] + w_bin[j]) * dE[i,j]/dp[d,i]  (either weight vector may be NULL): the
+ *   chain rule of any scalar built on the two kinds of sums, i.e. what autograd derives in the reference. */
+int64_t esr_kde_workspace_bytes(int64_t n_own, int64_t n_other);
+int esr_kde_sums(const void* own, int32_t own_is_f64, int64_t n_own, const void* other, int32_t other_is_f64,
+                 int64_t n_other, int32_t D, double period, double temperature, double eps, double* sums,
+                 void* workspace, void* stream);
+int esr_kde_grad(const float* samples, int64_t n_samples, const double* bins, int64_t n_bins, int32_t D, double period,
+                 double temperature, double eps, const double* w_sample, const double* w_bin, float* grad, void* stream);
+/* Host code, no GPU: the greedy patch selection of ReturnPatchExtractionMat (codes/Z_optimization.py:236-254).
+ * patches [n, D] int64 pixel indexes in visiting order; valid [n] and covered [span] (span = max - min index) are outputs. */
+int esr_patch_select(const int64_t* patches, int64_t n, int32_t D, double overlap, int64_t min_index, int64_t span,
+                     uint8_t* valid, uint8_t* covered);
+
 /* ------------------------------------------------- generator weight gradients (csrc/wgrad.cu)
  * What autograd computes for the generator's conv parameters in the reference's training step
  * (codes/models/SRRaGAN_model.py:463-547 with the block definitions of modules/block.py:129-155):

@@ -269,6 +269,32 @@ def gen_zopt2(CEMnet, networks, zopt):
     np.savez_compressed(os.path.join(OUT, "zopt2.npz"), **zres)
 
 
+def gen_zobj(CEMnet, networks, zopt):
+    """The rich objectives (Z_optimization.py:21-270, :371-523, :576-617) from the unmodified reference: SoftHistogramLoss
+    values / gradients / bins on the HIST_CASES of oracle/zobj_cases.py, and Z_optimizer trajectories of the ZOPT3 cases
+    through the reference's nb=2 G+CEM (GUI mode).  'scribble' has no reference run (zobj_cases.NO_REFERENCE_RUN)."""
+    from oracle import zobj_cases as zc
+    res = {}
+    for name in zc.HIST_CASES:
+        value, grad, bins = zc.run_hist_case(zopt.SoftHistogramLoss, name)
+        res["hist_%s_value" % name], res["hist_%s_grad" % name] = value.numpy().astype(np.float64), grad.numpy()
+        res["hist_%s_bins" % name] = bins.numpy()
+        print("hist", name, value, float(grad.abs().max()), tuple(bins.shape))
+    lr, z0 = synth.make_inputs(1, zc.ZOPT3_HW[0], zc.ZOPT3_HW[1], seed=11)
+    for name in zc.ZOPT3_CASES:
+        if name in zc.NO_REFERENCE_RUN:
+            continue
+        netG, cem = build_ref_G(CEMnet, networks, 2, "all_layers", "default", 5)
+        netG.train(False)
+        opt, Z = zc.run_zopt_case(zopt.Z_optimizer, RefModel(netG), netG, name, lr, z0, z_init=zc.zopt3_z_init(name))
+        res["zopt_%s_loss" % name] = np.array(opt.loss_values, dtype=np.float64)
+        res["zopt_%s_latest" % name] = np.array(opt.latest_Z_loss_values, dtype=np.float64).reshape(-1)
+        res["zopt_%s_Z" % name] = Z.numpy()
+        res["zopt_%s_initial_STD" % name] = opt.initial_STD.numpy()
+        print("zopt", name, opt.loss_values)
+    np.savez_compressed(os.path.join(OUT, "zobjectives.npz"), **res)
+
+
 CFG3_WINDOWS = [(0, 0), (464, 464), (928, 928), (0, 928)]      # top-left corners of the stored 96 x 96 HR windows
 CFG3_WIN = 96
 
@@ -311,6 +337,8 @@ def main():
         return gen_lr_domain(CEMnet, networks)
     if "zopt2" in sys.argv[1:]:           # only the extra Z_optimizer trajectories
         return gen_zopt2(CEMnet, networks, zopt)
+    if "zobj" in sys.argv[1:]:            # only the rich-objective fixture
+        return gen_zobj(CEMnet, networks, zopt)
     if "cfg3" in sys.argv[1:]:            # only the config-3-size output / gradient windows (about a minute, ~20 GB)
         return gen_cfg3(CEMnet, networks)
 
@@ -423,6 +451,7 @@ def main():
     # 8. LR-domain latent input ------------------------------------------------------------------
     gen_lr_domain(CEMnet, networks)
     gen_rearranged(CEMnet, networks)
+    gen_zobj(CEMnet, networks, zopt)
 
 
 if __name__ == "__main__":

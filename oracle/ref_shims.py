@@ -83,6 +83,14 @@ class _CpuDeviceTorch:
             return self._t.device("cpu")
         return self._t.device(*a, **kw)
 
+    def triu(self, x, *a, **kw):
+        """Z_optimization.py:118-120 builds a keep-mask as `torch.triu(mat).any(1) ^ 1`, written for torch < 1.2 where
+        comparisons were uint8: there the result is a uint8 MASK.  With bool tensors `^ 1` promotes to int64 and the
+        next line's `im[:, mask]` silently becomes a gather of columns 0 / 1.  Handing triu's result back as uint8
+        restores the dtype the line was written for (`.any()` of uint8 stays uint8), without touching the source."""
+        r = self._t.triu(x, *a, **kw)
+        return r.to(self._t.uint8) if r.dtype == self._t.bool else r
+
 
 def load_reference():
     """Returns (CEMnet module, networks module, architecture module, Z_optimization module)."""
@@ -92,8 +100,7 @@ def load_reference():
     import models.networks as networks
     import models.modules.architecture as arch
     import Z_optimization as zopt
-    if not torch.cuda.is_available():
-        zopt.torch = _CpuDeviceTorch(torch)
+    zopt.torch = _CpuDeviceTorch(torch)        # device('cuda') -> cpu only when there is no GPU; the triu dtype repair always
     return CEMnet, networks, arch, zopt
 
 

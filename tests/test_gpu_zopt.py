@@ -53,7 +53,7 @@ def test_l1_objective_training_mode(golden, cuda_device):
 def test_unbuilt_objective_is_loud(cuda_device):
     netG, model, data = _setup(cuda_device, train_mode=False)
     with pytest.raises(NotImplementedError):
-        Z_optimizer(objective="hist", Z_size=[32, 32], model=model, Z_range=1.0, max_iters=4, data=data, initial_LR=0.1)
+        Z_optimizer(objective="Adversarial", Z_size=[32, 32], model=model, Z_range=1.0, max_iters=4, data=data, initial_LR=0.1)
 
 
 # ------------------------------------------------------------------ more of the reference's Z_optimizer (zopt2.npz)

@@ -1,0 +1,157 @@
+"""Host logic of the rich Z objectives (esr_b200.z_objectives) on CPU.
+
+The density sums are CUDA kernels (csrc/zobj.cu) with no CPU path, so these tests put the oracle's restatement
+(oracle/zobjectives.kde_sums) in their place and check everything around them - patch tables and the native greedy
+selection, bin pruning, DC / STD normalisation, histogram normalisers, the objective classes, the Z_optimizer wiring -
+against the committed goldens (recorded from the unmodified reference) and, when /root/reference exists, against the
+reference's own classes run side by side.  tests/test_gpu_zobjectives.py checks the kernels themselves."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from esr_b200 import _capi as capi, synth, z_objectives as zo
+from esr_b200.z_optimization import Z_optimizer, SRModelShim
+from oracle import ref_shims, zobj_cases as zc, zobjectives as oracle_zobj
+
+warnings.filterwarnings("ignore")
+
+
+@pytest.fixture()
+def oracle_density(monkeypatch):
+    monkeypatch.setattr(zo, "kde_sums", oracle_zobj.kde_sums)
+
+
+@pytest.fixture(scope="module")
+def reference_zopt():
+    if not ref_shims.available():
+        pytest.skip("reference tree not present")
+    zopt = ref_shims.load_reference()[3]
+    return zopt
+
+
+def test_density_kernels_have_no_cpu_path():
+    with pytest.raises(capi.EsrError):
+        zo.kde_sums(torch.rand(1, 8), torch.rand(1, 4).double(), 1.0, 1e-3)
+
+
+@pytest.mark.parametrize("name", sorted(zc.HIST_CASES))
+def test_soft_histogram_loss_matches_reference_golden(golden, oracle_density, name):
+    """Values, image gradients and the pruned bins of SoftHistogramLoss (Z_optimization.py:21-228) for the gray / patch,
+    histogram / dictionary, DC- and STD-free variants Z_optimizer builds."""
+    g = golden("zobjectives")
+    value, grad, bins = zc.run_hist_case(zo.SoftHistogramLoss, name)
+    np.testing.assert_array_equal(bins.numpy(), g["hist_%s_bins" % name])
+    np.testing.assert_allclose(value.numpy().astype(np.float64), g["hist_%s_value" % name], rtol=1e-5, atol=1e-7)
+    ref = g["hist_%s_grad" % name]
+    np.testing.assert_allclose(grad.numpy(), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("patch,overlap", [(7, 1), (7, 0.5), (6, 30 / 36), (6, 0.5), (3, 0)])
+def test_patch_tables_equal_reference_extraction_matrix(reference_zopt, patch, overlap):
+    """The index table + native greedy selection against ReturnPatchExtractionMat's sparse matrix (:230-270), including
+    its non-covered pixel set, on a mask with a hole and ragged borders."""
+    H, W = 23, 31
+    mask = np.ones((H, W), dtype=bool)
+    mask[:2, :] = False
+    mask[9:12, 10:14] = False
+    mask[:, -1] = False
+    mat, rest = reference_zopt.ReturnPatchExtractionMat(mask.copy(), patch, torch.device("cpu"), patches_overlap=overlap,
+                                                        return_non_covered=True)
+    table, mine_rest = zo.patch_tables(mask.copy(), patch, torch.device("cpu"), overlap, return_non_covered=True)
+    img = torch.from_numpy(np.random.default_rng(0).random(H * W).astype(np.float32))
+    ref = torch.sparse.mm(mat, img.view(-1, 1)).view(patch ** 2, -1)
+    np.testing.assert_array_equal(table.extract(img).numpy(), ref.numpy())
+    if rest is None:
+        assert mine_rest is None
+    else:
+        ref_rest = torch.sparse.mm(rest, img.view(-1, 1)).view(-1)
+        np.testing.assert_array_equal(np.sort(mine_rest.extract(img).view(-1).numpy()), np.sort(ref_rest.numpy()))
+
+
+def test_patch_select_validates_arguments():
+    l = capi.lib()
+    assert l.esr_patch_select(None, 1, 4, 0.5, 0, 10, None, None) == -1
+    px = np.array([[0, 1, 50, 3]], dtype=np.int64)                 # 50 is outside [min, min + span]
+    valid, covered = np.zeros(1, np.uint8), np.zeros(10, np.uint8)
+    import ctypes as C
+    rc = l.esr_patch_select(px.ctypes.data_as(C.c_void_p), 1, 4, 0.5, 0, 10, valid.ctypes.data_as(C.c_void_p),
+                            covered.ctypes.data_as(C.c_void_p))
+    assert rc == -1 and b"outside" in l.esr_last_error()
+    assert l.esr_kde_workspace_bytes(0, 5) == -1
+    assert l.esr_kde_workspace_bytes(100, 100000) > 0              # few own vectors: the other range is split
+    assert l.esr_kde_workspace_bytes(1 << 20, 256) == 0
+
+
+def test_hsv_round_trip_and_known_colours():
+    rgb = np.random.default_rng(1).random((9, 11, 3)) * 255
+    np.testing.assert_allclose(zo.hsv2rgb(zo.rgb2hsv(rgb)), rgb, rtol=1e-12, atol=1e-9)
+    known = np.array([[[255, 0, 0], [0, 255, 0], [0, 0, 255], [128, 128, 128], [0, 0, 0], [255, 255, 0]]], dtype=np.float64)
+    hsv = zo.rgb2hsv(known)[0]
+    np.testing.assert_allclose(hsv[:, 0], [0, 1 / 3, 2 / 3, 0, 0, 1 / 6], atol=1e-12)
+    np.testing.assert_allclose(hsv[:, 1], [1, 1, 1, 0, 0, 1], atol=1e-12)
+    np.testing.assert_allclose(hsv[:, 2], [255, 255, 255, 128, 0, 255], atol=1e-12)
+
+
+@pytest.mark.parametrize("name", [n for n in zc.ZOPT3_CASES if n not in zc.NO_REFERENCE_RUN])
+def test_z_optimizer_objectives_match_reference_side_by_side(reference_zopt, oracle_density, name):
+    """Every rich objective through this package's Z_optimizer against the reference's own Z_optimizer (:326-655), both
+    around the same cheap stub generator on CPU: loss per iteration, per-image losses, returned Z."""
+    from oracle.gen_golden import RefModel
+    lr, z0 = synth.make_inputs(1, zc.ZOPT3_HW[0], zc.ZOPT3_HW[1], seed=11)
+    out = []
+    for cls, model_cls in ((reference_zopt.Z_optimizer, RefModel), (Z_optimizer, SRModelShim)):
+        netG = zc.StubGenerator()
+        opt, Z = zc.run_zopt_case(cls, model_cls(netG), netG, name, lr, z0, z_init=zc.zopt3_z_init(name))
+        out.append((np.array(opt.loss_values), np.array(opt.latest_Z_loss_values).reshape(-1), Z))
+    (l0, a0, Z0), (l1, a1, Z1) = out
+    np.testing.assert_allclose(l1, l0, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(a1, a0, rtol=1e-5, atol=1e-8)
+    assert float((Z0 - Z1).abs().max()) < 1e-4
+
+
+def test_scribble_objective_terms(oracle_density):
+    """No reference run exists for 'scribble' (zobj_cases.NO_REFERENCE_RUN): the objective's value is checked against
+    the formulas of Z_optimization.py:371-416 written out with explicit loops."""
+    lr, z0 = synth.make_inputs(1, 8, 8, seed=11)
+    netG = zc.StubGenerator()
+    opt, Z = zc.run_zopt_case(Z_optimizer, SRModelShim(netG), netG, "scribble", lr, z0)
+    assert len(opt.loss_values) == 3 and opt.loss_values[-1] < opt.loss_values[0]
+    H = W = 32
+    im_mask, _ = zc.region_masks(H, W)
+    ids = zc.scribble_mask(H, W)
+    fake = torch.from_numpy(np.random.default_rng(5).random((1, 3, H, W)).astype(np.float32))
+    value = float(opt._rich(fake).reshape(-1)[0])
+    l1_mask = im_mask * ((ids > 0) & (ids < 4))
+    expect = float(np.abs(fake.numpy()[0] * l1_mask - opt.GT_HR.numpy()[0] * l1_mask).mean())
+    f = fake.numpy()[0]
+    for region in (4, 5):
+        m = im_mask * (ids == region)
+        for dy, dx in ((-1, -1), (-1, 0), (0, -1), (1, -1)):
+            total = 0.0
+            for y in range(H):
+                for x in range(W):          # the two opposite crops pair pixel (y, x) with (y - dy, x - dx)
+                    y2, x2 = y - dy, x - dx
+                    if 0 <= y2 < H and 0 <= x2 < W:
+                        total += m[y, x] * m[y2, x2] * np.abs(f[:, y, x] - f[:, y2, x2]).sum()
+            expect += total / (3 * (H - abs(dy)) * (W - abs(dx)))
+    assert abs(value - expect) < 1e-5 * max(1.0, abs(expect))
+    # brighter / darker scribbles re-light the target: scaling V scales the colour, by the smoothed 1 +- brightness factor
+    shim = SRModelShim(netG)
+    shim.feed_data({"LR": lr, "Z": 0.5 * z0})
+    with torch.no_grad():
+        start = netG(shim.model_input).clamp(0, 1)[0]
+    y, x = H // 2 + 1, W // 4 + 3                # inside the 'brighter' box, 3x3 neighbourhood all inside
+    np.testing.assert_allclose(opt.GT_HR[0, :, y, x].numpy(), 1.2 * start[:, y, x].numpy(), rtol=1e-5)
+    y, x = H // 2 + 1, W // 2 + 3                # inside the 'darker' box
+    np.testing.assert_allclose(opt.GT_HR[0, :, y, x].numpy(), 0.8 * start[:, y, x].numpy(), rtol=1e-5)
+
+
+def test_unbuilt_objectives_are_loud():
+    for objective in ("Adversarial", "VGG", "desired_SVD", "random_VGG", "nonsense"):
+        assert zo.unsupported_reason(objective) is not None
+    assert zo.unsupported_reason("hist", auto_temperature=True) is not None
+    for objective in ("hist", "patchdict_noDC", "local_STD_increase", "max_local_STD", "local_Mag_decrease", "scribble",
+                      "nonInt_periodicity_1D", "local_STD_TV", "random_l1_limited", "l1"):
+        assert zo.unsupported_reason(objective) is None, objective
