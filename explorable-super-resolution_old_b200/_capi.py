@@ -161,7 +161,8 @@ SIGNATURES = {
     "esr_zopt_adam": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, _i32, _i32, _i32, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "esr_kde_workspace_bytes": (_i64, [_i64, _i64]),
     "esr_kde_sums": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp]),
-    "esr_kde_grad": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),
+    "esr_kde_grad_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "esr_kde_grad": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "esr_patch_select": (C.c_int, [_vp, _i64, _i32, C.c_double, _i64, _i64, _vp, _vp]),
     "esr_grad_combine": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32,
                                    _i32, _i32, _f, _f, _vp, _i32, _i32, _i32, _vp]),

@@ -9,10 +9,11 @@
 //   esr_kde_grad   d/dp[d,i] of any scalar built on those sums: sum_j (w_sample[i] + w_bin[j]) * E[i,j] * dlogE[i,j]/dp[d,i]
 //
 // One thread owns one "own" vector (kept in shared memory, column per thread), the "other" vectors stream through a
-// shared chunk that every thread reads as a broadcast.  The sums split the other range over blockIdx.y into partial
-// sums that a second kernel adds in a fixed order (deterministic, no atomics).  All arithmetic is fp64 like the reference
-// (`.type(torch.cuda.DoubleTensor)`, :172/:184); the samples arrive as fp32 (the generator's output) and the gradient
-// leaves as fp32 (what autograd's cast gives).
+// shared chunk that every thread reads as a broadcast.  Sums and gradients split the other range over blockIdx.y into
+// partial results (fp64) that a second kernel adds in a fixed order (deterministic, no atomics) whenever the own set alone
+// would leave SMs idle (3600 patches = 29 CTAs: the unsplit gradient pass took 13.3 ms of a 13.9 ms forward + backward).
+// All arithmetic is fp64 like the reference (`.type(torch.cuda.DoubleTensor)`, :172/:184); the samples arrive as fp32 (the
+// generator's output) and the gradient leaves as fp32 (what autograd's cast gives).
 //
 // Also here: the greedy patch selection of ReturnPatchExtractionMat (:236-254) as a host loop in native code (the
 // reference walks every candidate patch in Python).
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(kKdeBlock) kde_pair_kernel(const TOwn* __restr
                                                              const TOther* __restrict__ other, long long n_other, int D,
                                                              double period, double neg_inv_td, double eps,
                                                              const double* __restrict__ w_own, const double* __restrict__ w_other,
-                                                             double* __restrict__ sums, float* __restrict__ grad) {
+                                                             double* __restrict__ sums, float* __restrict__ grad,
+                                                             double* __restrict__ grad_partial) {
     extern __shared__ double kde_smem[];
     double* so = kde_smem;                                   // [D][kKdeBlock]
     double* sc = so + static_cast<size_t>(D) * kKdeBlock;    // [D][kKdeChunk]
@@ -95,8 +97,11 @@ __global__ void __launch_bounds__(kKdeBlock) kde_pair_kernel(const TOwn* __restr
     if (!live) return;
     if (!GRAD) {
         sums[static_cast<size_t>(blockIdx.y) * n_own + i] = sum;
-    } else {
+    } else if (gridDim.y == 1) {
         for (int d = 0; d < D; ++d) grad[static_cast<size_t>(d) * n_own + i] = static_cast<float>(sg[d * kKdeBlock + tid]);
+    } else {                         // few samples: the bin range is split like the sums', partial gradients in fp64
+        double* dst = grad_partial + static_cast<size_t>(blockIdx.y) * D * n_own;
+        for (int d = 0; d < D; ++d) dst[static_cast<size_t>(d) * n_own + i] = sg[d * kKdeBlock + tid];
     }
 }
 
@@ -106,6 +111,14 @@ __global__ void kde_reduce_kernel(const double* __restrict__ partial, int nsplit
     double s = 0.0;
     for (int k = 0; k < nsplit; ++k) s += partial[static_cast<size_t>(k) * n + i];
     out[i] = s;
+}
+
+__global__ void kde_reduce_grad_kernel(const double* __restrict__ partial, int nsplit, long long n, float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += partial[static_cast<size_t>(k) * n + i];
+    out[i] = static_cast<float>(s);
 }
 
 static int kde_nsplit(long long n_own, long long n_other) {
@@ -169,12 +182,12 @@ extern "C" int esr_kde_sums(const void* own, int32_t own_is_f64, int64_t n_own, 
         auto k = kde_pair_kernel<double, float, false>;
         if ((rc = kde_allow_smem(k, smem)) != ESR_OK) return rc;
         k<<<grid, kKdeBlock, smem, st>>>(static_cast<const double*>(own), n_own, static_cast<const float*>(other), n_other, D,
-                                        period, neg_inv_td, eps, nullptr, nullptr, dst, nullptr);
+                                        period, neg_inv_td, eps, nullptr, nullptr, dst, nullptr, nullptr);
     } else {
         auto k = kde_pair_kernel<float, double, false>;
         if ((rc = kde_allow_smem(k, smem)) != ESR_OK) return rc;
         k<<<grid, kKdeBlock, smem, st>>>(static_cast<const float*>(own), n_own, static_cast<const double*>(other), n_other, D,
-                                        period, neg_inv_td, eps, nullptr, nullptr, dst, nullptr);
+                                        period, neg_inv_td, eps, nullptr, nullptr, dst, nullptr, nullptr);
     }
     if ((rc = check_launch("kde_pair_kernel")) != ESR_OK) return rc;
     if (nsplit > 1) {
@@ -184,9 +197,15 @@ extern "C" int esr_kde_sums(const void* own, int32_t own_is_f64, int64_t n_own, 
     return rc;
 }
 
+extern "C" int64_t esr_kde_grad_workspace_bytes(int64_t n_samples, int64_t n_bins, int32_t D) {
+    if (n_samples <= 0 || n_bins <= 0 || D <= 0) return ESR_ERR_INVALID;
+    const int s = esr::kde_nsplit(n_samples, n_bins);
+    return s > 1 ? static_cast<int64_t>(s) * D * n_samples * static_cast<int64_t>(sizeof(double)) : 0;
+}
+
 extern "C" int esr_kde_grad(const float* samples, int64_t n_samples, const double* bins, int64_t n_bins, int32_t D,
                             double period, double temperature, double eps, const double* w_sample, const double* w_bin,
-                            float* grad, void* stream) {
+                            float* grad, void* workspace, void* stream) {
     using namespace esr;
     int rc = kde_check(samples, n_samples, bins, n_bins, D, period, temperature);
     if (rc != ESR_OK) return rc;
@@ -195,10 +214,19 @@ extern "C" int esr_kde_grad(const float* samples, int64_t n_samples, const doubl
     const size_t smem = kde_smem_bytes(D, true);
     auto k = kde_pair_kernel<float, double, true>;
     if ((rc = kde_allow_smem(k, smem)) != ESR_OK) return rc;
-    const dim3 grid(static_cast<unsigned>((n_samples + kKdeBlock - 1) / kKdeBlock), 1);
-    k<<<grid, kKdeBlock, smem, static_cast<cudaStream_t>(stream)>>>(samples, n_samples, bins, n_bins, D, period,
-                                                                   -1.0 / (temperature * D), eps, w_sample, w_bin, nullptr, grad);
-    return check_launch("kde_pair_kernel<grad>");
+    const int nsplit = kde_nsplit(n_samples, n_bins);
+    ESR_CHECK_ARG(nsplit == 1 || workspace != nullptr, "esr_kde_grad: %d partial gradients need the workspace of esr_kde_grad_workspace_bytes", nsplit);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid(static_cast<unsigned>((n_samples + kKdeBlock - 1) / kKdeBlock), nsplit);
+    k<<<grid, kKdeBlock, smem, st>>>(samples, n_samples, bins, n_bins, D, period, -1.0 / (temperature * D), eps, w_sample, w_bin,
+                                    nullptr, grad, static_cast<double*>(workspace));
+    if ((rc = check_launch("kde_pair_kernel<grad>")) != ESR_OK) return rc;
+    if (nsplit > 1) {
+        const long long n = static_cast<long long>(D) * n_samples;
+        kde_reduce_grad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(static_cast<const double*>(workspace), nsplit, n, grad);
+        rc = check_launch("kde_reduce_grad_kernel");
+    }
+    return rc;
 }
 
 // Greedy patch selection (codes/Z_optimization.py:236-254): candidates are visited in raster order; one is dropped when

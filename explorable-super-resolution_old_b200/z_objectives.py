@@ -49,9 +49,10 @@ def _kde_grad_device(samples, bins, period, temperature, eps, w_sample, w_bin):
     l = capi.lib()
     D, N = samples.shape
     grad = torch.empty_like(samples)
+    ws = torch.empty(max(1, int(l.esr_kde_grad_workspace_bytes(N, bins.shape[1], D)) // 8), device=samples.device, dtype=torch.float64)
     with torch.cuda.device(samples.device):
         capi.check(l.esr_kde_grad(capi.ptr(samples), N, capi.ptr(bins), bins.shape[1], D, period, temperature, eps,
-                                  capi.ptr(w_sample), capi.ptr(w_bin), capi.ptr(grad), capi.stream_ptr()))
+                                  capi.ptr(w_sample), capi.ptr(w_bin), capi.ptr(grad), capi.ptr(ws), capi.stream_ptr()))
     return grad
 
 

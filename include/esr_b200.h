@@ -380,8 +380,10 @@ int64_t esr_kde_workspace_bytes(int64_t n_own, int64_t n_other);
 int esr_kde_sums(const void* own, int32_t own_is_f64, int64_t n_own, const void* other, int32_t other_is_f64,
                  int64_t n_other, int32_t D, double period, double temperature, double eps, double* sums,
                  void* workspace, void* stream);
+int64_t esr_kde_grad_workspace_bytes(int64_t n_samples, int64_t n_bins, int32_t D);
 int esr_kde_grad(const float* samples, int64_t n_samples, const double* bins, int64_t n_bins, int32_t D, double period,
-                 double temperature, double eps, const double* w_sample, const double* w_bin, float* grad, void* stream);
+                 double temperature, double eps, const double* w_sample, const double* w_bin, float* grad, void* workspace,
+                 void* stream);
 /* Host code, no GPU: the greedy patch selection of ReturnPatchExtractionMat (codes/Z_optimization.py:236-254).
  * patches [n, D] int64 pixel indexes in visiting order; valid [n] and covered [span] (span = max - min index) are outputs. */
 int esr_patch_select(const int64_t* patches, int64_t n, int32_t D, double overlap, int64_t min_index, int64_t span,
