@@ -155,3 +155,37 @@ def test_unbuilt_objectives_are_loud():
     for objective in ("hist", "patchdict_noDC", "local_STD_increase", "max_local_STD", "local_Mag_decrease", "scribble",
                       "nonInt_periodicity_1D", "local_STD_TV", "random_l1_limited", "l1"):
         assert zo.unsupported_reason(objective) is None, objective
+
+
+@pytest.mark.parametrize("objective,max_iters,random_inits,bs", [("TV", 3, False, 1), ("max_STD", -2, False, 1),
+                                                                  ("STD_increase", 2, True, 3), ("random_l1", 2, True, 3)])
+def test_repeated_rounds_and_random_inits_match_reference(reference_zopt, objective, max_iters, random_inits, bs):
+    """The GUI's calling pattern (GUI.py:1596-1660): one Z_optimizer object, optimize() called round after round (cur_iter
+    and Adam's state carry over, :555-562, :645), the convergence window (max_iters < 0, :564-571), and random Z
+    initialisations (Randomize_Z, :307-313; the RNG is torch's, so on CPU both sides draw the same numbers)."""
+    from oracle.gen_golden import RefModel
+    lr, z0 = synth.make_inputs(1, 8, 8, seed=4)
+    out = []
+    for cls, model_cls in ((reference_zopt.Z_optimizer, RefModel), (Z_optimizer, SRModelShim)):
+        netG = zc.StubGenerator()
+        model = model_cls(netG)
+        data = {"LR": lr.repeat(bs, 1, 1, 1), "Z": (0.3 * z0).repeat(bs, 1, 1, 1), "STD_increment": 0.03}
+        model.feed_data(data)
+        with torch.no_grad():
+            model.fake_H = netG(model.model_input)
+        torch.manual_seed(11)
+        opt = cls(objective=objective, Z_size=[32, 32], model=model, Z_range=1.0, max_iters=max_iters, data=data, initial_LR=0.05,
+                  batch_size=bs, random_Z_inits=random_inits, initial_Z=0.3 * z0)
+        rounds = []
+        for _ in range(3):
+            Z = opt.optimize()
+            rounds.append((list(opt.loss_values), list(np.array(opt.latest_Z_loss_values).reshape(-1)), opt.cur_iter, Z.clone()))
+        pre_tanh, optimizer = opt.ReturnStatus()
+        out.append((rounds, pre_tanh.clone(), optimizer.state_dict()["state"][0]["exp_avg"].clone()))
+    (r0, p0, m0), (r1, p1, m1) = out
+    for (l0, a0, c0, Z0), (l1, a1, c1, Z1) in zip(r0, r1):
+        assert len(l0) == len(l1) and c0 == c1
+        np.testing.assert_allclose(l1, l0, rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(a1, a0, rtol=1e-5, atol=1e-8)
+        assert float((Z0 - Z1).abs().max()) < 1e-5
+    assert float((p0 - p1).abs().max()) < 1e-4 and float((m0 - m1).abs().max()) < 1e-6
