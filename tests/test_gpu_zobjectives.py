@@ -87,13 +87,20 @@ def test_objectives_through_the_generator_match_reference_trajectories(golden, c
     ref = g["zopt_%s_loss" % name]
     assert len(opt.loss_values) == len(ref)
     rtol = ZOPT3_RTOL[name]
+    dev_loss = float(np.max(np.abs(np.array(opt.loss_values) - ref) / np.maximum(np.abs(ref), 1e-30)))
+    dev_z = float((Z.cpu() - torch.from_numpy(g["zopt_%s_Z" % name])).abs().mean())
+    dev_std = float(np.max(np.abs(opt.initial_STD.cpu().numpy() - g["zopt_%s_initial_STD" % name])))
+    print("ZOPT3 %s: worst relative loss deviation %.3g (bound %g), mean |dZ| %.3g, worst initial-STD deviation %.3g" % (name, dev_loss, rtol, dev_z, dev_std))
     np.testing.assert_allclose(opt.initial_STD.cpu().numpy(), g["zopt_%s_initial_STD" % name], rtol=5e-3, atol=2e-3)
     np.testing.assert_allclose(np.array(opt.loss_values), ref, rtol=rtol, atol=rtol * np.abs(ref).max())
     np.testing.assert_allclose(np.array(opt.latest_Z_loss_values).reshape(-1), g["zopt_%s_latest" % name], rtol=rtol,
                                atol=rtol * np.abs(ref).max())
     # Adam's steps are lr-sized whatever the gradient's magnitude: where the objective's gradient is weak (the plain
     # dictionary over 256 uniform bins: ~1e-8) the bf16 noise of G's backward decides the step's sign
-    assert float((Z.cpu() - torch.from_numpy(g["zopt_%s_Z" % name])).abs().mean()) < (0.15 if name == "dict" else 3e-2)
+    # (measured on a B200, gpurun_out/zopt3_margins.log: <= 7e-3 everywhere except the two histogram cases, whose STD-preserving
+    # term with weight 1e4 makes the first steps overshoot - the loss GROWS 2e-4 -> 0.08 in the reference too: 0.025 / 0.010)
+    z_bound = {"dict": 0.15, "hist_keepstd": 0.1, "patchhist_noDC_keepstd": 0.06}.get(name, 3e-2)
+    assert dev_z < z_bound
 
 
 def test_scribble_objective_runs_on_the_generator(cuda_device):
