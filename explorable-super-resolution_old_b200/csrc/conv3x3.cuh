@@ -13,6 +13,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "esr_common.cuh"
 
 namespace esr {
@@ -154,6 +156,9 @@ constexpr int kEpiNchw = 4;      // bias -> f32 NCHW, first cout_real channels (
 constexpr int kEpiMask = 5;      // dgrad of a trunk conv: (acc + bias) * LeakyReLU'(stored activation) -> bf16 slice
 constexpr int kEpiDx0Mask = 7;   // kEpiDx0 whose 16-bit output is also scaled by LeakyReLU'(mask): the dgrads of the HR convs (f32 rows
                                  // for the latent + masked bf16 gradient of the conv below); round 1 ran them on the generic epilogue
+constexpr int kEpiOuter = 8;     // pair kernel, cout tile 64: bias [, alpha*. + gamma*res1] -> [blocked f32 +] 16-bit NHWC [2x2 replicated]:
+                                 // the first conv (f32 trunk + bf16 slice) and LR_conv (+ fea, nearest x2 for the upconv); they ran on
+                                 // the generic epilogue (126 / 78 us per launch at config 2 for ~35 us of work)
 constexpr int kEpiDx0 = 6;       // dgrad of a block input: per cout tile either v + out_f32 (accumulate, routed latent rows) or
                                  // alpha*v + gamma*res1 [, beta*. + res2] -> blocked f32 [+ scale*v as bf16]
 // The generic epilogue costs ~5000 clk per 128-pixel x 64-channel tile (issue bound: two epilogue warps per
@@ -243,6 +248,13 @@ __device__ __forceinline__ void conv_epilogue_prefetch(const esr_conv_desc& d, i
         P.m[1] = __ldg(m + 1);
         return;
     }
+    if constexpr (MODE == kEpiOuter) {
+        if (d.flags & ESR_EPI_RES1) {
+            ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0), P.r1);
+            ld_global_v8f(d.res1 + f32_off(d, true, d.res1_stride, n, y, x, d.res1_choff + co0 + 8), P.r1 + 8);
+        }
+        return;
+    }
     if constexpr (MODE == kEpiRes) {
         if (d.flags & ESR_EPI_RES1_HILO) {
             load16_hilo(d, (static_cast<size_t>(n) * d.H + y) * d.W + x, co0, P.r1);
@@ -315,8 +327,17 @@ __device__ __forceinline__ void conv_epilogue16(const esr_conv_desc& d, const fl
         st_global_v8(reinterpret_cast<__nv_bfloat16*>(d.out_bf16) + pix * d.out_bf16_stride + d.out_bf16_choff + co0, pk);
         return;
     }
-    if constexpr (MODE == kEpiAct) {
-        if (d.flags & ESR_EPI_LRELU) {
+    if constexpr (MODE == kEpiAct || MODE == kEpiOuter) {
+        if constexpr (MODE == kEpiOuter) {
+            if (d.flags & ESR_EPI_RES1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = d.alpha * v[i] + d.gamma * P.r1[i];
+            }
+            if (d.out_f32 != nullptr) {
+                st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0), v);
+                st_global_v8f(d.out_f32 + f32_off(d, true, d.out_f32_stride, n, y, x, d.out_f32_choff + co0 + 8), v + 8);
+            }
+        } else if (d.flags & ESR_EPI_LRELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], d.slope * v[i]);
         }
@@ -515,6 +536,10 @@ inline int classify_epilogue(const esr_conv_desc& d) {
     if ((f & ~static_cast<uint32_t>(ESR_EPI_F32_BLOCKED)) == ESR_EPI_MASK && bf_ok && d.out_f32 == nullptr && d.out_nchw == nullptr &&
         d.up == 1 && d.cout_tile == 32 && d.mask != nullptr && d.mask_stride % 8 == 0 && d.mask_choff % 8 == 0)
         return kEpiMask;
+    static const bool no_outer = []() { const char* v = getenv("ESR_NO_EPI_OUTER"); return v && atoi(v); }();   // A/B aid
+    if (!no_outer && d.pair && d.cout_tile == 64 && (f & ESR_EPI_F32_BLOCKED) && (f & ~static_cast<uint32_t>(ESR_EPI_RES1 | ESR_EPI_OUT_F16 | ESR_EPI_F32_BLOCKED)) == 0 &&
+        bf_ok && d.out_nchw == nullptr && d.out_lo == nullptr && (d.up == 1 || d.up == 2) && (!(f & ESR_EPI_RES1) || d.res1 != nullptr))
+        return kEpiOuter;
     return kEpiGeneric;
 }
 

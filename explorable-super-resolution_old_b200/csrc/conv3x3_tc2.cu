@@ -1013,17 +1013,17 @@ bool fill_launch_pair(ConvLaunch* L) {
 int launch_conv_tc2(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvLaunch& L, cudaStream_t stream, int use_pdl) {
     using namespace pair;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ConvLaunch);
-    // indexed by classify_epilogue(): Generic, Trunk, Res, Act, (Nchw -> Generic), Mask, Dx0
-    static const KernelFn kernels[2][8] = {
+    // indexed by classify_epilogue(): Generic, Trunk, Res, Act, (Nchw -> Generic), Mask, Dx0, Dx0Mask, Outer (cout tile 64 only)
+    static const KernelFn kernels[2][9] = {
         {conv3x3_tc2_kernel<32, kEpiGeneric>, conv3x3_tc2_kernel<32, kEpiTrunk>, conv3x3_tc2_kernel<32, kEpiRes>,
          conv3x3_tc2_kernel<32, kEpiAct>, conv3x3_tc2_kernel<32, kEpiGeneric>, conv3x3_tc2_kernel<32, kEpiMask>, conv3x3_tc2_kernel<32, kEpiDx0>,
-         conv3x3_tc2_kernel<32, kEpiDx0Mask>},
+         conv3x3_tc2_kernel<32, kEpiDx0Mask>, conv3x3_tc2_kernel<32, kEpiGeneric>},
         {conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiRes>,
          conv3x3_tc2_kernel<64, kEpiAct>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>,
-         conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>}};
+         conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiGeneric>, conv3x3_tc2_kernel<64, kEpiOuter>}};
     ESR_ONCE_PER_DEVICE(
         for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 8; ++b)
+            for (int b = 0; b < 9; ++b)
                 ESR_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     );
     const int nb = L.d.cout_tile == 32 ? 2 : 1;
