@@ -82,6 +82,14 @@ def test_patch_select_validates_arguments():
     assert l.esr_kde_workspace_bytes(0, 5) == -1
     assert l.esr_kde_workspace_bytes(100, 100000) > 0              # few own vectors: the other range is split
     assert l.esr_kde_workspace_bytes(1 << 20, 256) == 0
+    # the gradient pass splits the bin range the same way: fp64 partials of D x N values per split
+    assert l.esr_kde_grad_workspace_bytes(0, 5, 1) == -1
+    assert l.esr_kde_grad_workspace_bytes(1 << 20, 256, 1) == 0
+    few = l.esr_kde_grad_workspace_bytes(3600, 4000, 36)
+    assert few > 0 and few % (36 * 3600 * 8) == 0 and few // (36 * 3600 * 8) == l.esr_kde_workspace_bytes(3600, 4000) // (3600 * 8)
+    # compute entry points validate before touching the device (no GPU here): null pointers, D out of range, bad temperature
+    assert l.esr_kde_sums(None, 0, 10, None, 1, 10, 1, 1.0, 1e-3, 1e-7, None, None, None) == -1
+    assert l.esr_kde_grad(None, 10, None, 10, 1, 1.0, 1e-3, 1e-7, None, None, None, None, None) == -1
 
 
 def test_hsv_round_trip_and_known_colours():
