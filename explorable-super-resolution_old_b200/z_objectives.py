@@ -108,8 +108,9 @@ def patch_tables(mask, patch_size, device, patches_overlap=1, return_non_covered
     mask = _opened_mask(mask, patch_size)
     H, W = mask.shape
     labelled = np.where(mask, 1 + np.arange(mask.size, dtype=np.int64).reshape(H, W), 0)
-    windows = np.lib.stride_tricks.sliding_window_view(labelled, (patch_size, patch_size)).reshape(-1, patch_size ** 2)
-    indexes = np.ascontiguousarray(windows[np.all(windows > 0, axis=1)] - 1)
+    windows = np.lib.stride_tricks.sliding_window_view(labelled, (patch_size, patch_size))      # a view: nothing is copied
+    inside = windows.min(axis=(2, 3)) > 0                                                        # windows wholly in the mask
+    indexes = np.ascontiguousarray(windows[inside].reshape(-1, patch_size ** 2) - 1)             # raster order, only those
     non_covered = None
     if patches_overlap < 1:
         if indexes.size == 0:
