@@ -193,10 +193,12 @@ class SoftHistogramLoss(torch.nn.Module):
 
     def _prune(self, desired):
         """Drops a desired sample when a LATER one lies within half a bin width in every value (Desired_Im_2_Bins,
-        :106-130, with its pre-bool-dtype mask semantics).  Row blocks bound the memory of the pairwise comparison."""
+        :106-130, with its pre-bool-dtype mask semantics).  Row blocks bound the memory of the pairwise comparison; the
+        whole set is always pruned against itself (the reference splits the set into more and more sub-images until its
+        [D, N, N] tensor fits, :108-126, so for large N its result depends on the free memory of the moment)."""
         D, N = desired.shape
         keep = torch.ones(N, dtype=torch.bool, device=desired.device)
-        rows = builtins_max(1, (1 << 24) // builtins_max(1, N * D))
+        rows = builtins_max(1, (1 << 26) // builtins_max(1, N * D))       # <= 256 MiB of fp32 differences per block
         col = torch.arange(N, device=desired.device)
         for r0 in range(0, N, rows):
             blk = desired[:, r0:r0 + rows]
