@@ -8,8 +8,8 @@ What is different from the reference's formulation:
   (``csrc/zobj.cu``: ``esr_kde_sums`` / ``esr_kde_grad``) behind one autograd node, instead of [D, N, M] fp64 tensors;
 * patch extraction is an index table + gather (``PatchTable``) instead of a sparse 0/1 matrix product, and the greedy
   patch selection is a native host loop (``esr_patch_select``);
-* every objective is an object with ``prepare`` state and a ``__call__(fake_H) -> per-image loss``; ``resolve()`` maps the
-  GUI's objective strings (substring conventions of the reference) onto them once.
+* every objective is an object (its set-up in the constructor, ``__call__(fake_H) -> per-image loss``); ``resolve()`` maps
+  the GUI's objective strings (substring conventions of the reference) onto them once.
 
 Everything consumes the generator's output ``fake_H`` and hands back dL/d fake_H; G+CEM forward and the data gradient stay
 on this package's kernels.  No CPU path: the density kernels raise on CPU tensors."""
