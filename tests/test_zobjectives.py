@@ -197,3 +197,23 @@ def test_repeated_rounds_and_random_inits_match_reference(reference_zopt, object
         np.testing.assert_allclose(a1, a0, rtol=1e-5, atol=1e-8)
         assert float((Z0 - Z1).abs().max()) < 1e-5
     assert float((p0 - p1).abs().max()) < 1e-4 and float((m0 - m1).abs().max()) < 1e-6
+
+
+def test_feed_desired_hist_im_matches_reference(reference_zopt, oracle_density):
+    """Z_optimizer.feed_data's histogram branch (Z_optimization.py:547-548 -> Feed_Desired_Hist_Im, :97-104): new desired
+    images replace the target histograms of an existing loss."""
+    img, desired, dmasks, im = zc.hist_inputs("hist")
+    new_desired = torch.cat([zc.smooth_image(401, 1, *zc.HIST_HW), zc.smooth_image(402, 1, *zc.HIST_HW)], 0)      # [2, 3, H, W]
+    out = []
+    for cls in (reference_zopt.SoftHistogramLoss, zo.SoftHistogramLoss):
+        loss = cls(bins=256, min=0, max=1, desired_hist_image=[d.clone() for d in desired], desired_hist_image_mask=[m.copy() for m in dmasks],
+                   input_im_HR_mask=im.clone(), gray_scale=True, patch_size=1, temperature=5e-4)
+        before = float(loss(img))
+        loss.Feed_Desired_Hist_Im(new_desired.clone())
+        x = img.clone().requires_grad_(True)
+        after = loss(x)
+        grad, = torch.autograd.grad(after, x)
+        out.append((before, float(after), grad))
+    (b0, a0, g0), (b1, a1, g1) = out
+    assert abs(b0 - b1) <= 1e-6 * max(1.0, abs(b0)) and abs(a0 - a1) <= 1e-6 * max(1.0, abs(a0)) and abs(a0 - b0) > 1e-9
+    np.testing.assert_allclose(g1.numpy(), g0.numpy(), rtol=1e-4, atol=1e-7 * float(g0.abs().max()))
