@@ -217,3 +217,30 @@ def test_feed_desired_hist_im_matches_reference(reference_zopt, oracle_density):
     (b0, a0, g0), (b1, a1, g1) = out
     assert abs(b0 - b1) <= 1e-6 * max(1.0, abs(b0)) and abs(a0 - a1) <= 1e-6 * max(1.0, abs(a0)) and abs(a0 - b0) > 1e-9
     np.testing.assert_allclose(g1.numpy(), g0.numpy(), rtol=1e-4, atol=1e-7 * float(g0.abs().max()))
+
+
+@pytest.mark.parametrize("objective", ["l1", "dict"])
+def test_training_mode_with_hr_unpadder_matches_reference(reference_zopt, oracle_density, objective):
+    """The per-batch optimal-Z search of the training loop (SRRaGAN_model.py:144-147): HR_unpadder given, so every
+    iteration's output is cropped before the loss (:575-576), no per-image values are kept (:621) and one more
+    un-cropped forward follows the loop (:646-649)."""
+    from oracle.gen_golden import RefModel
+    lr, z0 = synth.make_inputs(2, 8, 8, seed=6)
+    crop = lambda t: t[:, :, 4:-4, 4:-4]          # noqa: E731
+    out = []
+    for cls, model_cls in ((reference_zopt.Z_optimizer, RefModel), (Z_optimizer, SRModelShim)):
+        netG = zc.StubGenerator()
+        model = model_cls(netG)
+        data = {"LR": lr, "Z": 0.2 * z0, "HR": crop(zc.smooth_image(77, 2, 32, 32))}
+        if objective == "dict":
+            data["HR"] = [zc.smooth_image(78, 1, 24, 24)]
+            data["Desired_Im_Mask"] = [np.ones((24, 24), dtype=bool)]
+        torch.manual_seed(5)
+        opt = cls(objective=objective, Z_size=[32, 32], model=model, Z_range=1.0, max_iters=3, data=data, initial_LR=0.05,
+                  batch_size=2, HR_unpadder=crop)
+        Z = opt.optimize()
+        out.append((list(opt.loss_values), Z, model.fake_H.detach().clone(), opt.cur_iter))
+    (l0, Z0, f0, c0), (l1, Z1, f1, c1) = out
+    assert c0 == c1 and tuple(f0.shape) == tuple(f1.shape) == (2, 3, 32, 32)          # the final forward is un-cropped
+    np.testing.assert_allclose(l1, l0, rtol=1e-5, atol=1e-8)
+    assert float((Z0 - Z1).abs().max()) < 1e-5 and float((f0 - f1).abs().max()) < 1e-5
