@@ -244,3 +244,37 @@ def test_training_mode_with_hr_unpadder_matches_reference(reference_zopt, oracle
     assert c0 == c1 and tuple(f0.shape) == tuple(f1.shape) == (2, 3, 32, 32)          # the final forward is un-cropped
     np.testing.assert_allclose(l1, l0, rtol=1e-5, atol=1e-8)
     assert float((Z0 - Z1).abs().max()) < 1e-5 and float((f0 - f1).abs().max()) < 1e-5
+
+
+def test_loggers_receive_the_same_records_as_in_the_reference(reference_zopt):
+    """loggers (one per image, GUI.py:1590-1594): every iteration each logger gets its image's loss (:609-613); with
+    loggers the host reads every value as it goes (no deferred reads)."""
+    from oracle.gen_golden import RefModel
+
+    class Recorder:
+        def __init__(self):
+            self.records = []
+
+        def print_format_results(self, mode, rlt, dont_print=False):
+            self.records.append((mode, rlt["iters"], rlt["lr"], rlt["Z_loss"], dont_print))
+
+    lr, z0 = synth.make_inputs(1, 8, 8, seed=8)
+    out = []
+    for cls, model_cls in ((reference_zopt.Z_optimizer, RefModel), (Z_optimizer, SRModelShim)):
+        netG = zc.StubGenerator()
+        model = model_cls(netG)
+        data = {"LR": lr.repeat(2, 1, 1, 1), "Z": (0.3 * z0).repeat(2, 1, 1, 1)}
+        model.feed_data(data)
+        with torch.no_grad():
+            model.fake_H = netG(model.model_input)
+        loggers = [Recorder(), Recorder()]
+        opt = cls(objective="TV", Z_size=[32, 32], model=model, Z_range=1.0, max_iters=3, data=data, initial_LR=0.05, batch_size=2,
+                  loggers=loggers, initial_Z=0.3 * z0)
+        opt.random_Z_inits = False
+        opt.Z_model.Z.data.copy_(zc.zopt3_z_init("random_l1")[:2])
+        opt.optimize()
+        out.append([lg.records for lg in loggers])
+    for ref_records, records in zip(*out):
+        assert len(ref_records) == len(records) == 3
+        for a, b in zip(ref_records, records):
+            assert a[:3] == b[:3] and a[4] == b[4] and abs(a[3] - b[3]) <= 1e-6 * max(1.0, abs(a[3]))
