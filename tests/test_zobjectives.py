@@ -278,3 +278,33 @@ def test_loggers_receive_the_same_records_as_in_the_reference(reference_zopt):
         assert len(ref_records) == len(records) == 3
         for a, b in zip(ref_records, records):
             assert a[:3] == b[:3] and a[4] == b[4] and abs(a[3] - b[3]) <= 1e-6 * max(1.0, abs(a[3]))
+
+
+class _OracleG(torch.nn.Module):
+    """The CPU oracle of G+CEM (oracle/rrdbnet.GCEMOracle, fp32) behind the nn.Module surface Z_optimizer expects."""
+
+    def __init__(self, nb=2, seed=5):
+        super().__init__()
+        from oracle.rrdbnet import GCEMOracle
+        self.anchor = torch.nn.Parameter(torch.zeros(1))            # Z_optimizer reads the device from a parameter
+        self.oracle = GCEMOracle(synth.make_weights("default", seed=seed, nb=nb), nb=nb)
+
+    def forward(self, x):
+        return self.oracle.forward(x)
+
+
+@pytest.mark.parametrize("name", [n for n in zc.ZOPT3_CASES if n not in zc.NO_REFERENCE_RUN])
+def test_objectives_around_the_oracle_generator_match_reference_golden(golden, oracle_density, name):
+    """The trajectories oracle/gen_golden.py recorded from the reference's Z_optimizer around the reference's nb = 2 G+CEM
+    (tests/golden/zobjectives.npz), reproduced by this package's Z_optimizer around the CPU oracle of G+CEM: needs
+    neither /root/reference nor a GPU.  tests/test_gpu_zobjectives.py runs the same cases through the CUDA generator."""
+    g = golden("zobjectives")
+    netG = _OracleG()
+    lr, z0 = synth.make_inputs(1, zc.ZOPT3_HW[0], zc.ZOPT3_HW[1], seed=11)
+    opt, Z = zc.run_zopt_case(Z_optimizer, SRModelShim(netG), netG, name, lr, z0, z_init=zc.zopt3_z_init(name))
+    ref = g["zopt_%s_loss" % name]
+    np.testing.assert_allclose(opt.initial_STD.numpy(), g["zopt_%s_initial_STD" % name], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(np.array(opt.loss_values), ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())
+    np.testing.assert_allclose(np.array(opt.latest_Z_loss_values).reshape(-1), g["zopt_%s_latest" % name], rtol=2e-4,
+                               atol=2e-4 * np.abs(ref).max())
+    assert float((Z - torch.from_numpy(g["zopt_%s_Z" % name])).abs().mean()) < 2e-3
