@@ -308,3 +308,45 @@ def test_objectives_around_the_oracle_generator_match_reference_golden(golden, o
     np.testing.assert_allclose(np.array(opt.latest_Z_loss_values).reshape(-1), g["zopt_%s_latest" % name], rtol=2e-4,
                                atol=2e-4 * np.abs(ref).max())
     assert float((Z - torch.from_numpy(g["zopt_%s_Z" % name])).abs().mean()) < 2e-3
+
+
+ZOPT2 = [("max_std", "max_STD", 4, False, 1), ("min_std", "min_STD", 3, False, 1), ("std_increase", "STD_increase", 4, False, 1),
+         ("std_decrease_mult", "STD_decrease", 3, False, 1), ("tv_converge", "TV", -3, False, 1), ("tv_masked", "TV", 4, True, 1),
+         ("tv_batch2", "TV", 3, False, 2)]
+
+
+@pytest.mark.parametrize("name,objective,max_iters,masked,bs", ZOPT2)
+def test_built_in_objectives_around_the_oracle_generator_match_reference_golden(golden, name, objective, max_iters, masked, bs):
+    """tests/golden/zopt2.npz (the reference's Z_optimizer on TV / STD objectives, convergence mode, masks, batch 2) through
+    this package's generic loop around the CPU oracle of G+CEM: the host logic of a17-a19 without a GPU.  The GPU test of
+    the same cases (tests/test_gpu_zopt.py) runs the CUDA generator and, where it applies, the single-graph loop."""
+    g = golden("zopt2")
+    netG = _OracleG()
+    lr, z0 = synth.make_inputs(1, 8, 8, seed=5)
+    model = SRModelShim(netG)
+    data = {"LR": lr.repeat(bs, 1, 1, 1), "Z": (0.5 * z0).repeat(bs, 1, 1, 1)}
+    if "increase" in objective or "decrease" in objective:
+        data["STD_increment"] = None if name.endswith("_mult") else 0.02
+    model.feed_data(data)
+    with torch.no_grad():
+        model.fake_H = netG(model.model_input)
+    kw = {}
+    if masked:
+        im = np.zeros((32, 32), dtype=np.float32)
+        im[8:24, 4:20] = 1
+        zm = np.zeros((32, 32), dtype=np.float32)
+        zm[4:28, :24] = 1
+        kw = dict(image_mask=im, Z_mask=zm, initial_Z=0.5 * z0)
+    opt = Z_optimizer(objective=objective, Z_size=[32, 32], model=model, Z_range=1.0, max_iters=max_iters, data=data,
+                      initial_LR=0.1, batch_size=bs, **kw)
+    np.testing.assert_allclose(opt.initial_STD.numpy(), g[name + "_initial_STD"], rtol=1e-4)
+    if bs > 1:
+        opt.random_Z_inits = False
+        opt.Z_model.Z.data.copy_(torch.from_numpy(g[name + "_Zinit"]))
+    Z = opt.optimize()
+    ref = g[name + "_loss"]
+    assert len(opt.loss_values) == len(ref) and opt.cur_iter == int(g[name + "_cur_iter"])
+    rtol = 2e-2 if ("increase" in objective or "decrease" in objective) else 5e-4       # squared differences of nearly equal STDs
+    np.testing.assert_allclose(np.array(opt.loss_values), ref, rtol=rtol, atol=1e-9)
+    np.testing.assert_allclose(np.array(opt.latest_Z_loss_values), g[name + "_latest"], rtol=rtol, atol=1e-9)
+    assert float((Z - torch.from_numpy(g[name + "_Z"])).abs().mean()) < 5e-3
