@@ -350,3 +350,22 @@ def test_built_in_objectives_around_the_oracle_generator_match_reference_golden(
     np.testing.assert_allclose(np.array(opt.loss_values), ref, rtol=rtol, atol=1e-9)
     np.testing.assert_allclose(np.array(opt.latest_Z_loss_values), g[name + "_latest"], rtol=rtol, atol=1e-9)
     assert float((Z - torch.from_numpy(g[name + "_Z"])).abs().mean()) < 5e-3
+
+
+def test_l1_training_mode_around_the_oracle_generator_matches_reference_golden(golden):
+    """tests/golden/zopt.npz, the training-mode l1 search (no pre-pad, HR_unpadder given) around the CPU oracle."""
+    g = golden("zopt")
+    netG = _OracleG()
+    netG.oracle.pre_pad = False                                  # netG.train(): CEM_PyTorch pads in eval mode only (CEMnet.py:170-181)
+    lr, z0 = synth.make_inputs(1, 8, 8, seed=5)
+    model = SRModelShim(netG)
+    data = {"LR": lr, "Z": 0.5 * z0, "HR": torch.from_numpy(g["l1_train_target"])}
+    model.feed_data(data)
+    opt = Z_optimizer(objective="l1", Z_size=[32, 32], model=model, Z_range=1.0, max_iters=4, data=data, initial_LR=0.1,
+                      batch_size=1, HR_unpadder=lambda t: t)
+    opt.feed_data(data)
+    opt.random_Z_inits = False
+    opt.Z_model.Z.data.copy_(torch.from_numpy(g["l1_train_Zinit"]))
+    Z = opt.optimize()
+    np.testing.assert_allclose(np.array(opt.loss_values), g["l1_train_loss"], rtol=5e-4)
+    assert float((Z - torch.from_numpy(g["l1_train_Z"])).abs().mean()) < 5e-3
