@@ -4,7 +4,12 @@ The density sums are CUDA kernels (csrc/zobj.cu) with no CPU path, so these test
 (oracle/zobjectives.kde_sums) in their place and check everything around them - patch tables and the native greedy
 selection, bin pruning, DC / STD normalisation, histogram normalisers, the objective classes, the Z_optimizer wiring -
 against the committed goldens (recorded from the unmodified reference) and, when /root/reference exists, against the
-reference's own classes run side by side.  tests/test_gpu_zobjectives.py checks the kernels themselves."""
+reference's own classes run side by side.  tests/test_gpu_zobjectives.py checks the kernels themselves.
+
+The second half of the file runs Z_optimizer's whole host loop on CPU - the built-in objectives included - around the
+CPU oracle of G+CEM against the trajectories recorded from the reference (zopt.npz, zopt2.npz, zobjectives.npz), and the
+GUI's calling patterns (repeated rounds, random initialisations, loggers, the training-mode search) side by side with the
+reference's class."""
 import warnings
 
 import numpy as np
